@@ -1,0 +1,264 @@
+"""ctypes front-end of the CPU oracle (oracle/qoracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this package; the product (quantized-gemm-for-transformer-inference_b200) never does.
+
+Each wrapper takes/returns numpy arrays and maps 1:1 onto a C function whose comment cites the
+reference file:line it restates.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libqoracle.so")
+
+MODE_REF_EXACT = 0
+MODE_TRUE_ABSMAX = 1
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/qoracle.c (and oracle/_ref when /root/reference exists)."""
+    src = os.path.join(_HERE, "qoracle.c")
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "libqoracle.so"], check=True, capture_output=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.qo_quant_code.restype = C.c_int
+        _lib.qo_quant_code.argtypes = [C.c_float, C.c_float]
+        _lib.qo_max_partial_sum.restype = C.c_int64
+        _lib.qo_signed_mean_f32.restype = C.c_float
+        _lib.qo_num_threads.restype = C.c_int
+        _lib.qo_quantized_mm_f32.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    a = np.asarray(a)
+    if a.dtype in (np.float16,):
+        a = a.astype(np.float32)
+    assert a.dtype == np.float32, a.dtype
+    return np.ascontiguousarray(a)
+
+
+def num_threads() -> int:
+    return int(lib().qo_num_threads())
+
+
+def absmax_rows(X, mode=MODE_REF_EXACT):
+    X = _f32(X)
+    M, K = X.shape
+    out = np.empty(M, np.float32)
+    lib().qo_absmax_rows_f32(_p(X), C.c_int(M), C.c_int(K), C.c_int64(K), C.c_int(mode), _p(out))
+    return out
+
+
+def absmax_cols(W, mode=MODE_REF_EXACT):
+    W = _f32(W)
+    K, N = W.shape
+    out = np.empty(N, np.float32)
+    lib().qo_absmax_cols_f32(_p(W), C.c_int(K), C.c_int(N), C.c_int64(N), C.c_int(mode), _p(out))
+    return out
+
+
+def inv_divide(c, b=127.0):
+    c = _f32(c)
+    out = np.empty_like(c)
+    lib().qo_inv_divide_f32(_p(c), C.c_int64(c.size), C.c_float(b), _p(out))
+    return out
+
+
+def quant_code(x: float, s: float) -> int:
+    return int(lib().qo_quant_code(C.c_float(x), C.c_float(s)))
+
+
+def quantize_rows(X, sx):
+    X = _f32(X)
+    sx = _f32(sx).reshape(-1)
+    M, K = X.shape
+    out = np.empty((M, K), np.int8)
+    lib().qo_quantize_rows_f32(_p(X), C.c_int(M), C.c_int(K), C.c_int64(K), _p(sx), _p(out), C.c_int64(K))
+    return out
+
+
+def quantize_cols(W, sw):
+    W = _f32(W)
+    sw = _f32(sw).reshape(-1)
+    K, N = W.shape
+    out = np.empty((K, N), np.int8)
+    lib().qo_quantize_cols_f32(_p(W), C.c_int(K), C.c_int(N), C.c_int64(N), _p(sw), _p(out), C.c_int64(N))
+    return out
+
+
+def absmax_quant_rows(X, range_=127.0, mode=MODE_REF_EXACT):
+    """a1 + a3 + a4 of SURVEY section 8: returns (Xq int8 [M,K], Cx f32 [M])."""
+    Cx = absmax_rows(X, mode)
+    return quantize_rows(X, inv_divide(Cx, range_)), Cx
+
+
+def absmax_quant_cols(W, range_=127.0, mode=MODE_REF_EXACT):
+    """a2 + a3 + a4: returns (Wq int8 [K,N], Cw f32 [N])."""
+    Cw = absmax_cols(W, mode)
+    return quantize_cols(W, inv_divide(Cw, range_)), Cw
+
+
+def gemm_s8s8s32(A, B):
+    A = np.ascontiguousarray(A, np.int8)
+    B = np.ascontiguousarray(B, np.int8)
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2
+    out = np.empty((M, N), np.int32)
+    lib().qo_gemm_s8s8s32(_p(A), _p(B), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int64(K), C.c_int64(N),
+                          _p(out), C.c_int64(N))
+    return out
+
+
+def gemm_s8_reff32(A, B):
+    """Literal emulation of the reference's fp32-FMA 'int' accumulator (small shapes)."""
+    A = np.ascontiguousarray(A, np.int8)
+    B = np.ascontiguousarray(B, np.int8)
+    M, K = A.shape
+    _, N = B.shape
+    out = np.empty((M, N), np.int32)
+    lib().qo_gemm_s8_reff32(_p(A), _p(B), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int64(K), C.c_int64(N),
+                            _p(out), C.c_int64(N))
+    return out
+
+
+def max_partial_sum(A, B) -> int:
+    A = np.ascontiguousarray(A, np.int8)
+    B = np.ascontiguousarray(B, np.int8)
+    M, K = A.shape
+    _, N = B.shape
+    return int(lib().qo_max_partial_sum(_p(A), _p(B), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int64(K),
+                                        C.c_int64(N)))
+
+
+def gemm_f32_ref(A, B):
+    A = _f32(A)
+    B = _f32(B)
+    M, K = A.shape
+    _, N = B.shape
+    out = np.empty((M, N), np.float32)
+    lib().qo_gemm_f32_ref(_p(A), _p(B), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int64(K), C.c_int64(N),
+                          _p(out), C.c_int64(N))
+    return out
+
+
+def dequant(acc, Cx, Cw, range_=127.0, bias=None):
+    acc = np.ascontiguousarray(acc, np.int32)
+    Cx = _f32(Cx).reshape(-1)
+    Cw = _f32(Cw).reshape(-1)
+    M, N = acc.shape
+    b = None if bias is None else _f32(bias).reshape(-1)
+    out = np.empty((M, N), np.float32)
+    lib().qo_dequant_f32(_p(acc), C.c_int64(N), _p(Cx), _p(Cw), _p(b), C.c_int(M), C.c_int(N),
+                         C.c_float(range_), _p(out), C.c_int64(N))
+    return out
+
+
+def quantized_mm(X, W, range_=127.0, mode=MODE_REF_EXACT, bias=None, return_parts=False):
+    """op_quantized_mm (src/ops/op_mm.cuh:67-101), optionally followed by the LinearLayer bias add."""
+    X = _f32(X)
+    W = _f32(W)
+    M, K = X.shape
+    K2, N = W.shape
+    assert K == K2
+    O = np.empty((M, N), np.float32)
+    b = None if bias is None else _f32(bias).reshape(-1)
+    if return_parts:
+        Cx = np.empty(M, np.float32)
+        Cw = np.empty(N, np.float32)
+        Xq = np.empty((M, K), np.int8)
+        Wq = np.empty((K, N), np.int8)
+        acc = np.empty((M, N), np.int32)
+    else:
+        Cx = Cw = Xq = Wq = acc = None
+    rc = lib().qo_quantized_mm_f32(_p(X), _p(W), _p(O), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int64(K),
+                                   C.c_int64(N), C.c_int64(N), C.c_float(range_), C.c_int(mode), _p(b),
+                                   _p(Cx), _p(Cw), _p(Xq), _p(Wq), _p(acc))
+    if rc != 0:
+        raise MemoryError("qo_quantized_mm_f32")
+    if return_parts:
+        return O, dict(Cx=Cx, Cw=Cw, Xq=Xq, Wq=Wq, acc=acc)
+    return O
+
+
+def outlier_mask(A, thr):
+    A = _f32(A)
+    M, K = A.shape
+    out = np.empty((M, K), np.float32)
+    lib().qo_outlier_mask_f32(_p(A), C.c_int(M), C.c_int(K), C.c_int64(K), C.c_float(thr), _p(out),
+                              C.c_int64(K))
+    return out
+
+
+def signed_mean(A) -> float:
+    A = _f32(A)
+    M, N = A.shape
+    return float(lib().qo_signed_mean_f32(_p(A), C.c_int(M), C.c_int(N), C.c_int64(N)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Extensions the reference does not implement (parity UNPINNED; the spec is ours)
+# ---------------------------------------------------------------------------------------------
+
+def round_to(dtype: str, y):
+    """fp32 -> output dtype conversion of the fused epilogue (round to nearest even)."""
+    if dtype == "f32":
+        return y
+    if dtype == "f16":
+        return y.astype(np.float16)
+    if dtype == "bf16":
+        import torch
+
+        return torch.from_numpy(y).to(torch.bfloat16)
+    raise ValueError(dtype)
+
+
+def outlier_columns(X, thr):
+    """K-indices that hold at least one |x| > thr (strict, NaN counts) -- column-reduction of
+    the reference's elementwise mask primitive (src/ops/op_elemwise.cuh:292-306,698-708)."""
+    return np.nonzero(outlier_mask(X, thr).max(axis=0) > 0)[0].astype(np.int32)
+
+
+def quantized_mm_outlier(X, W, thr, range_=127.0, mode=MODE_REF_EXACT, bias=None, side_dtype=np.float16):
+    """LLM.int8()-style mixed decomposition (parity unpinned):
+    int8 path on X with outlier feature columns zeroed (row scales from the remaining entries),
+    W quantized over all rows, plus an fp16 side product X[:,O] @ W[O,:] accumulated in fp32
+    (k ascending fma), added after dequantization and before the bias."""
+    X = _f32(X)
+    W = _f32(W)
+    idx = outlier_columns(X, thr)
+    Xr = X.copy()
+    Xr[:, idx] = 0.0
+    O, parts = quantized_mm(Xr, W, range_, mode, None, return_parts=True)
+    if idx.size:
+        Xo = X[:, idx].astype(side_dtype).astype(np.float32)
+        Wo = W[idx, :].astype(side_dtype).astype(np.float32)
+        side = gemm_f32_ref(Xo, Wo)
+        O = O + side
+    if bias is not None:
+        O = O + _f32(bias).reshape(1, -1)
+    parts["outlier_idx"] = idx
+    return O.astype(np.float32), parts

@@ -1,0 +1,206 @@
+// ref_driver.cu -- C API over the REFERENCE's own CUDA kernels.  TEST INFRASTRUCTURE ONLY.
+//
+// Built by oracle/Makefile with `nvcc -I /root/reference/src` into oracle/_ref/libref_qmm.so.
+// The reference headers are included where they lie; nothing of them is copied into this repo.
+// It lets tests/ and bench.py run the unmodified reference operators (op_absmax, op_inv_divide,
+// op_multiply<float,int8_t>, op_mm<int8_t,int>, op_mm<float,float>, op_dequantize,
+// op_multiply(const), op_quantized_mm; src/ops/*.cuh) on a B200, on the same inputs as our
+// kernels, to pin the CPU oracle and to time "the reference's own GPU kernel".
+#include <sys/time.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "utils/tensor.cuh"
+#include "ops/op_elemwise.cuh"
+#undef N  // src/ops/op_elemwise.cuh:10 defines N as 256
+#include "ops/op_reduction.cuh"
+#include "ops/op_mm.cuh"
+
+unsigned long long randgen_seed = 0;  // the ops `extern` this (src/ops/op_elemwise.cuh:12)
+
+namespace {
+
+template <typename T>
+Tensor<T> view(T *dptr, int h, int w) {  // non-owning [h,w] row-major view of device memory
+  Tensor<T> t;
+  t.h = h; t.w = w; t.stride_h = w; t.stride_w = 1; t.offset = 0;
+  t.rawp = dptr; t.on_device = true;
+  return t;
+}
+
+template <typename T>
+void d2h(void *dst, const Tensor<T> &t) {
+  if (dst) cudaMemcpy(dst, t.rawp, sizeof(T) * (size_t)t.h * t.w, cudaMemcpyDeviceToHost);
+}
+
+int status() {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return (int)e;
+}
+
+// The op sequence of op_quantized_mm / timing_quantize.cu:38-58 with every intermediate kept.
+struct Pipeline {
+  Tensor<float> Cx, Cw, sx, sw, Outer;
+  Tensor<int8_t> Xq, Wq;
+  Tensor<int> acc;
+  Pipeline(int m, int n, int k)
+      : Cx{m, 1, true}, Cw{1, n, true}, sx{m, 1, true}, sw{1, n, true}, Outer{m, n, true},
+        Xq{m, k, true}, Wq{k, n, true}, acc{m, n, true} {}
+  void run(const Tensor<float> &X, const Tensor<float> &W, Tensor<float> &O, float range) {
+    op_absmax(X, Cx);
+    op_absmax(W, Cw);
+    op_inv_divide(Cx, range, sx);
+    op_inv_divide(Cw, range, sw);
+    op_multiply(X, sx, Xq);
+    op_multiply(W, sw, Wq);
+    op_mm(Xq, Wq, acc);
+    op_mm(Cx, Cw, Outer);
+    op_dequantize(acc, Outer, O);
+    op_multiply(O, 1 / (range * range), O);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ref_version() { return 1; }
+
+// Host in / host out; returns every intermediate that is non-NULL.
+int ref_quantized_mm_parts(const float *X, const float *W, int m, int n, int k, float range,
+                           float *O, float *Cx, float *Cw, int8_t *Xq, int8_t *Wq, int32_t *acc) {
+  Tensor<float> dX{m, k, true}, dW{k, n, true}, dO{m, n, true};
+  cudaMemcpy(dX.rawp, X, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
+  cudaMemcpy(dW.rawp, W, sizeof(float) * (size_t)k * n, cudaMemcpyHostToDevice);
+  Pipeline p(m, n, k);
+  p.run(dX, dW, dO, range);
+  int rc = status();
+  d2h(O, dO); d2h(Cx, p.Cx); d2h(Cw, p.Cw); d2h(Xq, p.Xq); d2h(Wq, p.Wq); d2h(acc, p.acc);
+  return rc;
+}
+
+// The reference's own entry point, src/ops/op_mm.cuh:67-101, host in / host out.
+int ref_op_quantized_mm(const float *X, const float *W, int m, int n, int k, float range, float *O) {
+  Tensor<float> dX{m, k, true}, dW{k, n, true}, dO{m, n, true};
+  cudaMemcpy(dX.rawp, X, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
+  cudaMemcpy(dW.rawp, W, sizeof(float) * (size_t)k * n, cudaMemcpyHostToDevice);
+  op_quantized_mm(dX, dW, dO, range);
+  int rc = status();
+  d2h(O, dO);
+  return rc;
+}
+
+// op_mm<float,float>, host in / host out (the unquantized comparison product).
+int ref_mm_f32(const float *A, const float *B, int m, int n, int k, float *C) {
+  Tensor<float> dA{m, k, true}, dB{k, n, true}, dC{m, n, true};
+  cudaMemcpy(dA.rawp, A, sizeof(float) * (size_t)m * k, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB.rawp, B, sizeof(float) * (size_t)k * n, cudaMemcpyHostToDevice);
+  op_mm(dA, dB, dC);
+  int rc = status();
+  d2h(C, dC);
+  return rc;
+}
+
+// op_mm<int8_t,int>, host in / host out.
+int ref_mm_s8(const int8_t *A, const int8_t *B, int m, int n, int k, int32_t *C) {
+  Tensor<int8_t> dA{m, k, true}, dB{k, n, true};
+  Tensor<int> dC{m, n, true};
+  cudaMemcpy(dA.rawp, A, (size_t)m * k, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB.rawp, B, (size_t)k * n, cudaMemcpyHostToDevice);
+  op_mm(dA, dB, dC);
+  int rc = status();
+  d2h(C, dC);
+  return rc;
+}
+
+// Inputs the way the timing driver draws them (src/timing_quantize.cu:17-20): cuRAND XORWOW,
+// U(-1,1], X first then W from one generator seeded with `seed`.  Host out.
+int ref_uniform_inputs(unsigned long long seed, int m, int n, int k, float *X, float *W) {
+  curandGenerator_t gen;
+  if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS) return -1;
+  curandSetPseudoRandomGeneratorSeed(gen, seed);
+  Tensor<float> dX{m, k, true}, dW{k, n, true};
+  curandGenerateUniform(gen, dX.rawp, (size_t)m * k);
+  op_add<float>(dX, -1.0f / 2.0f, dX);      // op_uniform_init: op_add(t, min/(max-min), t)
+  op_multiply(dX, 2.0f, dX);                //                  op_multiply(t, max-min, t)
+  curandGenerateUniform(gen, dW.rawp, (size_t)k * n);
+  op_add<float>(dW, -1.0f / 2.0f, dW);
+  op_multiply(dW, 2.0f, dW);
+  int rc = status();
+  d2h(X, dX); d2h(W, dW);
+  curandDestroyGenerator(gen);
+  return rc;
+}
+
+// Device-resident timing of the reference kernels on caller-owned device buffers.
+//   ms_events : CUDA-event time per iteration of the 10-kernel pipeline with every temporary
+//               pre-allocated (kernels only).
+//   ms_wall   : reference-style per-call time of op_quantized_mm itself -- gettimeofday around the
+//               call + cudaDeviceSynchronize, temporaries cudaMalloc'ed/cudaFree'd inside
+//               (src/timing_quantize.cu:38-65).
+int ref_time_quantized_mm_dev(float *dXp, float *dWp, float *dOp, int m, int n, int k, float range,
+                              int warmup, int iters, double *ms_events, double *ms_wall) {
+  Tensor<float> X = view(dXp, m, k), W = view(dWp, k, n), O = view(dOp, m, n);
+  {
+    Pipeline p(m, n, k);
+    for (int i = 0; i < warmup; i++) p.run(X, W, O, range);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < iters; i++) p.run(X, W, O, range);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_events) *ms_events = (double)ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  if (ms_wall) {
+    for (int i = 0; i < warmup; i++) op_quantized_mm(X, W, O, range);
+    cudaDeviceSynchronize();
+    struct timeval t0, t1;
+    gettimeofday(&t0, NULL);
+    for (int i = 0; i < iters; i++) {
+      op_quantized_mm(X, W, O, range);
+      cudaDeviceSynchronize();
+    }
+    gettimeofday(&t1, NULL);
+    *ms_wall = ((t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_usec - t0.tv_usec)) / 1e3 / iters;
+  }
+  return status();
+}
+
+// Same for the unquantized fp32 op_mm (src/timing_quantize.cu:27-35).
+int ref_time_mm_f32_dev(float *dXp, float *dWp, float *dOp, int m, int n, int k, int warmup,
+                        int iters, double *ms_events) {
+  Tensor<float> X = view(dXp, m, k), W = view(dWp, k, n), O = view(dOp, m, n);
+  for (int i = 0; i < warmup; i++) op_mm(X, W, O);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < iters; i++) op_mm(X, W, O);
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_events) *ms_events = (double)ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return status();
+}
+
+// Host-buffer end-to-end call of the reference op (H2D, op_quantized_mm, D2H), wall clock.
+int ref_time_quantized_mm_host(const float *X, const float *W, float *O, int m, int n, int k,
+                               float range, int warmup, int iters, double *ms_wall) {
+  for (int i = 0; i < warmup; i++) ref_op_quantized_mm(X, W, m, n, k, range, O);
+  struct timeval t0, t1;
+  gettimeofday(&t0, NULL);
+  int rc = 0;
+  for (int i = 0; i < iters; i++) rc |= ref_op_quantized_mm(X, W, m, n, k, range, O);
+  gettimeofday(&t1, NULL);
+  *ms_wall = ((t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_usec - t0.tv_usec)) / 1e3 / iters;
+  return rc;
+}
+
+}  // extern "C"
