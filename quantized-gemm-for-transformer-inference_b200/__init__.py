@@ -1,0 +1,301 @@
+"""B200-native quantized-linear hot path: Python binding of the C ABI in include/qgemm.h.
+
+This package is a thin ctypes layer over libqgemm.so (hand-written sm_100a CUDA: row / column
+absmax quantizers and a tcgen05 kind::i8 GEMM with a fused dequantize epilogue).  The functions
+carry the reference's operator names and argument order (/root/reference/src/ops/*.cuh) and
+operate on torch CUDA tensors, which are used only as device-memory handles.
+
+There is no CPU or PyTorch fallback: if libqgemm.so is missing, or no sm_100 GPU is visible,
+calls raise.  The CPU oracle under oracle/ is test infrastructure and is never imported here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqgemm.so")
+
+QG_F32, QG_F16, QG_BF16, QG_S32 = 0, 1, 2, 3
+MODE_REF_EXACT, MODE_TRUE_ABSMAX = 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TC_1SM, GEMM_TC_2SM = 0, 1, 2, 3
+
+# every symbol include/qgemm.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "qg_version", "qg_last_error", "qg_device_info", "qg_set_gemm_variant", "qg_launch_count",
+    "qg_absmax_rows", "qg_absmax_cols", "qg_inv_divide_f32", "qg_quantize_rows", "qg_quantize_cols",
+    "qg_absmax_quant_rows", "qg_absmax_quant_cols", "qg_gemm_s8s8s32", "qg_dequantize_s32",
+    "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_linear_forward",
+    "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_mm_f32",
+]
+
+
+class QGemmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libqgemm.so (built in-tree by build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise QGemmError(
+                f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (there is no fallback path)")
+        L = C.CDLL(LIB_PATH)
+        L.qg_last_error.restype = C.c_char_p
+        L.qg_workspace_bytes.restype = C.c_size_t
+        L.qg_launch_count.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().qg_last_error().decode(errors="replace")
+        raise QGemmError(f"{what} failed with status {rc}: {msg}")
+
+
+_DT = {torch.float32: QG_F32, torch.float16: QG_F16, torch.bfloat16: QG_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise AssertionError(f"unsupported dtype {t.dtype}") from None
+
+
+def _dev2d(t: torch.Tensor):
+    """(pointer, leading dimension) of a 2-D CUDA tensor with unit inner stride."""
+    assert t.is_cuda, "tensor must be on the device (the reference asserts on_device)"
+    assert t.dim() == 2 and t.stride(1) == 1, "row-major tensor with stride_w == 1 required"
+    return C.c_void_p(t.data_ptr()), C.c_int64(t.stride(0))
+
+
+def _vec(t: torch.Tensor, n: int):
+    assert t.is_cuda and t.dtype == torch.float32 and t.numel() == n and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_info():
+    sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().qg_device_info(C.byref(sm), C.byref(major), C.byref(minor)), "qg_device_info")
+    return sm.value, major.value, minor.value
+
+
+def set_gemm_variant(v: int) -> None:
+    _check(lib().qg_set_gemm_variant(C.c_int(v)), "qg_set_gemm_variant")
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().qg_launch_count(C.c_int(1 if reset else 0)))
+
+
+# ------------------------------------------------------------------------------------------
+# Reference-named operators (same argument order as /root/reference/src/ops/*.cuh)
+# ------------------------------------------------------------------------------------------
+
+def op_absmax(inp: torch.Tensor, out: torch.Tensor, mode: int = MODE_REF_EXACT) -> None:
+    """op_absmax(in, out), src/ops/op_reduction.cuh:195-204.  out [h,1] -> per-row reduce,
+    out [1,w] -> per-column reduce (direction picked from the output shape, :143)."""
+    h, w = inp.shape
+    assert (out.shape[0] == 1 and out.shape[1] == w) or (out.shape[1] == 1 and out.shape[0] == h)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    p, ld = _dev2d(inp)
+    if h > out.shape[0]:  # out [1,w]
+        _check(lib().qg_absmax_cols(p, _dt(inp), h, w, ld, mode, _vec(out, w), _stream()), "qg_absmax_cols")
+    else:
+        _check(lib().qg_absmax_rows(p, _dt(inp), h, w, ld, mode, _vec(out, h), _stream()), "qg_absmax_rows")
+
+
+def op_inv_divide(a: torch.Tensor, b: float, out: torch.Tensor) -> None:
+    """op_inv_divide(a, b, out) = b / a, src/ops/op_elemwise.cuh:657-667."""
+    assert out.shape == a.shape and a.is_contiguous() and out.is_contiguous()
+    _check(lib().qg_inv_divide_f32(_vec(a, a.numel()), C.c_int64(a.numel()), C.c_float(b), _vec(out, out.numel()),
+                                   _stream()), "qg_inv_divide_f32")
+
+
+def op_multiply(a: torch.Tensor, b, out: torch.Tensor) -> None:
+    """op_multiply<T,int8_t>(a, scale, out): quantizing multiply with broadcast,
+    src/ops/op_elemwise.cuh:629-640 (b [h,1] or [1,w])."""
+    assert out.dtype == torch.int8, "only the quantizing overload is on the hot path"
+    h, w = a.shape
+    assert out.shape == a.shape
+    pa, lda = _dev2d(a)
+    po, ldo = _dev2d(out)
+    if b.shape[1] == 1 and b.shape[0] == h and not (b.shape[0] == 1 and w == 1):
+        _check(lib().qg_quantize_rows(pa, _dt(a), h, w, lda, _vec(b, h), po, ldo, _stream()), "qg_quantize_rows")
+    else:
+        assert b.shape[0] == 1 and b.shape[1] == w
+        _check(lib().qg_quantize_cols(pa, _dt(a), h, w, lda, _vec(b, w), po, ldo, _stream()), "qg_quantize_cols")
+
+
+def op_mm(A: torch.Tensor, B: torch.Tensor, Cout: torch.Tensor) -> None:
+    """op_mm<T,OutT>(A, B, C), src/ops/op_mm.cuh:49-65: int8 x int8 -> int32, or fp32."""
+    assert A.shape[0] == Cout.shape[0] and B.shape[1] == Cout.shape[1] and A.shape[1] == B.shape[0]
+    M, K = A.shape
+    N = B.shape[1]
+    if A.dtype == torch.int8:
+        assert B.dtype == torch.int8 and Cout.dtype == torch.int32
+        pa, lda = _dev2d(A)
+        pb, ldb = _dev2d(B)
+        pc, ldc = _dev2d(Cout)
+        _check(lib().qg_gemm_s8s8s32(pa, lda, pb, ldb, M, N, K, pc, ldc, _stream()), "qg_gemm_s8s8s32")
+    else:
+        assert A.dtype == torch.float32 and B.dtype == torch.float32 and Cout.dtype == torch.float32
+        assert A.is_cuda and B.is_cuda and Cout.is_cuda and Cout.stride(1) == 1
+        _check(lib().qg_mm_f32(C.c_void_p(A.data_ptr()), C.c_int64(A.stride(0)), C.c_int64(A.stride(1)),
+                               C.c_void_p(B.data_ptr()), C.c_int64(B.stride(0)), C.c_int64(B.stride(1)),
+                               M, N, K, C.c_void_p(Cout.data_ptr()), C.c_int64(Cout.stride(0)), _stream()),
+               "qg_mm_f32")
+
+
+def op_dequantize(acc: torch.Tensor, Cx: torch.Tensor, Cw: torch.Tensor, out: torch.Tensor,
+                  range_: float = 127.0, bias: torch.Tensor | None = None) -> None:
+    """The reference's op_mm(Cx,Cw,outer); op_dequantize(acc, outer, O); op_multiply(O, 1/range^2, O)
+    (src/ops/op_mm.cuh:96-99) as one pass over stored accumulators."""
+    M, N = acc.shape
+    assert acc.dtype == torch.int32 and out.shape == acc.shape
+    pa, lda = _dev2d(acc)
+    po, ldo = _dev2d(out)
+    pb = None if bias is None else _vec(bias.reshape(-1), N)
+    _check(lib().qg_dequantize_s32(pa, lda, _vec(Cx.reshape(-1), M), _vec(Cw.reshape(-1), N), pb, M, N,
+                                   C.c_float(range_), po, _dt(out), ldo, _stream()), "qg_dequantize_s32")
+
+
+def op_outlier_extractor(a: torch.Tensor, b: float, out: torch.Tensor) -> None:
+    """op_outlier_extractor(a, b, out), src/ops/op_elemwise.cuh:698-708: out = |a| <= b ? 0 : 1."""
+    assert out.shape == a.shape and a.dtype == torch.float32 and out.dtype == torch.float32
+    pa, lda = _dev2d(a)
+    po, ldo = _dev2d(out)
+    _check(lib().qg_outlier_mask_f32(pa, a.shape[0], a.shape[1], lda, C.c_float(b), po, ldo, _stream()),
+           "qg_outlier_mask_f32")
+
+
+def absmax_quant_rows(X: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT,
+                      Xq: torch.Tensor | None = None, Cx: torch.Tensor | None = None):
+    """Fused a1+a3+a4 for activations: returns (Xq int8 [M,K], Cx f32 [M])."""
+    M, K = X.shape
+    if Xq is None:
+        Xq = torch.empty((M, K), dtype=torch.int8, device=X.device)
+    if Cx is None:
+        Cx = torch.empty(M, dtype=torch.float32, device=X.device)
+    px, ldx = _dev2d(X)
+    pq, ldq = _dev2d(Xq)
+    _check(lib().qg_absmax_quant_rows(px, _dt(X), M, K, ldx, C.c_float(range_), mode, pq, ldq, _vec(Cx, M),
+                                      _stream()), "qg_absmax_quant_rows")
+    return Xq, Cx
+
+
+def absmax_quant_cols(W: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT,
+                      Wq: torch.Tensor | None = None, Cw: torch.Tensor | None = None):
+    """Fused a2+a3+a4 for weights: returns (Wq int8 [K,N], Cw f32 [N])."""
+    K, N = W.shape
+    if Wq is None:
+        Wq = torch.empty((K, N), dtype=torch.int8, device=W.device)
+    if Cw is None:
+        Cw = torch.empty(N, dtype=torch.float32, device=W.device)
+    scratch = torch.empty(N, dtype=torch.float32, device=W.device)
+    pw, ldw = _dev2d(W)
+    pq, ldq = _dev2d(Wq)
+    _check(lib().qg_absmax_quant_cols(pw, _dt(W), K, N, ldw, C.c_float(range_), mode, pq, ldq, _vec(Cw, N),
+                                      _vec(scratch, N), _stream()), "qg_absmax_quant_cols")
+    return Wq, Cw
+
+
+def gemm_s8_dequant(Xq, Wq, Cx, Cw, out, range_: float = 127.0, bias=None) -> None:
+    """int8 GEMM with the dequantize / bias / cast epilogue fused (a5..a8, a10)."""
+    M, K = Xq.shape
+    N = Wq.shape[1]
+    assert Wq.shape[0] == K and out.shape == (M, N)
+    pa, lda = _dev2d(Xq)
+    pb, ldb = _dev2d(Wq)
+    po, ldo = _dev2d(out)
+    pbias = None if bias is None else _vec(bias.reshape(-1), N)
+    _check(lib().qg_gemm_s8_dequant(pa, lda, pb, ldb, _vec(Cx.reshape(-1), M), _vec(Cw.reshape(-1), N), pbias, M, N, K,
+                                    C.c_float(range_), po, _dt(out), ldo, _stream()), "qg_gemm_s8_dequant")
+
+
+def workspace_bytes(M: int, N: int, K: int) -> int:
+    return int(lib().qg_workspace_bytes(M, N, K))
+
+
+def op_quantized_mm(X: torch.Tensor, W: torch.Tensor, O: torch.Tensor, range_: float = 127.0,
+                    mode: int = MODE_REF_EXACT, bias: torch.Tensor | None = None,
+                    workspace: torch.Tensor | None = None) -> None:
+    """op_quantized_mm(X, W, O, range), src/ops/op_mm.cuh:67-101 (+ optional LinearLayer bias)."""
+    assert X.shape[0] == O.shape[0] and W.shape[1] == O.shape[1] and X.shape[1] == W.shape[0]
+    assert X.dtype == W.dtype
+    M, K = X.shape
+    N = W.shape[1]
+    px, ldx = _dev2d(X)
+    pw, ldw = _dev2d(W)
+    po, ldo = _dev2d(O)
+    pbias = None if bias is None else _vec(bias.reshape(-1), N)
+    ws_p, ws_n = (None, 0) if workspace is None else (C.c_void_p(workspace.data_ptr()), workspace.numel())
+    _check(lib().qg_quantized_mm(px, ldx, pw, ldw, _dt(X), po, ldo, _dt(O), M, N, K, C.c_float(range_), mode, pbias,
+                                 ws_p, C.c_size_t(ws_n), _stream()), "qg_quantized_mm")
+
+
+def quantized_mm_host(X, W, range_: float = 127.0, mode: int = MODE_REF_EXACT, bias=None, out=None):
+    """Host-buffer form: X, W (and out) are CPU float32 tensors (pinned for full PCIe rate)."""
+    assert not X.is_cuda and not W.is_cuda and X.dtype == torch.float32 and W.dtype == torch.float32
+    assert X.is_contiguous() and W.is_contiguous()
+    M, K = X.shape
+    N = W.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32)
+    pb = None if bias is None else C.c_void_p(bias.data_ptr())
+    _check(lib().qg_quantized_mm_host(C.c_void_p(X.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(out.data_ptr()),
+                                      M, N, K, C.c_float(range_), mode, pb), "qg_quantized_mm_host")
+    return out
+
+
+class LinearLayer:
+    """LinearLayer<float> (src/modules/linear.cuh:7-72), inference only: y = x @ w + b with the
+    product on the int8 tensor-core path.  w is [in_dim, out_dim], b is [1, out_dim]; the weights
+    are quantized once (column-wise) and cached."""
+
+    def __init__(self, in_dim: int, out_dim: int, device="cuda", dtype=torch.float32, range_: float = 127.0,
+                 mode: int = MODE_REF_EXACT):
+        self.in_dim, self.out_dim, self.range, self.mode = in_dim, out_dim, range_, mode
+        self.w = torch.empty((in_dim, out_dim), dtype=dtype, device=device)
+        self.b = torch.empty((1, out_dim), dtype=torch.float32, device=device)
+        self._wq = None
+        self._ws = None
+
+    def init_uniform(self, generator=None):  # linear.cuh:33-39
+        mx = 1.0 / (self.in_dim ** 0.5)
+        self.w.uniform_(-mx, mx, generator=generator)
+        self.b.uniform_(-mx, mx, generator=generator)
+        self._wq = None
+
+    def quantize_weights(self):
+        self._wq = absmax_quant_cols(self.w, self.range, self.mode)
+        return self._wq
+
+    def forward(self, x: torch.Tensor, y: torch.Tensor) -> None:  # linear.cuh:49-56
+        assert x.shape[1] == self.in_dim and y.shape == (x.shape[0], self.out_dim)
+        if self._wq is None:
+            self.quantize_weights()
+        Wq, Cw = self._wq
+        M, K, N = x.shape[0], self.in_dim, self.out_dim
+        need = workspace_bytes(M, N, K)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        px, ldx = _dev2d(x)
+        pq, ldq = _dev2d(Wq)
+        py, ldy = _dev2d(y)
+        _check(lib().qg_linear_forward(px, ldx, _dt(x), pq, ldq, _vec(Cw, N), _vec(self.b.reshape(-1), N), py, ldy,
+                                       _dt(y), M, N, K, C.c_float(self.range), self.mode,
+                                       C.c_void_p(self._ws.data_ptr()), C.c_size_t(self._ws.numel()), _stream()),
+               "qg_linear_forward")

@@ -1,0 +1,397 @@
+// capi.cu -- the extern "C" boundary declared in include/qgemm.h.
+//
+// Argument checking, workspace carving and kernel selection live here; the kernels are in
+// quantize.cu (a1-a4), gemm_i8_tc.cu (a5-a8, a10 fused, tcgen05) and gemm_simt.cu (generic paths).
+#include <atomic>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace qg {
+
+// ---- kernels / launchers defined in the other translation units ----
+int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, const float *sx,
+               int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st);
+int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
+               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, cudaStream_t st);
+int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
+int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
+int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K, void *O, int64_t ldo,
+                 int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st);
+int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
+           float *C, int64_t ldc, cudaStream_t st);
+int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
+                   float c, void *O, int out_dtype, int64_t ldo, cudaStream_t st);
+bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb);
+int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
+               void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
+               int num_sms, cudaStream_t st);
+
+// ---- error state ----
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_status(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return QG_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- device state ----
+struct DeviceState {
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  bool ok = false;
+  void *arena = nullptr;  // grow-only scratch used when the caller passes workspace == NULL
+  size_t arena_bytes = 0;
+  // host-buffer entry point
+  void *hx = nullptr, *hw = nullptr, *ho = nullptr, *hb = nullptr;
+  size_t hx_bytes = 0, hw_bytes = 0, ho_bytes = 0, hb_bytes = 0;
+  cudaStream_t hstream = nullptr;
+};
+static DeviceState g_dev[16];
+static std::mutex g_mu;
+static std::atomic<int> g_variant{QG_GEMM_AUTO};
+
+static int device_state(DeviceState **out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return QG_ENODEV;
+  }
+  if (dev < 0 || dev >= 16) { set_error("device ordinal %d out of range", dev); return QG_ENODEV; }
+  DeviceState &d = g_dev[dev];
+  if (!d.ok) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!d.ok) {
+      QG_CUDA_OK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+      QG_CUDA_OK(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+      QG_CUDA_OK(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+      if (d.cc_major != 10) {
+        set_error("libqgemm is built for sm_100a only; device %d is sm_%d%d (no fallback path)", dev, d.cc_major,
+                  d.cc_minor);
+        return QG_ENODEV;
+      }
+      const char *env = getenv("QG_GEMM_VARIANT");
+      if (env != nullptr) g_variant.store(atoi(env));
+      d.ok = true;
+    }
+  }
+  *out = &d;
+  return QG_OK;
+}
+
+static int grow(void **p, size_t *have, size_t want) {
+  if (*have >= want) return QG_OK;
+  if (*p != nullptr) { QG_CUDA_OK(cudaDeviceSynchronize()); QG_CUDA_OK(cudaFree(*p)); *p = nullptr; *have = 0; }
+  want = (size_t)round_up((int64_t)want, 1 << 20);
+  QG_CUDA_OK(cudaMalloc(p, want));
+  *have = want;
+  return QG_OK;
+}
+
+static bool valid_io(int dt) { return dt == QG_F32 || dt == QG_F16 || dt == QG_BF16; }
+
+// layout of the scratch block shared by qg_quantized_mm / qg_linear_forward
+struct Workspace {
+  int8_t *Xq, *Wq;
+  float *Cx, *Cw, *scratch;
+  int64_t ldxq, ldwq;
+  size_t bytes;
+};
+static Workspace carve(void *base, int M, int N, int K) {
+  Workspace w;
+  w.ldxq = round_up(K, 16);  // TMA: leading dimensions are multiples of 16 bytes
+  w.ldwq = round_up(N, 16);
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (size_t)round_up((int64_t)(off + n), 256); return o; };
+  const size_t oxq = take((size_t)M * w.ldxq), owq = take((size_t)K * w.ldwq);
+  const size_t ocx = take(sizeof(float) * M), ocw = take(sizeof(float) * N), osc = take(sizeof(float) * N);
+  char *b = reinterpret_cast<char *>(base);
+  w.Xq = reinterpret_cast<int8_t *>(b + oxq);
+  w.Wq = reinterpret_cast<int8_t *>(b + owq);
+  w.Cx = reinterpret_cast<float *>(b + ocx);
+  w.Cw = reinterpret_cast<float *>(b + ocw);
+  w.scratch = reinterpret_cast<float *>(b + osc);
+  w.bytes = off;
+  return w;
+}
+
+static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K,
+                         void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias,
+                         float c, cudaStream_t st) {
+  int variant = g_variant.load();
+  const bool tc_ok = gemm_i8_tc_supported(A, lda, B, ldb);
+  if (variant == QG_GEMM_AUTO) variant = tc_ok ? QG_GEMM_TC_1SM : QG_GEMM_SIMT;
+  if (variant == QG_GEMM_SIMT || !tc_ok)
+    return gemm_s8_simt(A, lda, B, ldb, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, st);
+  return gemm_i8_tc(variant == QG_GEMM_TC_2SM ? 2 : 1, A, lda, B, ldb, 0, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c,
+                    d->sm_count, st);
+}
+
+}  // namespace qg
+
+using namespace qg;
+
+extern "C" {
+
+int qg_version(void) { return 100; }
+const char *qg_last_error(void) { return g_err; }
+
+int qg_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  if (sm_count) *sm_count = d->sm_count;
+  if (cc_major) *cc_major = d->cc_major;
+  if (cc_minor) *cc_minor = d->cc_minor;
+  return QG_OK;
+}
+
+int qg_set_gemm_variant(int variant) {
+  if (variant < QG_GEMM_AUTO || variant > QG_GEMM_TC_2SM) { set_error("bad gemm variant %d", variant); return QG_EINVAL; }
+  g_variant.store(variant);
+  return QG_OK;
+}
+
+int64_t qg_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int qg_absmax_rows(const void *X, int dtype, int M, int K, int64_t ldx, int mode, float *Cx, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && Cx && M > 0 && K > 0 && ldx >= K && valid_io(dtype), "qg_absmax_rows: bad arguments");
+  return quant_rows(X, dtype, M, K, ldx, 127.0f, mode, nullptr, nullptr, 0, Cx, (cudaStream_t)stream);
+}
+
+int qg_absmax_cols(const void *W, int dtype, int K, int N, int64_t ldw, int mode, float *Cw, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(W && Cw && K > 0 && N > 0 && ldw >= N && valid_io(dtype), "qg_absmax_cols: bad arguments");
+  float *scratch = nullptr;  // N floats for the cross-CTA partial maxima, from the library arena
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if ((rc = grow(&d->arena, &d->arena_bytes, sizeof(float) * (size_t)N))) return rc;
+    scratch = reinterpret_cast<float *>(d->arena);
+  }
+  return quant_cols(W, dtype, K, N, ldw, 127.0f, mode, nullptr, nullptr, 0, Cw, scratch, (cudaStream_t)stream);
+}
+
+int qg_inv_divide_f32(const float *a, int64_t n, float b, float *out, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(a && out && n > 0, "qg_inv_divide_f32: bad arguments");
+  return inv_divide(a, n, b, out, (cudaStream_t)stream);
+}
+
+int qg_quantize_rows(const void *X, int dtype, int M, int K, int64_t ldx, const float *sx, int8_t *Xq, int64_t ldq,
+                     qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && sx && Xq && M > 0 && K > 0 && ldx >= K && ldq >= K && valid_io(dtype), "qg_quantize_rows: bad arguments");
+  return quant_rows(X, dtype, M, K, ldx, 127.0f, 0, sx, Xq, ldq, nullptr, (cudaStream_t)stream);
+}
+
+int qg_quantize_cols(const void *W, int dtype, int K, int N, int64_t ldw, const float *sw, int8_t *Wq, int64_t ldq,
+                     qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(W && sw && Wq && K > 0 && N > 0 && ldw >= N && ldq >= N && valid_io(dtype), "qg_quantize_cols: bad arguments");
+  return quant_cols(W, dtype, K, N, ldw, 127.0f, 0, sw, Wq, ldq, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int qg_absmax_quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq,
+                         int64_t ldq, float *Cx, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && Xq && Cx && M > 0 && K > 0 && ldx >= K && ldq >= K && valid_io(dtype),
+             "qg_absmax_quant_rows: bad arguments");
+  return quant_rows(X, dtype, M, K, ldx, range, mode, nullptr, Xq, ldq, Cx, (cudaStream_t)stream);
+}
+
+int qg_absmax_quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, int8_t *Wq,
+                         int64_t ldq, float *Cw, float *scratch, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(W && Wq && Cw && K > 0 && N > 0 && ldw >= N && ldq >= N && valid_io(dtype),
+             "qg_absmax_quant_cols: bad arguments");
+  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wq, ldq, Cw, scratch, (cudaStream_t)stream);
+}
+
+int qg_gemm_s8s8s32(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K, int32_t *C,
+                    int64_t ldc, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && lda >= K && ldb >= N && ldc >= N, "qg_gemm_s8s8s32: bad arguments");
+  return gemm_dispatch(d, A, lda, B, ldb, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f,
+                       (cudaStream_t)stream);
+}
+
+int qg_dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M,
+                      int N, float range, void *O, int out_dtype, int64_t ldo, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(acc && Cx && Cw && O && M > 0 && N > 0 && ldacc >= N && ldo >= N && valid_io(out_dtype),
+             "qg_dequantize_s32: bad arguments");
+  return dequantize_s32(acc, ldacc, Cx, Cw, bias, M, N, 1 / (range * range), O, out_dtype, ldo, (cudaStream_t)stream);
+}
+
+int qg_gemm_s8_dequant(const int8_t *Xq, int64_t ldxq, const int8_t *Wq, int64_t ldwq, const float *Cx,
+                       const float *Cw, const float *bias, int M, int N, int K, float range, void *O, int out_dtype,
+                       int64_t ldo, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(Xq && Wq && Cx && Cw && O && M > 0 && N > 0 && K > 0 && ldxq >= K && ldwq >= N && ldo >= N &&
+                 valid_io(out_dtype),
+             "qg_gemm_s8_dequant: bad arguments");
+  return gemm_dispatch(d, Xq, ldxq, Wq, ldwq, M, N, K, O, ldo, out_dtype, Cx, Cw, bias, 1 / (range * range),
+                       (cudaStream_t)stream);
+}
+
+size_t qg_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return carve(nullptr, M, N, K).bytes;
+}
+
+static int get_workspace(DeviceState *d, void *workspace, size_t workspace_bytes, int M, int N, int K, Workspace *w) {
+  const size_t need = carve(nullptr, M, N, K).bytes;
+  if (workspace == nullptr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = grow(&d->arena, &d->arena_bytes, need);
+    if (rc) return rc;
+    workspace = d->arena;
+  } else if (workspace_bytes < need) {
+    set_error("workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    return QG_ENOMEM;
+  } else if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("workspace must be 256-byte aligned");
+    return QG_EINVAL;
+  }
+  *w = carve(workspace, M, N, K);
+  return QG_OK;
+}
+
+int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ldw, int in_dtype, void *O, int64_t ldo,
+                    int out_dtype, int M, int N, int K, float range, int mode, const float *bias, void *workspace,
+                    size_t workspace_bytes, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && W && O && M > 0 && N > 0 && K > 0 && ldx >= K && ldw >= N && ldo >= N && valid_io(in_dtype) &&
+                 valid_io(out_dtype),
+             "qg_quantized_mm: bad arguments (M=%d N=%d K=%d)", M, N, K);
+  Workspace w;
+  rc = get_workspace(d, workspace, workspace_bytes, M, N, K, &w);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
+  if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, st);
+  if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
+  return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, M, N, K, O, ldo, out_dtype, w.Cx, w.Cw, bias,
+                       1 / (range * range), st);
+}
+
+int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wq, int64_t ldwq, const float *Cw,
+                      const float *bias, void *Y, int64_t ldy, int out_dtype, int M, int N, int K, float range, int mode,
+                      void *workspace, size_t workspace_bytes, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && Wq && Cw && Y && M > 0 && N > 0 && K > 0 && ldx >= K && ldwq >= N && ldy >= N && valid_io(in_dtype) &&
+                 valid_io(out_dtype),
+             "qg_linear_forward: bad arguments (M=%d N=%d K=%d)", M, N, K);
+  Workspace w;
+  rc = get_workspace(d, workspace, workspace_bytes, M, N, K, &w);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
+  if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+  return gemm_dispatch(d, w.Xq, w.ldxq, Wq, ldwq, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st);
+}
+
+int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host, int M, int N, int K, float range,
+                         int mode, const float *bias_host) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X_host && W_host && O_host && M > 0 && N > 0 && K > 0, "qg_quantized_mm_host: bad arguments");
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (d->hstream == nullptr) QG_CUDA_OK(cudaStreamCreateWithFlags(&d->hstream, cudaStreamNonBlocking));
+  const size_t xb = sizeof(float) * (size_t)M * K, wb = sizeof(float) * (size_t)K * N, ob = sizeof(float) * (size_t)M * N;
+  if ((rc = grow(&d->hx, &d->hx_bytes, xb))) return rc;
+  if ((rc = grow(&d->hw, &d->hw_bytes, wb))) return rc;
+  if ((rc = grow(&d->ho, &d->ho_bytes, ob))) return rc;
+  if (bias_host && (rc = grow(&d->hb, &d->hb_bytes, sizeof(float) * (size_t)N))) return rc;
+  if ((rc = grow(&d->arena, &d->arena_bytes, carve(nullptr, M, N, K).bytes))) return rc;
+  cudaStream_t st = d->hstream;
+  QG_CUDA_OK(cudaMemcpyAsync(d->hx, X_host, xb, cudaMemcpyHostToDevice, st));
+  QG_CUDA_OK(cudaMemcpyAsync(d->hw, W_host, wb, cudaMemcpyHostToDevice, st));
+  if (bias_host) QG_CUDA_OK(cudaMemcpyAsync(d->hb, bias_host, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+  Workspace w = carve(d->arena, M, N, K);
+  rc = quant_rows(d->hx, QG_F32, M, K, K, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
+  if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, st);
+  if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
+  rc = gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, M, N, K, d->ho, N, QG_F32, w.Cx, w.Cw,
+                     bias_host ? (const float *)d->hb : nullptr, 1 / (range * range), st);
+  if (rc) return rc;
+  QG_CUDA_OK(cudaMemcpyAsync(O_host, d->ho, ob, cudaMemcpyDeviceToHost, st));
+  QG_CUDA_OK(cudaStreamSynchronize(st));
+  return QG_OK;
+}
+
+int qg_outlier_mask_f32(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm,
+                        qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && mask && M > 0 && K > 0 && lda >= K && ldm >= K, "qg_outlier_mask_f32: bad arguments");
+  return outlier_mask(A, M, K, lda, thr, mask, ldm, (cudaStream_t)stream);
+}
+
+int qg_mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N,
+              int K, float *C, int64_t ldc, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N, "qg_mm_f32: bad arguments");
+  return mm_f32(A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc, (cudaStream_t)stream);
+}
+
+/* test hook (not part of the reference-facing surface): tcgen05 GEMM with B given as [N,K]
+ * (K-major operand), used to validate the MN-major descriptor path against the classic one. */
+QG_API int qg_test_gemm_s8_bt(int cg, const int8_t *A, int64_t lda, const int8_t *Bt, int64_t ldbt, int M, int N, int K,
+                              int32_t *C, int64_t ldc, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  return gemm_i8_tc(cg, A, lda, Bt, ldbt, 1, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f, d->sm_count,
+                    (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// gemm_i8_tc.cu -- int8 x int8 -> int32 GEMM on the Blackwell tensor cores (tcgen05 kind::i8),
+// with the dequantize / bias / cast epilogue fused in.
+//
+// Replaces op_matmul_kernel<int8_t,int> (src/ops/op_mm.cuh:9-46: int8 widened to fp32 smem tiles,
+// one FFMA + two converts per MAC on CUDA cores) plus the three elementwise passes that follow it
+// in op_quantized_mm (outer product, op_dequantize, op_multiply(1/range^2); src/ops/op_mm.cuh:96-99)
+// and LinearLayer's bias add (src/modules/linear.cuh:54).
+//
+// Structure (one persistent CTA per SM, or one CTA pair per TPC when CG == 2):
+//   warp 0 lane 0 : TMA producer   -- 128B-swizzled A [128 x 128B] and B tiles into a smem ring
+//   warp 1 lane 0 : MMA issuer     -- tcgen05.mma.kind::i8, accumulators in TMEM (2 x 256 columns,
+//                                     so tile i's epilogue overlaps tile i+1's main loop)
+//   warps 2..5    : epilogue       -- tcgen05.ld -> registers -> scale/bias/cast -> swizzled smem
+//                                     staging -> TMA store (or direct stores for odd ldo)
+// Operand layouts are the reference's: A = Xq [M,K] row-major (K-major operand), B = Wq [K,N]
+// row-major, consumed as an MN-major UMMA operand so no transpose of the weights is needed.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace qg {
+
+void count_launch(int n = 1);
+
+namespace {
+
+constexpr int BM = 128;     // accumulator rows per CTA (TMEM lanes)
+constexpr int BN = 256;     // accumulator columns per tile (UMMA N)
+constexpr int BK = 128;     // int8 elements (= bytes) of K per pipeline stage: one 128B swizzle atom
+constexpr int UK = 32;      // K per tcgen05.mma for 8-bit operands
+constexpr int kNumThreads = 192;
+constexpr int kStageOutBytes = 32 * 128;  // per-epilogue-warp staging tile: 32 rows x 128 B
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n;  // cluster tiles: (CG*128) x 256
+  void *out;             // [M,N] of the epilogue's type
+  int64_t ldo;           // elements
+  const float *Cx, *Cw, *bias;
+  float c;               // 1 / (range*range)
+  int tma_store;         // 1: epilogue leaves through TMA; 0: direct global stores
+  // MN-major B descriptor geometry (bytes).  Defaults: k-step 32 rows * 128 B, LBO = BK * 128 B
+  // (next 128-column chunk), SBO = 8 rows * 128 B.  Overridable through QG_DBG_B_* for bring-up.
+  uint32_t b_kstep, b_lbo, b_sbo;
+};
+
+template <int CG, bool B_MN>
+struct Cfg {
+  static constexpr int kBLoadN = BN / CG;                 // B columns this CTA stages
+  static constexpr int kABytes = BM * BK;                 // 16 KB
+  static constexpr int kBBytes = kBLoadN * BK;            // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = CG == 1 ? 4 : 6;
+  static constexpr int kOutStaging = 4 * kStageOutBytes;  // 16 KB
+  static constexpr int kScaleBytes = 2 * 2 * BN * 4;      // Cw + bias, double buffered
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStaging + kScaleBytes + kBarBytes + 1024;
+};
+
+template <int OUT> struct OutTraits;
+template <> struct OutTraits<QG_S32> { using T = int32_t; static constexpr int kCols = 32; };
+template <> struct OutTraits<QG_F32> { using T = float; static constexpr int kCols = 32; };
+template <> struct OutTraits<QG_F16> { using T = __half; static constexpr int kCols = 64; };
+template <> struct OutTraits<QG_BF16> { using T = __nv_bfloat16; static constexpr int kCols = 64; };
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, __half) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, __nv_bfloat16) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <int CG, bool B_MN, int OUT>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_o, const GemmParams p) {
+  using C = Cfg<CG, B_MN>;
+  using OT = OutTraits<OUT>;
+  using OutT = typename OT::T;
+  constexpr int kStages = C::kStages;
+  constexpr bool kDequant = OUT != QG_S32;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms repeat every 1024 B: align the ring
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *smem_out = smem + kStages * C::kStageBytes;
+  float *cw_s = reinterpret_cast<float *>(smem_out + C::kOutStaging);  // [2][BN]
+  float *bias_s = cw_s + 2 * BN;                                       // [2][BN]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 2 * BN);
+  uint64_t *full_bar = bars;                     // [kStages]  TMA -> MMA
+  uint64_t *empty_bar = bars + kStages;          // [kStages]  MMA -> TMA
+  uint64_t *tfull_bar = bars + 2 * kStages;      // [2]        MMA -> epilogue
+  uint64_t *tempty_bar = bars + 2 * kStages + 2; // [2]        epilogue -> MMA
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_o);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; i++) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 4 * CG);  // one arrive per epilogue warp of every CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(smem_u32(tmem_slot), 512);
+    tmem_relinquish<CG>();
+  }
+  tcgen05_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_clusters = gridDim.x / CG;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m_base = ((t % p.tiles_m) * CG + (int)cta_rank) * BM;
+        const int n_base = (t / p.tiles_m) * BN + (int)cta_rank * C::kBLoadN;
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
+          const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const int k0 = kb * BK;
+          if (CG == 1) {
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            mbar_arrive_expect_tx(fb, C::kStageBytes);
+            tma_load_2d(sa, &map_a, fb, k0, m_base);
+            if (B_MN) {  // two [128 k-rows x 128 n-bytes] boxes side by side
+              tma_load_2d(sb, &map_b, fb, n_base, k0);
+              tma_load_2d(sb + BK * 128, &map_b, fb, n_base + 128, k0);
+            } else {     // one [256 n-rows x 128 k-bytes] box
+              tma_load_2d(sb, &map_b, fb, k0, n_base);
+            }
+          } else {
+            // both CTAs' loads complete on the leader's barrier; the leader arms it for both
+            uint32_t fb;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(fb) : "r"(smem_u32(&full_bar[s])));
+            if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), 2 * C::kStageBytes);
+            tma_load_2d_2sm(sa, &map_a, fb, k0, m_base);
+            if (B_MN) tma_load_2d_2sm(sb, &map_b, fb, n_base, k0);
+            else tma_load_2d_2sm(sb, &map_b, fb, k0, n_base);
+          }
+        }
+      }
+    }
+    __syncwarp();  // reconverge before the aligned teardown barrier
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_i8(BM * CG, BN, 0, B_MN ? 1 : 0);
+      uint32_t it = 0, acc_it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, acc_it++) {
+        const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, 2);  // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph, 3);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UK; k++) {
+            // A: K-major, rows 128 B apart, 8-row groups 1024 B apart; +32 B per K step
+            const uint64_t adesc = umma_smem_desc_sw128(sa + k * UK, 16, 1024);
+            // B (MN-major): k-rows 128 B apart, 8-row groups 1024 B apart, next 128 columns
+            // BK*128 B further; +32 rows (4096 B) per K step.  B (K-major): like A.
+            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo)
+                                        : umma_smem_desc_sw128(sb + k * UK, 16, 1024);
+            umma_i8<CG>(tmem_d, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+          }
+          // frees the smem slot once the MMAs above have read it
+          if (CG == 1) umma_commit(smem_u32(&empty_bar[s]));
+          else umma_commit_2sm(smem_u32(&empty_bar[s]), 0x3);
+        }
+        if (CG == 1) umma_commit(smem_u32(&tfull_bar[as]));
+        else umma_commit_2sm(smem_u32(&tfull_bar[as]), 0x3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ===================================
+    const int q = warp & 3;  // TMEM lane quarter this warp is allowed to read
+    const int epi_tid = (warp - 2) * 32 + lane;
+    uint8_t *stage = smem_out + q * kStageOutBytes;
+    const uint32_t stage_u32 = smem_u32(stage);
+    uint32_t acc_it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, acc_it++) {
+      const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      const int m_base = ((t % p.tiles_m) * CG + (int)cta_rank) * BM;
+      const int n_base = (t / p.tiles_m) * BN;
+      const int row = m_base + q * 32 + lane;
+      float cx = 0.0f;
+      if (kDequant) {
+        for (int i = epi_tid; i < BN; i += 128) {
+          const int col = n_base + i;
+          cw_s[as * BN + i] = (col < p.N) ? p.Cw[col] : 0.0f;
+          bias_s[as * BN + i] = (p.bias != nullptr && col < p.N) ? p.bias[col] : 0.0f;
+        }
+        named_bar_sync(1, 128);
+        if (row < p.M) cx = p.Cx[row];
+      }
+      mbar_wait(smem_u32(&tfull_bar[as]), aph, 4);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      const float *cw = cw_s + as * BN;
+      const float *bs = bias_s + as * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += OT::kCols) {
+        if (n_base + c0 >= p.N) break;
+        uint32_t w[32];  // 128 bytes of output for this thread's row
+        if constexpr (OT::kCols == 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            if (kDequant) {
+              float v = dequant_ref((int)r[j], cx, cw[c0 + j], p.c);
+              if (p.bias != nullptr) v = __fadd_rn(v, bs[c0 + j]);
+              w[j] = __float_as_uint(v);
+            } else {
+              w[j] = r[j];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + c0 + h * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float v0 = dequant_ref((int)r[j], cx, cw[c0 + h * 32 + j], p.c);
+              float v1 = dequant_ref((int)r[j + 1], cx, cw[c0 + h * 32 + j + 1], p.c);
+              if (p.bias != nullptr) {
+                v0 = __fadd_rn(v0, bs[c0 + h * 32 + j]);
+                v1 = __fadd_rn(v1, bs[c0 + h * 32 + j + 1]);
+              }
+              w[h * 16 + j / 2] = pack16(v0, v1, OutT());
+            }
+          }
+        }
+        if (p.tma_store) {
+          if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading staging
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++)  // 128B-swizzled rows: conflict-free 16 B stores
+            *reinterpret_cast<uint4 *>(stage + lane * 128 + ((j4 ^ (lane & 7)) << 4)) =
+                make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_o, stage_u32, n_base + c0, m_base + q * 32);
+            tma_store_commit();
+          }
+        } else if (row < p.M) {
+          OutT *dst = reinterpret_cast<OutT *>(p.out) + (int64_t)row * p.ldo + n_base + c0;
+          const int ncols = min(OT::kCols, p.N - (n_base + c0));
+          if (ncols == OT::kCols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; j4++)
+              reinterpret_cast<uint4 *>(dst)[j4] = make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
+          } else if (sizeof(OutT) == 4) {  // ragged edge / unaligned rows: predicated scalar stores
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (j < ncols) reinterpret_cast<uint32_t *>(dst)[j] = w[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; j++)
+              if (j < ncols) reinterpret_cast<uint16_t *>(dst)[j] = (uint16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+          }
+        }
+      }
+      // accumulator stage is free for the MMA warp again
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(smem_u32(&tempty_bar[as]));
+        else mbar_arrive_cluster(smem_u32(&tempty_bar[as]), 0);
+      }
+    }
+    if (p.tma_store && lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores
+  }
+
+  // =============================== teardown =====================================
+  tcgen05_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<CG>(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved through the runtime so that libqgemm.so has no link-time dependency on libcuda
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      sym = nullptr;
+    return reinterpret_cast<EncodeFn>(sym);
+  }();
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols]
+int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, size_t esize, const void *base, uint64_t rows, uint64_t cols,
+                uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  EncodeFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return QG_ENODEV;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * esize};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    return QG_EINVAL;
+  }
+  return QG_OK;
+}
+
+template <int CG, bool B_MN, int OUT>
+int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const GemmParams &p, int num_sms,
+           cudaStream_t st) {
+  using C = Cfg<CG, B_MN>;
+  auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    QG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int max_clusters = num_sms / CG;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  QG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, p));
+  count_launch();
+  return QG_OK;
+}
+
+template <int CG, bool B_MN>
+int launch_out(int out_kind, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const GemmParams &p,
+               int num_sms, cudaStream_t st) {
+  switch (out_kind) {
+    case QG_S32: return launch<CG, B_MN, QG_S32>(ma, mb, mo, p, num_sms, st);
+    case QG_F32: if (B_MN) return launch<CG, true, QG_F32>(ma, mb, mo, p, num_sms, st); break;
+    case QG_F16: if (B_MN) return launch<CG, true, QG_F16>(ma, mb, mo, p, num_sms, st); break;
+    case QG_BF16: if (B_MN) return launch<CG, true, QG_BF16>(ma, mb, mo, p, num_sms, st); break;
+  }
+  set_error("gemm_i8_tc: unsupported output kind %d", out_kind);
+  return QG_ENOTSUP;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// True when the tensor-core path can take these operands (TMA needs 16-byte aligned bases and
+// leading dimensions that are multiples of 16 bytes).
+bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb) {
+  return aligned16(A) && aligned16(B) && lda % 16 == 0 && ldb % 16 == 0;
+}
+
+// A [M,K] int8 (lda).  b_kmajor == 0: B is [K,N] (ldb) as in the reference; 1: B is [N,K].
+// out_kind QG_S32 writes raw accumulators; otherwise the dequantize epilogue runs.
+int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
+               void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
+               int num_sms, cudaStream_t st) {
+  if (!gemm_i8_tc_supported(A, lda, B, ldb)) {
+    set_error("gemm_i8_tc: operands must be 16-byte aligned with leading dimensions multiple of 16");
+    return QG_EINVAL;
+  }
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (int)ceil_div(M, BM * cg);
+  p.tiles_n = (int)ceil_div(N, BN);
+  p.out = O; p.ldo = ldo; p.Cx = Cx; p.Cw = Cw; p.bias = bias; p.c = c;
+  const size_t osz = (out_kind == QG_F16 || out_kind == QG_BF16) ? 2 : 4;
+  p.tma_store = (aligned16(O) && (ldo * osz) % 16 == 0) ? 1 : 0;
+  if (getenv("QG_DBG_NO_TMA_STORE") != nullptr) p.tma_store = 0;
+  p.b_kstep = UK * 128; p.b_lbo = BK * 128; p.b_sbo = 1024;
+  if (const char *e = getenv("QG_DBG_B_KSTEP")) p.b_kstep = (uint32_t)atoi(e);
+  if (const char *e = getenv("QG_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);
+  if (const char *e = getenv("QG_DBG_B_SBO")) p.b_sbo = (uint32_t)atoi(e);
+
+  CUtensorMap ma, mb, mo;
+  int rc = make_map_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A, M, K, lda, BM, BK);
+  if (rc) return rc;
+  if (b_kmajor) rc = make_map_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, N, K, ldb, BN / cg, BK);
+  else rc = make_map_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, K, N, ldb, BK, 128);
+  if (rc) return rc;
+  if (p.tma_store) {
+    CUtensorMapDataType odt = out_kind == QG_S32   ? CU_TENSOR_MAP_DATA_TYPE_INT32
+                              : out_kind == QG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                              : out_kind == QG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                   : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    rc = make_map_2d(&mo, odt, osz, O, M, N, ldo, 32, (uint32_t)(128 / osz));
+    if (rc) return rc;
+  } else {
+    mo = ma;  // unused by the kernel
+  }
+  if (cg == 1) return b_kmajor ? launch_out<1, false>(out_kind, ma, mb, mo, p, num_sms, st)
+                               : launch_out<1, true>(out_kind, ma, mb, mo, p, num_sms, st);
+  if (cg == 2) return b_kmajor ? launch_out<2, false>(out_kind, ma, mb, mo, p, num_sms, st)
+                               : launch_out<2, true>(out_kind, ma, mb, mo, p, num_sms, st);
+  return QG_EINVAL;
+}
+
+}  // namespace qg

@@ -1,0 +1,204 @@
+// gemm_simt.cu -- CUDA-core kernels that back the C ABI for shapes / layouts the tcgen05 path
+// does not take (leading dimensions that are not multiples of 16 bytes, tiny matrices), the
+// unfused dequantize, and the fp32 product used for the unquantized comparison.
+//
+// These are correctness paths, not the product's hot loop: the hot loop is gemm_i8_tc.cu.
+#include "common.cuh"
+
+namespace qg {
+
+void count_launch(int n = 1);
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 32;  // block tile; 256 threads, 4x4 outputs per thread
+
+template <typename OutT>
+__device__ __forceinline__ void store_out(void *O, int64_t ldo, int r, int c, float v) {
+  reinterpret_cast<OutT *>(O)[(int64_t)r * ldo + c] = from_f32<OutT>(v);
+}
+
+// op_mm<int8_t,int> (src/ops/op_mm.cuh:9-46) with exact int32 accumulation; optional fused
+// dequantize epilogue (kDequant) identical to the tcgen05 kernel's.
+template <bool kDequant, typename OutT>
+__global__ void __launch_bounds__(256)
+gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__restrict__ B, int64_t ldb, int M,
+                    int N, int K, void *__restrict__ O, int64_t ldo, const float *__restrict__ Cx,
+                    const float *__restrict__ Cw, const float *__restrict__ bias, float c) {
+  __shared__ int8_t sA[TM][TK + 4];
+  __shared__ int8_t sB[TK][TN + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  int acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0;
+
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int e = threadIdx.x; e < TM * TK; e += 256) {
+      const int r = e / TK, kk = e % TK;
+      sA[r][kk] = (m0 + r < M && k0 + kk < K) ? A[(int64_t)(m0 + r) * lda + k0 + kk] : (int8_t)0;
+    }
+    for (int e = threadIdx.x; e < TK * TN; e += 256) {
+      const int kk = e / TN, cidx = e % TN;
+      sB[kk][cidx] = (k0 + kk < K && n0 + cidx < N) ? B[(int64_t)(k0 + kk) * ldb + n0 + cidx] : (int8_t)0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < TK; kk++) {
+      int a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = sA[ty * 4 + i][kk];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      if (kDequant) {
+        float v = dequant_ref(acc[i][j], Cx[r], Cw[col], c);
+        if (bias != nullptr) v = __fadd_rn(v, bias[col]);
+        store_out<OutT>(O, ldo, r, col, v);
+      } else {
+        reinterpret_cast<int32_t *>(O)[(int64_t)r * ldo + col] = acc[i][j];
+      }
+    }
+  }
+}
+
+// op_mm<float,float> (src/ops/op_mm.cuh:9-46): every output is the k-ascending chain
+// res = fma(a, b, res) starting from +0, so any tiling gives bit-identical results; a partial last
+// 32-wide tile adds fma(0,0,res) steps, which only turn -0 into +0.
+__global__ void __launch_bounds__(256)
+mm_f32_kernel(const float *__restrict__ A, int64_t sa_h, int64_t sa_w, const float *__restrict__ B, int64_t sb_h,
+              int64_t sb_w, int M, int N, int K, float *__restrict__ C, int64_t ldc) {
+  __shared__ float sA[TK][TM + 1];
+  __shared__ float sB[TK][TN + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int e = threadIdx.x; e < TM * TK; e += 256) {
+      const int r = e / TK, kk = e % TK;
+      sA[kk][r] = (m0 + r < M && k0 + kk < K) ? A[(int64_t)(m0 + r) * sa_h + (int64_t)(k0 + kk) * sa_w] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < TK * TN; e += 256) {
+      const int kk = e / TN, cidx = e % TN;
+      sB[kk][cidx] = (k0 + kk < K && n0 + cidx < N) ? B[(int64_t)(k0 + kk) * sb_h + (int64_t)(n0 + cidx) * sb_w] : 0.0f;
+    }
+    __syncthreads();
+    const int kmax = min(TK, K - k0);
+    for (int kk = 0; kk < kmax; kk++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool pad = (K % 32) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      C[(int64_t)r * ldc + col] = pad ? __fadd_rn(acc[i][j], 0.0f) : acc[i][j];
+    }
+  }
+}
+
+// a6+a7+a8(+a10) on stored accumulators: op_mm.cuh:96-99 / op_elemwise.cuh:93-103,118-129
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+dequantize_kernel(const int32_t *__restrict__ acc, int64_t ldacc, const float *__restrict__ Cx,
+                  const float *__restrict__ Cw, const float *__restrict__ bias, int M, int N, float c,
+                  OutT *__restrict__ O, int64_t ldo) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  const float cw = Cw[col];
+  const float b = bias ? bias[col] : 0.0f;
+  for (int r = blockIdx.y; r < M; r += gridDim.y) {
+    float v = dequant_ref(acc[(int64_t)r * ldacc + col], Cx[r], cw, c);
+    if (bias != nullptr) v = __fadd_rn(v, b);
+    O[(int64_t)r * ldo + col] = from_f32<OutT>(v);
+  }
+}
+
+}  // namespace
+
+int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K, void *O, int64_t ldo,
+                 int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
+  switch (out_dtype) {
+    case QG_S32:
+      gemm_s8_simt_kernel<false, float><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      break;
+    case QG_F32:
+      gemm_s8_simt_kernel<true, float><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      break;
+    case QG_F16:
+      gemm_s8_simt_kernel<true, __half><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      break;
+    case QG_BF16:
+      gemm_s8_simt_kernel<true, __nv_bfloat16><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      break;
+    default:
+      return QG_EINVAL;
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
+           float *C, int64_t ldc, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
+  mm_f32_kernel<<<grid, 256, 0, st>>>(A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
+                   float c, void *O, int out_dtype, int64_t ldo, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)(M < 8192 ? M : 8192));
+  switch (out_dtype) {
+    case QG_F32:
+      dequantize_kernel<float><<<grid, 256, 0, st>>>(acc, ldacc, Cx, Cw, bias, M, N, c, (float *)O, ldo);
+      break;
+    case QG_F16:
+      dequantize_kernel<__half><<<grid, 256, 0, st>>>(acc, ldacc, Cx, Cw, bias, M, N, c, (__half *)O, ldo);
+      break;
+    case QG_BF16:
+      dequantize_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(acc, ldacc, Cx, Cw, bias, M, N, c, (__nv_bfloat16 *)O, ldo);
+      break;
+    default:
+      return QG_EINVAL;
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace qg

@@ -1,0 +1,519 @@
+// quantize.cu -- vector-wise absmax quantizers.
+//
+// Replaces, per matrix, the reference's three launches
+//   op_absmax        (src/ops/op_reduction.cuh:195-204; one thread per vector, serial loop)
+//   op_inv_divide    (src/ops/op_elemwise.cuh:657-667)
+//   op_multiply<T,int8_t> (src/ops/op_elemwise.cuh:629-640; one element per thread, byte stores)
+// with HBM-bound kernels that read the matrix with 16-byte loads, reduce with warp shuffles and
+// write packed int8 codes plus the fp32 absmax.  The arithmetic (and its quirks: signed first
+// element, IEEE 127/x, truncate-and-wrap cast) is reproduced exactly; see oracle/qoracle.c.
+#include "common.cuh"
+
+namespace qg {
+
+void count_launch(int n = 1);
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint4 ldg16(const void *p) {
+  return __ldg(reinterpret_cast<const uint4 *>(p));
+}
+
+// unpack one 16-byte vector into fp32 lanes
+template <typename T> struct Unpack;
+template <> struct Unpack<float> {
+  static constexpr int EPV = 4;
+  __device__ static __forceinline__ void run(const uint4 &r, float (&f)[4]) {
+    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
+    f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+  }
+};
+template <> struct Unpack<__half> {
+  static constexpr int EPV = 8;
+  __device__ static __forceinline__ void run(const uint4 &r, float (&f)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float2 p = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+      f[2 * i] = p.x; f[2 * i + 1] = p.y;
+    }
+  }
+};
+template <> struct Unpack<__nv_bfloat16> {
+  static constexpr int EPV = 8;
+  __device__ static __forceinline__ void run(const uint4 &r, float (&f)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {  // bf16 -> fp32 is a 16-bit shift
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+// Fold the signed first element x0 with m = max_{j>=1, x_j not NaN} |x_j| (m = -inf when there is
+// no such j) the way AbsMaxFunc does (src/ops/op_reduction.cuh:7-25,80-83): strict '>' updates.
+// Returns true when the +-0 tie-break path is needed (all later entries are zeros, x0 < 0): the
+// reference then ends with -x_j of the first non-NaN j >= 1, whose zero sign the caller must fetch.
+__device__ __forceinline__ bool fold_first(float x0, float m, int mode, float &c) {
+  if (mode == QG_MODE_TRUE_ABSMAX) {
+    const float a0 = fabsf(x0);
+    c = (x0 != x0) ? x0 : ((m > a0) ? m : a0);
+    return false;
+  }
+  c = (x0 != x0) ? x0 : ((m > x0) ? m : x0);
+  return (m == 0.0f) && (x0 < 0.0f);
+}
+
+__device__ __forceinline__ float warp_max(float m) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// Rows (activations): G threads cooperate on one row, NV 16-byte vectors per thread kept in
+// registers between the reduction and the quantizing pass (NV == 0: row too long, re-read it;
+// the second read is served by L2).  One read of X, one write of Xq.
+//   sx_in != NULL : scales given (plain op_multiply<T,int8_t>), no reduction
+//   Xq   == NULL  : reduction only (plain op_absmax)
+// ------------------------------------------------------------------------------------------
+template <typename T, int G, int NV>
+__global__ void __launch_bounds__(kThreads)
+quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
+                  const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
+                  float *__restrict__ Cx) {
+  constexpr int EPV = Unpack<T>::EPV;
+  constexpr int RPB = kThreads / G;  // rows per block
+  constexpr int WPR = G / 32;        // warps per row
+  constexpr int NVC = NV > 0 ? NV : 1;
+  __shared__ float s_m[kThreads / 32];
+  __shared__ float s_x0[RPB];
+
+  const int rib = threadIdx.x / G;
+  const int g = threadIdx.x % G;
+  const int row = blockIdx.x * RPB + rib;
+  const bool active = row < M;
+  const int nvec = K / EPV;
+  const T *xr = X + (int64_t)(active ? row : 0) * ldx;
+
+  uint4 raw[NVC];
+  float scale;
+  if (sx_in == nullptr) {
+    float m = -INFINITY, x0 = 0.0f;
+    if (NV > 0) {
+#pragma unroll
+      for (int v = 0; v < NVC; v++) {
+        const int idx = v * G + g;
+        raw[v] = (active && idx < nvec) ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int v = 0; v < NVC; v++) {
+        const int idx = v * G + g;
+        if (idx < nvec) {
+          float f[EPV];
+          Unpack<T>::run(raw[v], f);
+          if (idx == 0) x0 = f[0];
+#pragma unroll
+          for (int e = 0; e < EPV; e++)
+            if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
+        }
+      }
+    } else {
+      for (int idx = g; idx < nvec && active; idx += G) {
+        float f[EPV];
+        Unpack<T>::run(ldg16(xr + (int64_t)idx * EPV), f);
+        if (idx == 0) x0 = f[0];
+#pragma unroll
+        for (int e = 0; e < EPV; e++)
+          if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
+      }
+    }
+    m = warp_max(m);
+    if (WPR > 1) {
+      if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+      if (g == 0) s_x0[rib] = x0;
+      __syncthreads();
+      m = s_m[rib * WPR];
+#pragma unroll
+      for (int w = 1; w < WPR; w++) m = fmaxf(m, s_m[rib * WPR + w]);
+      x0 = s_x0[rib];
+    } else {
+      x0 = __shfl_sync(0xffffffffu, x0, 0);
+    }
+    float c;
+    if (fold_first(x0, m, mode, c) && active) {
+      for (int j = 1; j < K; j++) {  // rare: sign of the first later zero decides (+-0 tie-break)
+        const float xj = to_f32(xr[j]);
+        if (xj == xj) { c = -xj; break; }
+      }
+    }
+    if (active && g == 0 && Cx != nullptr) Cx[row] = c;
+    scale = __fdiv_rn(range, c);  // InvDivideConstFunc: b / x, IEEE division
+  } else {
+    scale = active ? sx_in[row] : 0.0f;
+    if (NV > 0) {
+#pragma unroll
+      for (int v = 0; v < NVC; v++) {
+        const int idx = v * G + g;
+        raw[v] = (active && idx < nvec) ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  if (Xq == nullptr || !active) return;
+
+  int8_t *qr = Xq + (int64_t)row * ldq;
+  auto emit = [&](const uint4 &r, int idx) {
+    float f[EPV];
+    Unpack<T>::run(r, f);
+    uint32_t w[EPV / 4];
+#pragma unroll
+    for (int q = 0; q < EPV / 4; q++)
+      w[q] = quant_code_u8(f[4 * q], scale) | (quant_code_u8(f[4 * q + 1], scale) << 8) |
+             (quant_code_u8(f[4 * q + 2], scale) << 16) | (quant_code_u8(f[4 * q + 3], scale) << 24);
+    if (EPV == 4) *reinterpret_cast<uint32_t *>(qr + (int64_t)idx * 4) = w[0];
+    else *reinterpret_cast<uint2 *>(qr + (int64_t)idx * 8) = make_uint2(w[0], w[EPV / 4 - 1]);
+  };
+  if (NV > 0) {
+#pragma unroll
+    for (int v = 0; v < NVC; v++) {
+      const int idx = v * G + g;
+      if (idx < nvec) emit(raw[v], idx);
+    }
+  } else {
+    for (int idx = g; idx < nvec; idx += G) emit(ldg16(xr + (int64_t)idx * EPV), idx);
+  }
+}
+
+// Any K, any alignment: one warp per row, scalar accesses.  Same arithmetic.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
+                          const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
+                          float *__restrict__ Cx) {
+  const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const T *xr = X + (int64_t)row * ldx;
+  float scale;
+  if (sx_in == nullptr) {
+    float m = -INFINITY;
+    for (int j = lane; j < K; j += 32)
+      if (j > 0) m = fmaxf(m, fabsf(to_f32(xr[j])));
+    m = warp_max(m);
+    const float x0 = to_f32(xr[0]);
+    float c;
+    if (fold_first(x0, m, mode, c)) {
+      for (int j = 1; j < K; j++) {
+        const float xj = to_f32(xr[j]);
+        if (xj == xj) { c = -xj; break; }
+      }
+    }
+    if (lane == 0 && Cx != nullptr) Cx[row] = c;
+    scale = __fdiv_rn(range, c);
+  } else {
+    scale = sx_in[row];
+  }
+  if (Xq == nullptr) return;
+  for (int j = lane; j < K; j += 32)
+    Xq[(int64_t)row * ldq + j] = (int8_t)quant_code_u8(to_f32(xr[j]), scale);
+}
+
+// ------------------------------------------------------------------------------------------
+// Columns (weights, [K,N] row-major): pass 1 reduces |W[k,j]|, k >= 1, per column into
+// part[j] (fp32 bit pattern, combined across row-chunks with a signed-int atomicMax: every
+// candidate is >= +0 and the initial value is -inf); pass 2 folds in the signed row 0, forms the
+// scale and writes codes.  The second read of W is served largely by the 126 MB L2.
+// Thread layout: 32 x 8; a thread owns one 16-byte vector of columns and walks rows with stride 8.
+// ------------------------------------------------------------------------------------------
+__global__ void fill_f32_kernel(float *p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, int rows_per_cta,
+                           float *__restrict__ part) {
+  constexpr int EPV = Unpack<T>::EPV;
+  __shared__ float s_m[8][32 * EPV + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * EPV;
+  const int k0 = 1 + blockIdx.y * rows_per_cta;
+  const int k1 = min(K, k0 + rows_per_cta);
+  float m[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
+  if (col < N) {
+    const T *base = W + col;
+    int k = k0 + ty;
+    for (; k + 24 < k1; k += 32) {  // 4 independent 16-byte loads in flight per thread
+      uint4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) r[u] = ldg16(base + (int64_t)(k + 8 * u) * ldw);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float f[EPV];
+        Unpack<T>::run(r[u], f);
+#pragma unroll
+        for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
+      }
+    }
+    for (; k < k1; k += 8) {
+      float f[EPV];
+      Unpack<T>::run(ldg16(base + (int64_t)k * ldw), f);
+#pragma unroll
+      for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPV; e++) s_m[ty][tx * EPV + e] = m[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * EPV; c += kThreads) {
+    float r = s_m[0][c];
+#pragma unroll
+    for (int y = 1; y < 8; y++) r = fmaxf(r, s_m[y][c]);
+    const int gc = blockIdx.x * 32 * EPV + c;
+    if (gc < N && r >= 0.0f) atomicMax(reinterpret_cast<int *>(part) + gc, __float_as_int(r));
+  }
+}
+
+// finalize only (plain op_absmax on a [K,N] matrix): Cw[j] from row 0 and part[j]
+template <typename T>
+__global__ void absmax_cols_finalize_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, int mode,
+                                            const float *__restrict__ part, float *__restrict__ Cw) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float c;
+  if (fold_first(to_f32(W[j]), part[j], mode, c)) {
+    for (int k = 1; k < K; k++) {
+      const float x = to_f32(W[(int64_t)k * ldw + j]);
+      if (x == x) { c = -x; break; }
+    }
+  }
+  Cw[j] = c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
+                  int rows_per_cta, const float *__restrict__ part, const float *__restrict__ sw_in,
+                  int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
+  constexpr int EPV = Unpack<T>::EPV;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * EPV;
+  if (col >= N) return;
+  const T *base = W + col;
+  float s[EPV];
+  if (sw_in == nullptr) {
+    float x0[EPV];
+    Unpack<T>::run(ldg16(base), x0);
+#pragma unroll
+    for (int e = 0; e < EPV; e++) {
+      float c;
+      if (fold_first(x0[e], part[col + e], mode, c)) {
+        for (int k = 1; k < K; k++) {
+          const float x = to_f32(base[(int64_t)k * ldw + e]);
+          if (x == x) { c = -x; break; }
+        }
+      }
+      if (blockIdx.y == 0 && ty == 0 && Cw != nullptr) Cw[col + e] = c;
+      s[e] = __fdiv_rn(range, c);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPV; e++) s[e] = sw_in[col + e];
+  }
+  const int k0 = blockIdx.y * rows_per_cta;
+  const int k1 = min(K, k0 + rows_per_cta);
+  auto emit = [&](const uint4 &r, int k) {
+    float f[EPV];
+    Unpack<T>::run(r, f);
+    uint32_t w[EPV / 4];
+#pragma unroll
+    for (int q = 0; q < EPV / 4; q++)
+      w[q] = quant_code_u8(f[4 * q], s[4 * q]) | (quant_code_u8(f[4 * q + 1], s[4 * q + 1]) << 8) |
+             (quant_code_u8(f[4 * q + 2], s[4 * q + 2]) << 16) | (quant_code_u8(f[4 * q + 3], s[4 * q + 3]) << 24);
+    int8_t *dst = Wq + (int64_t)k * ldq + col;
+    if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
+    else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
+  };
+  int k = k0 + ty;
+  for (; k + 24 < k1; k += 32) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) r[u] = ldg16(base + (int64_t)(k + 8 * u) * ldw);
+#pragma unroll
+    for (int u = 0; u < 4; u++) emit(r[u], k + 8 * u);
+  }
+  for (; k < k1; k += 8) emit(ldg16(base + (int64_t)k * ldw), k);
+}
+
+// Any N / alignment: one thread per column (coalesced across threads), scalar accesses.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+quant_cols_generic_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
+                          const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq,
+                          float *__restrict__ Cw) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float scale;
+  if (sw_in == nullptr) {
+    float m = -INFINITY;
+    for (int k = 1; k < K; k++) m = fmaxf(m, fabsf(to_f32(W[(int64_t)k * ldw + j])));
+    float c;
+    if (fold_first(to_f32(W[j]), m, mode, c)) {
+      for (int k = 1; k < K; k++) {
+        const float x = to_f32(W[(int64_t)k * ldw + j]);
+        if (x == x) { c = -x; break; }
+      }
+    }
+    if (Cw != nullptr) Cw[j] = c;
+    scale = __fdiv_rn(range, c);
+  } else {
+    scale = sw_in[j];
+  }
+  if (Wq == nullptr) return;
+  for (int k = 0; k < K; k++)
+    Wq[(int64_t)k * ldq + j] = (int8_t)quant_code_u8(to_f32(W[(int64_t)k * ldw + j]), scale);
+}
+
+__global__ void inv_divide_kernel(const float *__restrict__ a, int64_t n, float b, float *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fdiv_rn(b, a[i]);
+}
+
+// AbsCompareLTEConstFunc, src/ops/op_elemwise.cuh:292-306
+__global__ void outlier_mask_kernel(const float *__restrict__ A, int M, int K, int64_t lda, float thr,
+                                    float *__restrict__ mask, int64_t ldm) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  for (int i = blockIdx.y; i < M; i += gridDim.y) {
+    const float a = A[(int64_t)i * lda + k];
+    const bool inl = ((a >= 0) & (a <= thr)) | ((a <= 0) & (-a <= thr));
+    mask[(int64_t)i * ldm + k] = inl ? 0.0f : 1.0f;
+  }
+}
+
+inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- row launcher ----
+template <typename T, int G, int NV>
+void launch_rows(const T *X, int M, int K, int64_t ldx, float range, int mode, const float *sx, int8_t *Xq,
+                 int64_t ldq, float *Cx, cudaStream_t st) {
+  constexpr int RPB = kThreads / G;
+  quant_rows_kernel<T, G, NV><<<(unsigned)ceil_div(M, RPB), kThreads, 0, st>>>(X, M, K, ldx, range, mode, sx, Xq,
+                                                                             ldq, Cx);
+  count_launch();
+}
+
+template <typename T>
+int rows_dispatch(const T *X, int M, int K, int64_t ldx, float range, int mode, const float *sx, int8_t *Xq,
+                  int64_t ldq, float *Cx, cudaStream_t st) {
+  constexpr int EPV = Unpack<T>::EPV;
+  const bool vec_ok = (K % EPV == 0) && aligned(X, 16) && ((ldx * sizeof(T)) % 16 == 0) &&
+                      (Xq == nullptr || (aligned(Xq, EPV) && ldq % EPV == 0));
+  if (!vec_ok) {
+    quant_rows_generic_kernel<T><<<(unsigned)ceil_div(M, kThreads / 32), kThreads, 0, st>>>(X, M, K, ldx, range, mode,
+                                                                                           sx, Xq, ldq, Cx);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  const int nvec = K / EPV;
+#define QG_ROWS(G, NV) launch_rows<T, G, NV>(X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st)
+  if (nvec <= 32) QG_ROWS(32, 1);
+  else if (nvec <= 64) QG_ROWS(32, 2);
+  else if (nvec <= 128) QG_ROWS(32, 4);
+  else if (nvec <= 256) QG_ROWS(64, 4);
+  else if (nvec <= 512) QG_ROWS(128, 4);
+  else if (nvec <= 1024) QG_ROWS(256, 4);
+  else if (nvec <= 2048) QG_ROWS(256, 8);
+  else if (nvec <= 4096) QG_ROWS(256, 16);
+  else QG_ROWS(256, 0);
+#undef QG_ROWS
+  return (int)cudaGetLastError();
+}
+
+// ---- column launcher ----
+inline int cols_rows_per_cta(int K, int col_tiles) {
+  // enough CTAs for ~4 waves of 148 SMs x 4 resident blocks, at least 32 rows per CTA
+  int64_t want = ceil_div((int64_t)148 * 16, col_tiles);
+  int64_t rows = ceil_div(K, want > 0 ? want : 1);
+  rows = round_up(rows < 32 ? 32 : rows, 32);
+  return (int)rows;
+}
+
+template <typename T>
+int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, const float *sw, int8_t *Wq,
+                  int64_t ldq, float *Cw, float *scratch, cudaStream_t st) {
+  constexpr int EPV = Unpack<T>::EPV;
+  const bool vec_ok = (N % EPV == 0) && aligned(W, 16) && ((ldw * sizeof(T)) % 16 == 0) &&
+                      (Wq == nullptr || (aligned(Wq, EPV) && ldq % EPV == 0)) && (sw != nullptr || scratch != nullptr);
+  if (!vec_ok) {
+    quant_cols_generic_kernel<T><<<(unsigned)ceil_div(N, kThreads), kThreads, 0, st>>>(W, K, N, ldw, range, mode, sw,
+                                                                                      Wq, ldq, Cw);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  const int col_tiles = (int)ceil_div(N, 32 * EPV);
+  const int rpc = cols_rows_per_cta(K, col_tiles);
+  if (sw == nullptr) {
+    fill_f32_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(scratch, N, -INFINITY);
+    count_launch();
+    if (K > 1) {
+      dim3 grid(col_tiles, (unsigned)ceil_div(K - 1, rpc));
+      absmax_cols_partial_kernel<T><<<grid, kThreads, 0, st>>>(W, K, N, ldw, rpc, scratch);
+      count_launch();
+    }
+    if (Wq == nullptr) {
+      absmax_cols_finalize_kernel<T><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(W, K, N, ldw, mode, scratch, Cw);
+      count_launch();
+      return (int)cudaGetLastError();
+    }
+  }
+  dim3 grid(col_tiles, (unsigned)ceil_div(K, rpc));
+  quant_cols_kernel<T><<<grid, kThreads, 0, st>>>(W, K, N, ldw, range, mode, rpc, scratch, sw, Wq, ldq, Cw);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// ---- entry points used by capi.cu ----
+int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, const float *sx,
+               int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st) {
+  switch (dtype) {
+    case QG_F32: return rows_dispatch((const float *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st);
+    case QG_F16: return rows_dispatch((const __half *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st);
+    case QG_BF16: return rows_dispatch((const __nv_bfloat16 *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st);
+  }
+  return QG_EINVAL;
+}
+
+int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
+               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, cudaStream_t st) {
+  switch (dtype) {
+    case QG_F32: return cols_dispatch((const float *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, st);
+    case QG_F16: return cols_dispatch((const __half *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, st);
+    case QG_BF16:
+      return cols_dispatch((const __nv_bfloat16 *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, st);
+  }
+  return QG_EINVAL;
+}
+
+int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st) {
+  inv_divide_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(a, n, b, out);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(K, 256), (unsigned)(M < 32768 ? M : 32768));
+  outlier_mask_kernel<<<grid, 256, 0, st>>>(A, M, K, lda, thr, mask, ldm);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace qg

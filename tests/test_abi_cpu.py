@@ -1,0 +1,59 @@
+"""CPU tests of the drop-in boundary: libqgemm.so loads without a GPU, exports every symbol
+include/qgemm.h declares, validates arguments, and fails loudly (no fallback) without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "qgemm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"QG_API\s+[\w\s\*]+?\b(qg_\w+)\s*\(", text)))
+
+
+def test_header_symbols_match_binding_list(qg):
+    assert declared_symbols() == sorted(qg.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(qg):
+    lib = qg.lib()
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"libqgemm.so does not export {name}"
+    assert lib.qg_version() >= 100
+
+
+def test_no_gpu_means_loud_failure_not_fallback(qg):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rc = qg.lib().qg_device_info(None, None, None)
+    assert rc != 0
+    assert b"CUDA" in qg.lib().qg_last_error() or b"device" in qg.lib().qg_last_error()
+    x = torch.zeros((4, 4))
+    with pytest.raises(AssertionError):
+        qg.op_quantized_mm(x, x, x)  # host tensors are rejected exactly like the reference's assert(on_device)
+
+
+def test_workspace_bytes_is_pure_host_logic(qg):
+    wb = qg.workspace_bytes(4096, 4096, 4096)
+    # int8 copies of X and W, three fp32 vectors, 256-byte aligned pieces
+    assert wb >= 2 * 4096 * 4096 + 3 * 4 * 4096
+    assert wb < 2 * 4096 * 4096 + 3 * 4 * 4096 + 5 * 256 + 1
+    assert qg.workspace_bytes(3, 2, 3) > 0 and qg.workspace_bytes(0, 1, 1) == 0
+    # odd sizes are padded to the 16-byte leading dimensions TMA needs
+    assert qg.workspace_bytes(3, 2, 3) >= 3 * 16 + 3 * 16
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "quantized-gemm-for-transformer-inference_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for needle in ("import oracle", "from oracle", "libqoracle", "oracle/_ref", '#include "qoracle'):
+                    assert needle not in text, (f, needle)

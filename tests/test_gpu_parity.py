@@ -1,0 +1,345 @@
+"""GPU parity tests: every call goes through the C ABI (libqgemm.so) and is compared with the CPU
+oracle on the same seeded inputs.  Bars: int8 codes, absmax vectors and
+int32 accumulators bit-exact; fp32 output bit-exact (same three roundings); fp16/bf16 output
+equal to round-to-nearest of the fp32 result."""
+import ctypes as C
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_edge_matrix
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEV = "cuda"
+TORCH_DT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+
+def seed_of(*args) -> int:
+    return zlib.crc32(repr(args).encode())
+
+
+def same_f32(a: np.ndarray, b: np.ndarray) -> bool:
+    """Bit-level equality that treats every NaN alike but distinguishes +0 from -0."""
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    if a.shape != b.shape:
+        return False
+    nan = np.isnan(a)
+    if not np.array_equal(nan, np.isnan(b)):
+        return False
+    return np.array_equal(a.view(np.int32)[~nan], b.view(np.int32)[~nan])
+
+
+def to_dev(x: np.ndarray, dt: str = "f32") -> torch.Tensor:
+    return torch.from_numpy(x).to(TORCH_DT[dt]).to(DEV)
+
+
+def as_f32_np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().float().cpu().numpy()
+
+
+def padded(t: torch.Tensor, mult: int) -> torch.Tensor:
+    """Copy of t whose leading dimension is a multiple of `mult` elements (stride(0) != shape[1])."""
+    r, c = t.shape
+    ld = (c + mult - 1) // mult * mult
+    buf = torch.zeros((r, ld), dtype=t.dtype, device=t.device)
+    buf[:, :c] = t
+    return buf[:, :c]
+
+
+# ------------------------------------------------------------------------------------------
+# golden vector of the reference's own test
+# ------------------------------------------------------------------------------------------
+def test_golden_3x3_through_c_abi(qg):
+    g = json.load(open(os.path.join(HERE, "golden", "test_quantize_3x3.json")))
+    X = to_dev(np.array(g["X"], np.float32))
+    W = to_dev(np.array(g["W"], np.float32))
+    O = torch.empty((3, 2), device=DEV)
+    qg.op_quantized_mm(X, W, O, g["range"])
+    np.testing.assert_allclose(as_f32_np(O), np.array(g["out"], np.float32), rtol=0, atol=5e-7)
+    Xq, Cx = qg.absmax_quant_rows(X)
+    Wq, Cw = qg.absmax_quant_cols(W)
+    assert Xq.cpu().numpy().tolist() == g["Xq"] and Wq.cpu().numpy().tolist() == g["Wq"]
+    assert Cx.cpu().numpy().tolist() == g["Cx"] and Cw.cpu().numpy().tolist() == g["Cw"]
+    acc = torch.empty((3, 2), dtype=torch.int32, device=DEV)
+    qg.op_mm(Xq, Wq, acc)
+    assert acc.cpu().numpy().tolist() == g["acc"]
+
+
+# ------------------------------------------------------------------------------------------
+# quantizers (a1-a4)
+# ------------------------------------------------------------------------------------------
+ROW_SHAPES = [(3, 3), (9, 1), (11, 5), (40, 128), (40, 512), (33, 1000), (70, 4096), (300, 1024),
+              (20, 8192), (9, 16384), (6, 20000), (4, 36864), (5, 1002)]
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("shape", ROW_SHAPES)
+def test_row_quantizer_bit_exact(qg, oracle, shape, dt):
+    rng = np.random.default_rng(seed_of(shape, dt))
+    X = to_dev(make_edge_matrix(rng, *shape), dt)
+    Xh = as_f32_np(X)  # what the kernel sees, widened exactly
+    for mode in (qg.MODE_REF_EXACT, qg.MODE_TRUE_ABSMAX):
+        Xq, Cx = qg.absmax_quant_rows(X, 127.0, mode)
+        eq, ecx = oracle.absmax_quant_rows(Xh, 127.0, mode)
+        assert same_f32(Cx.cpu().numpy(), ecx), f"Cx mismatch mode {mode}"
+        assert np.array_equal(Xq.cpu().numpy(), eq), f"codes mismatch mode {mode}"
+
+
+COL_SHAPES = [(3, 2), (1, 7), (5, 11), (128, 40), (512, 64), (1000, 36), (4096, 72), (1024, 300),
+              (777, 1024), (4097, 260), (64, 4096)]
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("shape", COL_SHAPES)
+def test_col_quantizer_bit_exact(qg, oracle, shape, dt):
+    rng = np.random.default_rng(seed_of(shape, dt, "c"))
+    K, N = shape
+    W = to_dev(np.ascontiguousarray(make_edge_matrix(rng, N, K).T), dt)
+    Wh = as_f32_np(W)
+    for mode in (qg.MODE_REF_EXACT, qg.MODE_TRUE_ABSMAX):
+        Wq, Cw = qg.absmax_quant_cols(W, 127.0, mode)
+        eq, ecw = oracle.absmax_quant_cols(Wh, 127.0, mode)
+        assert same_f32(Cw.cpu().numpy(), ecw), f"Cw mismatch mode {mode}"
+        assert np.array_equal(Wq.cpu().numpy(), eq), f"codes mismatch mode {mode}"
+
+
+def test_unfused_ops_match_reference_sequence(qg, oracle):
+    """op_absmax -> op_inv_divide -> op_multiply<float,int8_t>, the reference's own call sequence
+    (src/ops/op_mm.cuh:76-89), through the individual entry points."""
+    rng = np.random.default_rng(5)
+    X = make_edge_matrix(rng, 50, 640)
+    W = np.ascontiguousarray(make_edge_matrix(rng, 48, 640).T)
+    dX, dW = to_dev(X), to_dev(W)
+    Cx = torch.empty((50, 1), device=DEV)
+    Cw = torch.empty((1, 48), device=DEV)
+    qg.op_absmax(dX, Cx)
+    qg.op_absmax(dW, Cw)
+    assert same_f32(Cx.cpu().numpy().ravel(), oracle.absmax_rows(X))
+    assert same_f32(Cw.cpu().numpy().ravel(), oracle.absmax_cols(W))
+    sx, sw = torch.empty_like(Cx), torch.empty_like(Cw)
+    qg.op_inv_divide(Cx, 127.0, sx)
+    qg.op_inv_divide(Cw, 127.0, sw)
+    assert same_f32(sx.cpu().numpy().ravel(), oracle.inv_divide(oracle.absmax_rows(X)))
+    Xq = torch.empty((50, 640), dtype=torch.int8, device=DEV)
+    Wq = torch.empty((640, 48), dtype=torch.int8, device=DEV)
+    qg.op_multiply(dX, sx, Xq)
+    qg.op_multiply(dW, sw, Wq)
+    assert np.array_equal(Xq.cpu().numpy(), oracle.absmax_quant_rows(X)[0])
+    assert np.array_equal(Wq.cpu().numpy(), oracle.absmax_quant_cols(W)[0])
+
+
+def test_outlier_extractor(qg, oracle):
+    rng = np.random.default_rng(6)
+    A = (rng.standard_normal((37, 300)) * 4).astype(np.float32)
+    A[3, 7] = np.nan
+    A[4, 8] = 6.0
+    A[5, 9] = -6.0
+    out = torch.empty((37, 300), device=DEV)
+    qg.op_outlier_extractor(to_dev(A), 6.0, out)
+    assert np.array_equal(out.cpu().numpy(), oracle.outlier_mask(A, 6.0))
+
+
+# ------------------------------------------------------------------------------------------
+# int8 GEMM (a5): every kernel variant, exact int32
+# ------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(128, 256, 128), (1, 8, 16), (3, 2, 3), (100, 70, 33), (200, 300, 1000), (256, 512, 4096),
+               (129, 257, 129), (512, 1024, 640), (1024, 1024, 1024), (384, 768, 96)]
+VARIANTS = ["SIMT", "TC_1SM", "TC_2SM"]
+
+
+def codes(rng, r, c):
+    return rng.integers(-128, 128, (r, c), dtype=np.int8)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_s8s8s32_bit_exact(qg, oracle, shape, variant):
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape))
+    A, B = codes(rng, M, K), codes(rng, K, N)
+    dA, dB = padded(torch.from_numpy(A).to(DEV), 16), padded(torch.from_numpy(B).to(DEV), 16)
+    out = padded(torch.full((M, N), -7, dtype=torch.int32, device=DEV), 4)
+    qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
+    try:
+        qg.op_mm(dA, dB, out)
+        torch.cuda.synchronize()
+    finally:
+        qg.set_gemm_variant(qg.GEMM_AUTO)
+    assert np.array_equal(out.cpu().numpy(), oracle.gemm_s8s8s32(A, B))
+
+
+@pytest.mark.parametrize("variant", ["TC_1SM", "TC_2SM"])
+def test_gemm_large_sampled_rows(qg, oracle, variant):
+    """4096^3 (BASELINE target shape): full result against torch._int_mm is not the bar -- the
+    oracle is; it checks 96 sampled rows exactly, and a checksum of every row against int64 math."""
+    M = N = K = 4096
+    rng = np.random.default_rng(11)
+    A, B = codes(rng, M, K), codes(rng, K, N)
+    dA, dB = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
+    out = torch.empty((M, N), dtype=torch.int32, device=DEV)
+    qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
+    try:
+        qg.op_mm(dA, dB, out)
+        torch.cuda.synchronize()
+    finally:
+        qg.set_gemm_variant(qg.GEMM_AUTO)
+    rows = np.sort(rng.choice(M, 96, replace=False))
+    got = out.cpu().numpy()
+    assert np.array_equal(got[rows], oracle.gemm_s8s8s32(A[rows], B))
+    # linearity checksum over all rows: sum_j C[i,j] == A[i,:] . (B @ 1)
+    bsum = B.astype(np.int64).sum(axis=1)
+    assert np.array_equal(got.astype(np.int64).sum(axis=1), A.astype(np.int64) @ bsum)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_kmajor_b_hook(qg, oracle, cg):
+    """Same kernel with B supplied as [N,K] (classic K-major operand) -- cross-checks the MN-major
+    shared-memory descriptors used for the reference's [K,N] weight layout."""
+    M, N, K = 256, 512, 384
+    rng = np.random.default_rng(12)
+    A, B = codes(rng, M, K), codes(rng, K, N)
+    dA = torch.from_numpy(A).to(DEV)
+    dBt = torch.from_numpy(np.ascontiguousarray(B.T)).to(DEV)
+    out = torch.empty((M, N), dtype=torch.int32, device=DEV)
+    rc = qg.lib().qg_test_gemm_s8_bt(cg, C.c_void_p(dA.data_ptr()), C.c_int64(K), C.c_void_p(dBt.data_ptr()),
+                                     C.c_int64(K), M, N, K, C.c_void_p(out.data_ptr()), C.c_int64(N),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, qg.lib().qg_last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), oracle.gemm_s8s8s32(A, B))
+
+
+# ------------------------------------------------------------------------------------------
+# fused dequantize epilogue (a6-a8, a10) and the unfused form
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("shape,with_bias", [((128, 256, 128), False), ((200, 300, 520), True),
+                                             ((512, 768, 1024), True), ((64, 37, 200), True)])
+def test_gemm_dequant_epilogue(qg, oracle, shape, with_bias, dt, variant):
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape, dt))
+    A, B = codes(rng, M, K), codes(rng, K, N)
+    Cx = (rng.random(M, dtype=np.float32) + 0.05)
+    Cw = (rng.random(N, dtype=np.float32) + 0.05)
+    Cx[0] = 0.0
+    Cw[-1] = -0.0
+    bias = rng.standard_normal(N).astype(np.float32) if with_bias else None
+    dA, dB = padded(torch.from_numpy(A).to(DEV), 16), padded(torch.from_numpy(B).to(DEV), 16)
+    out = torch.empty((M, N), dtype=TORCH_DT[dt], device=DEV)
+    qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
+    try:
+        qg.gemm_s8_dequant(dA, dB, to_dev(Cx), to_dev(Cw), out, 127.0, None if bias is None else to_dev(bias))
+        torch.cuda.synchronize()
+    finally:
+        qg.set_gemm_variant(qg.GEMM_AUTO)
+    expect = oracle.dequant(oracle.gemm_s8s8s32(A, B), Cx, Cw, 127.0, bias)
+    if dt == "f32":
+        assert same_f32(out.cpu().numpy(), expect)
+    else:
+        assert torch.equal(out.cpu(), torch.from_numpy(expect).to(TORCH_DT[dt]))
+    # unfused entry point on stored accumulators gives the same bits
+    acc = torch.from_numpy(oracle.gemm_s8s8s32(A, B)).to(DEV)
+    out2 = torch.empty_like(out)
+    qg.op_dequantize(acc, to_dev(Cx), to_dev(Cw), out2, 127.0, None if bias is None else to_dev(bias))
+    assert torch.equal(out2.view(torch.int16 if dt != "f32" else torch.int32),
+                       out.view(torch.int16 if dt != "f32" else torch.int32))
+
+
+# ------------------------------------------------------------------------------------------
+# the whole op (a9) and LinearLayer::forward
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("shape", [(3, 2, 3), (37, 51, 129), (256, 256, 256), (512, 768, 1024), (2048, 512, 512)])
+def test_op_quantized_mm_bit_exact(qg, oracle, shape, variant):
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape))
+    X = make_edge_matrix(rng, M, K)
+    W = np.ascontiguousarray(make_edge_matrix(rng, N, K).T)
+    O = torch.empty((M, N), device=DEV)
+    qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
+    try:
+        qg.op_quantized_mm(to_dev(X), to_dev(W), O, 127.0)
+        torch.cuda.synchronize()
+    finally:
+        qg.set_gemm_variant(qg.GEMM_AUTO)
+    expect, parts = oracle.quantized_mm(X, W, 127.0, return_parts=True)
+    assert oracle.max_partial_sum(parts["Xq"], parts["Wq"]) < 2**24  # reference accumulator == int32 here
+    assert same_f32(O.cpu().numpy(), expect)
+
+
+def test_op_quantized_mm_uniform_2048_error_stats(qg, oracle):
+    """timing_quantize's default shape and distribution: report-level error figures
+    (signed-mean ~1e-4, mean-abs ~0.17, max-abs ~1.1 for 2048^3)."""
+    M = N = K = 2048
+    g = torch.Generator(device="cpu").manual_seed(0)
+    X = torch.rand((M, K), generator=g) * 2 - 1
+    W = torch.rand((K, N), generator=g) * 2 - 1
+    O = torch.empty((M, N), device=DEV)
+    qg.op_quantized_mm(X.to(DEV), W.to(DEV), O, 127.0)
+    Cref = (X.double() @ W.double())
+    err = Cref - O.cpu().double()
+    assert abs(err.mean().item()) < 2e-3
+    assert 0.10 < err.abs().mean().item() < 0.25
+    assert err.abs().max().item() < 2.0
+    rows = [0, 1, 777, 2047]
+    exp = oracle.quantized_mm(X.numpy(), W.numpy())[rows]
+    assert same_f32(O.cpu().numpy()[rows], exp)
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+def test_linear_layer_forward(qg, oracle, dt):
+    torch.manual_seed(3)
+    lin = qg.LinearLayer(640, 384, device=DEV, dtype=TORCH_DT[dt])
+    lin.init_uniform()
+    x = (torch.rand((200, 640), device=DEV) * 2 - 1).to(TORCH_DT[dt])
+    y = torch.empty((200, 384), dtype=TORCH_DT[dt], device=DEV)
+    lin.forward(x, y)
+    expect = oracle.quantized_mm(as_f32_np(x), as_f32_np(lin.w), 127.0, bias=lin.b.cpu().numpy())
+    if dt == "f32":
+        assert same_f32(y.cpu().numpy(), expect)
+    else:
+        assert torch.equal(y.cpu(), torch.from_numpy(expect).to(TORCH_DT[dt]))
+    # second call reuses the cached int8 weights and must give the same bits
+    y2 = torch.empty_like(y)
+    lin.forward(x, y2)
+    assert torch.equal(y.view(torch.int16 if dt != "f32" else torch.int32),
+                       y2.view(torch.int16 if dt != "f32" else torch.int32))
+
+
+def test_host_buffer_entry_point(qg, oracle):
+    rng = np.random.default_rng(9)
+    X = torch.from_numpy(make_edge_matrix(rng, 300, 520)).pin_memory()
+    W = torch.from_numpy(np.ascontiguousarray(make_edge_matrix(rng, 260, 520).T)).pin_memory()
+    out = qg.quantized_mm_host(X, W)
+    assert same_f32(out.numpy(), oracle.quantized_mm(X.numpy(), W.numpy()))
+
+
+def test_fp32_product_matches_reference_fma_order(qg, oracle):
+    rng = np.random.default_rng(10)
+    A = rng.standard_normal((70, 200)).astype(np.float32)
+    B = rng.standard_normal((200, 90)).astype(np.float32)
+    out = torch.empty((70, 90), device=DEV)
+    qg.op_mm(to_dev(A), to_dev(B), out)
+    assert same_f32(out.cpu().numpy(), oracle.gemm_f32_ref(A, B))
+    # transposed view as AttentionLayer passes K.transpose() (attention.cuh:58-60)
+    Bt = to_dev(np.ascontiguousarray(B.T)).t()
+    out2 = torch.empty((70, 90), device=DEV)
+    qg.op_mm(to_dev(A), Bt, out2)
+    assert torch.equal(out, out2)
+
+
+def test_argument_errors_are_reported(qg):
+    X = torch.zeros((4, 8), device=DEV)
+    W = torch.zeros((9, 4), device=DEV)
+    O = torch.zeros((4, 4), device=DEV)
+    with pytest.raises(AssertionError):  # the reference asserts X.w == W.h (op_mm.cuh:71)
+        qg.op_quantized_mm(X, W, O)
+    rc = qg.lib().qg_gemm_s8s8s32(None, C.c_int64(8), None, C.c_int64(8), 4, 4, 8, None, C.c_int64(4), None)
+    assert rc == -22 and b"bad arguments" in qg.lib().qg_last_error()

@@ -1,0 +1,128 @@
+"""CPU tests: the oracle against the reference's only known-answer input and against the
+arithmetic facts SURVEY.md section 8(c) / Appendix A pin (PTX-confirmed semantics)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def golden():
+    with open(os.path.join(HERE, "golden", "test_quantize_3x3.json")) as f:
+        return json.load(f)
+
+
+def test_golden_3x3(oracle):
+    g = golden()
+    X = np.array(g["X"], np.float32)
+    W = np.array(g["W"], np.float32)
+    O, p = oracle.quantized_mm(X, W, g["range"], return_parts=True)
+    assert np.array_equal(p["Cx"], np.array(g["Cx"], np.float32))
+    assert np.array_equal(p["Cw"], np.array(g["Cw"], np.float32))
+    assert np.array_equal(oracle.inv_divide(p["Cx"]), np.array(g["sx"], np.float32))
+    assert np.array_equal(oracle.inv_divide(p["Cw"]), np.array(g["sw"], np.float32))
+    assert np.array_equal(p["Xq"], np.array(g["Xq"], np.int8))
+    assert np.array_equal(p["Wq"], np.array(g["Wq"], np.int8))
+    assert np.array_equal(p["acc"], np.array(g["acc"], np.int32))
+    np.testing.assert_allclose(O, np.array(g["out"], np.float32), rtol=0, atol=5e-7)
+    C = oracle.gemm_f32_ref(X, W)
+    assert np.array_equal(C, np.array(g["fp32_product"], np.float32))
+    assert abs(oracle.signed_mean(C - O) - g["signed_mean_error"]) < 1e-8
+
+
+def test_absmax_first_element_quirk(oracle):
+    # op_reduction.cuh:80-83: accumulator starts from the SIGNED first element
+    X = np.array([[-3.0, 1.0, 2.0], [3.0, -1.0, -2.0], [-0.5, 0.0, 0.0], [-0.5, -0.0, 0.0]], np.float32)
+    c = oracle.absmax_rows(X)
+    assert c[0] == 2.0 and c[1] == 3.0
+    assert c[2] == 0.0 and np.signbit(c[2])       # -(+0.0): first later zero decides the sign
+    assert c[3] == 0.0 and not np.signbit(c[3])   # -(-0.0)
+    ct = oracle.absmax_rows(X, oracle.MODE_TRUE_ABSMAX)
+    assert ct[0] == 3.0 and ct[2] == 0.5
+    # columns behave the same way (op_reduction.cuh:105-108)
+    assert np.array_equal(oracle.absmax_cols(X.T.copy()), c)
+
+
+def test_quantizing_cast_truncates_and_wraps(oracle):
+    # op_elemwise.cuh:106-114 -> mul.f32; cvt.rzi.s32.f32; st.u8
+    assert oracle.quant_code(1.0, 126.99) == 126          # truncation, not rounding
+    assert oracle.quant_code(-1.0, 126.99) == -126
+    assert oracle.quant_code(-3.0, 63.5) == 66            # -190 wraps to 66 (low byte)
+    assert oracle.quant_code(3.0, 63.5) == -66
+    assert oracle.quant_code(float("nan"), 1.0) == 0      # cvt of NaN is 0
+    assert oracle.quant_code(0.0, float("inf")) == 0      # 0*inf = NaN
+    assert oracle.quant_code(1.0, float("inf")) == -1     # +inf clamps to INT_MAX, low byte 0xff
+    assert oracle.quant_code(-1.0, float("inf")) == 0     # -inf clamps to INT_MIN, low byte 0x00
+
+
+def test_wrapped_row_matches_sequential_definition(oracle):
+    rng = np.random.default_rng(0)
+    X = (rng.random((4, 64), dtype=np.float32) * 2 - 1)
+    X[1, 0] = -5.0
+    Xq, Cx = oracle.absmax_quant_rows(X)
+    s = np.float32(127.0) / Cx[1]
+    expect = np.trunc(X[1].astype(np.float32) * s).astype(np.int64)
+    assert np.array_equal(Xq[1].astype(np.int64), ((expect + 128) % 256) - 128)
+    assert abs(int(expect[0])) > 127 and int(Xq[1, 0]) != int(expect[0])  # the wrapped element
+
+
+def test_f32_accumulator_equals_int32_below_2_24(oracle):
+    rng = np.random.default_rng(1)
+    A = rng.integers(-127, 128, (33, 700), dtype=np.int8)
+    B = rng.integers(-127, 128, (700, 45), dtype=np.int8)
+    assert oracle.max_partial_sum(A, B) < 2 ** 24
+    exact = oracle.gemm_s8s8s32(A, B)
+    assert np.array_equal(exact, A.astype(np.int64) @ B.astype(np.int64))
+    assert np.array_equal(oracle.gemm_s8_reff32(A, B), exact)
+
+
+def test_f32_accumulator_diverges_above_2_24(oracle):
+    # documents the limit of "reference accumulator == int32": K * 127^2 must stay below 2^24
+    A = np.full((1, 2048), 127, np.int8)
+    B = np.full((2048, 1), 127, np.int8)
+    assert oracle.max_partial_sum(A, B) >= 2 ** 24
+    assert oracle.gemm_s8s8s32(A, B)[0, 0] == 2048 * 127 * 127
+    assert oracle.gemm_s8_reff32(A, B)[0, 0] != 2048 * 127 * 127
+
+
+def test_dequant_rounding_order(oracle):
+    rng = np.random.default_rng(2)
+    acc = rng.integers(-2_000_000, 2_000_000, (17, 19), dtype=np.int32)
+    Cx = rng.random(17, dtype=np.float32) + 0.1
+    Cw = rng.random(19, dtype=np.float32) + 0.1
+    bias = rng.random(19, dtype=np.float32)
+    c = np.float32(1.0) / (np.float32(127.0) * np.float32(127.0))
+    outer = (Cx[:, None] * Cw[None, :]).astype(np.float32)
+    expect = ((acc.astype(np.float32) * outer).astype(np.float32) * c).astype(np.float32)
+    assert np.array_equal(oracle.dequant(acc, Cx, Cw), expect)
+    assert np.array_equal(oracle.dequant(acc, Cx, Cw, bias=bias), (expect + bias[None, :]).astype(np.float32))
+    # not the same as multiplying by the reciprocal scales (last paragraph)
+    alt = acc.astype(np.float32) * (Cx[:, None] / np.float32(127)) * (Cw[None, :] / np.float32(127))
+    assert not np.array_equal(alt.astype(np.float32), expect)
+
+
+def test_outer_product_negative_zero(oracle):
+    acc = np.array([[5]], np.int32)
+    out = oracle.dequant(acc, np.array([-0.0], np.float32), np.array([1.0], np.float32))
+    assert out[0, 0] == 0.0 and not np.signbit(out[0, 0])  # fma(-0,1,+0) = +0 in the K=1 tiled product
+
+
+def test_full_pipeline_consistency(oracle):
+    rng = np.random.default_rng(3)
+    X = rng.random((37, 129), dtype=np.float32) * 2 - 1
+    W = rng.random((129, 51), dtype=np.float32) * 2 - 1
+    O, p = oracle.quantized_mm(X, W, return_parts=True)
+    Xq, Cx = oracle.absmax_quant_rows(X)
+    Wq, Cw = oracle.absmax_quant_cols(W)
+    assert np.array_equal(Xq, p["Xq"]) and np.array_equal(Wq, p["Wq"])
+    assert np.array_equal(oracle.dequant(oracle.gemm_s8s8s32(Xq, Wq), Cx, Cw), O)
+    C = X.astype(np.float64) @ W.astype(np.float64)
+    assert np.abs(O - C).mean() < 0.02 * np.sqrt((C ** 2).mean()) + 1e-3
+
+
+def test_outlier_mask(oracle):
+    A = np.array([[6.0, -6.0, 6.0001, -7.0, np.nan, 0.0]], np.float32)
+    assert oracle.outlier_mask(A, 6.0).tolist() == [[0.0, 0.0, 1.0, 1.0, 1.0, 0.0]]
+    assert oracle.outlier_columns(A, 6.0).tolist() == [2, 3, 4]
