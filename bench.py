@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the quantized-linear hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu]
+
+A step is one pass of the hot path over one batch of synthetic input: the reference's whole
+`op_quantized_mm` (row absmax-quantize X, column absmax-quantize W, int8 GEMM, dequantize) at
+M = N = K = 4096 with fp32 in / fp32 out, i.e. exactly what src/timing_quantize.cu:38-58 times.
+Nothing is cached between steps (W is re-quantized every step, as the reference does).
+
+  value     whole-job TOPS (2*M*N*K per GPU-step / device time), inputs resident in HBM
+  e2e       same op through the host-buffer C-ABI call (H2D of X and W, D2H of O inside the timing)
+  roofline  the dominant kernel (tcgen05 int8 GEMM + fused dequantize), CUDA-event timed per step
+  cpu_baseline  the CPU oracle (port of the reference math) on this box's host cores, bounded sample
+
+N > 1: column-parallel linear -- rank p owns W[:, p*N:(p+1)*N] (N = 4096 columns per GPU, weak
+scaling), quantizes the replicated X locally, and the fp32 outputs are all-gathered with NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "quantized-gemm-for-transformer-inference_b200"
+METRIC = "quantized linear TOPS at MxNxK (absmax quantize -> int8 GEMM -> dequantize, op_quantized_mm)"
+INT8_SPEC_TOPS = 4500.0
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if sm:
+            busy = [s for s, p in zip(sm, power) if p >= 0.6 * max(power)] or sm
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(power)}
+        return out
+
+
+def cpu_reference_tops(M, N, K, sample_rows, repeats=1):
+    """The CPU oracle (port of the reference arithmetic, oracle/qoracle.c) on the host cores.
+    Bounded sample: W is quantized in full, the activation side runs on `sample_rows` rows of X;
+    the full-step time is t_W + (M / sample_rows) * t_rows."""
+    import numpy as np
+
+    import oracle
+
+    rng = np.random.default_rng(0)
+    X = rng.random((sample_rows, K), dtype=np.float32) * 2 - 1
+    W = rng.random((K, N), dtype=np.float32) * 2 - 1
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        Wq, Cw = oracle.absmax_quant_cols(W)
+        t1 = time.perf_counter()
+        Xq, Cx = oracle.absmax_quant_rows(X)
+        acc = oracle.gemm_s8s8s32(Xq, Wq)
+        oracle.dequant(acc, Cx, Cw)
+        t2 = time.perf_counter()
+        est = (t1 - t0) + (M / sample_rows) * (t2 - t1)
+        best = est if best is None else min(best, est)
+    return 2.0 * M * N * K / best / 1e12, best, oracle.num_threads()
+
+
+def run_reference_cpu(args):
+    """--impl reference: the reference has no CPU implementation of its own (every op asserts
+    off-device, src/ops/op_elemwise.cuh:459-463), so the CPU arm is the oracle port."""
+    M = N = K = args.size
+    rows = args.cpu_sample_rows
+    vals = []
+    for i in range(args.warmup + args.steps):
+        tops, est, cores = cpu_reference_tops(M, N, K, rows)
+        if i >= args.warmup:
+            vals.append((tops, est))
+    tops = statistics.mean(v[0] for v in vals)
+    est = statistics.mean(v[1] for v in vals)
+    sample = (f"each step: column-quantize the full {K}x{N} W, then quantize/GEMM/dequantize rows 0..{rows - 1} of X; "
+              f"full-step time = t_W + ({M}/{rows}) * t_rows")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tops, "unit": "TOPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8 x int8 -> int32, fp32 scales", "data": "synthetic U(-1,1)",
+        "config": {"workload": f"op_quantized_mm {M}x{N}x{K} fp32 in/out, W re-quantized every step", "M": M, "N": N, "K": K},
+        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_reference_gpu(args):
+    """--impl reference-gpu: the reference's OWN CUDA kernels (oracle/_ref/libref_qmm.so, compiled
+    from /root/reference/src for sm_100a) on the same device-resident inputs."""
+    import ctypes as C
+
+    import torch
+
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_qmm.so")
+    if not os.path.exists(so):
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/libref_qmm.so not built"}))
+        return
+    ref = C.CDLL(so)
+    M = N = K = args.size
+    X = torch.rand((M, K), device="cuda") * 2 - 1
+    W = torch.rand((K, N), device="cuda") * 2 - 1
+    O = torch.empty((M, N), device="cuda")
+    ms_ev, ms_wall, ms_fp32 = C.c_double(), C.c_double(), C.c_double()
+    rc = ref.ref_time_quantized_mm_dev(C.c_void_p(X.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(O.data_ptr()),
+                                       M, N, K, C.c_float(127.0), max(1, args.warmup), max(1, args.steps),
+                                       C.byref(ms_ev), C.byref(ms_wall))
+    assert rc == 0, rc
+    rc = ref.ref_time_mm_f32_dev(C.c_void_p(X.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(O.data_ptr()), M, N, K,
+                                 1, max(1, args.steps // 2), C.byref(ms_fp32))
+    ops = 2.0 * M * N * K
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": METRIC, "value": ops / ms_ev.value / 1e9, "unit": "TOPS", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_ev.value, "higher_is_better": True,
+        "ms_per_call_reference_style": ms_wall.value, "fp32_op_mm_ms": ms_fp32.value,
+        "config": {"workload": f"reference op_quantized_mm kernels recompiled for sm_100a, {M}x{N}x{K}"},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    qg = importlib.import_module(PKG)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    M = N = K = args.size
+    peaks = measured_peaks()
+
+    # two rotating buffer sets: 2 x (X 64 MiB + W 64 MiB + O 64 MiB) = 384 MiB >> 126 MB L2
+    nset = 2
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    Xs = [torch.rand((M, K), device=dev, generator=g) * 2 - 1 for _ in range(nset)]
+    Ws = [torch.rand((K, N), device=dev, generator=g) * 2 - 1 for _ in range(nset)]
+    Os = [torch.empty((M, N), device=dev) for _ in range(nset)]
+    gathered = torch.empty((world, M, N), device=dev) if world > 1 else None
+    Xq = torch.empty((M, K), dtype=torch.int8, device=dev)
+    Wq = torch.empty((K, N), dtype=torch.int8, device=dev)
+    Cx = torch.empty(M, device=dev)
+    Cw = torch.empty(N, device=dev)
+
+    def step(i, ev=None):
+        s = i % nset
+        if ev is not None:
+            ev[0].record()
+        qg.absmax_quant_rows(Xs[s], 127.0, qg.MODE_REF_EXACT, Xq, Cx)
+        if ev is not None:
+            ev[1].record()
+        qg.absmax_quant_cols(Ws[s], 127.0, qg.MODE_REF_EXACT, Wq, Cw)
+        if ev is not None:
+            ev[2].record()
+        qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, Os[s], 127.0)
+        if ev is not None:
+            ev[3].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, Os[s])
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    qg.launch_count(reset=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(i, evs[i])
+    t_end.record()
+    torch.cuda.synchronize()
+    launches = qg.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = t_start.elapsed_time(t_end)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    ops = 2.0 * M * N * K
+    value = world * ops / ms_per_step / 1e9  # TOPS, whole job
+
+    rows_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    cols_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    gemm_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- e2e: host buffers through the C-ABI host call (H2D X, W; compute; D2H O) ----
+    e2e = None
+    if world == 1:
+        Xh = torch.empty((M, K), dtype=torch.float32).pin_memory()
+        Wh = torch.empty((K, N), dtype=torch.float32).pin_memory()
+        Oh = torch.empty((M, N), dtype=torch.float32).pin_memory()
+        Xh.copy_(Xs[0]); Wh.copy_(Ws[0])
+        for _ in range(2):
+            qg.quantized_mm_host(Xh, Wh, out=Oh)
+        torch.cuda.synchronize()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            qg.quantized_mm_host(Xh, Wh, out=Oh)  # blocks until Oh is written
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        e2e = {"value": ops / e2e_ms / 1e9, "unit": "TOPS", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": (M * K + K * N) * 4, "d2h_bytes_per_step": M * N * 4,
+               "api": "qg_quantized_mm_host (pinned host X, W -> host O)"}
+    else:
+        e2e = {"value": None, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "host-buffer call measured at N=1 only"}
+
+    # ---- library context: cuBLASLt int8 and fp16 GEMMs of the same shape (not on our path) ----
+    lib = {}
+    try:
+        a8 = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=dev)
+        b8 = torch.randint(-127, 128, (K, N), dtype=torch.int8, device=dev)
+        a16 = torch.randn((M, K), dtype=torch.float16, device=dev)
+        b16 = torch.randn((K, N), dtype=torch.float16, device=dev)
+        for name, fn in (("cublaslt_int8_tops", lambda: torch._int_mm(a8, b8)), ("cublas_fp16_tflops", lambda: a16 @ b16)):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            lib[name] = ops / (e0.elapsed_time(e1) / 10) / 1e9
+            lib[name.rsplit("_", 1)[0] + "_ms"] = e0.elapsed_time(e1) / 10
+    except Exception as ex:  # context only
+        lib["error"] = str(ex)[:200]
+
+    # ---- CPU baseline: oracle port on the host cores, bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        tops, est, cores = cpu_reference_tops(M, N, K, args.cpu_sample_rows)
+        cpu = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port",
+               "sample": f"full {K}x{N} W column-quantized once + rows 0..{args.cpu_sample_rows - 1} of X through "
+                         f"quantize/int8 GEMM/dequantize; full-step time = t_W + ({M}/{args.cpu_sample_rows}) * t_rows "
+                         f"= {est:.2f} s"}
+
+    int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
+    gemm_tops = ops / gemm_ms / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "TOPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), fp32 scales and output", "data": "synthetic U(-1,1), seeded",
+        "config": {"workload": f"op_quantized_mm {M}x{N}x{K} fp32 in / fp32 out per GPU, W re-quantized every step"
+                               + (f"; column-parallel over {world} GPUs + NCCL all-gather of the fp32 outputs" if world > 1 else ""),
+                   "M": M, "N": N * world, "K": K, "mode": "REF_EXACT",
+                   "l2": "2 rotating buffer sets, 384 MiB touched per 2 steps (> 126 MB L2); no explicit flush",
+                   "parallelism": f"column-parallel x{world}" if world > 1 else "single GPU"},
+        "roofline": {"bound": "tensor", "kernel": "gemm_i8_tc_kernel (tcgen05 kind::i8 + fused dequantize epilogue)",
+                     "achieved": gemm_tops, "peak": int8_peak, "unit": "TOP/s", "frac": gemm_tops / int8_peak,
+                     "peak_note": f"2 x bf16_tflops_sustained from MEASURED_PEAKS.json ({peaks['source']}); int8 dense "
+                                  f"rate is 2x bf16; spec 4500 TOP/s -> frac_spec {gemm_tops / INT8_SPEC_TOPS:.3f}",
+                     "frac_spec": gemm_tops / INT8_SPEC_TOPS, "ms": gemm_ms, "traffic": None},
+        "stages": {
+            "quant_rows": {"ms": rows_ms, "achieved": (M * K * 5 + 4 * M) / rows_ms / 1e6, "unit": "GB/s", "bound": "hbm",
+                           "frac": (M * K * 5 + 4 * M) / rows_ms / 1e6 / peaks["hbm_gbs"]},
+            "quant_cols": {"ms": cols_ms, "achieved": (K * N * 5 + 4 * N) / cols_ms / 1e6, "unit": "GB/s", "bound": "hbm",
+                           "frac": (K * N * 5 + 4 * N) / cols_ms / 1e6 / peaks["hbm_gbs"]},
+            "gemm_dequant": {"ms": gemm_ms, "tops": gemm_tops},
+        },
+        "library_context": lib,
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--size", type=int, default=4096, help="M = N = K")
+    ap.add_argument("--cpu-sample-rows", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference_cpu(args)
+        return
+    if args.impl == "reference-gpu":
+        if rank == 0:
+            run_reference_gpu(args)
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

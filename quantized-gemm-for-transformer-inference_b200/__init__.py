@@ -73,8 +73,9 @@ def _dt(t: torch.Tensor) -> int:
 def _dev2d(t: torch.Tensor):
     """(pointer, leading dimension) of a 2-D CUDA tensor with unit inner stride."""
     assert t.is_cuda, "tensor must be on the device (the reference asserts on_device)"
-    assert t.dim() == 2 and t.stride(1) == 1, "row-major tensor with stride_w == 1 required"
-    return C.c_void_p(t.data_ptr()), C.c_int64(t.stride(0))
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "row-major tensor with stride_w == 1 required"
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])  # size-1 dims carry arbitrary strides
+    return C.c_void_p(t.data_ptr()), C.c_int64(ld)
 
 
 def _vec(t: torch.Tensor, n: int):

@@ -1,0 +1,88 @@
+// test_quantize_dropin.cu -- the reference's quantization test flow (src/test_quantize.cu:34-87:
+// fixed 3x3 . 3x2 input, unquantized product, op_quantized_mm, signed-mean error) written against
+// the drop-in operator layer, with the assertions the reference's test defines but never calls
+// (assert_all_close_enough, :25-32) switched on.  Also runs a larger random shape twice to show
+// that repeated calls are deterministic.  Exit code 0 = pass.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "qg_dropin.cuh"
+
+using namespace qg_dropin;
+
+static bool is_close_enough(float a, float b) { return std::fabs(a - b) <= 0.0001f; }
+
+static int check_close(const Tensor<float> &t, const std::vector<float> &v, const char *what) {
+  int bad = 0;
+  for (int i = 0; i < t.h; i++)
+    for (int j = 0; j < t.w; j++)
+      if (!is_close_enough(t.at(i, j), v[i * t.w + j])) {
+        printf("%s mismatch at (%d,%d): %f vs %f\n", what, i, j, t.at(i, j), v[i * t.w + j]);
+        bad++;
+      }
+  return bad;
+}
+
+int main() {
+  int bad = 0;
+  const int m = 3, n = 2, k = 3;
+  Tensor<float> Xh{m, k}, Wh{k, n};
+  const float xv[9] = {2, -1, -1, 0, 3, 2, -1, -1, 0};
+  const float wv[6] = {-1, 0, 0, -2, -1, 2};
+  for (int i = 0; i < 9; i++) Xh.rawp[i] = xv[i];
+  for (int i = 0; i < 6; i++) Wh.rawp[i] = wv[i];
+  Tensor<float> X = Xh.toDevice(), W = Wh.toDevice();
+
+  Tensor<float> uQ{m, n, true};
+  op_mm(X, W, uQ);
+  Tensor<float> Q{m, n, true};
+  op_quantized_mm(X, W, Q, 127.0f);
+  cudaDeviceSynchronize();
+  Tensor<float> uQh = uQ.toHost(), Qh = Q.toHost();
+  printf("Unquantized result:\n");
+  for (int i = 0; i < m; i++) printf("%f %f\n", uQh.at(i, 0), uQh.at(i, 1));
+  printf("Quantized result:\n");
+  for (int i = 0; i < m; i++) printf("%f %f\n", Qh.at(i, 0), Qh.at(i, 1));
+  bad += check_close(uQh, {-1, 0, -2, -2, 1, 2}, "fp32 product");
+  bad += check_close(Qh, {-1.007874f, 0.0f, -1.984252f, -2.031496f, 1.0f, 2.0f}, "quantized product");
+  Tensor<float> err{m, n};
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++) err.at(i, j) = uQh.at(i, j) - Qh.at(i, j);
+  printf("Mean quantization error:\n%g\n", err.mean());
+  if (std::fabs(err.mean() - 0.003937006f) > 1e-7f) { printf("signed-mean error mismatch\n"); bad++; }
+
+  // step-by-step sequence of op_quantized_mm (src/ops/op_mm.cuh:76-93) through the single ops
+  Tensor<float> Cx{m, 1, true}, Cw{1, n, true}, sx{m, 1, true}, sw{1, n, true};
+  op_absmax(X, Cx);
+  op_absmax(W, Cw);
+  op_inv_divide(Cx, 127.0f, sx);
+  op_inv_divide(Cw, 127.0f, sw);
+  Tensor<int8_t> Xq{m, k, true}, Wq{k, n, true};
+  op_multiply(X, sx, Xq);
+  op_multiply(W, sw, Wq);
+  Tensor<int> acc{m, n, true};
+  op_mm(Xq, Wq, acc);
+  cudaDeviceSynchronize();
+  Tensor<int> acch = acc.toHost();
+  const int expect_acc[6] = {-8128, 0, -10668, -5461, 16129, 16129};
+  for (int i = 0; i < 6; i++)
+    if (acch.rawp[i] != expect_acc[i]) { printf("acc[%d] = %d, expected %d\n", i, acch.rawp[i], expect_acc[i]); bad++; }
+
+  // a larger shape, called twice: results must be identical
+  const int M = 512, N = 768, K = 1024;
+  Tensor<float> A{M, K}, B{K, N};
+  srand(1);
+  for (int i = 0; i < M * K; i++) A.rawp[i] = (float)rand() / RAND_MAX * 2 - 1;
+  for (int i = 0; i < K * N; i++) B.rawp[i] = (float)rand() / RAND_MAX * 2 - 1;
+  Tensor<float> dA = A.toDevice(), dB = B.toDevice(), O1{M, N, true}, O2{M, N, true};
+  op_quantized_mm(dA, dB, O1, 127.0f);
+  op_quantized_mm(dA, dB, O2, 127.0f);
+  cudaDeviceSynchronize();
+  Tensor<float> h1 = O1.toHost(), h2 = O2.toHost();
+  for (int i = 0; i < M * N; i++)
+    if (h1.rawp[i] != h2.rawp[i]) { bad++; break; }
+  printf(bad ? "FAILED (%d)\n" : "All tests completed successfully!\n", bad);
+  return bad ? 1 : 0;
+}

@@ -126,3 +126,27 @@ def test_outlier_mask(oracle):
     A = np.array([[6.0, -6.0, 6.0001, -7.0, np.nan, 0.0]], np.float32)
     assert oracle.outlier_mask(A, 6.0).tolist() == [[0.0, 0.0, 1.0, 1.0, 1.0, 0.0]]
     assert oracle.outlier_columns(A, 6.0).tolist() == [2, 3, 4]
+
+
+def _same_f32(a, b):
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    nan = np.isnan(a)
+    return a.shape == b.shape and np.array_equal(nan, np.isnan(b)) and np.array_equal(
+        a.view(np.int32)[~nan], b.view(np.int32)[~nan])
+
+
+@pytest.mark.parametrize("name", ["3x3", "edge_24x40x56", "rand_64x48x96", "normal_33x65x130", "curand_seed0_32x16x64"])
+def test_oracle_matches_reference_kernel_outputs(oracle, name):
+    """tests/golden/ref_*.npz were produced by the REFERENCE's own CUDA kernels on a B200
+    (tests/golden/make_ref_fixtures.py through oracle/_ref): every intermediate must match bit for bit
+    (signed zeros included, NaNs position-wise)."""
+    r = np.load(os.path.join(HERE, "golden", f"ref_{name}.npz"))
+    O, p = oracle.quantized_mm(r["X"], r["W"], 127.0, return_parts=True)
+    assert _same_f32(p["Cx"], r["Cx"]) and _same_f32(p["Cw"], r["Cw"])
+    assert np.array_equal(p["Xq"], r["Xq"]) and np.array_equal(p["Wq"], r["Wq"])
+    assert np.array_equal(p["acc"], r["acc"])
+    assert np.array_equal(oracle.gemm_s8_reff32(p["Xq"], p["Wq"]), r["acc"])
+    assert _same_f32(O, r["O"])          # step-by-step pipeline (timing_quantize.cu:38-58)
+    assert _same_f32(O, r["O_op"])       # the reference's op_quantized_mm itself (op_mm.cuh:67-101)
+    assert _same_f32(oracle.gemm_f32_ref(r["X"], r["W"]), r["C_fp32"])
