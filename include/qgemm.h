@@ -12,6 +12,8 @@
  *   - plain pointers and sizes only; all matrix pointers are DEVICE pointers unless the name
  *     ends in _host; matrices are row-major with a leading dimension in ELEMENTS (the
  *     reference's stride_h with stride_w == 1, src/utils/tensor.cuh:14,62-63).
+ *   - parameter names are lower case on purpose: the reference defines a macro `N`
+ *     (src/ops/op_elemwise.cuh:10) that would otherwise rewrite these prototypes.
  *   - X is [M,K] (activations), W is [K,N] (in_dim x out_dim, src/modules/linear.cuh:18),
  *     bias is [N] (the reference's [1,N]), Cx is [M], Cw is [N], codes are int8.
  *   - return value: 0 = QG_OK, QG_E* (negative) for argument errors, positive = cudaError_t.
@@ -69,10 +71,10 @@ QG_API int64_t qg_launch_count(int reset);
 
 /* ---- a1 / a2: op_absmax(in, out)  src/ops/op_reduction.cuh:195-204 ------------------------ */
 /* out [M,1]: per-row reduce (op_reduction_kernel_colwise, :71-92) */
-QG_API int qg_absmax_rows(const void *X, int dtype, int M, int K, int64_t ldx, int mode, float *Cx,
+QG_API int qg_absmax_rows(const void *X, int dtype, int m, int k, int64_t ldx, int mode, float *Cx,
                           qg_stream_t stream);
 /* out [1,N]: per-column reduce (op_reduction_kernel_rowwise, :96-117) */
-QG_API int qg_absmax_cols(const void *W, int dtype, int K, int N, int64_t ldw, int mode, float *Cw,
+QG_API int qg_absmax_cols(const void *W, int dtype, int k, int n, int64_t ldw, int mode, float *Cw,
                           qg_stream_t stream);
 
 /* ---- a3: op_inv_divide(a, b, out) = b / a   src/ops/op_elemwise.cuh:657-667 --------------- */
@@ -80,47 +82,47 @@ QG_API int qg_inv_divide_f32(const float *a, int64_t n, float b, float *out, qg_
 
 /* ---- a4: op_multiply<T,int8_t>(a, scale, out)  src/ops/op_elemwise.cuh:629-640 ------------- */
 /* scale [M,1] broadcast along columns (:416-419) */
-QG_API int qg_quantize_rows(const void *X, int dtype, int M, int K, int64_t ldx, const float *sx,
+QG_API int qg_quantize_rows(const void *X, int dtype, int m, int k, int64_t ldx, const float *sx,
                             int8_t *Xq, int64_t ldq, qg_stream_t stream);
 /* scale [1,N] broadcast along rows (:412-415) */
-QG_API int qg_quantize_cols(const void *W, int dtype, int K, int N, int64_t ldw, const float *sw,
+QG_API int qg_quantize_cols(const void *W, int dtype, int k, int n, int64_t ldw, const float *sw,
                             int8_t *Wq, int64_t ldq, qg_stream_t stream);
 
 /* ---- a1+a3+a4 fused: one pass over X writes int8 codes and the fp32 absmax ---------------- */
 /* replaces op_absmax + op_inv_divide + op_multiply at src/ops/op_mm.cuh:76-77,82-83,86-87 */
-QG_API int qg_absmax_quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range,
+QG_API int qg_absmax_quant_rows(const void *X, int dtype, int m, int k, int64_t ldx, float range,
                                 int mode, int8_t *Xq, int64_t ldq, float *Cx, qg_stream_t stream);
 /* replaces src/ops/op_mm.cuh:78-79,84-85,88-89.  scratch: N floats of device memory. */
-QG_API int qg_absmax_quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range,
+QG_API int qg_absmax_quant_cols(const void *W, int dtype, int k, int n, int64_t ldw, float range,
                                 int mode, int8_t *Wq, int64_t ldq, float *Cw, float *scratch,
                                 qg_stream_t stream);
 
 /* ---- a5: op_mm<int8_t,int>(A, B, C)  src/ops/op_mm.cuh:49-65 ------------------------------ */
 /* exact int32 accumulation (equals the reference's fp32-FMA accumulator while every partial
  * sum stays below 2^24).  A [M,K] lda, B [K,N] ldb, C [M,N] int32 ldc. */
-QG_API int qg_gemm_s8s8s32(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N,
-                           int K, int32_t *C, int64_t ldc, qg_stream_t stream);
+QG_API int qg_gemm_s8s8s32(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int m, int n,
+                           int k, int32_t *C, int64_t ldc, qg_stream_t stream);
 
 /* ---- a6+a7+a8 (+a10): op_mm(Cx,Cw,outer); op_dequantize; op_multiply(O,1/range^2) ---------- */
 /* src/ops/op_mm.cuh:96-99, src/ops/op_elemwise.cuh:614-625,644-654; bias add = op_add at
  * src/modules/linear.cuh:54 (bias may be NULL).  Unfused form, for callers holding accumulators. */
 QG_API int qg_dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw,
-                             const float *bias, int M, int N, float range, void *O, int out_dtype,
+                             const float *bias, int m, int n, float range, void *O, int out_dtype,
                              int64_t ldo, qg_stream_t stream);
 
 /* ---- a5..a8 (+a10) fused: int8 GEMM whose epilogue dequantizes, adds bias and casts --------- */
 QG_API int qg_gemm_s8_dequant(const int8_t *Xq, int64_t ldxq, const int8_t *Wq, int64_t ldwq,
-                              const float *Cx, const float *Cw, const float *bias, int M, int N, int K,
+                              const float *Cx, const float *Cw, const float *bias, int m, int n, int k,
                               float range, void *O, int out_dtype, int64_t ldo, qg_stream_t stream);
 
 /* ---- a9: op_quantized_mm(X, W, O, range)  src/ops/op_mm.cuh:67-101 ------------------------- */
 /* bytes of device scratch qg_quantized_mm / qg_linear_forward need for this shape */
-QG_API size_t qg_workspace_bytes(int M, int N, int K);
+QG_API size_t qg_workspace_bytes(int m, int n, int k);
 /* X,W of in_dtype, O of out_dtype; bias optional (LinearLayer::forward, linear.cuh:49-56).
  * The reference allocates 8 temporaries per call (op_mm.cuh:76-96); here the caller passes one
  * scratch block (workspace == NULL: the library keeps a grow-only per-device arena). */
 QG_API int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ldw, int in_dtype, void *O,
-                           int64_t ldo, int out_dtype, int M, int N, int K, float range, int mode,
+                           int64_t ldo, int out_dtype, int m, int n, int k, float range, int mode,
                            const float *bias, void *workspace, size_t workspace_bytes,
                            qg_stream_t stream);
 
@@ -128,25 +130,25 @@ QG_API int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ld
 /* src/modules/linear.cuh:49-56: y = x @ w + b.  Wq/Cw come from qg_absmax_quant_cols. */
 QG_API int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wq, int64_t ldwq,
                              const float *Cw, const float *bias, void *Y, int64_t ldy, int out_dtype,
-                             int M, int N, int K, float range, int mode, void *workspace,
+                             int m, int n, int k, float range, int mode, void *workspace,
                              size_t workspace_bytes, qg_stream_t stream);
 
 /* ---- host-buffer form of a9 (pageable or pinned host pointers; H2D + compute + D2H) --------- */
 /* what a caller holding host tensors (Tensor<T>{h,w,false}, toDevice/toHost at
  * src/utils/tensor.cuh:77-119) would otherwise spell by hand.  Blocks until O_host is written. */
-QG_API int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host, int M, int N,
-                                int K, float range, int mode, const float *bias_host);
+QG_API int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host, int m, int n,
+                                int k, float range, int mode, const float *bias_host);
 
 /* ---- a11: op_outlier_extractor(a, b, out)  src/ops/op_elemwise.cuh:698-708 ----------------- */
 /* elementwise mask out = (|a| <= thr) ? 0 : 1, same dtype as the reference (float mask) */
-QG_API int qg_outlier_mask_f32(const float *A, int M, int K, int64_t lda, float thr, float *mask,
+QG_API int qg_outlier_mask_f32(const float *A, int m, int k, int64_t lda, float thr, float *mask,
                                int64_t ldm, qg_stream_t stream);
 
 /* ---- op_mm<float,float>(A, B, C)  src/ops/op_mm.cuh:49-65 ---------------------------------- */
 /* fp32 product with the reference's k-ascending fma chain per output (bit-identical results);
  * general strides (sa_h, sa_w ...) because attention.cuh:58-60 passes K.transpose(). */
 QG_API int qg_mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w,
-                     int M, int N, int K, float *C, int64_t ldc, qg_stream_t stream);
+                     int m, int n, int k, float *C, int64_t ldc, qg_stream_t stream);
 
 #ifdef __cplusplus
 }

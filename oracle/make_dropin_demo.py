@@ -1,0 +1,66 @@
+"""Builds the drop-in demonstration (TEST INFRASTRUCTURE): the reference's OWN test driver,
+src/test_quantize.cu, compiled twice from a scratch copy of /root/reference/src under /tmp --
+
+  oracle/_ref/test_quantize_ref     unmodified reference (its kernels, sm_100a)
+  oracle/_ref/test_quantize_dropin  same driver, but the body of op_quantized_mm
+                                    (src/ops/op_mm.cuh:67-101) replaced by the one-line call into
+                                    qg_dropin.cuh / libqgemm.so that INTEGRATION.md describes
+
+Both print the same three blocks (unquantized result, quantized result, mean error); the GPU test
+tests/test_gpu_dropin.py runs them and compares the text.  Nothing from the reference is written
+into this repository: the edited copy lives in /tmp, only the two binaries land in oracle/_ref/.
+"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("REF", "/root/reference")
+PKG = os.path.join(ROOT, "quantized-gemm-for-transformer-inference_b200")
+OUT = os.path.join(ROOT, "oracle", "_ref")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "--expt-relaxed-constexpr", "-O2", "-w"]
+
+
+def replace_body(text: str, func: str, new_body: str) -> str:
+    m = re.search(r"void\s+" + func + r"\s*\(", text)
+    assert m, func
+    i = text.index("{", m.end())
+    depth, j = 0, i
+    while True:
+        depth += text[j] == "{"
+        depth -= text[j] == "}"
+        if depth == 0:
+            break
+        j += 1
+    return text[:i] + "{\n" + new_body + "\n}" + text[j + 1:]
+
+
+def main():
+    if not os.path.isdir(os.path.join(REF, "src", "ops")):
+        print("reference tree not present; keeping prebuilt binaries")
+        return
+    os.makedirs(OUT, exist_ok=True)
+    tmp = "/tmp/qg_dropin_tree"
+    shutil.rmtree(tmp, ignore_errors=True)
+    shutil.copytree(os.path.join(REF, "src"), os.path.join(tmp, "src"))
+    src = os.path.join(tmp, "src")
+    subprocess.run([NVCC, *FLAGS, "-I", src, os.path.join(src, "test_quantize.cu"), "-o",
+                    os.path.join(OUT, "test_quantize_ref"), "-lcurand"], check=True)
+    path = os.path.join(src, "ops", "op_mm.cuh")
+    text = open(path).read()
+    text = text.replace("#pragma once", '#pragma once\n#include "qg_dropin.cuh"', 1)
+    text = replace_body(text, "op_quantized_mm", "    qg_dropin::op_quantized_mm(X, W, O, range);")
+    open(path, "w").write(text)
+    subprocess.run([NVCC, *FLAGS, "-I", src, "-I", os.path.join(PKG, "cpp"), os.path.join(src, "test_quantize.cu"), "-o",
+                    os.path.join(OUT, "test_quantize_dropin"), "-lcurand", "-L", PKG, "-lqgemm",
+                    "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../quantized-gemm-for-transformer-inference_b200"],
+                   check=True)
+    shutil.rmtree(tmp, ignore_errors=True)
+    print("built", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
