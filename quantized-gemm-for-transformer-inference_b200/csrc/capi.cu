@@ -26,6 +26,7 @@ int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t s
 int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
                    float c, void *O, int out_dtype, int64_t ldo, cudaStream_t st);
 bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb);
+void gemm_i8_tc_set_stats(long long *dev_ptr);
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
                int num_sms, cudaStream_t st);
@@ -48,6 +49,15 @@ int cuda_status(cudaError_t e, const char *what) {
 
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// programmatic dependent launch between the kernels of one call; QG_PDL=0 switches it off
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("QG_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
 
 // ---- device state ----
 struct DeviceState {
@@ -381,6 +391,13 @@ int qg_mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_
   if (rc) return rc;
   QG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N, "qg_mm_f32: bad arguments");
   return mm_f32(A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc, (cudaStream_t)stream);
+}
+
+/* bring-up hook: device buffer (8 x int64 per CTA) that the tcgen05 GEMM fills with pipeline wait
+ * counters; NULL switches the instrumentation off. */
+QG_API int qg_debug_gemm_stats(long long *dev_ptr) {
+  gemm_i8_tc_set_stats(dev_ptr);
+  return QG_OK;
 }
 
 /* test hook (not part of the reference-facing surface): tcgen05 GEMM with B given as [N,K]

@@ -32,6 +32,28 @@ int cuda_status(cudaError_t e, const char *what);
     }                                    \
   } while (0)
 
+void count_launch(int n = 1);
+bool pdl_enabled();
+
+// Launch through cudaLaunchKernelEx so that consecutive kernels of one call can overlap their
+// launch latency and prologue (programmatic stream serialization); every kernel of this library
+// executes griddep_wait() before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 static inline size_t dtype_size(int dt) { return dt == QG_F32 ? 4 : 2; }
@@ -239,6 +261,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- programmatic dependent launch (PDL) ----
+// wait: blocks until every prerequisite grid has completed and its writes are visible (no-op when the
+// kernel was launched without a programmatic dependency).  launch_dependents: lets the next kernel
+// in the stream start its prologue while this grid is still running.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -22,8 +22,6 @@
 
 namespace qg {
 
-void count_launch(int n = 1);
-
 namespace {
 
 constexpr int BM = 128;     // accumulator rows per CTA (TMEM lanes)
@@ -44,6 +42,9 @@ struct GemmParams {
   // MN-major B descriptor geometry (bytes).  Defaults: k-step 32 rows * 128 B, LBO = BK * 128 B
   // (next 128-column chunk), SBO = 8 rows * 128 B.  Overridable through QG_DBG_B_* for bring-up.
   uint32_t b_kstep, b_lbo, b_sbo;
+  // optional per-CTA pipeline counters (cycles): [0] producer wait-empty, [1] producer total,
+  // [2] mma wait-full, [3] mma wait-tmem-empty, [4] mma total, [5] epilogue wait-tmem-full, [6] epilogue total
+  long long *stats;
 };
 
 template <int CG, bool B_MN>
@@ -126,6 +127,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
+  // preceding kernel; from here on its outputs (Xq, Wq, Cx, Cw) are read
+  griddep_wait();
 
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_clusters = gridDim.x / CG;
@@ -136,12 +140,20 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t it = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int m_base = ((t % p.tiles_m) * CG + (int)cta_rank) * BM;
         const int n_base = (t / p.tiles_m) * BN + (int)cta_rank * C::kBLoadN;
         for (int kb = 0; kb < num_kb; kb++, it++) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
+          if (p.stats) {
+            const long long t0 = clock64();
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
+            w_empty += clock64() - t0;
+          } else {
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
+          }
           const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
           const int k0 = kb * BK;
@@ -166,6 +178,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
         }
       }
+      if (p.stats) {
+        p.stats[blockIdx.x * 8 + 0] = w_empty;
+        p.stats[blockIdx.x * 8 + 1] = clock64() - t_begin;
+      }
     }
     __syncwarp();  // reconverge before the aligned teardown barrier
   } else if (warp == 1) {
@@ -173,14 +189,28 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_i8(BM * CG, BN, 0, B_MN ? 1 : 0);
       uint32_t it = 0, acc_it = 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_begin = clock64();
       for (int t = cluster_id; t < num_tiles; t += num_clusters, acc_it++) {
         const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-        mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, 2);  // epilogue drained this accumulator
+        if (p.stats) {
+          const long long t0 = clock64();
+          mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, 2);
+          w_tempty += clock64() - t0;
+        } else {
+          mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, 2);  // epilogue drained this accumulator
+        }
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; kb++, it++) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(smem_u32(&full_bar[s]), ph, 3);
+          if (p.stats) {
+            const long long t0 = clock64();
+            mbar_wait(smem_u32(&full_bar[s]), ph, 3);
+            w_full += clock64() - t0;
+          } else {
+            mbar_wait(smem_u32(&full_bar[s]), ph, 3);
+          }
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
@@ -201,6 +231,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (CG == 1) umma_commit(smem_u32(&tfull_bar[as]));
         else umma_commit_2sm(smem_u32(&tfull_bar[as]), 0x3);
       }
+      if (p.stats) {
+        p.stats[blockIdx.x * 8 + 2] = w_full;
+        p.stats[blockIdx.x * 8 + 3] = w_tempty;
+        p.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
     }
     __syncwarp();
   } else {
@@ -210,6 +245,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint8_t *stage = smem_out + q * kStageOutBytes;
     const uint32_t stage_u32 = smem_u32(stage);
     uint32_t acc_it = 0;
+    long long w_tfull = 0;
+    const long long t_begin = clock64();
     for (int t = cluster_id; t < num_tiles; t += num_clusters, acc_it++) {
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       const int m_base = ((t % p.tiles_m) * CG + (int)cta_rank) * BM;
@@ -225,7 +262,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         named_bar_sync(1, 128);
         if (row < p.M) cx = p.Cx[row];
       }
-      mbar_wait(smem_u32(&tfull_bar[as]), aph, 4);
+      if (p.stats) {
+        const long long t0 = clock64();
+        mbar_wait(smem_u32(&tfull_bar[as]), aph, 4);
+        w_tfull += clock64() - t0;
+      } else {
+        mbar_wait(smem_u32(&tfull_bar[as]), aph, 4);
+      }
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       const float *cw = cw_s + as * BN;
@@ -306,6 +349,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
     if (p.tma_store && lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores
+    if (p.stats && warp == 2 && lane == 0) {
+      p.stats[blockIdx.x * 8 + 5] = w_tfull;
+      p.stats[blockIdx.x * 8 + 6] = clock64() - t_begin;
+    }
   }
 
   // =============================== teardown =====================================
@@ -377,13 +424,15 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, 
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   QG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, p));
   count_launch();
   return QG_OK;
@@ -404,7 +453,11 @@ int launch_out(int out_kind, const CUtensorMap &ma, const CUtensorMap &mb, const
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+long long *g_stats = nullptr;  // device buffer of 8 counters per CTA, or NULL
+
 }  // namespace
+
+void gemm_i8_tc_set_stats(long long *dev_ptr) { g_stats = dev_ptr; }
 
 // True when the tensor-core path can take these operands (TMA needs 16-byte aligned bases and
 // leading dimensions that are multiples of 16 bytes).
@@ -429,6 +482,7 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   const size_t osz = (out_kind == QG_F16 || out_kind == QG_BF16) ? 2 : 4;
   p.tma_store = (aligned16(O) && (ldo * osz) % 16 == 0) ? 1 : 0;
   if (getenv("QG_DBG_NO_TMA_STORE") != nullptr) p.tma_store = 0;
+  p.stats = g_stats;
   p.b_kstep = UK * 128; p.b_lbo = BK * 128; p.b_sbo = 1024;
   if (const char *e = getenv("QG_DBG_B_KSTEP")) p.b_kstep = (uint32_t)atoi(e);
   if (const char *e = getenv("QG_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);

@@ -7,8 +7,6 @@
 
 namespace qg {
 
-void count_launch(int n = 1);
-
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 32;  // block tile; 256 threads, 4x4 outputs per thread
@@ -29,6 +27,7 @@ gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__r
   __shared__ int8_t sB[TK][TN + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  griddep_wait();
   int acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -88,6 +87,7 @@ mm_f32_kernel(const float *__restrict__ A, int64_t sa_h, int64_t sa_w, const flo
   __shared__ float sB[TK][TN + 1];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  griddep_wait();
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -138,6 +138,7 @@ dequantize_kernel(const int32_t *__restrict__ acc, int64_t ldacc, const float *_
                   const float *__restrict__ Cw, const float *__restrict__ bias, int M, int N, float c,
                   OutT *__restrict__ O, int64_t ldo) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (col >= N) return;
   const float cw = Cw[col];
   const float b = bias ? bias[col] : 0.0f;
@@ -155,29 +156,27 @@ int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int
   dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
   switch (out_dtype) {
     case QG_S32:
-      gemm_s8_simt_kernel<false, float><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<false, float>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     case QG_F32:
-      gemm_s8_simt_kernel<true, float><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, float>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     case QG_F16:
-      gemm_s8_simt_kernel<true, __half><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, __half>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     case QG_BF16:
-      gemm_s8_simt_kernel<true, __nv_bfloat16><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, __nv_bfloat16>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     default:
       return QG_EINVAL;
   }
-  count_launch();
   return (int)cudaGetLastError();
 }
 
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
            float *C, int64_t ldc, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
-  mm_f32_kernel<<<grid, 256, 0, st>>>(A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc);
-  count_launch();
+  launch_kernel(mm_f32_kernel, grid, dim3(256), st, A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc);
   return (int)cudaGetLastError();
 }
 
@@ -186,18 +185,17 @@ int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const flo
   dim3 grid((unsigned)ceil_div(N, 256), (unsigned)(M < 8192 ? M : 8192));
   switch (out_dtype) {
     case QG_F32:
-      dequantize_kernel<float><<<grid, 256, 0, st>>>(acc, ldacc, Cx, Cw, bias, M, N, c, (float *)O, ldo);
+      launch_kernel(dequantize_kernel<float>, grid, dim3(256), st, acc, ldacc, Cx, Cw, bias, M, N, c, (float *)O, ldo);
       break;
     case QG_F16:
-      dequantize_kernel<__half><<<grid, 256, 0, st>>>(acc, ldacc, Cx, Cw, bias, M, N, c, (__half *)O, ldo);
+      launch_kernel(dequantize_kernel<__half>, grid, dim3(256), st, acc, ldacc, Cx, Cw, bias, M, N, c, (__half *)O, ldo);
       break;
     case QG_BF16:
-      dequantize_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(acc, ldacc, Cx, Cw, bias, M, N, c, (__nv_bfloat16 *)O, ldo);
+      launch_kernel(dequantize_kernel<__nv_bfloat16>, grid, dim3(256), st, acc, ldacc, Cx, Cw, bias, M, N, c, (__nv_bfloat16 *)O, ldo);
       break;
     default:
       return QG_EINVAL;
   }
-  count_launch();
   return (int)cudaGetLastError();
 }
 

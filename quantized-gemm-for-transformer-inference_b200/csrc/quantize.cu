@@ -7,11 +7,13 @@
 // with HBM-bound kernels that read the matrix with 16-byte loads, reduce with warp shuffles and
 // write packed int8 codes plus the fp32 absmax.  The arithmetic (and its quirks: signed first
 // element, IEEE 127/x, truncate-and-wrap cast) is reproduced exactly; see oracle/qoracle.c.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace qg {
-
-void count_launch(int n = 1);
 
 namespace {
 
@@ -86,104 +88,118 @@ quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float rang
                   const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
                   float *__restrict__ Cx) {
   constexpr int EPV = Unpack<T>::EPV;
-  constexpr int RPB = kThreads / G;  // rows per block
+  constexpr int RPB = kThreads / G;  // rows per block iteration
   constexpr int WPR = G / 32;        // warps per row
   constexpr int NVC = NV > 0 ? NV : 1;
-  __shared__ float s_m[kThreads / 32];
-  __shared__ float s_x0[RPB];
+  constexpr bool kPrefetch = NV > 0 && NV <= 8;  // next row block's vectors are loaded ahead
+  __shared__ float s_m[2][kThreads / 32];
+  __shared__ float s_x0[2][RPB];
 
   const int rib = threadIdx.x / G;
   const int g = threadIdx.x % G;
-  const int row = blockIdx.x * RPB + rib;
-  const bool active = row < M;
   const int nvec = K / EPV;
-  const T *xr = X + (int64_t)(active ? row : 0) * ldx;
+  const int nrb = (M + RPB - 1) / RPB;
 
-  uint4 raw[NVC];
-  float scale;
-  if (sx_in == nullptr) {
-    float m = -INFINITY, x0 = 0.0f;
-    if (NV > 0) {
+  auto load = [&](uint4 (&dst)[NVC], int rb) {
+    const int row = rb * RPB + rib;
+    const T *xr = X + (int64_t)(row < M ? row : 0) * ldx;
 #pragma unroll
-      for (int v = 0; v < NVC; v++) {
-        const int idx = v * G + g;
-        raw[v] = (active && idx < nvec) ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
-      }
+    for (int v = 0; v < NVC; v++) {
+      const int idx = v * G + g;
+      dst[v] = (row < M && idx < nvec) ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
+    }
+  };
+
+  uint4 raw[NVC], nxt[NVC];
+  int rb = blockIdx.x;
+  griddep_wait();
+  if (NV > 0 && rb < nrb) load(raw, rb);
+  for (int it = 0; rb < nrb; rb += gridDim.x, it++) {
+    if (kPrefetch && rb + (int)gridDim.x < nrb) load(nxt, rb + gridDim.x);
+    else griddep_launch_dependents();  // last row block of this CTA: let the next kernel ramp up
+    const int row = rb * RPB + rib;
+    const bool active = row < M;
+    const T *xr = X + (int64_t)(active ? row : 0) * ldx;
+    float scale;
+    if (sx_in == nullptr) {
+      float m = -INFINITY, x0 = 0.0f;
+      if (NV > 0) {
 #pragma unroll
-      for (int v = 0; v < NVC; v++) {
-        const int idx = v * G + g;
-        if (idx < nvec) {
+        for (int v = 0; v < NVC; v++) {
+          const int idx = v * G + g;
+          if (idx < nvec) {
+            float f[EPV];
+            Unpack<T>::run(raw[v], f);
+            if (idx == 0) x0 = f[0];
+#pragma unroll
+            for (int e = 0; e < EPV; e++)
+              if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
+          }
+        }
+      } else {
+        for (int idx = g; idx < nvec && active; idx += G) {
           float f[EPV];
-          Unpack<T>::run(raw[v], f);
+          Unpack<T>::run(ldg16(xr + (int64_t)idx * EPV), f);
           if (idx == 0) x0 = f[0];
 #pragma unroll
           for (int e = 0; e < EPV; e++)
             if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
         }
       }
+      m = warp_max(m);
+      if (WPR > 1) {  // double-buffered by iteration parity: one barrier per iteration is enough
+        float *sm = s_m[it & 1], *sx0 = s_x0[it & 1];
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+        if (g == 0) sx0[rib] = x0;
+        __syncthreads();
+        m = sm[rib * WPR];
+#pragma unroll
+        for (int w = 1; w < WPR; w++) m = fmaxf(m, sm[rib * WPR + w]);
+        x0 = sx0[rib];
+      } else {
+        x0 = __shfl_sync(0xffffffffu, x0, 0);
+      }
+      float c;
+      if (fold_first(x0, m, mode, c) && active) {
+        for (int j = 1; j < K; j++) {  // rare: sign of the first later zero decides (+-0 tie-break)
+          const float xj = to_f32(xr[j]);
+          if (xj == xj) { c = -xj; break; }
+        }
+      }
+      if (active && g == 0 && Cx != nullptr) Cx[row] = c;
+      scale = __fdiv_rn(range, c);  // InvDivideConstFunc: b / x, IEEE division
     } else {
-      for (int idx = g; idx < nvec && active; idx += G) {
+      scale = active ? sx_in[row] : 0.0f;
+    }
+    if (Xq != nullptr && active) {
+      int8_t *qr = Xq + (int64_t)row * ldq;
+      auto emit = [&](const uint4 &r, int idx) {
         float f[EPV];
-        Unpack<T>::run(ldg16(xr + (int64_t)idx * EPV), f);
-        if (idx == 0) x0 = f[0];
+        Unpack<T>::run(r, f);
+        uint32_t w[EPV / 4];
 #pragma unroll
-        for (int e = 0; e < EPV; e++)
-          if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
+        for (int q = 0; q < EPV / 4; q++)
+          w[q] = quant_code_u8(f[4 * q], scale) | (quant_code_u8(f[4 * q + 1], scale) << 8) |
+                 (quant_code_u8(f[4 * q + 2], scale) << 16) | (quant_code_u8(f[4 * q + 3], scale) << 24);
+        if (EPV == 4) *reinterpret_cast<uint32_t *>(qr + (int64_t)idx * 4) = w[0];
+        else *reinterpret_cast<uint2 *>(qr + (int64_t)idx * 8) = make_uint2(w[0], w[EPV / 4 - 1]);
+      };
+      if (NV > 0) {
+#pragma unroll
+        for (int v = 0; v < NVC; v++) {
+          const int idx = v * G + g;
+          if (idx < nvec) emit(raw[v], idx);
+        }
+      } else {
+        for (int idx = g; idx < nvec; idx += G) emit(ldg16(xr + (int64_t)idx * EPV), idx);
       }
     }
-    m = warp_max(m);
-    if (WPR > 1) {
-      if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
-      if (g == 0) s_x0[rib] = x0;
-      __syncthreads();
-      m = s_m[rib * WPR];
+    if (kPrefetch) {
 #pragma unroll
-      for (int w = 1; w < WPR; w++) m = fmaxf(m, s_m[rib * WPR + w]);
-      x0 = s_x0[rib];
-    } else {
-      x0 = __shfl_sync(0xffffffffu, x0, 0);
+      for (int v = 0; v < NVC; v++) raw[v] = nxt[v];
+    } else if (NV > 0 && rb + (int)gridDim.x < nrb) {
+      load(raw, rb + gridDim.x);
     }
-    float c;
-    if (fold_first(x0, m, mode, c) && active) {
-      for (int j = 1; j < K; j++) {  // rare: sign of the first later zero decides (+-0 tie-break)
-        const float xj = to_f32(xr[j]);
-        if (xj == xj) { c = -xj; break; }
-      }
-    }
-    if (active && g == 0 && Cx != nullptr) Cx[row] = c;
-    scale = __fdiv_rn(range, c);  // InvDivideConstFunc: b / x, IEEE division
-  } else {
-    scale = active ? sx_in[row] : 0.0f;
-    if (NV > 0) {
-#pragma unroll
-      for (int v = 0; v < NVC; v++) {
-        const int idx = v * G + g;
-        raw[v] = (active && idx < nvec) ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
-      }
-    }
-  }
-  if (Xq == nullptr || !active) return;
-
-  int8_t *qr = Xq + (int64_t)row * ldq;
-  auto emit = [&](const uint4 &r, int idx) {
-    float f[EPV];
-    Unpack<T>::run(r, f);
-    uint32_t w[EPV / 4];
-#pragma unroll
-    for (int q = 0; q < EPV / 4; q++)
-      w[q] = quant_code_u8(f[4 * q], scale) | (quant_code_u8(f[4 * q + 1], scale) << 8) |
-             (quant_code_u8(f[4 * q + 2], scale) << 16) | (quant_code_u8(f[4 * q + 3], scale) << 24);
-    if (EPV == 4) *reinterpret_cast<uint32_t *>(qr + (int64_t)idx * 4) = w[0];
-    else *reinterpret_cast<uint2 *>(qr + (int64_t)idx * 8) = make_uint2(w[0], w[EPV / 4 - 1]);
-  };
-  if (NV > 0) {
-#pragma unroll
-    for (int v = 0; v < NVC; v++) {
-      const int idx = v * G + g;
-      if (idx < nvec) emit(raw[v], idx);
-    }
-  } else {
-    for (int idx = g; idx < nvec; idx += G) emit(ldg16(xr + (int64_t)idx * EPV), idx);
   }
 }
 
@@ -195,6 +211,7 @@ quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, fl
                           float *__restrict__ Cx) {
   const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  griddep_wait();
   if (row >= M) return;
   const T *xr = X + (int64_t)row * ldx;
   float scale;
@@ -230,6 +247,7 @@ quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, fl
 // ------------------------------------------------------------------------------------------
 __global__ void fill_f32_kernel(float *p, int n, float v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (i < n) p[i] = v;
 }
 
@@ -243,6 +261,7 @@ absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, i
   const int col = (blockIdx.x * 32 + tx) * EPV;
   const int k0 = 1 + blockIdx.y * rows_per_cta;
   const int k1 = min(K, k0 + rows_per_cta);
+  griddep_wait();
   float m[EPV];
 #pragma unroll
   for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
@@ -285,6 +304,7 @@ template <typename T>
 __global__ void absmax_cols_finalize_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, int mode,
                                             const float *__restrict__ part, float *__restrict__ Cw) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (j >= N) return;
   float c;
   if (fold_first(to_f32(W[j]), part[j], mode, c)) {
@@ -304,6 +324,7 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
   constexpr int EPV = Unpack<T>::EPV;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * EPV;
+  griddep_wait();
   if (col >= N) return;
   const T *base = W + col;
   float s[EPV];
@@ -351,6 +372,117 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
   for (; k < k1; k += 8) emit(ldg16(base + (int64_t)k * ldw), k);
 }
 
+// ------------------------------------------------------------------------------------------
+// Columns, one read of W: a thread-block cluster owns a strip of 128 bytes of columns (32 fp32 /
+// 64 half) over all K rows.  Each CTA keeps its K/cs rows of the strip in REGISTERS (NIT 16-byte
+// vectors per thread), the per-column maxima are combined across the cluster through distributed
+// shared memory, and the codes are produced from the registers: W is read once, Wq written once.
+// Thread layout: 8 threads span a 128-byte row segment, 32 row lanes per iteration.
+// ------------------------------------------------------------------------------------------
+template <typename T, int NIT>
+__global__ void __launch_bounds__(kThreads)
+quant_cols_cluster_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
+                          int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
+  namespace cg = cooperative_groups;
+  constexpr int EPV = Unpack<T>::EPV;
+  constexpr int SC = 8 * EPV;  // columns per strip
+  __shared__ float s_red[kThreads / 32][SC];
+  __shared__ float s_cmax[SC];   // this CTA's maxima over its rows (rows >= 1 only)
+  __shared__ float s_x0[SC];     // row 0 of the strip (meaningful in cluster rank 0)
+  __shared__ float s_final[SC];  // Cw of the strip
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
+  const int strip = blockIdx.x / cs;
+  const int cchunk = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int col = strip * SC + cchunk * EPV;
+  const int r0 = (int)rank * NIT * 32;
+  const bool col_ok = col < N;
+  const T *base = W + col;
+
+  griddep_wait();
+  uint4 raw[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; it++) {
+    const int r = r0 + it * 32 + ty;
+    raw[it] = (col_ok && r < K) ? ldg16(base + (int64_t)r * ldw) : make_uint4(0, 0, 0, 0);
+  }
+  griddep_launch_dependents();
+  float m[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < NIT; it++) {
+    const int r = r0 + it * 32 + ty;
+    if (col_ok && r < K) {
+      float f[EPV];
+      Unpack<T>::run(raw[it], f);
+      if (r == 0) {
+#pragma unroll
+        for (int e = 0; e < EPV; e++) s_x0[cchunk * EPV + e] = f[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
+      }
+    }
+  }
+  // rows of one warp: lanes l, l^8, l^16, l^24 hold the same columns
+#pragma unroll
+  for (int e = 0; e < EPV; e++) {
+    m[e] = fmaxf(m[e], __shfl_xor_sync(0xffffffffu, m[e], 8));
+    m[e] = fmaxf(m[e], __shfl_xor_sync(0xffffffffu, m[e], 16));
+  }
+  if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+    for (int e = 0; e < EPV; e++) s_red[threadIdx.x >> 5][cchunk * EPV + e] = m[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < SC) {
+    float r = s_red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; w++) r = fmaxf(r, s_red[w][threadIdx.x]);
+    s_cmax[threadIdx.x] = r;
+  }
+  cluster.sync();
+  if (threadIdx.x < SC) {
+    float mm = -INFINITY;
+    for (unsigned rk = 0; rk < cs; rk++) mm = fmaxf(mm, cluster.map_shared_rank(s_cmax, rk)[threadIdx.x]);
+    const float x0 = cluster.map_shared_rank(s_x0, 0)[threadIdx.x];
+    const int c = strip * SC + threadIdx.x;
+    float cw = 0.0f;
+    if (c < N) {
+      if (fold_first(x0, mm, mode, cw)) {
+        for (int k = 1; k < K; k++) {  // rare +-0 tie-break: sign of the first later non-NaN zero
+          const float x = to_f32(W[(int64_t)k * ldw + c]);
+          if (x == x) { cw = -x; break; }
+        }
+      }
+      if (rank == 0 && Cw != nullptr) Cw[c] = cw;
+    }
+    s_final[threadIdx.x] = cw;
+  }
+  cluster.sync();  // also keeps every CTA's smem alive until all remote reads are done
+  float s[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; e++) s[e] = __fdiv_rn(range, s_final[cchunk * EPV + e]);
+  if (Wq == nullptr || !col_ok) return;
+#pragma unroll
+  for (int it = 0; it < NIT; it++) {
+    const int r = r0 + it * 32 + ty;
+    if (r < K) {
+      float f[EPV];
+      Unpack<T>::run(raw[it], f);
+      uint32_t w[EPV / 4];
+#pragma unroll
+      for (int q = 0; q < EPV / 4; q++)
+        w[q] = quant_code_u8(f[4 * q], s[4 * q]) | (quant_code_u8(f[4 * q + 1], s[4 * q + 1]) << 8) |
+               (quant_code_u8(f[4 * q + 2], s[4 * q + 2]) << 16) | (quant_code_u8(f[4 * q + 3], s[4 * q + 3]) << 24);
+      int8_t *dst = Wq + (int64_t)r * ldq + col;
+      if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
+      else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
+    }
+  }
+}
+
 // Any N / alignment: one thread per column (coalesced across threads), scalar accesses.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -358,6 +490,7 @@ quant_cols_generic_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, fl
                           const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq,
                           float *__restrict__ Cw) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (j >= N) return;
   float scale;
   if (sw_in == nullptr) {
@@ -382,6 +515,7 @@ quant_cols_generic_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, fl
 
 __global__ void inv_divide_kernel(const float *__restrict__ a, int64_t n, float b, float *__restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (i < n) out[i] = __fdiv_rn(b, a[i]);
 }
 
@@ -389,6 +523,7 @@ __global__ void inv_divide_kernel(const float *__restrict__ a, int64_t n, float 
 __global__ void outlier_mask_kernel(const float *__restrict__ A, int M, int K, int64_t lda, float thr,
                                     float *__restrict__ mask, int64_t ldm) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
   if (k >= K) return;
   for (int i = blockIdx.y; i < M; i += gridDim.y) {
     const float a = A[(int64_t)i * lda + k];
@@ -404,9 +539,17 @@ template <typename T, int G, int NV>
 void launch_rows(const T *X, int M, int K, int64_t ldx, float range, int mode, const float *sx, int8_t *Xq,
                  int64_t ldq, float *Cx, cudaStream_t st) {
   constexpr int RPB = kThreads / G;
-  quant_rows_kernel<T, G, NV><<<(unsigned)ceil_div(M, RPB), kThreads, 0, st>>>(X, M, K, ldx, range, mode, sx, Xq,
-                                                                             ldq, Cx);
-  count_launch();
+  static int resident = 0;  // CTAs that fit on the device at once (per instantiation)
+  if (resident == 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quant_rows_kernel<T, G, NV>, kThreads, 0);
+    resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+  }
+  const int64_t nrb = ceil_div(M, RPB);
+  const unsigned grid = (unsigned)(nrb < resident ? nrb : resident);
+  launch_kernel(quant_rows_kernel<T, G, NV>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, sx, Xq, ldq, Cx);
 }
 
 template <typename T>
@@ -416,10 +559,8 @@ int rows_dispatch(const T *X, int M, int K, int64_t ldx, float range, int mode, 
   const bool vec_ok = (K % EPV == 0) && aligned(X, 16) && ((ldx * sizeof(T)) % 16 == 0) &&
                       (Xq == nullptr || (aligned(Xq, EPV) && ldq % EPV == 0));
   if (!vec_ok) {
-    quant_rows_generic_kernel<T><<<(unsigned)ceil_div(M, kThreads / 32), kThreads, 0, st>>>(X, M, K, ldx, range, mode,
-                                                                                           sx, Xq, ldq, Cx);
-    count_launch();
-    return (int)cudaGetLastError();
+    return (int)launch_kernel(quant_rows_generic_kernel<T>, dim3((unsigned)ceil_div(M, kThreads / 32)), dim3(kThreads), st,
+                              X, M, K, ldx, range, mode, sx, Xq, ldq, Cx);
   }
   const int nvec = K / EPV;
 #define QG_ROWS(G, NV) launch_rows<T, G, NV>(X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st)
@@ -450,33 +591,49 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
                   int64_t ldq, float *Cw, float *scratch, cudaStream_t st) {
   constexpr int EPV = Unpack<T>::EPV;
   const bool vec_ok = (N % EPV == 0) && aligned(W, 16) && ((ldw * sizeof(T)) % 16 == 0) &&
-                      (Wq == nullptr || (aligned(Wq, EPV) && ldq % EPV == 0)) && (sw != nullptr || scratch != nullptr);
+                      (Wq == nullptr || (aligned(Wq, EPV) && ldq % EPV == 0)) &&
+                      (sw != nullptr || scratch != nullptr || (Wq != nullptr && K <= 8 * 32 * 32));
   if (!vec_ok) {
-    quant_cols_generic_kernel<T><<<(unsigned)ceil_div(N, kThreads), kThreads, 0, st>>>(W, K, N, ldw, range, mode, sw,
-                                                                                      Wq, ldq, Cw);
+    return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
+                              N, ldw, range, mode, sw, Wq, ldq, Cw);
+  }
+  // one-read cluster kernel: the strip's K rows must fit the registers of <= 8 CTAs
+  if (sw == nullptr && Wq != nullptr && K <= 8 * 32 * 32 && getenv("QG_COLS_TWO_PASS") == nullptr) {
+    const int nit = K <= 8 * 16 * 32 ? 16 : 32;
+    int cs = (int)ceil_div(K, nit * 32);
+    cs = cs <= 1 ? 1 : cs <= 2 ? 2 : cs <= 4 ? 4 : 8;
+    const int strips = (int)ceil_div(N, 8 * EPV);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(strips * cs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     count_launch();
-    return (int)cudaGetLastError();
+    if (nit == 16) return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, 16>, W, K, N, ldw, range, mode, Wq, ldq, Cw);
+    return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, 32>, W, K, N, ldw, range, mode, Wq, ldq, Cw);
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
   const int rpc = cols_rows_per_cta(K, col_tiles);
   if (sw == nullptr) {
-    fill_f32_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(scratch, N, -INFINITY);
-    count_launch();
+    launch_kernel(fill_f32_kernel, dim3((unsigned)ceil_div(N, 256)), dim3(256), st, scratch, N, -INFINITY);
     if (K > 1) {
       dim3 grid(col_tiles, (unsigned)ceil_div(K - 1, rpc));
-      absmax_cols_partial_kernel<T><<<grid, kThreads, 0, st>>>(W, K, N, ldw, rpc, scratch);
-      count_launch();
+      launch_kernel(absmax_cols_partial_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, rpc, scratch);
     }
     if (Wq == nullptr) {
-      absmax_cols_finalize_kernel<T><<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(W, K, N, ldw, mode, scratch, Cw);
-      count_launch();
-      return (int)cudaGetLastError();
+      return (int)launch_kernel(absmax_cols_finalize_kernel<T>, dim3((unsigned)ceil_div(N, 256)), dim3(256), st, W, K, N,
+                                ldw, mode, scratch, Cw);
     }
   }
   dim3 grid(col_tiles, (unsigned)ceil_div(K, rpc));
-  quant_cols_kernel<T><<<grid, kThreads, 0, st>>>(W, K, N, ldw, range, mode, rpc, scratch, sw, Wq, ldq, Cw);
-  count_launch();
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(quant_cols_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode, rpc, scratch, sw, Wq,
+                            ldq, Cw);
 }
 
 }  // namespace
@@ -504,16 +661,12 @@ int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range,
 }
 
 int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st) {
-  inv_divide_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(a, n, b, out);
-  count_launch();
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(inv_divide_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), st, a, n, b, out);
 }
 
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(K, 256), (unsigned)(M < 32768 ? M : 32768));
-  outlier_mask_kernel<<<grid, 256, 0, st>>>(A, M, K, lda, thr, mask, ldm);
-  count_launch();
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(outlier_mask_kernel, grid, dim3(256), st, A, M, K, lda, thr, mask, ldm);
 }
 
 }  // namespace qg

@@ -1,0 +1,243 @@
+"""Performance experiments on the GPU box (each in its own subprocess so environment switches such
+as QG_PDL / QG_COLS_TWO_PASS / QG_GEMM_VARIANT take effect).  Writes gpurun_out/perf.json.
+
+    python tools/gpu_perf.py [--only name1,name2]
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def pkg():
+    return importlib.import_module("quantized-gemm-for-transformer-inference_b200")
+
+
+def bench(fn, iters=30, warm=5):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def gemm_stats(variant, size, out="f32"):
+    """Pipeline wait counters of the tcgen05 GEMM (cycles, averaged over CTAs)."""
+    import torch
+
+    qg = pkg()
+    M = N = K = size
+    A = torch.randint(-127, 128, (M, K), dtype=torch.int8, device="cuda")
+    B = torch.randint(-127, 128, (K, N), dtype=torch.int8, device="cuda")
+    Cx, Cw = torch.rand(M, device="cuda"), torch.rand(N, device="cuda")
+    dt = {"f32": torch.float32, "f16": torch.float16, "s32": torch.int32}[out]
+    O = torch.empty((M, N), dtype=dt, device="cuda")
+    qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
+
+    def run():
+        if out == "s32":
+            qg.op_mm(A, B, O)
+        else:
+            qg.gemm_s8_dequant(A, B, Cx, Cw, O)
+
+    us = bench(run)
+    stats = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+    qg.lib().qg_debug_gemm_stats(C.c_void_p(stats.data_ptr()))
+    run()
+    torch.cuda.synchronize()
+    us_stats = bench(run, iters=5, warm=1)
+    qg.lib().qg_debug_gemm_stats(None)
+    s = stats.cpu().double()
+    used = s[:, 4] > 0 if variant == "TC_1SM" else s[:, 1] > 0
+    names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tempty", "mma_total", "epi_wait_tfull", "epi_total"]
+    res = {"us": us, "us_with_stats": us_stats, "tops": 2.0 * M * N * K / us / 1e6}
+    lead = s[s[:, 4] > 0]
+    for i, n in enumerate(names):
+        col = s[:, i]
+        nz = col[col > 0] if n.startswith("mma") else col[used]
+        res[n] = float(nz.mean()) if nz.numel() else 0.0
+    res["mma_total_max"] = float(lead[:, 4].max()) if lead.numel() else 0.0
+    res["mma_total_min"] = float(lead[:, 4].min()) if lead.numel() else 0.0
+    return res
+
+
+def gemm_kmajor(cg, size):
+    """B supplied as [N,K] (K-major operand) vs the reference's [K,N] (MN-major operand)."""
+    import torch
+
+    qg = pkg()
+    M = N = K = size
+    A = torch.randint(-127, 128, (M, K), dtype=torch.int8, device="cuda")
+    B = torch.randint(-127, 128, (K, N), dtype=torch.int8, device="cuda")
+    Bt = B.t().contiguous()
+    O = torch.empty((M, N), dtype=torch.int32, device="cuda")
+    qg.set_gemm_variant(qg.GEMM_TC_2SM if cg == 2 else qg.GEMM_TC_1SM)
+    us_mn = bench(lambda: qg.op_mm(A, B, O))
+    ref = O.clone()
+
+    def km():
+        rc = qg.lib().qg_test_gemm_s8_bt(cg, C.c_void_p(A.data_ptr()), C.c_int64(K), C.c_void_p(Bt.data_ptr()), C.c_int64(K),
+                                         M, N, K, C.c_void_p(O.data_ptr()), C.c_int64(N), None)
+        assert rc == 0
+
+    us_k = bench(km)
+    torch.cuda.synchronize()
+    ops = 2.0 * M * N * K
+    return {"mn_major_us": us_mn, "k_major_us": us_k, "mn_tops": ops / us_mn / 1e6, "k_tops": ops / us_k / 1e6,
+            "same": bool(torch.equal(ref, O))}
+
+
+def quantizers(size, dt="f32"):
+    import torch
+
+    qg = pkg()
+    M = N = K = size
+    tdt = {"f32": torch.float32, "f16": torch.float16}[dt]
+    es = 4 if dt == "f32" else 2
+    X = (torch.rand((M, K), device="cuda") * 2 - 1).to(tdt)
+    W = (torch.rand((K, N), device="cuda") * 2 - 1).to(tdt)
+    X2 = X.clone()
+    W2 = W.clone()
+    Xq = torch.empty((M, K), dtype=torch.int8, device="cuda")
+    Wq = torch.empty((K, N), dtype=torch.int8, device="cuda")
+    Cx, Cw = torch.empty(M, device="cuda"), torch.empty(N, device="cuda")
+    flip = [0]
+
+    def rows():
+        flip[0] ^= 1
+        qg.absmax_quant_rows(X if flip[0] else X2, 127.0, 0, Xq, Cx)
+
+    def cols():
+        flip[0] ^= 1
+        qg.absmax_quant_cols(W if flip[0] else W2, 127.0, 0, Wq, Cw)
+
+    r, c = bench(rows), bench(cols)
+    return {"rows_us": r, "rows_gbs": (M * K * (es + 1) + 4 * M) / r / 1e3, "cols_us": c,
+            "cols_gbs": (K * N * (es + 1) + 4 * N) / c / 1e3}
+
+
+def full_op(size, out="f32"):
+    import torch
+
+    qg = pkg()
+    M = N = K = size
+    X = [torch.rand((M, K), device="cuda") * 2 - 1 for _ in range(2)]
+    W = [torch.rand((K, N), device="cuda") * 2 - 1 for _ in range(2)]
+    O = torch.empty((M, N), dtype=torch.float32 if out == "f32" else torch.float16, device="cuda")
+    ws = torch.empty(qg.workspace_bytes(M, N, K), dtype=torch.uint8, device="cuda")
+    flip = [0]
+
+    def run():
+        flip[0] ^= 1
+        qg.op_quantized_mm(X[flip[0]], W[flip[0]], O, 127.0, workspace=ws)
+
+    us = bench(run)
+    # the same three calls captured in a CUDA graph
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        run()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            run()
+            run()
+    torch.cuda.synchronize()
+    us_graph = bench(lambda: g.replay()) / 2
+    lin = qg.LinearLayer(K, N)
+    lin.init_uniform()
+    lin.quantize_weights()
+    us_lin = bench(lambda: lin.forward(X[0], O if out == "f32" else O))
+    ops = 2.0 * M * N * K
+    return {"full_us": us, "full_tops": ops / us / 1e6, "full_graph_us": us_graph, "full_graph_tops": ops / us_graph / 1e6,
+            "linear_cached_w_us": us_lin, "linear_cached_w_tops": ops / us_lin / 1e6}
+
+
+def lib_ref(size):
+    import torch
+
+    M = N = K = size
+    a8 = torch.randint(-127, 128, (M, K), dtype=torch.int8, device="cuda")
+    b8 = torch.randint(-127, 128, (K, N), dtype=torch.int8, device="cuda")
+    a16 = torch.randn((M, K), dtype=torch.float16, device="cuda")
+    b16 = torch.randn((K, N), dtype=torch.float16, device="cuda")
+    u8, u16 = bench(lambda: torch._int_mm(a8, b8)), bench(lambda: a16 @ b16)
+    ops = 2.0 * M * N * K
+    return {"cublaslt_int8_us": u8, "cublaslt_int8_tops": ops / u8 / 1e6, "cublas_fp16_us": u16, "cublas_fp16_tflops": ops / u16 / 1e6}
+
+
+EXPERIMENTS = {
+    # name: (function, args, env)
+    "lib_4096": (lib_ref, (4096,), {}),
+    "lib_8192": (lib_ref, (8192,), {}),
+    "stats_1sm_4096_f32": (gemm_stats, ("TC_1SM", 4096, "f32"), {}),
+    "stats_2sm_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {}),
+    "stats_1sm_4096_s32": (gemm_stats, ("TC_1SM", 4096, "s32"), {}),
+    "stats_2sm_4096_f16": (gemm_stats, ("TC_2SM", 4096, "f16"), {}),
+    "stats_1sm_8192_f32": (gemm_stats, ("TC_1SM", 8192, "f32"), {}),
+    "stats_2sm_8192_f32": (gemm_stats, ("TC_2SM", 8192, "f32"), {}),
+    "stats_2sm_2048_f32": (gemm_stats, ("TC_2SM", 2048, "f32"), {}),
+    "stats_1sm_2048_f32": (gemm_stats, ("TC_1SM", 2048, "f32"), {}),
+    "kmajor_1sm_4096": (gemm_kmajor, (1, 4096), {}),
+    "kmajor_2sm_4096": (gemm_kmajor, (2, 4096), {}),
+    "kmajor_2sm_8192": (gemm_kmajor, (2, 8192), {}),
+    "quant_4096": (quantizers, (4096,), {}),
+    "quant_4096_twopass": (quantizers, (4096,), {"QG_COLS_TWO_PASS": "1"}),
+    "quant_4096_f16": (quantizers, (4096, "f16"), {}),
+    "quant_8192": (quantizers, (8192,), {}),
+    "quant_8192_twopass": (quantizers, (8192,), {"QG_COLS_TWO_PASS": "1"}),
+    "full_4096_pdl": (full_op, (4096,), {}),
+    "full_4096_nopdl": (full_op, (4096,), {"QG_PDL": "0"}),
+    "full_4096_2sm": (full_op, (4096,), {"QG_GEMM_VARIANT": "3"}),
+    "full_2048_pdl": (full_op, (2048,), {}),
+    "full_2048_nopdl": (full_op, (2048,), {"QG_PDL": "0"}),
+    "full_8192_2sm": (full_op, (8192,), {"QG_GEMM_VARIANT": "3"}),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--one")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default=os.path.join(OUT, "perf.json"))
+    args = ap.parse_args()
+    if args.one:
+        fn, a, _ = EXPERIMENTS[args.one]
+        print("PERF_RESULT " + json.dumps(fn(*a)))
+        return
+    os.makedirs(OUT, exist_ok=True)
+    results = {}
+    names = [n for n in EXPERIMENTS if not args.only or any(n.startswith(p) for p in args.only.split(","))]
+    for name in names:
+        env = dict(os.environ)
+        env.update(EXPERIMENTS[name][2])
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", name], capture_output=True, text=True,
+                               timeout=240, env=env)
+            line = [l for l in r.stdout.splitlines() if l.startswith("PERF_RESULT ")]
+            results[name] = json.loads(line[-1][12:]) if line else {"error": (r.stdout + r.stderr)[-1500:]}
+        except subprocess.TimeoutExpired:
+            results[name] = {"error": "timeout"}
+        results[name]["secs"] = round(time.time() - t0, 1)
+        print(name, json.dumps(results[name])[:500], flush=True)
+        with open(args.out, "w") as f:
+            json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
