@@ -127,8 +127,17 @@ QG_API int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ld
                            qg_stream_t stream);
 
 /* ---- LinearLayer<T>::forward(x, y) with weights quantized once ----------------------------- */
-/* src/modules/linear.cuh:49-56: y = x @ w + b.  Wq/Cw come from qg_absmax_quant_cols. */
-QG_API int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wq, int64_t ldwq,
+/* Column-quantize W [K,N] once into the layout the tensor-core GEMM runs fastest on: Wt [N, ldwt]
+ * (codes of column j contiguous along K, ldwt >= K and a multiple of 16) plus Cw [N].  Same
+ * arithmetic as qg_absmax_quant_cols; only the placement of the codes differs. */
+QG_API int qg_prepare_weights(const void *W, int dtype, int k, int n, int64_t ldw, float range, int mode,
+                              int8_t *Wt, int64_t ldwt, float *Cw, qg_stream_t stream);
+/* a5..a8 (+a10) on prepared weights; out_dtype QG_S32 writes raw accumulators (Cx, Cw unused) */
+QG_API int qg_gemm_s8t_dequant(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_t ldwt,
+                               const float *Cx, const float *Cw, const float *bias, int m, int n, int k,
+                               float range, void *O, int out_dtype, int64_t ldo, qg_stream_t stream);
+/* src/modules/linear.cuh:49-56: y = x @ w + b.  Wt/Cw come from qg_prepare_weights. */
+QG_API int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt, int64_t ldwt,
                              const float *Cw, const float *bias, void *Y, int64_t ldy, int out_dtype,
                              int m, int n, int k, float range, int mode, void *workspace,
                              size_t workspace_bytes, qg_stream_t stream);

@@ -27,7 +27,8 @@ ABI_SYMBOLS = [
     "qg_version", "qg_last_error", "qg_device_info", "qg_set_gemm_variant", "qg_launch_count",
     "qg_absmax_rows", "qg_absmax_cols", "qg_inv_divide_f32", "qg_quantize_rows", "qg_quantize_cols",
     "qg_absmax_quant_rows", "qg_absmax_quant_cols", "qg_gemm_s8s8s32", "qg_dequantize_s32",
-    "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_linear_forward",
+    "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_prepare_weights", "qg_gemm_s8t_dequant",
+    "qg_linear_forward",
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_mm_f32",
 ]
 
@@ -226,6 +227,40 @@ def gemm_s8_dequant(Xq, Wq, Cx, Cw, out, range_: float = 127.0, bias=None) -> No
                                     C.c_float(range_), po, _dt(out), ldo, _stream()), "qg_gemm_s8_dequant")
 
 
+def prepare_weights(W: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT,
+                    Wt: torch.Tensor | None = None, Cw: torch.Tensor | None = None):
+    """Column-quantize W [K,N] once into the GEMM's preferred operand layout: returns
+    (Wt int8 [N, K] view with a 16-byte aligned leading dimension, Cw f32 [N])."""
+    K, N = W.shape
+    if Wt is None:
+        ldk = (K + 15) // 16 * 16
+        Wt = torch.zeros((N, ldk), dtype=torch.int8, device=W.device)[:, :K]
+    if Cw is None:
+        Cw = torch.empty(N, dtype=torch.float32, device=W.device)
+    assert Wt.shape == (N, K) and Wt.dtype == torch.int8
+    pw, ldw = _dev2d(W)
+    pt, ldt = _dev2d(Wt)
+    _check(lib().qg_prepare_weights(pw, _dt(W), K, N, ldw, C.c_float(range_), mode, pt, ldt, _vec(Cw, N), _stream()),
+           "qg_prepare_weights")
+    return Wt, Cw
+
+
+def gemm_s8t_dequant(Xq, Wt, Cx, Cw, out, range_: float = 127.0, bias=None) -> None:
+    """GEMM on prepared (transposed, K-major) weights; out int32 -> raw accumulators."""
+    M, K = Xq.shape
+    N = Wt.shape[0]
+    assert Wt.shape[1] == K and out.shape == (M, N)
+    pa, lda = _dev2d(Xq)
+    pb, ldb = _dev2d(Wt)
+    po, ldo = _dev2d(out)
+    od = QG_S32 if out.dtype == torch.int32 else _dt(out)
+    pcx = None if Cx is None else _vec(Cx.reshape(-1), M)
+    pcw = None if Cw is None else _vec(Cw.reshape(-1), N)
+    pbias = None if bias is None else _vec(bias.reshape(-1), N)
+    _check(lib().qg_gemm_s8t_dequant(pa, lda, pb, ldb, pcx, pcw, pbias, M, N, K, C.c_float(range_), po, od, ldo,
+                                     _stream()), "qg_gemm_s8t_dequant")
+
+
 def workspace_bytes(M: int, N: int, K: int) -> int:
     return int(lib().qg_workspace_bytes(M, N, K))
 
@@ -281,20 +316,20 @@ class LinearLayer:
         self._wq = None
 
     def quantize_weights(self):
-        self._wq = absmax_quant_cols(self.w, self.range, self.mode)
+        self._wq = prepare_weights(self.w, self.range, self.mode)  # (Wt [N,K] int8, Cw)
         return self._wq
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> None:  # linear.cuh:49-56
         assert x.shape[1] == self.in_dim and y.shape == (x.shape[0], self.out_dim)
         if self._wq is None:
             self.quantize_weights()
-        Wq, Cw = self._wq
+        Wt, Cw = self._wq
         M, K, N = x.shape[0], self.in_dim, self.out_dim
         need = workspace_bytes(M, N, K)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         px, ldx = _dev2d(x)
-        pq, ldq = _dev2d(Wq)
+        pq, ldq = _dev2d(Wt)
         py, ldy = _dev2d(y)
         _check(lib().qg_linear_forward(px, ldx, _dt(x), pq, ldq, _vec(Cw, N), _vec(self.b.reshape(-1), N), py, ldy,
                                        _dt(y), M, N, K, C.c_float(self.range), self.mode,

@@ -1,0 +1,99 @@
+"""Column-parallel quantized linear over the GPUs of one box.
+
+The reference has no multi-GPU code; this is the sharding BASELINE.json's multi-GPU configs name.
+Column scale Cw[j] and every output column O[:, j] depend only on W[:, j] and the whole X, so W
+splits along N with no cross-GPU arithmetic: rank p owns W[:, lo:hi], quantizes the replicated X
+locally, computes O[:, lo:hi], and the only exchange is the gather of the output blocks.  Results
+are bit-identical to the single-GPU op.
+
+Two exchange paths:
+  * "nccl"  : all_gather_into_tensor of the [M, N/P] blocks, then one permute into [M, N];
+  * "fused" : the GEMM epilogue TMA-stores every output tile straight into the [M, N] buffer of
+              every peer (symmetric memory over NVLink), so the transfer overlaps the main loop
+              and no permute pass exists (qg_gemm_s8_dequant_multi).
+
+`compute` is injectable so that the host-side logic (shard bounds, gather layout) is testable with
+the gloo backend on CPU, where tests plug in the CPU oracle.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int, align: int = 1) -> tuple[int, int]:
+    """Contiguous column range [lo, hi) of `rank`; shard sizes differ by at most `align` columns
+    and every boundary is a multiple of `align` (TMA wants 16-byte aligned column offsets)."""
+    assert 0 <= rank < world and n >= 0 and align >= 1
+    units = (n + align - 1) // align
+    base, extra = divmod(units, world)
+    lo_u = rank * base + min(rank, extra)
+    hi_u = lo_u + base + (1 if rank < extra else 0)
+    return min(lo_u * align, n), min(hi_u * align, n)
+
+
+def gather_columns(local: torch.Tensor, n: int, world: int, rank: int, group=None, align: int = 1,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """All-gather column blocks [M, hi-lo] into a row-major [M, n] tensor on every rank.
+    Blocks may have different widths (n not divisible by world): they are padded to the widest."""
+    m = local.shape[0]
+    widths = [hi - lo for lo, hi in (shard_bounds(n, world, r, align) for r in range(world))]
+    wmax = max(widths)
+    send = local
+    if local.shape[1] != wmax:
+        send = torch.zeros((m, wmax), dtype=local.dtype, device=local.device)
+        send[:, : local.shape[1]] = local
+    buf = torch.empty((world, m, wmax), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(buf, send.contiguous(), group=group)
+    else:  # gloo (CPU tests) has no flat all-gather
+        dist.all_gather([buf[r] for r in range(world)], send.contiguous(), group=group)
+    if out is None:
+        out = torch.empty((m, n), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r, align)
+        out[:, lo:hi] = buf[r, :, : hi - lo]
+    return out
+
+
+class ColumnParallelLinear:
+    """y = x @ W + b with W [K, N] sharded by columns over `world` ranks.
+
+    compute(x, w_shard, bias_shard) -> [M, hi-lo] is the per-rank quantized linear; the default
+    runs the C-ABI path (quantize once, cached int8 shard) on the current CUDA device.
+    """
+
+    def __init__(self, w_full: torch.Tensor, bias: Optional[torch.Tensor], rank: int, world: int, group=None,
+                 compute: Optional[Callable] = None, align: int = 16, range_: float = 127.0, mode: int = 0):
+        self.rank, self.world, self.group, self.align = rank, world, group, align
+        self.k, self.n = w_full.shape
+        self.lo, self.hi = shard_bounds(self.n, world, rank, align)
+        self.w = w_full[:, self.lo:self.hi].contiguous()
+        self.b = None if bias is None else bias.reshape(-1)[self.lo:self.hi].contiguous()
+        self.range, self.mode = range_, mode
+        self._compute = compute
+        self._cache = None
+
+    def local_forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._compute is not None:
+            return self._compute(x, self.w, self.b)
+        from . import LinearLayer  # product path: C ABI on the current device
+
+        if self._cache is None:
+            lin = LinearLayer(self.k, self.hi - self.lo, device=x.device, dtype=self.w.dtype, range_=self.range,
+                              mode=self.mode)
+            lin.w = self.w.to(x.device)
+            lin.b = (torch.zeros(self.hi - self.lo, device=x.device) if self.b is None else self.b.to(x.device)).reshape(1, -1).float()
+            lin.quantize_weights()
+            self._cache = lin
+        y = torch.empty((x.shape[0], self.hi - self.lo), dtype=x.dtype, device=x.device)
+        self._cache.forward(x, y)
+        return y
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = self.local_forward(x)
+        if self.world == 1:
+            return y
+        return gather_columns(y, self.n, self.world, self.rank, self.group, self.align, out)

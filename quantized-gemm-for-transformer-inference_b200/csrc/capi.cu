@@ -16,11 +16,11 @@ namespace qg {
 int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, const float *sx,
                int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st);
 int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
-               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, cudaStream_t st);
+               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, bool transpose, cudaStream_t st);
 int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
-int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K, void *O, int64_t ldo,
-                 int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st);
+int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
+                 int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st);
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
            float *C, int64_t ldc, cudaStream_t st);
 int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
@@ -125,10 +125,10 @@ struct Workspace {
 static Workspace carve(void *base, int M, int N, int K) {
   Workspace w;
   w.ldxq = round_up(K, 16);  // TMA: leading dimensions are multiples of 16 bytes
-  w.ldwq = round_up(N, 16);
+  w.ldwq = round_up(K, 16);  // weights are kept transposed, Wt [N, ldwq]: the K-major operand layout
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = (size_t)round_up((int64_t)(off + n), 256); return o; };
-  const size_t oxq = take((size_t)M * w.ldxq), owq = take((size_t)K * w.ldwq);
+  const size_t oxq = take((size_t)M * w.ldxq), owq = take((size_t)N * w.ldwq);
   const size_t ocx = take(sizeof(float) * M), ocw = take(sizeof(float) * N), osc = take(sizeof(float) * N);
   char *b = reinterpret_cast<char *>(base);
   w.Xq = reinterpret_cast<int8_t *>(b + oxq);
@@ -140,16 +140,19 @@ static Workspace carve(void *base, int M, int N, int K) {
   return w;
 }
 
-static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K,
-                         void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias,
-                         float c, cudaStream_t st) {
+// b_kmajor == 0: B is the reference's [K,N] (MN-major tensor-core operand); 1: B is Wt [N,K]
+static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M,
+                         int N, int K, void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw,
+                         const float *bias, float c, cudaStream_t st) {
   int variant = g_variant.load();
   const bool tc_ok = gemm_i8_tc_supported(A, lda, B, ldb);
-  if (variant == QG_GEMM_AUTO) variant = tc_ok ? QG_GEMM_TC_1SM : QG_GEMM_SIMT;
+  // the 2-SM tile (256x256 per CTA pair) halves the shared-memory traffic per MAC; one CTA row
+  // of work is all a problem with M <= 128 has, so it takes the 1-SM kernel
+  if (variant == QG_GEMM_AUTO) variant = !tc_ok ? QG_GEMM_SIMT : (M > 128 ? QG_GEMM_TC_2SM : QG_GEMM_TC_1SM);
   if (variant == QG_GEMM_SIMT || !tc_ok)
-    return gemm_s8_simt(A, lda, B, ldb, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, st);
-  return gemm_i8_tc(variant == QG_GEMM_TC_2SM ? 2 : 1, A, lda, B, ldb, 0, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c,
-                    d->sm_count, st);
+    return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, st);
+  return gemm_i8_tc(variant == QG_GEMM_TC_2SM ? 2 : 1, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias,
+                    c, d->sm_count, st);
 }
 
 }  // namespace qg
@@ -200,7 +203,7 @@ int qg_absmax_cols(const void *W, int dtype, int K, int N, int64_t ldw, int mode
     if ((rc = grow(&d->arena, &d->arena_bytes, sizeof(float) * (size_t)N))) return rc;
     scratch = reinterpret_cast<float *>(d->arena);
   }
-  return quant_cols(W, dtype, K, N, ldw, 127.0f, mode, nullptr, nullptr, 0, Cw, scratch, (cudaStream_t)stream);
+  return quant_cols(W, dtype, K, N, ldw, 127.0f, mode, nullptr, nullptr, 0, Cw, scratch, false, (cudaStream_t)stream);
 }
 
 int qg_inv_divide_f32(const float *a, int64_t n, float b, float *out, qg_stream_t stream) {
@@ -226,7 +229,7 @@ int qg_quantize_cols(const void *W, int dtype, int K, int N, int64_t ldw, const 
   int rc = device_state(&d);
   if (rc) return rc;
   QG_REQUIRE(W && sw && Wq && K > 0 && N > 0 && ldw >= N && ldq >= N && valid_io(dtype), "qg_quantize_cols: bad arguments");
-  return quant_cols(W, dtype, K, N, ldw, 127.0f, 0, sw, Wq, ldq, nullptr, nullptr, (cudaStream_t)stream);
+  return quant_cols(W, dtype, K, N, ldw, 127.0f, 0, sw, Wq, ldq, nullptr, nullptr, false, (cudaStream_t)stream);
 }
 
 int qg_absmax_quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq,
@@ -246,7 +249,7 @@ int qg_absmax_quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, fl
   if (rc) return rc;
   QG_REQUIRE(W && Wq && Cw && K > 0 && N > 0 && ldw >= N && ldq >= N && valid_io(dtype),
              "qg_absmax_quant_cols: bad arguments");
-  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wq, ldq, Cw, scratch, (cudaStream_t)stream);
+  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wq, ldq, Cw, scratch, false, (cudaStream_t)stream);
 }
 
 int qg_gemm_s8s8s32(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K, int32_t *C,
@@ -255,7 +258,7 @@ int qg_gemm_s8s8s32(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, 
   int rc = device_state(&d);
   if (rc) return rc;
   QG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && lda >= K && ldb >= N && ldc >= N, "qg_gemm_s8s8s32: bad arguments");
-  return gemm_dispatch(d, A, lda, B, ldb, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f,
+  return gemm_dispatch(d, A, lda, B, ldb, 0, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f,
                        (cudaStream_t)stream);
 }
 
@@ -278,7 +281,7 @@ int qg_gemm_s8_dequant(const int8_t *Xq, int64_t ldxq, const int8_t *Wq, int64_t
   QG_REQUIRE(Xq && Wq && Cx && Cw && O && M > 0 && N > 0 && K > 0 && ldxq >= K && ldwq >= N && ldo >= N &&
                  valid_io(out_dtype),
              "qg_gemm_s8_dequant: bad arguments");
-  return gemm_dispatch(d, Xq, ldxq, Wq, ldwq, M, N, K, O, ldo, out_dtype, Cx, Cw, bias, 1 / (range * range),
+  return gemm_dispatch(d, Xq, ldxq, Wq, ldwq, 0, M, N, K, O, ldo, out_dtype, Cx, Cw, bias, 1 / (range * range),
                        (cudaStream_t)stream);
 }
 
@@ -320,19 +323,41 @@ int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ldw, int 
   cudaStream_t st = (cudaStream_t)stream;
   rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, st);
+  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, true, st);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, M, N, K, O, ldo, out_dtype, w.Cx, w.Cw, bias,
+  return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 1, M, N, K, O, ldo, out_dtype, w.Cx, w.Cw, bias,
                        1 / (range * range), st);
 }
 
-int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wq, int64_t ldwq, const float *Cw,
+int qg_prepare_weights(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, int8_t *Wt,
+                       int64_t ldwt, float *Cw, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(W && Wt && Cw && K > 0 && N > 0 && ldw >= N && ldwt >= K && valid_io(dtype), "qg_prepare_weights: bad arguments");
+  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wt, ldwt, Cw, nullptr, true, (cudaStream_t)stream);
+}
+
+int qg_gemm_s8t_dequant(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_t ldwt, const float *Cx, const float *Cw,
+                        const float *bias, int M, int N, int K, float range, void *O, int out_dtype, int64_t ldo,
+                        qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(Xq && Wt && O && M > 0 && N > 0 && K > 0 && ldxq >= K && ldwt >= K && ldo >= N &&
+                 (out_dtype == QG_S32 || (valid_io(out_dtype) && Cx && Cw)),
+             "qg_gemm_s8t_dequant: bad arguments");
+  return gemm_dispatch(d, Xq, ldxq, Wt, ldwt, 1, M, N, K, O, ldo, out_dtype, Cx, Cw, bias, 1 / (range * range),
+                       (cudaStream_t)stream);
+}
+
+int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt, int64_t ldwt, const float *Cw,
                       const float *bias, void *Y, int64_t ldy, int out_dtype, int M, int N, int K, float range, int mode,
                       void *workspace, size_t workspace_bytes, qg_stream_t stream) {
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
-  QG_REQUIRE(X && Wq && Cw && Y && M > 0 && N > 0 && K > 0 && ldx >= K && ldwq >= N && ldy >= N && valid_io(in_dtype) &&
+  QG_REQUIRE(X && Wt && Cw && Y && M > 0 && N > 0 && K > 0 && ldx >= K && ldwt >= K && ldy >= N && valid_io(in_dtype) &&
                  valid_io(out_dtype),
              "qg_linear_forward: bad arguments (M=%d N=%d K=%d)", M, N, K);
   Workspace w;
@@ -341,7 +366,7 @@ int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wq
   cudaStream_t st = (cudaStream_t)stream;
   rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  return gemm_dispatch(d, w.Xq, w.ldxq, Wq, ldwq, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st);
+  return gemm_dispatch(d, w.Xq, w.ldxq, Wt, ldwt, 1, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st);
 }
 
 int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host, int M, int N, int K, float range,
@@ -365,9 +390,9 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
   Workspace w = carve(d->arena, M, N, K);
   rc = quant_rows(d->hx, QG_F32, M, K, K, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, st);
+  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, true, st);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  rc = gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, M, N, K, d->ho, N, QG_F32, w.Cx, w.Cw,
+  rc = gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 1, M, N, K, d->ho, N, QG_F32, w.Cx, w.Cw,
                      bias_host ? (const float *)d->hb : nullptr, 1 / (range * range), st);
   if (rc) return rc;
   QG_CUDA_OK(cudaMemcpyAsync(O_host, d->ho, ob, cudaMemcpyDeviceToHost, st));

@@ -34,6 +34,10 @@ constexpr int kStageOutBytes = 32 * 128;  // per-epilogue-warp staging tile: 32 
 struct GemmParams {
   int M, N, K;
   int tiles_m, tiles_n;  // cluster tiles: (CG*128) x 256
+  // Tail splitting: the first `full_tiles` tiles are 256 columns wide; when the remaining tiles
+  // would fill at most half of the machine, each is cut into `tail_split` = 2 tiles of 128
+  // columns so the last wave takes half as long (4096^3 on 74 CTA pairs: 3.5 rounds instead of 4).
+  int full_tiles, total_tiles, tail_split;
   void *out;             // [M,N] of the epilogue's type
   int64_t ldo;           // elements
   const float *Cx, *Cw, *bias;
@@ -78,7 +82,8 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, __nv_bfloat16) {
 template <int CG, bool B_MN, int OUT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const __grid_constant__ CUtensorMap map_o, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_o,
+                  const GemmParams p) {
   using C = Cfg<CG, B_MN>;
   using OT = OutTraits<OUT>;
   using OutT = typename OT::T;
@@ -106,6 +111,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.tail_split > 1) tma_prefetch_desc(&map_bh);
     if (p.tma_store) tma_prefetch_desc(&map_o);
   }
   if (warp == 1 && lane == 0) {
@@ -131,7 +137,20 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // preceding kernel; from here on its outputs (Xq, Wq, Cx, Cw) are read
   griddep_wait();
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.total_tiles;
+  // tile index -> (row block, first column, width)
+  auto tile_coords = [&](int t, int &m_blk, int &n0, int &bn) {
+    int ft = t, part = 0;
+    bn = BN;
+    if (t >= p.full_tiles) {
+      const int idx = t - p.full_tiles;
+      ft = p.full_tiles + idx / p.tail_split;
+      part = idx % p.tail_split;
+      bn = BN / p.tail_split;
+    }
+    m_blk = ft % p.tiles_m;
+    n0 = (ft / p.tiles_m) * BN + part * bn;
+  };
   const int num_clusters = gridDim.x / CG;
   const int cluster_id = blockIdx.x / CG;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -143,8 +162,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       long long w_empty = 0;
       const long long t_begin = clock64();
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m_base = ((t % p.tiles_m) * CG + (int)cta_rank) * BM;
-        const int n_base = (t / p.tiles_m) * BN + (int)cta_rank * C::kBLoadN;
+        int m_blk, n0, bn;
+        tile_coords(t, m_blk, n0, bn);
+        const int m_base = (m_blk * CG + (int)cta_rank) * BM;
+        const int n_base = n0 + (int)cta_rank * (bn / CG);
+        const bool half = bn != BN;  // only generated for K-major B (see host side)
+        const uint32_t stage_tx = C::kABytes + (uint32_t)(bn / CG) * BK;
         for (int kb = 0; kb < num_kb; kb++, it++) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           if (p.stats) {
@@ -159,22 +182,22 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int k0 = kb * BK;
           if (CG == 1) {
             const uint32_t fb = smem_u32(&full_bar[s]);
-            mbar_arrive_expect_tx(fb, C::kStageBytes);
+            mbar_arrive_expect_tx(fb, stage_tx);
             tma_load_2d(sa, &map_a, fb, k0, m_base);
             if (B_MN) {  // two [128 k-rows x 128 n-bytes] boxes side by side
               tma_load_2d(sb, &map_b, fb, n_base, k0);
               tma_load_2d(sb + BK * 128, &map_b, fb, n_base + 128, k0);
             } else {     // one [256 n-rows x 128 k-bytes] box
-              tma_load_2d(sb, &map_b, fb, k0, n_base);
+              tma_load_2d(sb, half ? &map_bh : &map_b, fb, k0, n_base);
             }
           } else {
             // both CTAs' loads complete on the leader's barrier; the leader arms it for both
             uint32_t fb;
             asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(fb) : "r"(smem_u32(&full_bar[s])));
-            if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), 2 * C::kStageBytes);
+            if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), 2 * stage_tx);
             tma_load_2d_2sm(sa, &map_a, fb, k0, m_base);
             if (B_MN) tma_load_2d_2sm(sb, &map_b, fb, n_base, k0);
-            else tma_load_2d_2sm(sb, &map_b, fb, k0, n_base);
+            else tma_load_2d_2sm(sb, half ? &map_bh : &map_b, fb, k0, n_base);
           }
         }
       }
@@ -187,7 +210,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_i8(BM * CG, BN, 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_nofield = umma_idesc_i8(BM * CG, 0, 0, B_MN ? 1 : 0);
       uint32_t it = 0, acc_it = 0;
       long long w_full = 0, w_tempty = 0;
       const long long t_begin = clock64();
@@ -202,6 +225,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        int m_blk, n0, bn;
+        tile_coords(t, m_blk, n0, bn);
+        const uint32_t idesc = idesc_nofield | ((uint32_t)(bn >> 3) << 17);  // UMMA N of this tile
         for (int kb = 0; kb < num_kb; kb++, it++) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           if (p.stats) {
@@ -249,12 +275,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const long long t_begin = clock64();
     for (int t = cluster_id; t < num_tiles; t += num_clusters, acc_it++) {
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-      const int m_base = ((t % p.tiles_m) * CG + (int)cta_rank) * BM;
-      const int n_base = (t / p.tiles_m) * BN;
+      int m_blk, n_base, bn;
+      tile_coords(t, m_blk, n_base, bn);
+      const int m_base = (m_blk * CG + (int)cta_rank) * BM;
       const int row = m_base + q * 32 + lane;
       float cx = 0.0f;
       if (kDequant) {
-        for (int i = epi_tid; i < BN; i += 128) {
+        for (int i = epi_tid; i < bn; i += 128) {
           const int col = n_base + i;
           cw_s[as * BN + i] = (col < p.N) ? p.Cw[col] : 0.0f;
           bias_s[as * BN + i] = (p.bias != nullptr && col < p.N) ? p.bias[col] : 0.0f;
@@ -274,7 +301,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const float *cw = cw_s + as * BN;
       const float *bs = bias_s + as * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += OT::kCols) {
+      for (int c0 = 0; c0 < bn; c0 += OT::kCols) {
         if (n_base + c0 >= p.N) break;
         uint32_t w[32];  // 128 bytes of output for this thread's row
         if constexpr (OT::kCols == 32) {
@@ -407,8 +434,8 @@ int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, size_t esize, const vo
 }
 
 template <int CG, bool B_MN, int OUT>
-int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const GemmParams &p, int num_sms,
-           cudaStream_t st) {
+int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo, GemmParams p,
+           int num_sms, cudaStream_t st) {
   using C = Cfg<CG, B_MN>;
   auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT>;
   static bool configured = false;  // per instantiation
@@ -416,8 +443,18 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, 
     QG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int base_tiles = p.tiles_m * p.tiles_n;
   const int max_clusters = num_sms / CG;
+  p.full_tiles = base_tiles;
+  p.total_tiles = base_tiles;
+  p.tail_split = 1;
+  const int rem = base_tiles % max_clusters;
+  if (!B_MN && base_tiles > max_clusters && rem > 0 && 2 * rem <= max_clusters && getenv("QG_NO_TAIL_SPLIT") == nullptr) {
+    p.full_tiles = base_tiles - rem;
+    p.tail_split = 2;
+    p.total_tiles = p.full_tiles + 2 * rem;
+  }
+  const int num_tiles = p.total_tiles;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CG));
@@ -433,19 +470,19 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  QG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, p));
+  QG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mbh, mo, p));
   count_launch();
   return QG_OK;
 }
 
 template <int CG, bool B_MN>
-int launch_out(int out_kind, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const GemmParams &p,
-               int num_sms, cudaStream_t st) {
+int launch_out(int out_kind, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo,
+               const GemmParams &p, int num_sms, cudaStream_t st) {
   switch (out_kind) {
-    case QG_S32: return launch<CG, B_MN, QG_S32>(ma, mb, mo, p, num_sms, st);
-    case QG_F32: if (B_MN) return launch<CG, true, QG_F32>(ma, mb, mo, p, num_sms, st); break;
-    case QG_F16: if (B_MN) return launch<CG, true, QG_F16>(ma, mb, mo, p, num_sms, st); break;
-    case QG_BF16: if (B_MN) return launch<CG, true, QG_BF16>(ma, mb, mo, p, num_sms, st); break;
+    case QG_S32: return launch<CG, B_MN, QG_S32>(ma, mb, mbh, mo, p, num_sms, st);
+    case QG_F32: return launch<CG, B_MN, QG_F32>(ma, mb, mbh, mo, p, num_sms, st);
+    case QG_F16: return launch<CG, B_MN, QG_F16>(ma, mb, mbh, mo, p, num_sms, st);
+    case QG_BF16: return launch<CG, B_MN, QG_BF16>(ma, mb, mbh, mo, p, num_sms, st);
   }
   set_error("gemm_i8_tc: unsupported output kind %d", out_kind);
   return QG_ENOTSUP;
@@ -488,11 +525,17 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   if (const char *e = getenv("QG_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);
   if (const char *e = getenv("QG_DBG_B_SBO")) p.b_sbo = (uint32_t)atoi(e);
 
-  CUtensorMap ma, mb, mo;
+  CUtensorMap ma, mb, mbh, mo;
   int rc = make_map_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A, M, K, lda, BM, BK);
   if (rc) return rc;
-  if (b_kmajor) rc = make_map_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, N, K, ldb, BN / cg, BK);
-  else rc = make_map_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, K, N, ldb, BK, 128);
+  if (b_kmajor) {
+    rc = make_map_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, N, K, ldb, BN / cg, BK);
+    if (rc) return rc;
+    rc = make_map_2d(&mbh, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, N, K, ldb, BN / cg / 2, BK);  // half-width tail tiles
+  } else {
+    rc = make_map_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, K, N, ldb, BK, 128);
+    mbh = mb;
+  }
   if (rc) return rc;
   if (p.tma_store) {
     CUtensorMapDataType odt = out_kind == QG_S32   ? CU_TENSOR_MAP_DATA_TYPE_INT32
@@ -504,10 +547,10 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   } else {
     mo = ma;  // unused by the kernel
   }
-  if (cg == 1) return b_kmajor ? launch_out<1, false>(out_kind, ma, mb, mo, p, num_sms, st)
-                               : launch_out<1, true>(out_kind, ma, mb, mo, p, num_sms, st);
-  if (cg == 2) return b_kmajor ? launch_out<2, false>(out_kind, ma, mb, mo, p, num_sms, st)
-                               : launch_out<2, true>(out_kind, ma, mb, mo, p, num_sms, st);
+  if (cg == 1) return b_kmajor ? launch_out<1, false>(out_kind, ma, mb, mbh, mo, p, num_sms, st)
+                               : launch_out<1, true>(out_kind, ma, mb, mbh, mo, p, num_sms, st);
+  if (cg == 2) return b_kmajor ? launch_out<2, false>(out_kind, ma, mb, mbh, mo, p, num_sms, st)
+                               : launch_out<2, true>(out_kind, ma, mb, mbh, mo, p, num_sms, st);
   return QG_EINVAL;
 }
 

@@ -20,8 +20,8 @@ __device__ __forceinline__ void store_out(void *O, int64_t ldo, int r, int c, fl
 // dequantize epilogue (kDequant) identical to the tcgen05 kernel's.
 template <bool kDequant, typename OutT>
 __global__ void __launch_bounds__(256)
-gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__restrict__ B, int64_t ldb, int M,
-                    int N, int K, void *__restrict__ O, int64_t ldo, const float *__restrict__ Cx,
+gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__restrict__ B, int64_t sb_k, int64_t sb_n,
+                    int M, int N, int K, void *__restrict__ O, int64_t ldo, const float *__restrict__ Cx,
                     const float *__restrict__ Cw, const float *__restrict__ bias, float c) {
   __shared__ int8_t sA[TM][TK + 4];
   __shared__ int8_t sB[TK][TN + 4];
@@ -41,7 +41,7 @@ gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__r
     }
     for (int e = threadIdx.x; e < TK * TN; e += 256) {
       const int kk = e / TN, cidx = e % TN;
-      sB[kk][cidx] = (k0 + kk < K && n0 + cidx < N) ? B[(int64_t)(k0 + kk) * ldb + n0 + cidx] : (int8_t)0;
+      sB[kk][cidx] = (k0 + kk < K && n0 + cidx < N) ? B[(int64_t)(k0 + kk) * sb_k + (int64_t)(n0 + cidx) * sb_n] : (int8_t)0;
     }
     __syncthreads();
 #pragma unroll 8
@@ -151,21 +151,23 @@ dequantize_kernel(const int32_t *__restrict__ acc, int64_t ldacc, const float *_
 
 }  // namespace
 
-int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K, void *O, int64_t ldo,
-                 int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st) {
+// b_kmajor == 0: B is [K,N] with leading dimension ldb; 1: B is [N,K]
+int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
+                 int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st) {
+  const int64_t sb_k = b_kmajor ? 1 : ldb, sb_n = b_kmajor ? ldb : 1;
   dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
   switch (out_dtype) {
     case QG_S32:
-      launch_kernel(gemm_s8_simt_kernel<false, float>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<false, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     case QG_F32:
-      launch_kernel(gemm_s8_simt_kernel<true, float>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     case QG_F16:
-      launch_kernel(gemm_s8_simt_kernel<true, __half>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, __half>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     case QG_BF16:
-      launch_kernel(gemm_s8_simt_kernel<true, __nv_bfloat16>, grid, dim3(256), st, A, lda, B, ldb, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, __nv_bfloat16>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
       break;
     default:
       return QG_EINVAL;

@@ -373,104 +373,111 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
 }
 
 // ------------------------------------------------------------------------------------------
-// Columns, one read of W: a thread-block cluster owns a strip of 128 bytes of columns (32 fp32 /
-// 64 half) over all K rows.  Each CTA keeps its K/cs rows of the strip in REGISTERS (NIT 16-byte
-// vectors per thread), the per-column maxima are combined across the cluster through distributed
-// shared memory, and the codes are produced from the registers: W is read once, Wq written once.
-// Thread layout: 8 threads span a 128-byte row segment, 32 row lanes per iteration.
+// Columns, ONE kernel and (for strips that stay in L2) one HBM read of W: a thread-block cluster
+// owns a strip of 512 bytes of columns (128 fp32 / 256 half) over all K rows, rank r handling rows
+// [r*rpc, (r+1)*rpc).  Phase 1 streams the strip and reduces |w| per column; the per-CTA maxima
+// are combined across the cluster through distributed shared memory; phase 2 re-reads the strip
+// (a few MB, read microseconds earlier by the same cluster: L2 hits) and writes the codes.
+// kTranspose: codes go out as Wt[n][k] (K contiguous), the K-major operand layout the tensor-core
+// GEMM runs fastest on -- staged through a swizzled smem tile so the stores are 128-byte rows.
+// (A first design kept the strip in registers: one read, but the 128-byte strip rows it could
+// afford used HBM badly -- 29 us vs 26 us for two passes at 4096^2 -- and it was dropped.)
 // ------------------------------------------------------------------------------------------
-template <typename T, int NIT>
+template <typename T, bool kTranspose>
 __global__ void __launch_bounds__(kThreads)
-quant_cols_cluster_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
+quant_cols_cluster_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int rpc,
                           int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
   namespace cg = cooperative_groups;
   constexpr int EPV = Unpack<T>::EPV;
-  constexpr int SC = 8 * EPV;  // columns per strip
+  constexpr int SC = 32 * EPV;  // columns per strip
   __shared__ float s_red[kThreads / 32][SC];
   __shared__ float s_cmax[SC];   // this CTA's maxima over its rows (rows >= 1 only)
   __shared__ float s_x0[SC];     // row 0 of the strip (meaningful in cluster rank 0)
   __shared__ float s_final[SC];  // Cw of the strip
+  __shared__ uint32_t s_tile[kTranspose ? SC * 32 : 1];  // [column][32 words = 128 k-bytes], word-swizzled
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
   const int strip = blockIdx.x / cs;
-  const int cchunk = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int col = strip * SC + cchunk * EPV;
-  const int r0 = (int)rank * NIT * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = strip * SC + lane * EPV;
+  const int r0 = (int)rank * rpc;
+  const int r1 = min(K, r0 + rpc);
   const bool col_ok = col < N;
   const T *base = W + col;
 
   griddep_wait();
-  uint4 raw[NIT];
-#pragma unroll
-  for (int it = 0; it < NIT; it++) {
-    const int r = r0 + it * 32 + ty;
-    raw[it] = (col_ok && r < K) ? ldg16(base + (int64_t)r * ldw) : make_uint4(0, 0, 0, 0);
-  }
-  griddep_launch_dependents();
+  // ---------------- phase 1: column maxima of this CTA's rows ----------------
   float m[EPV];
 #pragma unroll
   for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
-#pragma unroll
-  for (int it = 0; it < NIT; it++) {
-    const int r = r0 + it * 32 + ty;
-    if (col_ok && r < K) {
+  if (col_ok) {
+    int r = r0 + warp;
+    if (r0 == 0 && warp == 0 && r < r1) {  // row 0 is folded in signed, not by magnitude
       float f[EPV];
-      Unpack<T>::run(raw[it], f);
-      if (r == 0) {
+      Unpack<T>::run(ldg16(base), f);
 #pragma unroll
-        for (int e = 0; e < EPV; e++) s_x0[cchunk * EPV + e] = f[e];
-      } else {
+      for (int e = 0; e < EPV; e++) s_x0[lane * EPV + e] = f[e];
+      r += 8;
+    }
+    for (; r + 56 < r1; r += 64) {  // 8 independent 16-byte loads in flight per thread
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = ldg16(base + (int64_t)(r + 8 * u) * ldw);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        float f[EPV];
+        Unpack<T>::run(v[u], f);
 #pragma unroll
         for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
       }
     }
-  }
-  // rows of one warp: lanes l, l^8, l^16, l^24 hold the same columns
+    for (; r < r1; r += 8) {
+      float f[EPV];
+      Unpack<T>::run(ldg16(base + (int64_t)r * ldw), f);
 #pragma unroll
-  for (int e = 0; e < EPV; e++) {
-    m[e] = fmaxf(m[e], __shfl_xor_sync(0xffffffffu, m[e], 8));
-    m[e] = fmaxf(m[e], __shfl_xor_sync(0xffffffffu, m[e], 16));
+      for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
+    }
   }
-  if ((threadIdx.x & 31) < 8) {
 #pragma unroll
-    for (int e = 0; e < EPV; e++) s_red[threadIdx.x >> 5][cchunk * EPV + e] = m[e];
-  }
+  for (int e = 0; e < EPV; e++) s_red[warp][lane * EPV + e] = m[e];
   __syncthreads();
-  if (threadIdx.x < SC) {
-    float r = s_red[0][threadIdx.x];
+  for (int c = threadIdx.x; c < SC; c += kThreads) {
+    float r = s_red[0][c];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; w++) r = fmaxf(r, s_red[w][threadIdx.x]);
-    s_cmax[threadIdx.x] = r;
+    for (int w = 1; w < kThreads / 32; w++) r = fmaxf(r, s_red[w][c]);
+    s_cmax[c] = r;
   }
   cluster.sync();
-  if (threadIdx.x < SC) {
+  // ---------------- cluster-wide combine through DSMEM ----------------
+  for (int c = threadIdx.x; c < SC; c += kThreads) {
     float mm = -INFINITY;
-    for (unsigned rk = 0; rk < cs; rk++) mm = fmaxf(mm, cluster.map_shared_rank(s_cmax, rk)[threadIdx.x]);
-    const float x0 = cluster.map_shared_rank(s_x0, 0)[threadIdx.x];
-    const int c = strip * SC + threadIdx.x;
+    for (unsigned rk = 0; rk < cs; rk++) mm = fmaxf(mm, cluster.map_shared_rank(s_cmax, rk)[c]);
+    const int gc = strip * SC + c;
     float cw = 0.0f;
-    if (c < N) {
+    if (gc < N) {
+      const float x0 = cluster.map_shared_rank(s_x0, 0)[c];
       if (fold_first(x0, mm, mode, cw)) {
         for (int k = 1; k < K; k++) {  // rare +-0 tie-break: sign of the first later non-NaN zero
-          const float x = to_f32(W[(int64_t)k * ldw + c]);
+          const float x = to_f32(W[(int64_t)k * ldw + gc]);
           if (x == x) { cw = -x; break; }
         }
       }
-      if (rank == 0 && Cw != nullptr) Cw[c] = cw;
+      if (rank == 0 && Cw != nullptr) Cw[gc] = cw;
     }
-    s_final[threadIdx.x] = cw;
+    s_final[c] = cw;
   }
   cluster.sync();  // also keeps every CTA's smem alive until all remote reads are done
+  griddep_launch_dependents();
+  if (Wq == nullptr) return;
+  // ---------------- phase 2: codes (strip re-read is served by L2) ----------------
   float s[EPV];
 #pragma unroll
-  for (int e = 0; e < EPV; e++) s[e] = __fdiv_rn(range, s_final[cchunk * EPV + e]);
-  if (Wq == nullptr || !col_ok) return;
-#pragma unroll
-  for (int it = 0; it < NIT; it++) {
-    const int r = r0 + it * 32 + ty;
-    if (r < K) {
+  for (int e = 0; e < EPV; e++) s[e] = __fdiv_rn(range, s_final[lane * EPV + e]);
+  if (!kTranspose) {
+    if (!col_ok) return;
+    auto emit = [&](const uint4 &v, int r) {
       float f[EPV];
-      Unpack<T>::run(raw[it], f);
+      Unpack<T>::run(v, f);
       uint32_t w[EPV / 4];
 #pragma unroll
       for (int q = 0; q < EPV / 4; q++)
@@ -479,6 +486,54 @@ quant_cols_cluster_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, fl
       int8_t *dst = Wq + (int64_t)r * ldq + col;
       if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
       else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
+    };
+    int r = r0 + warp;
+    for (; r + 56 < r1; r += 64) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = ldg16(base + (int64_t)(r + 8 * u) * ldw);
+#pragma unroll
+      for (int u = 0; u < 8; u++) emit(v[u], r + 8 * u);
+    }
+    for (; r < r1; r += 8) emit(ldg16(base + (int64_t)r * ldw), r);
+  } else {
+    // chunks of 128 rows; warp w owns row quads w, w+8, w+16, w+24 of the chunk
+    for (int rb = r0; rb < r1; rb += 128) {
+      uint4 v[4][4];
+#pragma unroll
+      for (int qi = 0; qi < 4; qi++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int r = rb + 4 * (warp + 8 * qi) + i;
+          v[qi][i] = (col_ok && r < r1) ? ldg16(base + (int64_t)r * ldw) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+      for (int qi = 0; qi < 4; qi++) {
+        const int rq = warp + 8 * qi;
+        float f[4][EPV];
+#pragma unroll
+        for (int i = 0; i < 4; i++) Unpack<T>::run(v[qi][i], f[i]);
+#pragma unroll
+        for (int e = 0; e < EPV; e++) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int r = rb + 4 * rq + i;
+            const uint32_t code = (r < r1) ? quant_code_u8(f[i][e], s[e]) : 0u;  // rows past K: zero padding
+            w |= code << (8 * i);
+          }
+          // word index rotated by the writer's lane: conflict-free here and in the read-back below
+          s_tile[(lane * EPV + e) * 32 + ((rq + lane) & 31)] = w;
+        }
+      }
+      __syncthreads();
+      for (int c = warp; c < SC; c += kThreads / 32) {  // one warp writes one 128-byte row of Wt
+        const int gc = strip * SC + c;
+        const int r = rb + 4 * lane;
+        if (gc < N && r < r1)
+          *reinterpret_cast<uint32_t *>(Wq + (int64_t)gc * ldq + r) = s_tile[c * 32 + ((lane + c / EPV) & 31)];
+      }
+      __syncthreads();
     }
   }
 }
@@ -488,7 +543,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 quant_cols_generic_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
                           const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq,
-                          float *__restrict__ Cw) {
+                          float *__restrict__ Cw, bool transpose) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
   if (j >= N) return;
@@ -509,8 +564,11 @@ quant_cols_generic_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, fl
     scale = sw_in[j];
   }
   if (Wq == nullptr) return;
-  for (int k = 0; k < K; k++)
-    Wq[(int64_t)k * ldq + j] = (int8_t)quant_code_u8(to_f32(W[(int64_t)k * ldw + j]), scale);
+  for (int k = 0; k < K; k++) {
+    const int8_t q = (int8_t)quant_code_u8(to_f32(W[(int64_t)k * ldw + j]), scale);
+    if (transpose) Wq[(int64_t)j * ldq + k] = q;
+    else Wq[(int64_t)k * ldq + j] = q;
+  }
 }
 
 __global__ void inv_divide_kernel(const float *__restrict__ a, int64_t n, float b, float *__restrict__ out) {
@@ -588,21 +646,24 @@ inline int cols_rows_per_cta(int K, int col_tiles) {
 
 template <typename T>
 int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, const float *sw, int8_t *Wq,
-                  int64_t ldq, float *Cw, float *scratch, cudaStream_t st) {
+                  int64_t ldq, float *Cw, float *scratch, bool transpose, cudaStream_t st) {
   constexpr int EPV = Unpack<T>::EPV;
+  if (transpose && Wq != nullptr && !(aligned(Wq, 4) && ldq % 4 == 0))
+    return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
+                              N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   const bool vec_ok = (N % EPV == 0) && aligned(W, 16) && ((ldw * sizeof(T)) % 16 == 0) &&
                       (Wq == nullptr || (aligned(Wq, EPV) && ldq % EPV == 0)) &&
-                      (sw != nullptr || scratch != nullptr || (Wq != nullptr && K <= 8 * 32 * 32));
+                      (sw != nullptr || scratch != nullptr || Wq != nullptr) && !(transpose && sw != nullptr);
   if (!vec_ok) {
     return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
-                              N, ldw, range, mode, sw, Wq, ldq, Cw);
+                              N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   }
-  // one-read cluster kernel: the strip's K rows must fit the registers of <= 8 CTAs
-  if (sw == nullptr && Wq != nullptr && K <= 8 * 32 * 32 && getenv("QG_COLS_TWO_PASS") == nullptr) {
-    const int nit = K <= 8 * 16 * 32 ? 16 : 32;
-    int cs = (int)ceil_div(K, nit * 32);
-    cs = cs <= 1 ? 1 : cs <= 2 ? 2 : cs <= 4 ? 4 : 8;
-    const int strips = (int)ceil_div(N, 8 * EPV);
+  // fused absmax + quantize: one cluster kernel (QG_COLS_TWO_PASS=1 keeps the three-launch path)
+  if (sw == nullptr && Wq != nullptr && (transpose || getenv("QG_COLS_TWO_PASS") == nullptr)) {
+    int cs = 1;
+    while (cs < 8 && (int64_t)K > (int64_t)cs * 512) cs *= 2;      // >= ~512 rows per CTA, at most 8 CTAs
+    const int rpc_c = (int)round_up(ceil_div(K, cs), 128);
+    const int strips = (int)ceil_div(N, 32 * EPV);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(strips * cs));
     cfg.blockDim = dim3(kThreads);
@@ -615,8 +676,9 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     count_launch();
-    if (nit == 16) return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, 16>, W, K, N, ldw, range, mode, Wq, ldq, Cw);
-    return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, 32>, W, K, N, ldw, range, mode, Wq, ldq, Cw);
+    if (transpose)
+      return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, true>, W, K, N, ldw, range, mode, rpc_c, Wq, ldq, Cw);
+    return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, false>, W, K, N, ldw, range, mode, rpc_c, Wq, ldq, Cw);
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
   const int rpc = cols_rows_per_cta(K, col_tiles);
@@ -649,13 +711,14 @@ int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range,
   return QG_EINVAL;
 }
 
+// transpose: codes are written as Wt[n][k] with leading dimension ldq (K-major operand layout)
 int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
-               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, cudaStream_t st) {
+               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, bool transpose, cudaStream_t st) {
   switch (dtype) {
-    case QG_F32: return cols_dispatch((const float *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, st);
-    case QG_F16: return cols_dispatch((const __half *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, st);
+    case QG_F32: return cols_dispatch((const float *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, transpose, st);
+    case QG_F16: return cols_dispatch((const __half *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, transpose, st);
     case QG_BF16:
-      return cols_dispatch((const __nv_bfloat16 *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, st);
+      return cols_dispatch((const __nv_bfloat16 *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, transpose, st);
   }
   return QG_EINVAL;
 }

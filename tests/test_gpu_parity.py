@@ -109,6 +109,73 @@ def test_col_quantizer_bit_exact(qg, oracle, shape, dt):
         assert np.array_equal(Wq.cpu().numpy(), eq), f"codes mismatch mode {mode}"
 
 
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("shape", COL_SHAPES + [(4096, 4096), (300, 2050)])
+def test_prepare_weights_is_transposed_column_quantizer(qg, oracle, shape, dt):
+    """qg_prepare_weights: same codes and Cw as the column quantizer, stored as Wt [N,K]."""
+    rng = np.random.default_rng(seed_of(shape, dt, "t"))
+    K, N = shape
+    W = to_dev(np.ascontiguousarray(make_edge_matrix(rng, N, K).T), dt)
+    Wh = as_f32_np(W)
+    for mode in (qg.MODE_REF_EXACT, qg.MODE_TRUE_ABSMAX):
+        Wt, Cw = qg.prepare_weights(W, 127.0, mode)
+        eq, ecw = oracle.absmax_quant_cols(Wh, 127.0, mode)
+        assert same_f32(Cw.cpu().numpy(), ecw), f"Cw mismatch mode {mode}"
+        assert np.array_equal(Wt.cpu().numpy(), eq.T), f"codes mismatch mode {mode}"
+
+
+@pytest.mark.parametrize("variant", ["SIMT", "TC_1SM", "TC_2SM"])
+@pytest.mark.parametrize("shape", [(128, 256, 128), (200, 300, 1000), (512, 768, 1024), (3, 2, 3), (129, 257, 129)])
+def test_gemm_on_prepared_weights(qg, oracle, shape, variant):
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape, "prep"))
+    A, B = codes(rng, M, K), codes(rng, K, N)
+    Cx = rng.random(M, dtype=np.float32) + 0.05
+    Cw = rng.random(N, dtype=np.float32) + 0.05
+    bias = rng.standard_normal(N).astype(np.float32)
+    dA = padded(torch.from_numpy(A).to(DEV), 16)
+    dBt = padded(torch.from_numpy(np.ascontiguousarray(B.T)).to(DEV), 16)
+    acc = padded(torch.empty((M, N), dtype=torch.int32, device=DEV), 4)
+    out = torch.empty((M, N), device=DEV)
+    qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
+    try:
+        qg.gemm_s8t_dequant(dA, dBt, None, None, acc)
+        qg.gemm_s8t_dequant(dA, dBt, to_dev(Cx), to_dev(Cw), out, 127.0, to_dev(bias))
+        torch.cuda.synchronize()
+    finally:
+        qg.set_gemm_variant(qg.GEMM_AUTO)
+    exp = oracle.gemm_s8s8s32(A, B)
+    assert np.array_equal(acc.cpu().numpy(), exp)
+    assert same_f32(out.cpu().numpy(), oracle.dequant(exp, Cx, Cw, 127.0, bias))
+
+
+@pytest.mark.parametrize("variant", ["TC_1SM", "TC_2SM"])
+@pytest.mark.parametrize("shape", [(4096, 4096, 512), (3000, 4000, 256), (4096, 4096, 4096)])
+def test_gemm_prepared_weights_tail_split_tiles(qg, oracle, shape, variant):
+    """Shapes whose last wave is cut into half-width tiles by the tile scheduler (more than one wave,
+    remainder at most half the machine): sampled rows exact against the oracle + a checksum of all rows."""
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape, "tail"))
+    A, B = codes(rng, M, K), codes(rng, K, N)
+    dA = torch.from_numpy(A).to(DEV)
+    dBt = torch.from_numpy(np.ascontiguousarray(B.T)).to(DEV)
+    acc = torch.empty((M, N), dtype=torch.int32, device=DEV)
+    qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
+    try:
+        qg.gemm_s8t_dequant(dA, dBt, None, None, acc)
+        torch.cuda.synchronize()
+    finally:
+        qg.set_gemm_variant(qg.GEMM_AUTO)
+    got = acc.cpu().numpy()
+    rows = np.sort(rng.choice(M, 64, replace=False))
+    assert np.array_equal(got[rows], oracle.gemm_s8s8s32(A[rows], B))
+    bsum = B.astype(np.int64).sum(axis=1)
+    assert np.array_equal(got.astype(np.int64).sum(axis=1), A.astype(np.int64) @ bsum)
+    # column checksum as well (catches tiles written to the wrong column block)
+    asum = A.astype(np.int64).sum(axis=0)
+    assert np.array_equal(got.astype(np.int64).sum(axis=0), asum @ B.astype(np.int64))
+
+
 def test_unfused_ops_match_reference_sequence(qg, oracle):
     """op_absmax -> op_inv_divide -> op_multiply<float,int8_t>, the reference's own call sequence
     (src/ops/op_mm.cuh:76-89), through the individual entry points."""

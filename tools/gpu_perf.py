@@ -36,7 +36,7 @@ def bench(fn, iters=30, warm=5):
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
 
-def gemm_stats(variant, size, out="f32"):
+def gemm_stats(variant, size, out="f32", kmajor=True):
     """Pipeline wait counters of the tcgen05 GEMM (cycles, averaged over CTAs)."""
     import torch
 
@@ -49,8 +49,12 @@ def gemm_stats(variant, size, out="f32"):
     O = torch.empty((M, N), dtype=dt, device="cuda")
     qg.set_gemm_variant(getattr(qg, "GEMM_" + variant))
 
+    Bt = B.t().contiguous()
+
     def run():
-        if out == "s32":
+        if kmajor:
+            qg.gemm_s8t_dequant(A, Bt, Cx, Cw, O)
+        elif out == "s32":
             qg.op_mm(A, B, O)
         else:
             qg.gemm_s8_dequant(A, B, Cx, Cw, O)
@@ -126,9 +130,15 @@ def quantizers(size, dt="f32"):
         flip[0] ^= 1
         qg.absmax_quant_cols(W if flip[0] else W2, 127.0, 0, Wq, Cw)
 
-    r, c = bench(rows), bench(cols)
+    Wt = torch.empty((N, K), dtype=torch.int8, device="cuda")
+
+    def cols_t():
+        flip[0] ^= 1
+        qg.prepare_weights(W if flip[0] else W2, 127.0, 0, Wt, Cw)
+
+    r, c, ct = bench(rows), bench(cols), bench(cols_t)
     return {"rows_us": r, "rows_gbs": (M * K * (es + 1) + 4 * M) / r / 1e3, "cols_us": c,
-            "cols_gbs": (K * N * (es + 1) + 4 * N) / c / 1e3}
+            "cols_gbs": (K * N * (es + 1) + 4 * N) / c / 1e3, "cols_t_us": ct, "cols_t_gbs": (K * N * (es + 1) + 4 * N) / ct / 1e3}
 
 
 def full_op(size, out="f32"):
@@ -186,15 +196,18 @@ EXPERIMENTS = {
     "lib_8192": (lib_ref, (8192,), {}),
     "stats_1sm_4096_f32": (gemm_stats, ("TC_1SM", 4096, "f32"), {}),
     "stats_2sm_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {}),
-    "stats_1sm_4096_s32": (gemm_stats, ("TC_1SM", 4096, "s32"), {}),
+    "stats_2sm_4096_f32_nosplit": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_NO_TAIL_SPLIT": "1"}),
+    "stats_1sm_4096_f32_nosplit": (gemm_stats, ("TC_1SM", 4096, "f32"), {"QG_NO_TAIL_SPLIT": "1"}),
+    "stats_2sm_4096_s32": (gemm_stats, ("TC_2SM", 4096, "s32"), {}),
     "stats_2sm_4096_f16": (gemm_stats, ("TC_2SM", 4096, "f16"), {}),
+    "stats_2sm_4096_f32_mnmajor": (gemm_stats, ("TC_2SM", 4096, "f32", False), {}),
     "stats_1sm_8192_f32": (gemm_stats, ("TC_1SM", 8192, "f32"), {}),
     "stats_2sm_8192_f32": (gemm_stats, ("TC_2SM", 8192, "f32"), {}),
+    "stats_2sm_8192_f16": (gemm_stats, ("TC_2SM", 8192, "f16"), {}),
     "stats_2sm_2048_f32": (gemm_stats, ("TC_2SM", 2048, "f32"), {}),
     "stats_1sm_2048_f32": (gemm_stats, ("TC_1SM", 2048, "f32"), {}),
-    "kmajor_1sm_4096": (gemm_kmajor, (1, 4096), {}),
-    "kmajor_2sm_4096": (gemm_kmajor, (2, 4096), {}),
-    "kmajor_2sm_8192": (gemm_kmajor, (2, 8192), {}),
+    "stats_2sm_1024_f32": (gemm_stats, ("TC_2SM", 1024, "f32"), {}),
+    "stats_1sm_1024_f32": (gemm_stats, ("TC_1SM", 1024, "f32"), {}),
     "quant_4096": (quantizers, (4096,), {}),
     "quant_4096_twopass": (quantizers, (4096,), {"QG_COLS_TWO_PASS": "1"}),
     "quant_4096_f16": (quantizers, (4096, "f16"), {}),
@@ -202,10 +215,11 @@ EXPERIMENTS = {
     "quant_8192_twopass": (quantizers, (8192,), {"QG_COLS_TWO_PASS": "1"}),
     "full_4096_pdl": (full_op, (4096,), {}),
     "full_4096_nopdl": (full_op, (4096,), {"QG_PDL": "0"}),
-    "full_4096_2sm": (full_op, (4096,), {"QG_GEMM_VARIANT": "3"}),
+    "full_4096_1sm": (full_op, (4096,), {"QG_GEMM_VARIANT": "2"}),
     "full_2048_pdl": (full_op, (2048,), {}),
     "full_2048_nopdl": (full_op, (2048,), {"QG_PDL": "0"}),
-    "full_8192_2sm": (full_op, (8192,), {"QG_GEMM_VARIANT": "3"}),
+    "full_8192": (full_op, (8192,), {}),
+    "full_1024": (full_op, (1024,), {}),
 }
 
 
