@@ -153,6 +153,23 @@ QG_API int qg_quantized_mm_host(const float *X_host, const float *W_host, float 
 QG_API int qg_outlier_mask_f32(const float *A, int m, int k, int64_t lda, float thr, float *mask,
                                int64_t ldm, qg_stream_t stream);
 
+/* ---- LLM.int8()-style outlier decomposition (new; the reference stops at the mask above) ------ */
+/* Column reduction of the mask: ascending K-indices with at least one |x| > thr (strict, NaN counts),
+ * written to idx[0..min(count,max_idx)) on the device; *count (device) receives the total. */
+QG_API int qg_outlier_cols(const void *X, int dtype, int m, int k, int64_t ldx, float thr, int *idx,
+                           int max_idx, int *count, qg_stream_t stream);
+QG_API size_t qg_outlier_workspace_bytes(int m, int n, int k);
+/* LinearLayer::forward with the feature columns idx[0..n_idx) (device, ascending, n_idx <= 16) taken
+ * out of the int8 path: X's outlier columns are zeroed before the row quantizer, and
+ * fp16(X[:,idx]) @ fp16(W[idx,:]) (bf16 when X is bf16) is accumulated in fp32 inside the GEMM
+ * epilogue: y = fl(fl(dequant + side) + bias).  W is the original [K,N] weight, Wt/Cw its prepared
+ * int8 form (qg_prepare_weights: column scales over ALL rows, so they do not depend on idx). */
+QG_API int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, const void *W, int64_t ldw,
+                                     int w_dtype, const int8_t *Wt, int64_t ldwt, const float *Cw,
+                                     const float *bias, const int *idx, int n_idx, void *Y, int64_t ldy,
+                                     int out_dtype, int m, int n, int k, float range, int mode,
+                                     void *workspace, size_t workspace_bytes, qg_stream_t stream);
+
 /* ---- op_mm<float,float>(A, B, C)  src/ops/op_mm.cuh:49-65 ---------------------------------- */
 /* fp32 product with the reference's k-ascending fma chain per output (bit-identical results);
  * general strides (sa_h, sa_w ...) because attention.cuh:58-60 passes K.transpose(). */

@@ -242,23 +242,43 @@ def outlier_columns(X, thr):
     return np.nonzero(outlier_mask(X, thr).max(axis=0) > 0)[0].astype(np.int32)
 
 
-def quantized_mm_outlier(X, W, thr, range_=127.0, mode=MODE_REF_EXACT, bias=None, side_dtype=np.float16):
-    """LLM.int8()-style mixed decomposition (parity unpinned):
-    int8 path on X with outlier feature columns zeroed (row scales from the remaining entries),
-    W quantized over all rows, plus an fp16 side product X[:,O] @ W[O,:] accumulated in fp32
-    (k ascending fma), added after dequantization and before the bias."""
+def side_gemm(Xo, Wo):
+    """fp32-accumulated side product of already-rounded operands (k ascending fma from +0)."""
+    Xo = _f32(Xo)
+    Wo = _f32(Wo)
+    M, no = Xo.shape
+    N = Wo.shape[1]
+    out = np.empty((M, N), np.float32)
+    lib().qo_side_gemm_f32(_p(Xo), _p(Wo), C.c_int(M), C.c_int(N), C.c_int(no), C.c_int64(no), C.c_int64(N), _p(out),
+                           C.c_int64(N))
+    return out
+
+
+def _round_side(a, side_dtype):
+    if side_dtype == "bf16":
+        import torch
+
+        return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+    return a.astype(np.float16).astype(np.float32)
+
+
+def quantized_mm_outlier(X, W, thr, range_=127.0, mode=MODE_REF_EXACT, bias=None, side_dtype="f16", idx=None):
+    """LLM.int8()-style mixed decomposition (parity unpinned; specification ours):
+    int8 path on X with the outlier feature columns zeroed (row scales from the remaining entries),
+    W column-quantized over ALL rows (so the weights can be prepared once), plus a 16-bit side
+    product X[:,O] @ W[O,:] accumulated in fp32; out = fl(fl(dequant + side) + bias)."""
     X = _f32(X)
     W = _f32(W)
-    idx = outlier_columns(X, thr)
+    if idx is None:
+        idx = outlier_columns(X, thr)
+    idx = np.asarray(idx, np.int32)
     Xr = X.copy()
     Xr[:, idx] = 0.0
     O, parts = quantized_mm(Xr, W, range_, mode, None, return_parts=True)
     if idx.size:
-        Xo = X[:, idx].astype(side_dtype).astype(np.float32)
-        Wo = W[idx, :].astype(side_dtype).astype(np.float32)
-        side = gemm_f32_ref(Xo, Wo)
-        O = O + side
+        side = side_gemm(_round_side(X[:, idx], side_dtype), _round_side(W[idx, :], side_dtype))
+        O = (O + side).astype(np.float32)
     if bias is not None:
-        O = O + _f32(bias).reshape(1, -1)
+        O = (O + _f32(bias).reshape(1, -1)).astype(np.float32)
     parts["outlier_idx"] = idx
-    return O.astype(np.float32), parts
+    return O, parts

@@ -29,7 +29,8 @@ ABI_SYMBOLS = [
     "qg_absmax_quant_rows", "qg_absmax_quant_cols", "qg_gemm_s8s8s32", "qg_dequantize_s32",
     "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_prepare_weights", "qg_gemm_s8t_dequant",
     "qg_linear_forward",
-    "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_mm_f32",
+    "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
+    "qg_linear_forward_outlier", "qg_mm_f32",
 ]
 
 
@@ -50,6 +51,7 @@ def lib() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         L.qg_last_error.restype = C.c_char_p
         L.qg_workspace_bytes.restype = C.c_size_t
+        L.qg_outlier_workspace_bytes.restype = C.c_size_t
         L.qg_launch_count.restype = C.c_int64
         _lib = L
     return _lib
@@ -296,6 +298,22 @@ def quantized_mm_host(X, W, range_: float = 127.0, mode: int = MODE_REF_EXACT, b
     return out
 
 
+MAX_OUTLIER_COLS = 16
+
+
+def outlier_cols(X: torch.Tensor, thr: float, max_idx: int = 1024):
+    """Feature columns of X [M,K] holding at least one |x| > thr: returns (idx int32 [count] on the
+    device, ascending; count).  Reads the count back, i.e. synchronises the stream."""
+    M, K = X.shape
+    idx = torch.empty(max_idx, dtype=torch.int32, device=X.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=X.device)
+    px, ldx = _dev2d(X)
+    _check(lib().qg_outlier_cols(px, _dt(X), M, K, ldx, C.c_float(thr), C.c_void_p(idx.data_ptr()), max_idx,
+                                 C.c_void_p(cnt.data_ptr()), _stream()), "qg_outlier_cols")
+    n = int(cnt.item())
+    return idx[: min(n, max_idx)], n
+
+
 class LinearLayer:
     """LinearLayer<float> (src/modules/linear.cuh:7-72), inference only: y = x @ w + b with the
     product on the int8 tensor-core path.  w is [in_dim, out_dim], b is [1, out_dim]; the weights
@@ -318,6 +336,28 @@ class LinearLayer:
     def quantize_weights(self):
         self._wq = prepare_weights(self.w, self.range, self.mode)  # (Wt [N,K] int8, Cw)
         return self._wq
+
+    def forward_outlier(self, x: torch.Tensor, y: torch.Tensor, idx: torch.Tensor) -> None:
+        """forward with the feature columns `idx` (int32, device, ascending; e.g. from outlier_cols or a
+        calibrated fixed set) routed through the 16-bit side product (LLM.int8()-style decomposition)."""
+        assert x.shape[1] == self.in_dim and y.shape == (x.shape[0], self.out_dim)
+        assert idx.dtype == torch.int32 and idx.is_cuda and idx.numel() <= MAX_OUTLIER_COLS
+        if self._wq is None:
+            self.quantize_weights()
+        Wt, Cw = self._wq
+        M, K, N = x.shape[0], self.in_dim, self.out_dim
+        need = int(lib().qg_outlier_workspace_bytes(M, N, K))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        px, ldx = _dev2d(x)
+        pw, ldw = _dev2d(self.w)
+        pq, ldq = _dev2d(Wt)
+        py, ldy = _dev2d(y)
+        _check(lib().qg_linear_forward_outlier(px, ldx, _dt(x), pw, ldw, _dt(self.w), pq, ldq, _vec(Cw, N),
+                                               _vec(self.b.reshape(-1), N), C.c_void_p(idx.data_ptr()), int(idx.numel()),
+                                               py, ldy, _dt(y), M, N, K, C.c_float(self.range), self.mode,
+                                               C.c_void_p(self._ws.data_ptr()), C.c_size_t(self._ws.numel()), _stream()),
+               "qg_linear_forward_outlier")
 
     def forward(self, x: torch.Tensor, y: torch.Tensor) -> None:  # linear.cuh:49-56
         assert x.shape[1] == self.in_dim and y.shape == (x.shape[0], self.out_dim)

@@ -20,7 +20,16 @@ int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range,
 int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
-                 int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st);
+                 int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c,
+                 const SideArgs *side, cudaStream_t st);
+int outlier_detect(const void *X, int dtype, int M, int K, int64_t ldx, float thr, uint32_t *mask, cudaStream_t st);
+int outlier_index(const uint32_t *mask, int K, int *idx, int max_idx, int *count, int *wbase, cudaStream_t st);
+int outlier_mask_from_idx(const int *idx, int n_idx, int K, uint32_t *mask, int *wbase, cudaStream_t st);
+int quant_rows_outlier(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq, int64_t ldq,
+                       float *Cx, const uint32_t *mask, const int *wbase, void *Xo, int64_t ldxo, int side_bf16,
+                       cudaStream_t st);
+int gather_wo(const void *W, int dtype, int64_t ldw, const int *idx, int n_idx, int no_pad, int N, void *Wo, int64_t ldwo,
+              int side_bf16, cudaStream_t st);
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
            float *C, int64_t ldc, cudaStream_t st);
 int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
@@ -29,7 +38,7 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 void gemm_i8_tc_set_stats(long long *dev_ptr);
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               int num_sms, cudaStream_t st);
+               const SideArgs *side, int num_sms, cudaStream_t st);
 
 // ---- error state ----
 static thread_local char g_err[512] = "";
@@ -143,16 +152,16 @@ static Workspace carve(void *base, int M, int N, int K) {
 // b_kmajor == 0: B is the reference's [K,N] (MN-major tensor-core operand); 1: B is Wt [N,K]
 static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M,
                          int N, int K, void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw,
-                         const float *bias, float c, cudaStream_t st) {
+                         const float *bias, float c, cudaStream_t st, const SideArgs *side = nullptr) {
   int variant = g_variant.load();
   const bool tc_ok = gemm_i8_tc_supported(A, lda, B, ldb);
   // the 2-SM tile (256x256 per CTA pair) halves the shared-memory traffic per MAC; one CTA row
   // of work is all a problem with M <= 128 has, so it takes the 1-SM kernel
   if (variant == QG_GEMM_AUTO) variant = !tc_ok ? QG_GEMM_SIMT : (M > 128 ? QG_GEMM_TC_2SM : QG_GEMM_TC_1SM);
   if (variant == QG_GEMM_SIMT || !tc_ok)
-    return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, st);
+    return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st);
   return gemm_i8_tc(variant == QG_GEMM_TC_2SM ? 2 : 1, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias,
-                    c, d->sm_count, st);
+                    c, side, d->sm_count, st);
 }
 
 }  // namespace qg
@@ -369,6 +378,105 @@ int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt
   return gemm_dispatch(d, w.Xq, w.ldxq, Wt, ldwt, 1, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st);
 }
 
+// ---- outlier decomposition ------------------------------------------------------------------
+static const int kMaxOutlierCols = 16;  // what the fused epilogue takes (gemm_i8_tc.cu: kSideMax)
+
+struct OutlierWs {
+  uint32_t *mask;
+  int *wbase;
+  void *Xo, *Wo;
+  int64_t ldxo, ldwo;
+  size_t bytes;
+};
+static OutlierWs carve_outlier(void *base, int M, int N, int K) {
+  OutlierWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (size_t)round_up((int64_t)(off + n), 256); return o; };
+  const size_t words = (size_t)ceil_div(K, 32);
+  w.ldxo = kMaxOutlierCols;
+  w.ldwo = round_up(N, 8);
+  const size_t om = take(4 * words), ob = take(4 * words), ox = take(2 * (size_t)M * w.ldxo),
+               ow = take(2 * (size_t)kMaxOutlierCols * w.ldwo);
+  char *b = reinterpret_cast<char *>(base);
+  w.mask = reinterpret_cast<uint32_t *>(b + om);
+  w.wbase = reinterpret_cast<int *>(b + ob);
+  w.Xo = b + ox;
+  w.Wo = b + ow;
+  w.bytes = off;
+  return w;
+}
+
+int qg_outlier_cols(const void *X, int dtype, int M, int K, int64_t ldx, float thr, int *idx, int max_idx, int *count,
+                    qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && count && M > 0 && K > 0 && ldx >= K && max_idx >= 0 && valid_io(dtype), "qg_outlier_cols: bad arguments");
+  const size_t words = (size_t)ceil_div(K, 32);
+  uint32_t *mask;
+  int *wbase;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if ((rc = grow(&d->arena, &d->arena_bytes, 8 * words + 512))) return rc;
+    mask = reinterpret_cast<uint32_t *>(d->arena);
+    wbase = reinterpret_cast<int *>(reinterpret_cast<char *>(d->arena) + round_up((int64_t)(4 * words), 256));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = outlier_detect(X, dtype, M, K, ldx, thr, mask, st);
+  if (rc) return cuda_status((cudaError_t)rc, "outlier detection");
+  rc = outlier_index(mask, K, idx, max_idx, count, wbase, st);
+  return rc ? cuda_status((cudaError_t)rc, "outlier index") : QG_OK;
+}
+
+size_t qg_outlier_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return carve(nullptr, M, 1, K).bytes + carve_outlier(nullptr, M, N, K).bytes;
+}
+
+int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, const void *W, int64_t ldw, int w_dtype,
+                              const int8_t *Wt, int64_t ldwt, const float *Cw, const float *bias, const int *idx, int n_idx,
+                              void *Y, int64_t ldy, int out_dtype, int M, int N, int K, float range, int mode,
+                              void *workspace, size_t workspace_bytes, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && W && Wt && Cw && Y && M > 0 && N > 0 && K > 0 && ldx >= K && ldw >= N && ldwt >= K && ldy >= N &&
+                 valid_io(in_dtype) && valid_io(w_dtype) && valid_io(out_dtype) && n_idx >= 0 && (n_idx == 0 || idx),
+             "qg_linear_forward_outlier: bad arguments");
+  if (n_idx > kMaxOutlierCols) {
+    set_error("qg_linear_forward_outlier: %d outlier columns, the fused side product takes at most %d", n_idx,
+              kMaxOutlierCols);
+    return QG_ENOTSUP;
+  }
+  const size_t need = qg_outlier_workspace_bytes(M, N, K);
+  if (workspace == nullptr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if ((rc = grow(&d->arena, &d->arena_bytes, need))) return rc;
+    workspace = d->arena;
+  } else {
+    QG_REQUIRE(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "qg_linear_forward_outlier: workspace too small or misaligned (%zu bytes needed)", need);
+  }
+  Workspace w = carve(workspace, M, 1, K);
+  OutlierWs o = carve_outlier(reinterpret_cast<char *>(workspace) + w.bytes, M, N, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int no_pad = (int)round_up(n_idx, 8);
+  const int side_bf16 = (in_dtype == QG_BF16) ? 1 : 0;
+  rc = outlier_mask_from_idx(idx, n_idx, K, o.mask, o.wbase, st);
+  if (rc) return cuda_status((cudaError_t)rc, "outlier mask");
+  if (no_pad > 0) {
+    QG_CUDA_OK(cudaMemsetAsync(o.Xo, 0, 2 * (size_t)M * o.ldxo, st));
+    rc = gather_wo(W, w_dtype, ldw, idx, n_idx, no_pad, N, o.Wo, o.ldwo, side_bf16, st);
+    if (rc) return cuda_status((cudaError_t)rc, "outlier weight gather");
+  }
+  rc = quant_rows_outlier(X, in_dtype, M, K, ldx, range, mode, w.Xq, w.ldxq, w.Cx, o.mask, o.wbase, o.Xo, o.ldxo, side_bf16,
+                          st);
+  if (rc) return cuda_status((cudaError_t)rc, "masking row quantizer");
+  SideArgs side = {o.Xo, o.ldxo, o.Wo, o.ldwo, no_pad, side_bf16};
+  return gemm_dispatch(d, w.Xq, w.ldxq, Wt, ldwt, 1, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st,
+                       no_pad > 0 ? &side : nullptr);
+}
+
 int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host, int M, int N, int K, float range,
                          int mode, const float *bias_host) {
   DeviceState *d;
@@ -432,8 +540,8 @@ QG_API int qg_test_gemm_s8_bt(int cg, const int8_t *A, int64_t lda, const int8_t
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
-  return gemm_i8_tc(cg, A, lda, Bt, ldbt, 1, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f, d->sm_count,
-                    (cudaStream_t)stream);
+  return gemm_i8_tc(cg, A, lda, Bt, ldbt, 1, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f, nullptr,
+                    d->sm_count, (cudaStream_t)stream);
 }
 
 }  // extern "C"

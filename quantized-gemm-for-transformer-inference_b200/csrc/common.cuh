@@ -54,6 +54,16 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// optional outlier side product of the GEMM epilogue (see outlier.cu / gemm_i8_tc.cu)
+struct SideArgs {
+  const void *Xo;  // [M, ldxo] 16-bit, columns = rank of the outlier feature, zero padded to no_pad
+  int64_t ldxo;
+  const void *Wo;  // [no_pad, ldwo] 16-bit rows W[idx[o], :]
+  int64_t ldwo;
+  int no_pad;      // 0, 8 or 16
+  int side_bf16;   // 0: fp16 operands, 1: bf16
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 static inline size_t dtype_size(int dt) { return dt == QG_F32 ? 4 : 2; }

@@ -49,19 +49,27 @@ struct GemmParams {
   // optional per-CTA pipeline counters (cycles): [0] producer wait-empty, [1] producer total,
   // [2] mma wait-full, [3] mma wait-tmem-empty, [4] mma total, [5] epilogue wait-tmem-full, [6] epilogue total
   long long *stats;
+  // outlier side product (SIDE kernels only): Xo [M, ldxo] and Wo [no_pad, ldwo] are 16-bit
+  // (fp16, or bf16 when side_bf16), no_pad in {0, 8, 16}; side = sum_o Xo[i,o] * Wo[o,j] in fp32
+  const void *Xo, *Wo;
+  int64_t ldxo, ldwo;
+  int no_pad, side_bf16;
 };
 
-template <int CG, bool B_MN>
+constexpr int kSideMax = 16;  // outlier columns the fused epilogue can take
+
+template <int CG, bool B_MN, bool SIDE = false>
 struct Cfg {
   static constexpr int kBLoadN = BN / CG;                 // B columns this CTA stages
   static constexpr int kABytes = BM * BK;                 // 16 KB
   static constexpr int kBBytes = kBLoadN * BK;            // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = CG == 1 ? 4 : 6;
+  static constexpr int kStages = (CG == 1 ? 4 : 6) - (SIDE ? 1 : 0);  // one stage pays for the Wo tile
+  static constexpr int kSideBytes = SIDE ? 2 * kSideMax * BN * 4 : 0;  // fp32 Wo tile, double buffered
   static constexpr int kOutStaging = 4 * kStageOutBytes;  // 16 KB
   static constexpr int kScaleBytes = 2 * 2 * BN * 4;      // Cw + bias, double buffered
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStaging + kScaleBytes + kBarBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStaging + kScaleBytes + kSideBytes + kBarBytes + 1024;
 };
 
 template <int OUT> struct OutTraits;
@@ -79,12 +87,12 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, __nv_bfloat16) {
   return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <int CG, bool B_MN, int OUT>
+template <int CG, bool B_MN, int OUT, bool SIDE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_o,
                   const GemmParams p) {
-  using C = Cfg<CG, B_MN>;
+  using C = Cfg<CG, B_MN, SIDE>;
   using OT = OutTraits<OUT>;
   using OutT = typename OT::T;
   constexpr int kStages = C::kStages;
@@ -96,7 +104,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint8_t *smem_out = smem + kStages * C::kStageBytes;
   float *cw_s = reinterpret_cast<float *>(smem_out + C::kOutStaging);  // [2][BN]
   float *bias_s = cw_s + 2 * BN;                                       // [2][BN]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 2 * BN);
+  float *wo_s = bias_s + 2 * BN;                                       // [2][kSideMax][BN] (SIDE only)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wo_s + (SIDE ? 2 * kSideMax * BN : 0));
   uint64_t *full_bar = bars;                     // [kStages]  TMA -> MMA
   uint64_t *empty_bar = bars + kStages;          // [kStages]  MMA -> TMA
   uint64_t *tfull_bar = bars + 2 * kStages;      // [2]        MMA -> epilogue
@@ -286,9 +295,66 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           cw_s[as * BN + i] = (col < p.N) ? p.Cw[col] : 0.0f;
           bias_s[as * BN + i] = (p.bias != nullptr && col < p.N) ? p.bias[col] : 0.0f;
         }
+        if (SIDE) {
+          for (int i = epi_tid; i < p.no_pad * bn; i += 128) {
+            const int o = i / bn, cc = i - o * bn, col = n_base + cc;
+            float wv = 0.0f;
+            if (col < p.N) {
+              if (p.side_bf16) wv = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p.Wo)[(int64_t)o * p.ldwo + col]);
+              else wv = __half2float(reinterpret_cast<const __half *>(p.Wo)[(int64_t)o * p.ldwo + col]);
+            }
+            wo_s[(as * kSideMax + o) * BN + cc] = wv;
+          }
+        }
         named_bar_sync(1, 128);
         if (row < p.M) cx = p.Cx[row];
       }
+      float xo[SIDE ? kSideMax : 1];
+      if (SIDE) {
+#pragma unroll
+        for (int o8 = 0; o8 < kSideMax; o8 += 8) {
+          uint4 xv = make_uint4(0, 0, 0, 0);
+          if (o8 < p.no_pad && row < p.M)
+            xv = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(p.Xo) + (int64_t)row * p.ldxo + o8);
+          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            if (p.side_bf16) {
+              xo[o8 + 2 * i] = __uint_as_float(xw[i] << 16);
+              xo[o8 + 2 * i + 1] = __uint_as_float(xw[i] & 0xffff0000u);
+            } else {
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&xw[i]));
+              xo[o8 + 2 * i] = f2.x;
+              xo[o8 + 2 * i + 1] = f2.y;
+            }
+          }
+        }
+      }
+      // side[j] = sum_o xo[o] * Wo[o][cbase + j], o ascending, fp32 fma chain from +0
+      auto side_chunk = [&](int cbase, float (&sd)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) sd[j] = 0.0f;
+        if (SIDE) {
+          const float *wo = wo_s + as * kSideMax * BN + cbase;
+#pragma unroll
+          for (int ob = 0; ob < kSideMax; ob += 8) {
+            if (ob < p.no_pad) {
+#pragma unroll
+              for (int o = ob; o < ob + 8; o++) {
+                const float4 *wp = reinterpret_cast<const float4 *>(wo + o * BN);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) {
+                  const float4 wv = wp[j4];
+                  sd[4 * j4] = __fmaf_rn(xo[o], wv.x, sd[4 * j4]);
+                  sd[4 * j4 + 1] = __fmaf_rn(xo[o], wv.y, sd[4 * j4 + 1]);
+                  sd[4 * j4 + 2] = __fmaf_rn(xo[o], wv.z, sd[4 * j4 + 2]);
+                  sd[4 * j4 + 3] = __fmaf_rn(xo[o], wv.w, sd[4 * j4 + 3]);
+                }
+              }
+            }
+          }
+        }
+      };
       if (p.stats) {
         const long long t0 = clock64();
         mbar_wait(smem_u32(&tfull_bar[as]), aph, 4);
@@ -307,11 +373,14 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if constexpr (OT::kCols == 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
+          float sd[SIDE ? 32 : 1];
+          if constexpr (SIDE) side_chunk(c0, sd);  // CUDA-core work overlaps the TMEM load
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             if (kDequant) {
               float v = dequant_ref((int)r[j], cx, cw[c0 + j], p.c);
+              if constexpr (SIDE) { if (p.no_pad > 0) v = __fadd_rn(v, sd[j]); }
               if (p.bias != nullptr) v = __fadd_rn(v, bs[c0 + j]);
               w[j] = __float_as_uint(v);
             } else {
@@ -323,11 +392,16 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int h = 0; h < 2; h++) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(taddr + c0 + h * 32, r);
+            float sd[SIDE ? 32 : 1];
+            if constexpr (SIDE) side_chunk(c0 + h * 32, sd);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               float v0 = dequant_ref((int)r[j], cx, cw[c0 + h * 32 + j], p.c);
               float v1 = dequant_ref((int)r[j + 1], cx, cw[c0 + h * 32 + j + 1], p.c);
+              if constexpr (SIDE) {
+                if (p.no_pad > 0) { v0 = __fadd_rn(v0, sd[j]); v1 = __fadd_rn(v1, sd[j + 1]); }
+              }
               if (p.bias != nullptr) {
                 v0 = __fadd_rn(v0, bs[c0 + h * 32 + j]);
                 v1 = __fadd_rn(v1, bs[c0 + h * 32 + j + 1]);
@@ -433,11 +507,11 @@ int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, size_t esize, const vo
   return QG_OK;
 }
 
-template <int CG, bool B_MN, int OUT>
+template <int CG, bool B_MN, int OUT, bool SIDE = false>
 int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo, GemmParams p,
            int num_sms, cudaStream_t st) {
-  using C = Cfg<CG, B_MN>;
-  auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT>;
+  using C = Cfg<CG, B_MN, SIDE>;
+  auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT, SIDE>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     QG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -478,6 +552,17 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
 template <int CG, bool B_MN>
 int launch_out(int out_kind, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo,
                const GemmParams &p, int num_sms, cudaStream_t st) {
+  if (p.Xo != nullptr) {  // outlier side product: prepared (K-major) weights, floating-point output
+    if constexpr (!B_MN) {
+      switch (out_kind) {
+        case QG_F32: return launch<CG, false, QG_F32, true>(ma, mb, mbh, mo, p, num_sms, st);
+        case QG_F16: return launch<CG, false, QG_F16, true>(ma, mb, mbh, mo, p, num_sms, st);
+        case QG_BF16: return launch<CG, false, QG_BF16, true>(ma, mb, mbh, mo, p, num_sms, st);
+      }
+    }
+    set_error("gemm_i8_tc: the side product needs prepared weights and an f32/f16/bf16 output");
+    return QG_ENOTSUP;
+  }
   switch (out_kind) {
     case QG_S32: return launch<CG, B_MN, QG_S32>(ma, mb, mbh, mo, p, num_sms, st);
     case QG_F32: return launch<CG, B_MN, QG_F32>(ma, mb, mbh, mo, p, num_sms, st);
@@ -506,7 +591,7 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 // out_kind QG_S32 writes raw accumulators; otherwise the dequantize epilogue runs.
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               int num_sms, cudaStream_t st) {
+               const SideArgs *side, int num_sms, cudaStream_t st) {
   if (!gemm_i8_tc_supported(A, lda, B, ldb)) {
     set_error("gemm_i8_tc: operands must be 16-byte aligned with leading dimensions multiple of 16");
     return QG_EINVAL;
@@ -520,6 +605,15 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   p.tma_store = (aligned16(O) && (ldo * osz) % 16 == 0) ? 1 : 0;
   if (getenv("QG_DBG_NO_TMA_STORE") != nullptr) p.tma_store = 0;
   p.stats = g_stats;
+  if (side != nullptr && side->no_pad > 0) {
+    if (side->no_pad > kSideMax || side->no_pad % 8 != 0 || (side->ldxo % 8) != 0 ||
+        (reinterpret_cast<uintptr_t>(side->Xo) & 15) != 0) {
+      set_error("gemm_i8_tc: side product takes at most %d outlier columns (padded to 8), 16-byte aligned Xo", kSideMax);
+      return QG_ENOTSUP;
+    }
+    p.Xo = side->Xo; p.ldxo = side->ldxo; p.Wo = side->Wo; p.ldwo = side->ldwo;
+    p.no_pad = side->no_pad; p.side_bf16 = side->side_bf16;
+  }
   p.b_kstep = UK * 128; p.b_lbo = BK * 128; p.b_sbo = 1024;
   if (const char *e = getenv("QG_DBG_B_KSTEP")) p.b_kstep = (uint32_t)atoi(e);
   if (const char *e = getenv("QG_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);

@@ -22,7 +22,7 @@ template <bool kDequant, typename OutT>
 __global__ void __launch_bounds__(256)
 gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__restrict__ B, int64_t sb_k, int64_t sb_n,
                     int M, int N, int K, void *__restrict__ O, int64_t ldo, const float *__restrict__ Cx,
-                    const float *__restrict__ Cw, const float *__restrict__ bias, float c) {
+                    const float *__restrict__ Cw, const float *__restrict__ bias, float c, SideArgs side) {
   __shared__ int8_t sA[TM][TK + 4];
   __shared__ int8_t sB[TK][TN + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -68,6 +68,21 @@ gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__r
       if (col >= N) continue;
       if (kDequant) {
         float v = dequant_ref(acc[i][j], Cx[r], Cw[col], c);
+        if (side.no_pad > 0) {  // outlier side product, o ascending fp32 fma chain
+          float sd = 0.0f;
+          for (int o = 0; o < side.no_pad; o++) {
+            float xo, wo;
+            if (side.side_bf16) {
+              xo = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(side.Xo)[(int64_t)r * side.ldxo + o]);
+              wo = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(side.Wo)[(int64_t)o * side.ldwo + col]);
+            } else {
+              xo = __half2float(reinterpret_cast<const __half *>(side.Xo)[(int64_t)r * side.ldxo + o]);
+              wo = __half2float(reinterpret_cast<const __half *>(side.Wo)[(int64_t)o * side.ldwo + col]);
+            }
+            sd = __fmaf_rn(xo, wo, sd);
+          }
+          v = __fadd_rn(v, sd);
+        }
         if (bias != nullptr) v = __fadd_rn(v, bias[col]);
         store_out<OutT>(O, ldo, r, col, v);
       } else {
@@ -153,21 +168,24 @@ dequantize_kernel(const int32_t *__restrict__ acc, int64_t ldacc, const float *_
 
 // b_kmajor == 0: B is [K,N] with leading dimension ldb; 1: B is [N,K]
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
-                 int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c, cudaStream_t st) {
+                 int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c,
+                 const SideArgs *side_in, cudaStream_t st) {
   const int64_t sb_k = b_kmajor ? 1 : ldb, sb_n = b_kmajor ? ldb : 1;
+  SideArgs side = {};
+  if (side_in != nullptr) side = *side_in;
   dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
   switch (out_dtype) {
     case QG_S32:
-      launch_kernel(gemm_s8_simt_kernel<false, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<false, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
       break;
     case QG_F32:
-      launch_kernel(gemm_s8_simt_kernel<true, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
       break;
     case QG_F16:
-      launch_kernel(gemm_s8_simt_kernel<true, __half>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, __half>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
       break;
     case QG_BF16:
-      launch_kernel(gemm_s8_simt_kernel<true, __nv_bfloat16>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c);
+      launch_kernel(gemm_s8_simt_kernel<true, __nv_bfloat16>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
       break;
     default:
       return QG_EINVAL;

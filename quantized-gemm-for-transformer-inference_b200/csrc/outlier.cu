@@ -1,0 +1,416 @@
+// outlier.cu -- LLM.int8()-style mixed decomposition: the pieces around the GEMM.
+//
+// The reference only has the elementwise mask primitive (op_outlier_extractor,
+// src/ops/op_elemwise.cuh:292-306,698-708), never called and never reduced: detection of outlier
+// feature columns, the split and the 16-bit side product are new here (specification in DESIGN.md,
+// CPU restatement in oracle.quantized_mm_outlier; parity unpinned).
+//
+//   outlier columns  O = { k : some |X[i,k]| > thr }   (strict; NaN counts, like the reference functor)
+//   int8 path        X with the columns in O zeroed, row scales from the remaining entries
+//   side product     fp16(X[:,O]) @ fp16(W[O,:]) accumulated in fp32 inside the GEMM epilogue
+//
+// Kernels: column detection (HBM-bound, one read of X), index compaction, bit-mask construction
+// from a given index list, the masking row quantizer (also gathers X[:,O]), and the W[O,:] gather.
+#include "quant_common.cuh"
+
+namespace qg {
+
+namespace {
+
+// ---- detection: mask bit k set <=> column k holds an outlier --------------------------------
+// 32 x 8 threads; a thread owns one 16-byte vector of columns and walks rows with stride 8.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+outlier_detect_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float thr, int rows_per_cta,
+                      uint32_t *__restrict__ mask) {
+  constexpr int EPV = Unpack<T>::EPV;
+  __shared__ uint32_t s_bits[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * EPV;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  griddep_wait();
+  uint32_t bits = 0;
+  if (col < K) {
+    const T *base = X + col;
+    auto scan = [&](const uint4 &v) {
+      float f[EPV];
+      Unpack<T>::run(v, f);
+#pragma unroll
+      for (int e = 0; e < EPV; e++) {
+        const float a = f[e];  // AbsCompareLTEConstFunc: inlier iff (a>=0 & a<=thr) | (a<=0 & -a<=thr)
+        const bool inl = ((a >= 0) & (a <= thr)) | ((a <= 0) & (-a <= thr));
+        bits |= (inl ? 0u : 1u) << e;
+      }
+    };
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = ldg16(base + (int64_t)(r + 8 * u) * ldx);
+#pragma unroll
+      for (int u = 0; u < 4; u++) scan(v[u]);
+    }
+    for (; r < r1; r += 8) scan(ldg16(base + (int64_t)r * ldx));
+  }
+  s_bits[ty][tx] = bits;
+  __syncthreads();
+  if (ty == 0 && col < K) {
+#pragma unroll
+    for (int y = 1; y < 8; y++) bits |= s_bits[y][tx];
+    if (bits) atomicOr(mask + (col >> 5), bits << (col & 31));
+  }
+}
+
+template <typename T>
+__global__ void outlier_detect_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float thr,
+                                              uint32_t *__restrict__ mask) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
+  if (k >= K) return;
+  bool out = false;
+  for (int i = 0; i < M; i++) {
+    const float a = to_f32(X[(int64_t)i * ldx + k]);
+    out |= !(((a >= 0) & (a <= thr)) | ((a <= 0) & (-a <= thr)));
+  }
+  if (out) atomicOr(mask + (k >> 5), 1u << (k & 31));
+}
+
+// ---- block-wide exclusive prefix of per-word popcounts (single block of 1024 threads) -------
+// wbase[w] = number of set bits in mask words < w; returns the total in every thread.
+__device__ int mask_prefix(const uint32_t *mask, int words, int *wbase) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int w0 = 0; w0 < words; w0 += 1024) {
+    const int w = w0 + threadIdx.x;
+    const int cnt = w < words ? __popc(mask[w]) : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if ((threadIdx.x & 31) >= off) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int v = s_warp[threadIdx.x];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, off);
+        if (threadIdx.x >= off) v += t;
+      }
+      s_warp[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int before = carry + (threadIdx.x >= 32 ? s_warp[(threadIdx.x >> 5) - 1] : 0) + incl - cnt;
+    if (w < words) wbase[w] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = before + cnt;
+    __syncthreads();
+  }
+  return s_carry;
+}
+
+// mask -> ascending index list (first max_idx entries), total count, per-word prefix
+__global__ void __launch_bounds__(1024)
+outlier_index_kernel(const uint32_t *__restrict__ mask, int K, int *__restrict__ idx, int max_idx,
+                     int *__restrict__ count, int *__restrict__ wbase) {
+  griddep_wait();
+  const int words = (K + 31) / 32;
+  const int total = mask_prefix(mask, words, wbase);
+  for (int w = threadIdx.x; w < words; w += 1024) {
+    uint32_t m = mask[w];
+    int pos = wbase[w];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (pos < max_idx && idx != nullptr) idx[pos] = w * 32 + b;
+      pos++;
+    }
+  }
+  if (threadIdx.x == 0 && count != nullptr) *count = total;
+}
+
+// given ascending indices -> bit mask + per-word prefix
+__global__ void __launch_bounds__(1024)
+outlier_mask_from_idx_kernel(const int *__restrict__ idx, int n_idx, int K, uint32_t *__restrict__ mask,
+                             int *__restrict__ wbase) {
+  griddep_wait();
+  const int words = (K + 31) / 32;
+  for (int w = threadIdx.x; w < words; w += 1024) mask[w] = 0;
+  __syncthreads();
+  for (int o = threadIdx.x; o < n_idx; o += 1024) {
+    const int k = idx[o];
+    if (k >= 0 && k < K) atomicOr(mask + (k >> 5), 1u << (k & 31));
+  }
+  __syncthreads();
+  mask_prefix(mask, words, wbase);
+}
+
+// ---- masking row quantizer --------------------------------------------------------------------
+struct RowOutlier {
+  const uint32_t *mask;  // K bits
+  const int *wbase;      // prefix popcount per mask word
+  void *Xo;              // [M, ldxo] 16-bit side operand, columns = rank of k inside O (pre-zeroed)
+  int64_t ldxo;
+  int side_bf16;         // 0: fp16, 1: bf16
+};
+
+// Removes the outlier elements of one 16-byte vector (vector index vi of `row`) from the int8 path
+// (sets them to +0) and, when `write`, stores them into the side operand.
+template <typename T>
+__device__ __forceinline__ void strip_outliers(uint4 &r, int vi, int row, const RowOutlier &ro, bool write) {
+  constexpr int EPV = Unpack<T>::EPV;
+  const int c0 = vi * EPV, b0 = c0 & 31;
+  const uint32_t word = __ldg(ro.mask + (c0 >> 5));
+  uint32_t bits = (word >> b0) & ((1u << EPV) - 1u);
+  if (bits == 0) return;
+  float f[EPV];
+  Unpack<T>::run(r, f);
+  int pos = __ldg(ro.wbase + (c0 >> 5)) + __popc(word & ((1u << b0) - 1u));
+  uint32_t *w = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+  for (int e = 0; e < EPV; e++) {
+    if ((bits >> e) & 1u) {
+      if (write) {
+        if (ro.side_bf16) reinterpret_cast<__nv_bfloat16 *>(ro.Xo)[(int64_t)row * ro.ldxo + pos] = __float2bfloat16_rn(f[e]);
+        else reinterpret_cast<__half *>(ro.Xo)[(int64_t)row * ro.ldxo + pos] = __float2half_rn(f[e]);
+      }
+      pos++;
+      if (sizeof(T) == 4) w[e] = 0u;
+      else w[e >> 1] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+    }
+  }
+}
+
+// One CTA per row (persistent loop); NV 16-byte vectors per thread cached in registers (NV == 0:
+// row too long, second pass re-reads it).  Same arithmetic as quant_rows_kernel on the zeroed row.
+template <typename T, int NV>
+__global__ void __launch_bounds__(kThreads)
+quant_rows_outlier_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
+                          int8_t *__restrict__ Xq, int64_t ldq, float *__restrict__ Cx, RowOutlier ro) {
+  constexpr int EPV = Unpack<T>::EPV;
+  constexpr int NVC = NV > 0 ? NV : 1;
+  __shared__ float s_m[2][kThreads / 32];
+  __shared__ float s_x0[2];
+  const int g = threadIdx.x;
+  const int nvec = K / EPV;
+  griddep_wait();
+  int it = 0;
+  for (int row = blockIdx.x; row < M; row += gridDim.x, it++) {
+    const T *xr = X + (int64_t)row * ldx;
+    uint4 raw[NVC];
+    float m = -INFINITY, x0 = 0.0f;
+    auto fold_vec = [&](const uint4 &r, int idx) {
+      float f[EPV];
+      Unpack<T>::run(r, f);
+      if (idx == 0) x0 = f[0];
+#pragma unroll
+      for (int e = 0; e < EPV; e++)
+        if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
+    };
+    if (NV > 0) {
+#pragma unroll
+      for (int v = 0; v < NVC; v++) {
+        const int idx = v * kThreads + g;
+        raw[v] = idx < nvec ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int v = 0; v < NVC; v++) {
+        const int idx = v * kThreads + g;
+        if (idx < nvec) {
+          strip_outliers<T>(raw[v], idx, row, ro, true);
+          fold_vec(raw[v], idx);
+        }
+      }
+    } else {
+      for (int idx = g; idx < nvec; idx += kThreads) {
+        uint4 r = ldg16(xr + (int64_t)idx * EPV);
+        strip_outliers<T>(r, idx, row, ro, true);
+        fold_vec(r, idx);
+      }
+    }
+    m = warp_max(m);
+    float *sm = s_m[it & 1];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    if (g == 0) s_x0[it & 1] = x0;
+    __syncthreads();
+    m = sm[0];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; w++) m = fmaxf(m, sm[w]);
+    x0 = s_x0[it & 1];
+    float c;
+    if (fold_first(x0, m, mode, c)) {
+      for (int j = 1; j < K; j++) {  // +-0 tie-break on the zeroed row: outlier columns read as +0
+        const bool outl = (__ldg(ro.mask + (j >> 5)) >> (j & 31)) & 1u;
+        const float xj = outl ? 0.0f : to_f32(xr[j]);
+        if (xj == xj) { c = -xj; break; }
+      }
+    }
+    if (g == 0 && Cx != nullptr) Cx[row] = c;
+    const float scale = __fdiv_rn(range, c);
+    int8_t *qr = Xq + (int64_t)row * ldq;
+    auto emit = [&](const uint4 &r, int idx) {
+      float f[EPV];
+      Unpack<T>::run(r, f);
+      uint32_t w[EPV / 4];
+#pragma unroll
+      for (int q = 0; q < EPV / 4; q++)
+        w[q] = quant_code_u8(f[4 * q], scale) | (quant_code_u8(f[4 * q + 1], scale) << 8) |
+               (quant_code_u8(f[4 * q + 2], scale) << 16) | (quant_code_u8(f[4 * q + 3], scale) << 24);
+      if (EPV == 4) *reinterpret_cast<uint32_t *>(qr + (int64_t)idx * 4) = w[0];
+      else *reinterpret_cast<uint2 *>(qr + (int64_t)idx * 8) = make_uint2(w[0], w[EPV / 4 - 1]);
+    };
+    if (NV > 0) {
+#pragma unroll
+      for (int v = 0; v < NVC; v++) {
+        const int idx = v * kThreads + g;
+        if (idx < nvec) emit(raw[v], idx);
+      }
+    } else {
+      for (int idx = g; idx < nvec; idx += kThreads) {
+        uint4 r = ldg16(xr + (int64_t)idx * EPV);
+        strip_outliers<T>(r, idx, row, ro, false);
+        emit(r, idx);
+      }
+    }
+  }
+}
+
+// generic shapes: one warp per row, scalar accesses
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+quant_rows_outlier_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
+                                  int8_t *__restrict__ Xq, int64_t ldq, float *__restrict__ Cx, RowOutlier ro) {
+  const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  griddep_wait();
+  if (row >= M) return;
+  const T *xr = X + (int64_t)row * ldx;
+  auto is_out = [&](int j) { return ((__ldg(ro.mask + (j >> 5)) >> (j & 31)) & 1u) != 0; };
+  auto pos_of = [&](int j) { return __ldg(ro.wbase + (j >> 5)) + __popc(__ldg(ro.mask + (j >> 5)) & ((1u << (j & 31)) - 1u)); };
+  float m = -INFINITY;
+  for (int j = lane; j < K; j += 32) {
+    const float x = to_f32(xr[j]);
+    if (is_out(j)) {
+      if (ro.side_bf16) reinterpret_cast<__nv_bfloat16 *>(ro.Xo)[(int64_t)row * ro.ldxo + pos_of(j)] = __float2bfloat16_rn(x);
+      else reinterpret_cast<__half *>(ro.Xo)[(int64_t)row * ro.ldxo + pos_of(j)] = __float2half_rn(x);
+    } else if (j > 0) {
+      m = fmaxf(m, fabsf(x));
+    }
+    if (is_out(j) && j > 0) m = fmaxf(m, 0.0f);
+  }
+  m = warp_max(m);
+  const float x0 = is_out(0) ? 0.0f : to_f32(xr[0]);
+  float c;
+  if (fold_first(x0, m, mode, c)) {
+    for (int j = 1; j < K; j++) {
+      const float xj = is_out(j) ? 0.0f : to_f32(xr[j]);
+      if (xj == xj) { c = -xj; break; }
+    }
+  }
+  if (lane == 0 && Cx != nullptr) Cx[row] = c;
+  const float scale = __fdiv_rn(range, c);
+  for (int j = lane; j < K; j += 32)
+    Xq[(int64_t)row * ldq + j] = (int8_t)quant_code_u8(is_out(j) ? 0.0f : to_f32(xr[j]), scale);
+}
+
+// Wo[o][j] = 16-bit(W[idx[o], j]), zero rows for o >= n_idx
+template <typename T>
+__global__ void gather_wo_kernel(const T *__restrict__ W, int64_t ldw, const int *__restrict__ idx, int n_idx, int N,
+                                 void *__restrict__ Wo, int64_t ldwo, int side_bf16) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y;
+  griddep_wait();
+  if (j >= N) return;
+  const float v = o < n_idx ? to_f32(W[(int64_t)idx[o] * ldw + j]) : 0.0f;
+  if (side_bf16) reinterpret_cast<__nv_bfloat16 *>(Wo)[(int64_t)o * ldwo + j] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half *>(Wo)[(int64_t)o * ldwo + j] = __float2half_rn(v);
+}
+
+inline bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template <typename T>
+int detect_t(const T *X, int M, int K, int64_t ldx, float thr, uint32_t *mask, cudaStream_t st) {
+  constexpr int EPV = Unpack<T>::EPV;
+  cudaError_t e = cudaMemsetAsync(mask, 0, sizeof(uint32_t) * (size_t)ceil_div(K, 32), st);
+  if (e != cudaSuccess) return (int)e;
+  if (K % EPV == 0 && aligned_to(X, 16) && (ldx * sizeof(T)) % 16 == 0) {
+    const int col_tiles = (int)ceil_div(K, 32 * EPV);
+    int64_t want = ceil_div((int64_t)148 * 16, col_tiles);
+    const int rpc = (int)round_up(ceil_div(M, want > 0 ? want : 1) < 32 ? 32 : ceil_div(M, want > 0 ? want : 1), 32);
+    return (int)launch_kernel(outlier_detect_kernel<T>, dim3(col_tiles, (unsigned)ceil_div(M, rpc)), dim3(kThreads), st, X, M, K,
+                              ldx, thr, rpc, mask);
+  }
+  return (int)launch_kernel(outlier_detect_generic_kernel<T>, dim3((unsigned)ceil_div(K, 256)), dim3(256), st, X, M, K, ldx,
+                            thr, mask);
+}
+
+template <typename T>
+int rows_outlier_t(const T *X, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq, int64_t ldq, float *Cx,
+                   const RowOutlier &ro, cudaStream_t st) {
+  constexpr int EPV = Unpack<T>::EPV;
+  const bool vec_ok = (K % EPV == 0) && aligned_to(X, 16) && ((ldx * sizeof(T)) % 16 == 0) && aligned_to(Xq, EPV) &&
+                      ldq % EPV == 0;
+  if (!vec_ok)
+    return (int)launch_kernel(quant_rows_outlier_generic_kernel<T>, dim3((unsigned)ceil_div(M, kThreads / 32)), dim3(kThreads),
+                              st, X, M, K, ldx, range, mode, Xq, ldq, Cx, ro);
+  const int nvec = K / EPV;
+  const unsigned grid = (unsigned)(M < 148 * 6 ? M : 148 * 6);
+  if (nvec <= 2 * kThreads)
+    return (int)launch_kernel(quant_rows_outlier_kernel<T, 2>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, Xq,
+                              ldq, Cx, ro);
+  if (nvec <= 8 * kThreads)
+    return (int)launch_kernel(quant_rows_outlier_kernel<T, 8>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, Xq,
+                              ldq, Cx, ro);
+  return (int)launch_kernel(quant_rows_outlier_kernel<T, 0>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, Xq, ldq,
+                            Cx, ro);
+}
+
+}  // namespace
+
+// ---- entry points used by capi.cu ----
+int outlier_detect(const void *X, int dtype, int M, int K, int64_t ldx, float thr, uint32_t *mask, cudaStream_t st) {
+  switch (dtype) {
+    case QG_F32: return detect_t((const float *)X, M, K, ldx, thr, mask, st);
+    case QG_F16: return detect_t((const __half *)X, M, K, ldx, thr, mask, st);
+    case QG_BF16: return detect_t((const __nv_bfloat16 *)X, M, K, ldx, thr, mask, st);
+  }
+  return QG_EINVAL;
+}
+
+int outlier_index(const uint32_t *mask, int K, int *idx, int max_idx, int *count, int *wbase, cudaStream_t st) {
+  return (int)launch_kernel(outlier_index_kernel, dim3(1), dim3(1024), st, mask, K, idx, max_idx, count, wbase);
+}
+
+int outlier_mask_from_idx(const int *idx, int n_idx, int K, uint32_t *mask, int *wbase, cudaStream_t st) {
+  return (int)launch_kernel(outlier_mask_from_idx_kernel, dim3(1), dim3(1024), st, idx, n_idx, K, mask, wbase);
+}
+
+int quant_rows_outlier(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq, int64_t ldq,
+                       float *Cx, const uint32_t *mask, const int *wbase, void *Xo, int64_t ldxo, int side_bf16,
+                       cudaStream_t st) {
+  RowOutlier ro = {mask, wbase, Xo, ldxo, side_bf16};
+  switch (dtype) {
+    case QG_F32: return rows_outlier_t((const float *)X, M, K, ldx, range, mode, Xq, ldq, Cx, ro, st);
+    case QG_F16: return rows_outlier_t((const __half *)X, M, K, ldx, range, mode, Xq, ldq, Cx, ro, st);
+    case QG_BF16: return rows_outlier_t((const __nv_bfloat16 *)X, M, K, ldx, range, mode, Xq, ldq, Cx, ro, st);
+  }
+  return QG_EINVAL;
+}
+
+int gather_wo(const void *W, int dtype, int64_t ldw, const int *idx, int n_idx, int no_pad, int N, void *Wo, int64_t ldwo,
+              int side_bf16, cudaStream_t st) {
+  if (no_pad <= 0) return 0;
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)no_pad);
+  switch (dtype) {
+    case QG_F32: return (int)launch_kernel(gather_wo_kernel<float>, grid, dim3(256), st, (const float *)W, ldw, idx, n_idx, N, Wo, ldwo, side_bf16);
+    case QG_F16: return (int)launch_kernel(gather_wo_kernel<__half>, grid, dim3(256), st, (const __half *)W, ldw, idx, n_idx, N, Wo, ldwo, side_bf16);
+    case QG_BF16: return (int)launch_kernel(gather_wo_kernel<__nv_bfloat16>, grid, dim3(256), st, (const __nv_bfloat16 *)W, ldw, idx, n_idx, N, Wo, ldwo, side_bf16);
+  }
+  return QG_EINVAL;
+}
+
+}  // namespace qg

@@ -7,73 +7,13 @@
 // with HBM-bound kernels that read the matrix with 16-byte loads, reduce with warp shuffles and
 // write packed int8 codes plus the fp32 absmax.  The arithmetic (and its quirks: signed first
 // element, IEEE 127/x, truncate-and-wrap cast) is reproduced exactly; see oracle/qoracle.c.
-#include <cooperative_groups.h>
-
 #include <cstdlib>
 
-#include "common.cuh"
+#include "quant_common.cuh"
 
 namespace qg {
 
 namespace {
-
-constexpr int kThreads = 256;
-
-__device__ __forceinline__ uint4 ldg16(const void *p) {
-  return __ldg(reinterpret_cast<const uint4 *>(p));
-}
-
-// unpack one 16-byte vector into fp32 lanes
-template <typename T> struct Unpack;
-template <> struct Unpack<float> {
-  static constexpr int EPV = 4;
-  __device__ static __forceinline__ void run(const uint4 &r, float (&f)[4]) {
-    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
-    f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
-  }
-};
-template <> struct Unpack<__half> {
-  static constexpr int EPV = 8;
-  __device__ static __forceinline__ void run(const uint4 &r, float (&f)[8]) {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      float2 p = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
-      f[2 * i] = p.x; f[2 * i + 1] = p.y;
-    }
-  }
-};
-template <> struct Unpack<__nv_bfloat16> {
-  static constexpr int EPV = 8;
-  __device__ static __forceinline__ void run(const uint4 &r, float (&f)[8]) {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {  // bf16 -> fp32 is a 16-bit shift
-      f[2 * i] = __uint_as_float(w[i] << 16);
-      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-  }
-};
-
-// Fold the signed first element x0 with m = max_{j>=1, x_j not NaN} |x_j| (m = -inf when there is
-// no such j) the way AbsMaxFunc does (src/ops/op_reduction.cuh:7-25,80-83): strict '>' updates.
-// Returns true when the +-0 tie-break path is needed (all later entries are zeros, x0 < 0): the
-// reference then ends with -x_j of the first non-NaN j >= 1, whose zero sign the caller must fetch.
-__device__ __forceinline__ bool fold_first(float x0, float m, int mode, float &c) {
-  if (mode == QG_MODE_TRUE_ABSMAX) {
-    const float a0 = fabsf(x0);
-    c = (x0 != x0) ? x0 : ((m > a0) ? m : a0);
-    return false;
-  }
-  c = (x0 != x0) ? x0 : ((m > x0) ? m : x0);
-  return (m == 0.0f) && (x0 < 0.0f);
-}
-
-__device__ __forceinline__ float warp_max(float m) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  return m;
-}
 
 // ------------------------------------------------------------------------------------------
 // Rows (activations): G threads cooperate on one row, NV 16-byte vectors per thread kept in
@@ -373,168 +313,194 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
 }
 
 // ------------------------------------------------------------------------------------------
-// Columns, ONE kernel and (for strips that stay in L2) one HBM read of W: a thread-block cluster
-// owns a strip of 512 bytes of columns (128 fp32 / 256 half) over all K rows, rank r handling rows
-// [r*rpc, (r+1)*rpc).  Phase 1 streams the strip and reduces |w| per column; the per-CTA maxima
-// are combined across the cluster through distributed shared memory; phase 2 re-reads the strip
-// (a few MB, read microseconds earlier by the same cluster: L2 hits) and writes the codes.
+// Columns, ONE launch and one HBM read of W: "decoupled" two-phase kernel.
+// W is cut into column panels (kPanelTiles tiles of 512 bytes of columns; 16 MB of fp32 at
+// K = 4096).  The block list interleaves the phases of neighbouring panels,
+//     P1(0) P1(1) P2(0) P1(2) P2(1) ... P2(last)
+// P1 blocks reduce |w| of a [32 rows x 512 B] patch into part[col] (atomicMax on fp32 bit
+// patterns) and then bump the panel's arrival counter; P2 blocks wait for that counter (they only
+// ever wait for blocks with a SMALLER block index, which the hardware dispatches first, so the wait
+// cannot deadlock), fold in the signed row 0, and re-read their patch -- fetched from HBM two
+// groups earlier, now an L2 hit -- to emit the codes.  The last P2 block of a panel resets part[]
+// and the counters, so the persistent scratch is clean for the next call.
 // kTranspose: codes go out as Wt[n][k] (K contiguous), the K-major operand layout the tensor-core
-// GEMM runs fastest on -- staged through a swizzled smem tile so the stores are 128-byte rows.
-// (A first design kept the strip in registers: one read, but the 128-byte strip rows it could
-// afford used HBM badly -- 29 us vs 26 us for two passes at 4096^2 -- and it was dropped.)
+// GEMM runs fastest on, staged through a word-swizzled smem tile so stores are 32-byte sectors
+// (neighbouring row chunks, which run concurrently, complete the 128-byte lines in L2).
+// (Two earlier designs were measured and dropped: a thread-block-cluster kernel that kept a
+// 128-byte-wide strip in registers -- one read, but narrow rows use HBM badly, 29 us at 4096^2 --
+// and a cluster kernel re-reading a 512-byte strip through L2 with a DSMEM max exchange -- too
+// few CTAs in flight, 34-40 us.  A first cut of this kernel with 128-row patches (16 loads and
+// ~110 registers per thread, 2 CTAs per SM) read W from HBM once, as intended, but was latency
+// bound at 35 us; 32-row patches trade that for 6+ CTAs per SM.  Three separate launches: 26 us.)
 // ------------------------------------------------------------------------------------------
+constexpr int kPanelTiles = 8;
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct ColqScratch {
+  float *part;    // [N] running maxima, -inf when idle
+  int *arrived;   // [panels] P1 blocks done
+  int *finished;  // [panels] P2 blocks done
+};
+
+constexpr int kPatchRows = 32;  // rows per block: one row quad (4 rows) per warp
+
 template <typename T, bool kTranspose>
 __global__ void __launch_bounds__(kThreads)
-quant_cols_cluster_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int rpc,
-                          int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
-  namespace cg = cooperative_groups;
+quant_cols_decoupled_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int panels,
+                            int chunks, int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw, ColqScratch sc) {
   constexpr int EPV = Unpack<T>::EPV;
-  constexpr int SC = 32 * EPV;  // columns per strip
-  __shared__ float s_red[kThreads / 32][SC];
-  __shared__ float s_cmax[SC];   // this CTA's maxima over its rows (rows >= 1 only)
-  __shared__ float s_x0[SC];     // row 0 of the strip (meaningful in cluster rank 0)
-  __shared__ float s_final[SC];  // Cw of the strip
-  __shared__ uint32_t s_tile[kTranspose ? SC * 32 : 1];  // [column][32 words = 128 k-bytes], word-swizzled
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
-  const int strip = blockIdx.x / cs;
+  constexpr int SC = 32 * EPV;  // columns per tile (512 bytes of input per row)
+  // phase 1: [8 warps][SC] partial maxima; phase 2 (transposed): [SC columns][8 words of 4 k-bytes]
+  __shared__ uint32_t s_buf[(kThreads / 32) * SC];
+  __shared__ int s_last;
+  const int G = kPanelTiles * chunks;  // blocks per phase group
+  const int g = blockIdx.x / G, r = blockIdx.x % G;
+  int panel, phase;
+  if (g == 0) { phase = 1; panel = 0; }
+  else if (g == 2 * panels - 1) { phase = 2; panel = panels - 1; }
+  else if (g & 1) { phase = 1; panel = (g + 1) / 2; }
+  else { phase = 2; panel = g / 2 - 1; }
+  const int chunk = r / kPanelTiles, tile = panel * kPanelTiles + r % kPanelTiles;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = strip * SC + lane * EPV;
-  const int r0 = (int)rank * rpc;
-  const int r1 = min(K, r0 + rpc);
+  const int col = tile * SC + lane * EPV;
   const bool col_ok = col < N;
+  const int rb = chunk * kPatchRows, r1 = min(K, rb + kPatchRows);
+  const int row0 = rb + 4 * warp;  // this warp's row quad
   const T *base = W + col;
 
   griddep_wait();
-  // ---------------- phase 1: column maxima of this CTA's rows ----------------
-  float m[EPV];
+  uint4 v[4];
 #pragma unroll
-  for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
-  if (col_ok) {
-    int r = r0 + warp;
-    if (r0 == 0 && warp == 0 && r < r1) {  // row 0 is folded in signed, not by magnitude
-      float f[EPV];
-      Unpack<T>::run(ldg16(base), f);
+  for (int i = 0; i < 4; i++)
+    v[i] = (col_ok && row0 + i < r1) ? ldg16(base + (int64_t)(row0 + i) * ldw) : make_uint4(0, 0, 0, 0);
+
+  if (phase == 1) {
+    float m[EPV];
 #pragma unroll
-      for (int e = 0; e < EPV; e++) s_x0[lane * EPV + e] = f[e];
-      r += 8;
-    }
-    for (; r + 56 < r1; r += 64) {  // 8 independent 16-byte loads in flight per thread
-      uint4 v[8];
+    for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = ldg16(base + (int64_t)(r + 8 * u) * ldw);
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
+    for (int i = 0; i < 4; i++) {
+      const int row = row0 + i;
+      if (col_ok && row < r1 && row > 0) {  // row 0 is folded in signed, in phase 2
         float f[EPV];
-        Unpack<T>::run(v[u], f);
+        Unpack<T>::run(v[i], f);
 #pragma unroll
         for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
       }
     }
-    for (; r < r1; r += 8) {
-      float f[EPV];
-      Unpack<T>::run(ldg16(base + (int64_t)r * ldw), f);
+    float *s_red = reinterpret_cast<float *>(s_buf);
 #pragma unroll
-      for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
+    for (int e = 0; e < EPV; e++) s_red[warp * SC + lane * EPV + e] = m[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < SC; c += kThreads) {
+      float mm = s_red[c];
+#pragma unroll
+      for (int w = 1; w < kThreads / 32; w++) mm = fmaxf(mm, s_red[w * SC + c]);
+      const int gc = tile * SC + c;
+      if (gc < N && mm >= 0.0f) atomicMax(reinterpret_cast<int *>(sc.part) + gc, __float_as_int(mm));
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(sc.arrived + panel, 1);
+    return;
+  }
+
+  // ---------------- phase 2 ----------------
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(sc.arrived + panel) < G) {
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000LL) {
+        printf("[qgemm] column quantizer: panel %d never completed phase 1\n", panel);
+        __trap();
+      }
     }
   }
-#pragma unroll
-  for (int e = 0; e < EPV; e++) s_red[warp][lane * EPV + e] = m[e];
   __syncthreads();
-  for (int c = threadIdx.x; c < SC; c += kThreads) {
-    float r = s_red[0][c];
+  float s[EPV];
+  if (col_ok) {
+    float x0[EPV];
+    Unpack<T>::run(ldg16(base), x0);
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; w++) r = fmaxf(r, s_red[w][c]);
-    s_cmax[c] = r;
-  }
-  cluster.sync();
-  // ---------------- cluster-wide combine through DSMEM ----------------
-  for (int c = threadIdx.x; c < SC; c += kThreads) {
-    float mm = -INFINITY;
-    for (unsigned rk = 0; rk < cs; rk++) mm = fmaxf(mm, cluster.map_shared_rank(s_cmax, rk)[c]);
-    const int gc = strip * SC + c;
-    float cw = 0.0f;
-    if (gc < N) {
-      const float x0 = cluster.map_shared_rank(s_x0, 0)[c];
-      if (fold_first(x0, mm, mode, cw)) {
+    for (int e = 0; e < EPV; e++) {
+      const float mm = __ldcg(sc.part + col + e);
+      float cw;
+      if (fold_first(x0[e], mm, mode, cw)) {
         for (int k = 1; k < K; k++) {  // rare +-0 tie-break: sign of the first later non-NaN zero
-          const float x = to_f32(W[(int64_t)k * ldw + gc]);
+          const float x = to_f32(base[(int64_t)k * ldw + e]);
           if (x == x) { cw = -x; break; }
         }
       }
-      if (rank == 0 && Cw != nullptr) Cw[gc] = cw;
+      if (chunk == 0 && warp == 0 && Cw != nullptr) Cw[col + e] = cw;
+      s[e] = __fdiv_rn(range, cw);
     }
-    s_final[c] = cw;
-  }
-  cluster.sync();  // also keeps every CTA's smem alive until all remote reads are done
-  griddep_launch_dependents();
-  if (Wq == nullptr) return;
-  // ---------------- phase 2: codes (strip re-read is served by L2) ----------------
-  float s[EPV];
-#pragma unroll
-  for (int e = 0; e < EPV; e++) s[e] = __fdiv_rn(range, s_final[lane * EPV + e]);
-  if (!kTranspose) {
-    if (!col_ok) return;
-    auto emit = [&](const uint4 &v, int r) {
-      float f[EPV];
-      Unpack<T>::run(v, f);
-      uint32_t w[EPV / 4];
-#pragma unroll
-      for (int q = 0; q < EPV / 4; q++)
-        w[q] = quant_code_u8(f[4 * q], s[4 * q]) | (quant_code_u8(f[4 * q + 1], s[4 * q + 1]) << 8) |
-               (quant_code_u8(f[4 * q + 2], s[4 * q + 2]) << 16) | (quant_code_u8(f[4 * q + 3], s[4 * q + 3]) << 24);
-      int8_t *dst = Wq + (int64_t)r * ldq + col;
-      if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
-      else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
-    };
-    int r = r0 + warp;
-    for (; r + 56 < r1; r += 64) {
-      uint4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = ldg16(base + (int64_t)(r + 8 * u) * ldw);
-#pragma unroll
-      for (int u = 0; u < 8; u++) emit(v[u], r + 8 * u);
-    }
-    for (; r < r1; r += 8) emit(ldg16(base + (int64_t)r * ldw), r);
   } else {
-    // chunks of 128 rows; warp w owns row quads w, w+8, w+16, w+24 of the chunk
-    for (int rb = r0; rb < r1; rb += 128) {
-      uint4 v[4][4];
 #pragma unroll
-      for (int qi = 0; qi < 4; qi++)
+    for (int e = 0; e < EPV; e++) s[e] = 0.0f;
+  }
+  if (Wq != nullptr) {
+    float f[4][EPV];
+#pragma unroll
+    for (int i = 0; i < 4; i++) Unpack<T>::run(v[i], f[i]);
+    if (kTranspose) {
+#pragma unroll
+      for (int e = 0; e < EPV; e++) {
+        uint32_t w = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          const int r = rb + 4 * (warp + 8 * qi) + i;
-          v[qi][i] = (col_ok && r < r1) ? ldg16(base + (int64_t)r * ldw) : make_uint4(0, 0, 0, 0);
+          const uint32_t code = (row0 + i < r1) ? quant_code_u8(f[i][e], s[e]) : 0u;  // rows past K: zero padding
+          w |= code << (8 * i);
         }
-#pragma unroll
-      for (int qi = 0; qi < 4; qi++) {
-        const int rq = warp + 8 * qi;
-        float f[4][EPV];
-#pragma unroll
-        for (int i = 0; i < 4; i++) Unpack<T>::run(v[qi][i], f[i]);
-#pragma unroll
-        for (int e = 0; e < EPV; e++) {
-          uint32_t w = 0;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int r = rb + 4 * rq + i;
-            const uint32_t code = (r < r1) ? quant_code_u8(f[i][e], s[e]) : 0u;  // rows past K: zero padding
-            w |= code << (8 * i);
-          }
-          // word index rotated by the writer's lane: conflict-free here and in the read-back below
-          s_tile[(lane * EPV + e) * 32 + ((rq + lane) & 31)] = w;
-        }
+        // [8 k-words][SC columns]; a lane's EPV columns are rotated by lane / (32 / EPV) so that the
+        // 32 lanes of a warp (same e) fall into 32 different banks
+        s_buf[warp * SC + lane * EPV + ((e + lane / (32 / EPV)) & (EPV - 1))] = w;
       }
       __syncthreads();
-      for (int c = warp; c < SC; c += kThreads / 32) {  // one warp writes one 128-byte row of Wt
-        const int gc = strip * SC + c;
-        const int r = rb + 4 * lane;
-        if (gc < N && r < r1)
-          *reinterpret_cast<uint32_t *>(Wq + (int64_t)gc * ldq + r) = s_tile[c * 32 + ((lane + c / EPV) & 31)];
+      // SC columns x 32 bytes: a thread moves one 16-byte half of a column's 32-byte row of Wt
+      for (int t = threadIdx.x; t < SC * 2; t += kThreads) {
+        const int h = t / SC, c = t - h * SC;
+        const int gc = tile * SC + c;
+        const int wl = c / EPV;  // lane that wrote this column
+        const int pos = wl * EPV + (((c & (EPV - 1)) + wl / (32 / EPV)) & (EPV - 1));
+        uint32_t w4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w4[j] = s_buf[(4 * h + j) * SC + pos];
+        const int row = rb + 16 * h;
+        if (gc < N && row < r1)
+          *reinterpret_cast<uint4 *>(Wq + (int64_t)gc * ldq + row) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
-      __syncthreads();
+    } else if (col_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int row = row0 + i;
+        if (row < r1) {
+          uint32_t w[EPV / 4];
+#pragma unroll
+          for (int q = 0; q < EPV / 4; q++)
+            w[q] = quant_code_u8(f[i][4 * q], s[4 * q]) | (quant_code_u8(f[i][4 * q + 1], s[4 * q + 1]) << 8) |
+                   (quant_code_u8(f[i][4 * q + 2], s[4 * q + 2]) << 16) | (quant_code_u8(f[i][4 * q + 3], s[4 * q + 3]) << 24);
+          int8_t *dst = Wq + (int64_t)row * ldq + col;
+          if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
+          else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
+        }
+      }
     }
+  }
+  // last phase-2 block of the panel leaves the scratch clean for the next call
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(sc.finished + panel, 1) == G - 1);
+  __syncthreads();
+  if (s_last) {
+    for (int c = threadIdx.x; c < kPanelTiles * SC; c += kThreads) {
+      const int gc = panel * kPanelTiles * SC + c;
+      if (gc < N) sc.part[gc] = -INFINITY;
+    }
+    if (threadIdx.x == 0) { sc.arrived[panel] = 0; sc.finished[panel] = 0; }
   }
 }
 
@@ -591,6 +557,37 @@ __global__ void outlier_mask_kernel(const float *__restrict__ A, int M, int K, i
 }
 
 inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+__global__ void colq_scratch_init_kernel(float *part, int n, int *counters, int nc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) part[i] = -INFINITY;
+  if (i < nc) counters[i] = 0;
+}
+
+// Persistent per-device scratch of the decoupled column quantizer: clean (-inf / 0) between calls,
+// because the kernel resets what it used.  Grown (and initialised on `st`) on demand.  Calls that
+// quantize weights are therefore not re-entrant across streams of one device.
+int colq_scratch(int N, int panels, ColqScratch *out, cudaStream_t st) {
+  struct State { float *part = nullptr; int *counters = nullptr; int n = 0, panels = 0; };
+  static State state[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  State &s = state[dev & 15];
+  if (s.n < N || s.panels < panels) {
+    if (s.part) { cudaDeviceSynchronize(); cudaFree(s.part); cudaFree(s.counters); }
+    s.n = (int)round_up(N < 16384 ? 16384 : N, 4096);
+    s.panels = (int)round_up(panels < 256 ? 256 : panels, 64);
+    if (cudaMalloc(&s.part, sizeof(float) * (size_t)s.n) != cudaSuccess) { s = State(); return (int)cudaGetLastError(); }
+    if (cudaMalloc(&s.counters, sizeof(int) * 2 * (size_t)s.panels) != cudaSuccess) { s = State(); return (int)cudaGetLastError(); }
+    const int total = s.n > 2 * s.panels ? s.n : 2 * s.panels;
+    colq_scratch_init_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(s.part, s.n, s.counters, 2 * s.panels);
+    count_launch();
+  }
+  out->part = s.part;
+  out->arrived = s.counters;
+  out->finished = s.counters + s.panels;
+  return 0;
+}
 
 // ---- row launcher ----
 template <typename T, int G, int NV>
@@ -658,27 +655,20 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
     return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   }
-  // fused absmax + quantize: one cluster kernel (QG_COLS_TWO_PASS=1 keeps the three-launch path)
+  // fused absmax + quantize in one launch (QG_COLS_TWO_PASS=1 keeps the three-launch path)
   if (sw == nullptr && Wq != nullptr && (transpose || getenv("QG_COLS_TWO_PASS") == nullptr)) {
-    int cs = 1;
-    while (cs < 8 && (int64_t)K > (int64_t)cs * 512) cs *= 2;      // >= ~512 rows per CTA, at most 8 CTAs
-    const int rpc_c = (int)round_up(ceil_div(K, cs), 128);
-    const int strips = (int)ceil_div(N, 32 * EPV);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(strips * cs));
-    cfg.blockDim = dim3(kThreads);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    count_launch();
+    const int tiles = (int)ceil_div(N, 32 * EPV);
+    const int panels = (int)ceil_div(tiles, kPanelTiles);
+    const int chunks = (int)ceil_div(K, kPatchRows);
+    ColqScratch sc;
+    int rc = colq_scratch(N, panels, &sc, st);
+    if (rc) return rc;
+    const dim3 grid((unsigned)((int64_t)2 * panels * kPanelTiles * chunks));
     if (transpose)
-      return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, true>, W, K, N, ldw, range, mode, rpc_c, Wq, ldq, Cw);
-    return (int)cudaLaunchKernelEx(&cfg, quant_cols_cluster_kernel<T, false>, W, K, N, ldw, range, mode, rpc_c, Wq, ldq, Cw);
+      return (int)launch_kernel(quant_cols_decoupled_kernel<T, true>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode,
+                                panels, chunks, Wq, ldq, Cw, sc);
+    return (int)launch_kernel(quant_cols_decoupled_kernel<T, false>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode,
+                              panels, chunks, Wq, ldq, Cw, sc);
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
   const int rpc = cols_rows_per_cta(K, col_tiles);

@@ -1,0 +1,62 @@
+"""Multi-GPU test (needs >= 2 GPUs on the box; skipped otherwise): column-parallel quantized linear
+over NCCL, one process per GPU -- the gathered result must equal the single-GPU op bit for bit."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = "quantized-gemm-for-transformer-inference_b200"
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, shape, dt, ret):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        sys.path.insert(0, ROOT)
+        qg = importlib.import_module(PKG)
+        cp = importlib.import_module(PKG + ".colpar")
+        M, N, K = shape
+        tdt = {"f32": torch.float32, "f16": torch.float16}[dt]
+        g = torch.Generator().manual_seed(7)
+        X = (torch.rand((M, K), generator=g) * 2 - 1).to(tdt).cuda()
+        W = (torch.rand((K, N), generator=g) * 2 - 1).to(tdt).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        layer = cp.ColumnParallelLinear(W, b, rank, world)
+        y = layer.forward(X)
+        full = torch.empty((M, N), dtype=tdt, device="cuda")
+        qg.op_quantized_mm(X, W, full, 127.0, bias=b)
+        torch.cuda.synchronize()
+        ret[rank] = bool(torch.equal(y.view(torch.int32 if dt == "f32" else torch.int16),
+                                     full.view(torch.int32 if dt == "f32" else torch.int16)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,dt", [((512, 1024, 768), "f32"), ((300, 2000, 520), "f16")])
+def test_column_parallel_matches_single_gpu(shape, dt):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), shape, dt, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
