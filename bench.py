@@ -252,7 +252,7 @@ def run_ours(args):
     Os = [torch.empty((M, N), device=dev) for _ in range(nset)]
     gathered = torch.empty((world, M, N), device=dev) if world > 1 else None
     Xq = torch.empty((M, K), dtype=torch.int8, device=dev)
-    Wt = torch.empty((N, K), dtype=torch.int8, device=dev)  # weights are kept K-major (transposed) internally
+    Wq = torch.empty((K, N), dtype=torch.int8, device=dev)
     Cx = torch.empty(M, device=dev)
     Cw = torch.empty(N, device=dev)
 
@@ -261,10 +261,10 @@ def run_ours(args):
         # bracketed by CUDA events inside the timed region
         s = i % nset
         qg.absmax_quant_rows(Xs[s], 127.0, qg.MODE_REF_EXACT, Xq, Cx)
-        qg.prepare_weights(Ws[s], 127.0, qg.MODE_REF_EXACT, Wt, Cw)
+        qg.absmax_quant_cols(Ws[s], 127.0, qg.MODE_REF_EXACT, Wq, Cw)
         if ev is not None:
             ev[0].record()
-        qg.gemm_s8t_dequant(Xq, Wt, Cx, Cw, Os[s], 127.0)
+        qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, Os[s], 127.0)
         if ev is not None:
             ev[1].record()
         if world > 1:
@@ -319,7 +319,7 @@ def run_ours(args):
         return e0.elapsed_time(e1) / n
 
     rows_ms = stage_ms(lambda j: qg.absmax_quant_rows(Xs[j % nset], 127.0, qg.MODE_REF_EXACT, Xq, Cx))
-    cols_ms = stage_ms(lambda j: qg.prepare_weights(Ws[j % nset], 127.0, qg.MODE_REF_EXACT, Wt, Cw))
+    cols_ms = stage_ms(lambda j: qg.absmax_quant_cols(Ws[j % nset], 127.0, qg.MODE_REF_EXACT, Wq, Cw))
 
     if rank != 0:
         if world > 1:
@@ -347,6 +347,19 @@ def run_ours(args):
     else:
         e2e = {"value": None, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "host-buffer call measured at N=1 only"}
+
+    # ---- context: LinearLayer::forward with the weights prepared once (K-major int8), fp32 and fp16 I/O ----
+    cached = {}
+    if world == 1:
+        for name, tdt in (("f32", torch.float32), ("f16", torch.float16)):
+            lin = qg.LinearLayer(K, N, device=dev, dtype=tdt)
+            lin.init_uniform()
+            lin.quantize_weights()
+            xin = [x.to(tdt) for x in Xs]
+            yout = torch.empty((M, N), dtype=tdt, device=dev)
+            ms = stage_ms(lambda j: lin.forward(xin[j % nset], yout))
+            cached[name] = {"ms": ms, "tops": ops / ms / 1e9}
+            del lin, xin, yout
 
     # ---- library context: cuBLASLt int8 and fp16 GEMMs of the same shape (not on our path) ----
     lib = {}
@@ -404,6 +417,7 @@ def run_ours(args):
                            "frac": (K * N * 5 + 4 * N) / cols_ms / 1e6 / peaks["hbm_gbs"]},
             "gemm_dequant": {"ms": gemm_ms, "tops": gemm_tops},
         },
+        "linear_prepared_weights": cached,
         "library_context": lib,
         "cpu_baseline": cpu,
         "e2e": e2e,

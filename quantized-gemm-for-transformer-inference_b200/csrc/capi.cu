@@ -134,10 +134,10 @@ struct Workspace {
 static Workspace carve(void *base, int M, int N, int K) {
   Workspace w;
   w.ldxq = round_up(K, 16);  // TMA: leading dimensions are multiples of 16 bytes
-  w.ldwq = round_up(K, 16);  // weights are kept transposed, Wt [N, ldwq]: the K-major operand layout
+  w.ldwq = round_up(N, 16);  // per-call weight codes Wq [K, ldwq] (the reference's layout)
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = (size_t)round_up((int64_t)(off + n), 256); return o; };
-  const size_t oxq = take((size_t)M * w.ldxq), owq = take((size_t)N * w.ldwq);
+  const size_t oxq = take((size_t)M * w.ldxq), owq = take((size_t)K * w.ldwq);
   const size_t ocx = take(sizeof(float) * M), ocw = take(sizeof(float) * N), osc = take(sizeof(float) * N);
   char *b = reinterpret_cast<char *>(base);
   w.Xq = reinterpret_cast<int8_t *>(b + oxq);
@@ -332,9 +332,11 @@ int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ldw, int 
   cudaStream_t st = (cudaStream_t)stream;
   rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, true, st);
+  // per-call weight quantization: row-major codes (two coalesced passes) feeding the GEMM as an MN-major
+  // operand beat transposed codes + K-major GEMM here; prepared weights (qg_prepare_weights) take the latter
+  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, false, st);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 1, M, N, K, O, ldo, out_dtype, w.Cx, w.Cw, bias,
+  return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 0, M, N, K, O, ldo, out_dtype, w.Cx, w.Cw, bias,
                        1 / (range * range), st);
 }
 
@@ -498,9 +500,9 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
   Workspace w = carve(d->arena, M, N, K);
   rc = quant_rows(d->hx, QG_F32, M, K, K, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, true, st);
+  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, false, st);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  rc = gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 1, M, N, K, d->ho, N, QG_F32, w.Cx, w.Cw,
+  rc = gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 0, M, N, K, d->ho, N, QG_F32, w.Cx, w.Cw,
                      bias_host ? (const float *)d->hb : nullptr, 1 / (range * range), st);
   if (rc) return rc;
   QG_CUDA_OK(cudaMemcpyAsync(O_host, d->ho, ob, cudaMemcpyDeviceToHost, st));

@@ -185,16 +185,16 @@ quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, fl
 // scale and writes codes.  The second read of W is served largely by the 126 MB L2.
 // Thread layout: 32 x 8; a thread owns one 16-byte vector of columns and walks rows with stride 8.
 // ------------------------------------------------------------------------------------------
-__global__ void fill_f32_kernel(float *p, int n, float v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  griddep_wait();
-  if (i < n) p[i] = v;
+// part[j] = (epoch << 32) | fp32 bits of the running maximum; every call uses a fresh epoch, so stale
+// entries lose every atomicMax and nothing has to be initialised between calls
+__device__ __forceinline__ float part_value(unsigned long long v, uint32_t epoch) {
+  return (uint32_t)(v >> 32) == epoch ? __uint_as_float((uint32_t)v) : -INFINITY;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, int rows_per_cta,
-                           float *__restrict__ part) {
+                           unsigned long long *__restrict__ part, uint32_t epoch) {
   constexpr int EPV = Unpack<T>::EPV;
   __shared__ float s_m[8][32 * EPV + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -235,19 +235,20 @@ absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, i
 #pragma unroll
     for (int y = 1; y < 8; y++) r = fmaxf(r, s_m[y][c]);
     const int gc = blockIdx.x * 32 * EPV + c;
-    if (gc < N && r >= 0.0f) atomicMax(reinterpret_cast<int *>(part) + gc, __float_as_int(r));
+    if (gc < N && r >= 0.0f) atomicMax(part + gc, ((unsigned long long)epoch << 32) | __float_as_uint(r));
   }
 }
 
 // finalize only (plain op_absmax on a [K,N] matrix): Cw[j] from row 0 and part[j]
 template <typename T>
 __global__ void absmax_cols_finalize_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, int mode,
-                                            const float *__restrict__ part, float *__restrict__ Cw) {
+                                            const unsigned long long *__restrict__ part, uint32_t epoch,
+                                            float *__restrict__ Cw) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
   if (j >= N) return;
   float c;
-  if (fold_first(to_f32(W[j]), part[j], mode, c)) {
+  if (fold_first(to_f32(W[j]), part_value(part[j], epoch), mode, c)) {
     for (int k = 1; k < K; k++) {
       const float x = to_f32(W[(int64_t)k * ldw + j]);
       if (x == x) { c = -x; break; }
@@ -259,8 +260,8 @@ __global__ void absmax_cols_finalize_kernel(const T *__restrict__ W, int K, int 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
-                  int rows_per_cta, const float *__restrict__ part, const float *__restrict__ sw_in,
-                  int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
+                  int rows_per_cta, const unsigned long long *__restrict__ part, uint32_t epoch,
+                  const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
   constexpr int EPV = Unpack<T>::EPV;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * EPV;
@@ -274,7 +275,7 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
 #pragma unroll
     for (int e = 0; e < EPV; e++) {
       float c;
-      if (fold_first(x0[e], part[col + e], mode, c)) {
+      if (fold_first(x0[e], part_value(part[col + e], epoch), mode, c)) {
         for (int k = 1; k < K; k++) {
           const float x = to_f32(base[(int64_t)k * ldw + e]);
           if (x == x) { c = -x; break; }
@@ -331,7 +332,9 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
 // and a cluster kernel re-reading a 512-byte strip through L2 with a DSMEM max exchange -- too
 // few CTAs in flight, 34-40 us.  A first cut of this kernel with 128-row patches (16 loads and
 // ~110 registers per thread, 2 CTAs per SM) read W from HBM once, as intended, but was latency
-// bound at 35 us; 32-row patches trade that for 6+ CTAs per SM.  Three separate launches: 26 us.)
+// bound at 35 us, and one-shot CTAs on 32-row patches were worse still (46 us: per-CTA start-up,
+// fence and wait latencies are not amortised).  Hence persistent CTAs with a register double buffer.
+// Three separate launches: 26 us.)
 // ------------------------------------------------------------------------------------------
 constexpr int kPanelTiles = 8;
 
@@ -347,160 +350,204 @@ struct ColqScratch {
   int *finished;  // [panels] P2 blocks done
 };
 
-constexpr int kPatchRows = 32;  // rows per block: one row quad (4 rows) per warp
+constexpr int kPatchRows = 32;  // rows per work item: one row quad (4 rows) per warp
 
+// Work item i of the interleaved list -> (phase, panel, row chunk, column tile)
+struct ColqItem { int phase, panel, chunk, tile; };
+__device__ __forceinline__ ColqItem colq_decode(int i, int G, int panels) {
+  const int g = i / G, r = i - g * G;
+  ColqItem it;
+  if (g == 0) { it.phase = 1; it.panel = 0; }
+  else if (g == 2 * panels - 1) { it.phase = 2; it.panel = panels - 1; }
+  else if (g & 1) { it.phase = 1; it.panel = (g + 1) / 2; }
+  else { it.phase = 2; it.panel = g / 2 - 1; }
+  it.chunk = r / kPanelTiles;
+  it.tile = it.panel * kPanelTiles + r % kPanelTiles;
+  return it;
+}
+
+// Persistent CTAs walk the item list with stride gridDim.x, loading the next item's four row
+// vectors before working on the current one (register double buffer), so HBM/L2 latency overlaps
+// the reduction / quantization of the previous patch.  A CTA announces a panel's phase 1 once,
+// after its last phase-1 item of that panel; phase-2 items wait until `expected` CTAs have done so.
+// All CTAs are co-resident (the grid is sized from the occupancy), and every CTA meets its own
+// phase-1 items of a panel before any phase-2 item of it, so the wait always ends.
 template <typename T, bool kTranspose>
 __global__ void __launch_bounds__(kThreads)
 quant_cols_decoupled_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int panels,
                             int chunks, int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw, ColqScratch sc) {
   constexpr int EPV = Unpack<T>::EPV;
   constexpr int SC = 32 * EPV;  // columns per tile (512 bytes of input per row)
-  // phase 1: [8 warps][SC] partial maxima; phase 2 (transposed): [SC columns][8 words of 4 k-bytes]
+  // phase 1: [8 warps][SC] partial maxima; phase 2 (transposed): [8 k-words][SC columns]
   __shared__ uint32_t s_buf[(kThreads / 32) * SC];
   __shared__ int s_last;
-  const int G = kPanelTiles * chunks;  // blocks per phase group
-  const int g = blockIdx.x / G, r = blockIdx.x % G;
-  int panel, phase;
-  if (g == 0) { phase = 1; panel = 0; }
-  else if (g == 2 * panels - 1) { phase = 2; panel = panels - 1; }
-  else if (g & 1) { phase = 1; panel = (g + 1) / 2; }
-  else { phase = 2; panel = g / 2 - 1; }
-  const int chunk = r / kPanelTiles, tile = panel * kPanelTiles + r % kPanelTiles;
+  const int G = kPanelTiles * chunks;  // items per phase group
+  const int total = 2 * panels * G;
+  const int expected = min(G, (int)gridDim.x);  // CTAs that own at least one item of a group
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = tile * SC + lane * EPV;
-  const bool col_ok = col < N;
-  const int rb = chunk * kPatchRows, r1 = min(K, rb + kPatchRows);
-  const int row0 = rb + 4 * warp;  // this warp's row quad
-  const T *base = W + col;
+
+  auto load = [&](const ColqItem &it, uint4 (&v)[4]) {
+    const int col = it.tile * SC + lane * EPV;
+    const int row0 = it.chunk * kPatchRows + 4 * warp;
+    const int r1 = min(K, (it.chunk + 1) * kPatchRows);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      v[i] = (col < N && row0 + i < r1) ? ldg16(W + (int64_t)(row0 + i) * ldw + col) : make_uint4(0, 0, 0, 0);
+  };
 
   griddep_wait();
-  uint4 v[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-    v[i] = (col_ok && row0 + i < r1) ? ldg16(base + (int64_t)(row0 + i) * ldw) : make_uint4(0, 0, 0, 0);
+  int i = blockIdx.x;
+  if (i >= total) return;
+  ColqItem cur = colq_decode(i, G, panels);
+  uint4 v[4], vn[4];
+  load(cur, v);
+  int waited_panel = -1;
+  for (; i < total; i += gridDim.x) {
+    const int inext = i + gridDim.x;
+    ColqItem nxt = cur;
+    const bool has_next = inext < total;
+    if (has_next) {
+      nxt = colq_decode(inext, G, panels);
+      load(nxt, vn);
+    }
+    const int col = cur.tile * SC + lane * EPV;
+    const bool col_ok = col < N;
+    const int rb = cur.chunk * kPatchRows, r1 = min(K, rb + kPatchRows);
+    const int row0 = rb + 4 * warp;
 
-  if (phase == 1) {
-    float m[EPV];
+    if (cur.phase == 1) {
+      float m[EPV];
 #pragma unroll
-    for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
+      for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int row = row0 + i;
-      if (col_ok && row < r1 && row > 0) {  // row 0 is folded in signed, in phase 2
-        float f[EPV];
-        Unpack<T>::run(v[i], f);
+      for (int q = 0; q < 4; q++) {
+        const int row = row0 + q;
+        if (col_ok && row < r1 && row > 0) {  // row 0 is folded in signed, in phase 2
+          float f[EPV];
+          Unpack<T>::run(v[q], f);
 #pragma unroll
-        for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
-      }
-    }
-    float *s_red = reinterpret_cast<float *>(s_buf);
-#pragma unroll
-    for (int e = 0; e < EPV; e++) s_red[warp * SC + lane * EPV + e] = m[e];
-    __syncthreads();
-    for (int c = threadIdx.x; c < SC; c += kThreads) {
-      float mm = s_red[c];
-#pragma unroll
-      for (int w = 1; w < kThreads / 32; w++) mm = fmaxf(mm, s_red[w * SC + c]);
-      const int gc = tile * SC + c;
-      if (gc < N && mm >= 0.0f) atomicMax(reinterpret_cast<int *>(sc.part) + gc, __float_as_int(mm));
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(sc.arrived + panel, 1);
-    return;
-  }
-
-  // ---------------- phase 2 ----------------
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    while (ld_acquire_gpu(sc.arrived + panel) < G) {
-      __nanosleep(64);
-      if (clock64() - t0 > 4000000000LL) {
-        printf("[qgemm] column quantizer: panel %d never completed phase 1\n", panel);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
-  float s[EPV];
-  if (col_ok) {
-    float x0[EPV];
-    Unpack<T>::run(ldg16(base), x0);
-#pragma unroll
-    for (int e = 0; e < EPV; e++) {
-      const float mm = __ldcg(sc.part + col + e);
-      float cw;
-      if (fold_first(x0[e], mm, mode, cw)) {
-        for (int k = 1; k < K; k++) {  // rare +-0 tie-break: sign of the first later non-NaN zero
-          const float x = to_f32(base[(int64_t)k * ldw + e]);
-          if (x == x) { cw = -x; break; }
+          for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
         }
       }
-      if (chunk == 0 && warp == 0 && Cw != nullptr) Cw[col + e] = cw;
-      s[e] = __fdiv_rn(range, cw);
-    }
-  } else {
+      float *s_red = reinterpret_cast<float *>(s_buf);
 #pragma unroll
-    for (int e = 0; e < EPV; e++) s[e] = 0.0f;
-  }
-  if (Wq != nullptr) {
-    float f[4][EPV];
-#pragma unroll
-    for (int i = 0; i < 4; i++) Unpack<T>::run(v[i], f[i]);
-    if (kTranspose) {
-#pragma unroll
-      for (int e = 0; e < EPV; e++) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint32_t code = (row0 + i < r1) ? quant_code_u8(f[i][e], s[e]) : 0u;  // rows past K: zero padding
-          w |= code << (8 * i);
-        }
-        // [8 k-words][SC columns]; a lane's EPV columns are rotated by lane / (32 / EPV) so that the
-        // 32 lanes of a warp (same e) fall into 32 different banks
-        s_buf[warp * SC + lane * EPV + ((e + lane / (32 / EPV)) & (EPV - 1))] = w;
-      }
+      for (int e = 0; e < EPV; e++) s_red[warp * SC + lane * EPV + e] = m[e];
       __syncthreads();
-      // SC columns x 32 bytes: a thread moves one 16-byte half of a column's 32-byte row of Wt
-      for (int t = threadIdx.x; t < SC * 2; t += kThreads) {
-        const int h = t / SC, c = t - h * SC;
-        const int gc = tile * SC + c;
-        const int wl = c / EPV;  // lane that wrote this column
-        const int pos = wl * EPV + (((c & (EPV - 1)) + wl / (32 / EPV)) & (EPV - 1));
-        uint32_t w4[4];
+      for (int c = threadIdx.x; c < SC; c += kThreads) {
+        float mm = s_red[c];
 #pragma unroll
-        for (int j = 0; j < 4; j++) w4[j] = s_buf[(4 * h + j) * SC + pos];
-        const int row = rb + 16 * h;
-        if (gc < N && row < r1)
-          *reinterpret_cast<uint4 *>(Wq + (int64_t)gc * ldq + row) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        for (int w = 1; w < kThreads / 32; w++) mm = fmaxf(mm, s_red[w * SC + c]);
+        const int gc = cur.tile * SC + c;
+        if (gc < N && mm >= 0.0f) atomicMax(reinterpret_cast<int *>(sc.part) + gc, __float_as_int(mm));
       }
-    } else if (col_ok) {
+      const bool last_of_panel = !has_next || nxt.phase != 1 || nxt.panel != cur.panel;
+      if (last_of_panel) __threadfence();
+      __syncthreads();
+      if (last_of_panel && threadIdx.x == 0) atomicAdd(sc.arrived + cur.panel, 1);
+    } else {
+      if (waited_panel != cur.panel) {
+        if (threadIdx.x == 0) {
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(sc.arrived + cur.panel) < expected) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000LL) {
+              printf("[qgemm] column quantizer: panel %d never completed phase 1\n", cur.panel);
+              __trap();
+            }
+          }
+        }
+        __syncthreads();
+        waited_panel = cur.panel;
+      }
+      float s[EPV];
+      if (col_ok) {
+        float x0[EPV];
+        Unpack<T>::run(ldg16(W + col), x0);
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int row = row0 + i;
-        if (row < r1) {
-          uint32_t w[EPV / 4];
+        for (int e = 0; e < EPV; e++) {
+          const float mm = __ldcg(sc.part + col + e);
+          float cw;
+          if (fold_first(x0[e], mm, mode, cw)) {
+            for (int k = 1; k < K; k++) {  // rare +-0 tie-break: sign of the first later non-NaN zero
+              const float x = to_f32(W[(int64_t)k * ldw + col + e]);
+              if (x == x) { cw = -x; break; }
+            }
+          }
+          if (cur.chunk == 0 && warp == 0 && Cw != nullptr) Cw[col + e] = cw;
+          s[e] = __fdiv_rn(range, cw);
+        }
+      } else {
 #pragma unroll
-          for (int q = 0; q < EPV / 4; q++)
-            w[q] = quant_code_u8(f[i][4 * q], s[4 * q]) | (quant_code_u8(f[i][4 * q + 1], s[4 * q + 1]) << 8) |
-                   (quant_code_u8(f[i][4 * q + 2], s[4 * q + 2]) << 16) | (quant_code_u8(f[i][4 * q + 3], s[4 * q + 3]) << 24);
-          int8_t *dst = Wq + (int64_t)row * ldq + col;
-          if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
-          else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
+        for (int e = 0; e < EPV; e++) s[e] = 0.0f;
+      }
+      if (Wq != nullptr) {
+        float f[4][EPV];
+#pragma unroll
+        for (int q = 0; q < 4; q++) Unpack<T>::run(v[q], f[q]);
+        if (kTranspose) {
+#pragma unroll
+          for (int e = 0; e < EPV; e++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const uint32_t code = (row0 + q < r1) ? quant_code_u8(f[q][e], s[e]) : 0u;  // rows past K: zero padding
+              w |= code << (8 * q);
+            }
+            // [8 k-words][SC columns]; a lane's EPV columns are rotated by lane / (32 / EPV) so that
+            // the 32 lanes of a warp (same e) fall into 32 different banks
+            s_buf[warp * SC + lane * EPV + ((e + lane / (32 / EPV)) & (EPV - 1))] = w;
+          }
+          __syncthreads();
+          // SC columns x 32 bytes: a thread moves one 16-byte half of a column's 32-byte row of Wt
+          for (int t = threadIdx.x; t < SC * 2; t += kThreads) {
+            const int h = t / SC, c = t - h * SC;
+            const int gc = cur.tile * SC + c;
+            const int wl = c / EPV;  // lane that wrote this column
+            const int pos = wl * EPV + (((c & (EPV - 1)) + wl / (32 / EPV)) & (EPV - 1));
+            uint32_t w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) w4[j] = s_buf[(4 * h + j) * SC + pos];
+            const int row = rb + 16 * h;
+            if (gc < N && row < r1)
+              *reinterpret_cast<uint4 *>(Wq + (int64_t)gc * ldq + row) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+          __syncthreads();
+        } else if (col_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int row = row0 + q;
+            if (row < r1) {
+              uint32_t w[EPV / 4];
+#pragma unroll
+              for (int qq = 0; qq < EPV / 4; qq++)
+                w[qq] = quant_code_u8(f[q][4 * qq], s[4 * qq]) | (quant_code_u8(f[q][4 * qq + 1], s[4 * qq + 1]) << 8) |
+                        (quant_code_u8(f[q][4 * qq + 2], s[4 * qq + 2]) << 16) |
+                        (quant_code_u8(f[q][4 * qq + 3], s[4 * qq + 3]) << 24);
+              int8_t *dst = Wq + (int64_t)row * ldq + col;
+              if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
+              else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
+            }
+          }
+        }
+      }
+      // a CTA's last phase-2 item of the panel: the last CTA to get there cleans the scratch
+      const bool last_of_panel = !has_next || nxt.phase != 2 || nxt.panel != cur.panel;
+      if (last_of_panel) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(sc.finished + cur.panel, 1) == expected - 1);
+        __syncthreads();
+        if (s_last) {
+          for (int c = threadIdx.x; c < kPanelTiles * SC; c += kThreads) {
+            const int gc = cur.panel * kPanelTiles * SC + c;
+            if (gc < N) sc.part[gc] = -INFINITY;
+          }
+          if (threadIdx.x == 0) { sc.arrived[cur.panel] = 0; sc.finished[cur.panel] = 0; }
         }
       }
     }
-  }
-  // last phase-2 block of the panel leaves the scratch clean for the next call
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(sc.finished + panel, 1) == G - 1);
-  __syncthreads();
-  if (s_last) {
-    for (int c = threadIdx.x; c < kPanelTiles * SC; c += kThreads) {
-      const int gc = panel * kPanelTiles * SC + c;
-      if (gc < N) sc.part[gc] = -INFINITY;
-    }
-    if (threadIdx.x == 0) { sc.arrived[panel] = 0; sc.finished[panel] = 0; }
+    cur = nxt;
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = vn[q];
   }
 }
 
@@ -562,6 +609,25 @@ __global__ void colq_scratch_init_kernel(float *part, int n, int *counters, int 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) part[i] = -INFINITY;
   if (i < nc) counters[i] = 0;
+}
+
+// Epoch-tagged scratch of the two-launch column path: zero-initialised once, never reset.
+int twopass_scratch(int N, unsigned long long **part, uint32_t *epoch) {
+  struct State { unsigned long long *part = nullptr; int n = 0; uint32_t epoch = 0; };
+  static State state[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  State &s = state[dev & 15];
+  if (s.n < N) {
+    if (s.part) { cudaDeviceSynchronize(); cudaFree(s.part); }
+    s.n = (int)round_up(N < 16384 ? 16384 : N, 4096);
+    if (cudaMalloc(&s.part, sizeof(unsigned long long) * (size_t)s.n) != cudaSuccess) { s = State(); return (int)cudaGetLastError(); }
+    if (cudaMemset(s.part, 0, sizeof(unsigned long long) * (size_t)s.n) != cudaSuccess) return (int)cudaGetLastError();
+    s.epoch = 0;
+  }
+  *part = s.part;
+  *epoch = ++s.epoch;  // 0 is never used, so zero-initialised entries never match
+  return 0;
 }
 
 // Persistent per-device scratch of the decoupled column quantizer: clean (-inf / 0) between calls,
@@ -650,20 +716,32 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   const bool vec_ok = (N % EPV == 0) && aligned(W, 16) && ((ldw * sizeof(T)) % 16 == 0) &&
                       (Wq == nullptr || (aligned(Wq, EPV) && ldq % EPV == 0)) &&
-                      (sw != nullptr || scratch != nullptr || Wq != nullptr) && !(transpose && sw != nullptr);
+                      !(transpose && sw != nullptr);
   if (!vec_ok) {
     return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   }
-  // fused absmax + quantize in one launch (QG_COLS_TWO_PASS=1 keeps the three-launch path)
-  if (sw == nullptr && Wq != nullptr && (transpose || getenv("QG_COLS_TWO_PASS") == nullptr)) {
+  // transposed (K-major) codes: the single-launch decoupled kernel; row-major codes: two launches,
+  // which measured faster (26 us vs 34-45 us at 4096^2; QG_COLS_DECOUPLED=1 forces the former)
+  if (sw == nullptr && Wq != nullptr && (transpose || getenv("QG_COLS_DECOUPLED") != nullptr)) {
     const int tiles = (int)ceil_div(N, 32 * EPV);
     const int panels = (int)ceil_div(tiles, kPanelTiles);
     const int chunks = (int)ceil_div(K, kPatchRows);
     ColqScratch sc;
     int rc = colq_scratch(N, panels, &sc, st);
     if (rc) return rc;
-    const dim3 grid((unsigned)((int64_t)2 * panels * kPanelTiles * chunks));
+    const int64_t total = (int64_t)2 * panels * kPanelTiles * chunks;
+    static int resident[2] = {0, 0};  // co-resident CTAs per instantiation (the kernel's wait relies on it)
+    int &res = resident[transpose ? 1 : 0];
+    if (res == 0) {
+      int per_sm = 0, dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (transpose) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quant_cols_decoupled_kernel<T, true>, kThreads, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quant_cols_decoupled_kernel<T, false>, kThreads, 0);
+      res = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    }
+    const dim3 grid((unsigned)(total < res ? total : res));
     if (transpose)
       return (int)launch_kernel(quant_cols_decoupled_kernel<T, true>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode,
                                 panels, chunks, Wq, ldq, Cw, sc);
@@ -672,20 +750,22 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
   const int rpc = cols_rows_per_cta(K, col_tiles);
+  unsigned long long *part = nullptr;
+  uint32_t epoch = 0;
   if (sw == nullptr) {
-    launch_kernel(fill_f32_kernel, dim3((unsigned)ceil_div(N, 256)), dim3(256), st, scratch, N, -INFINITY);
+    int rc = twopass_scratch(N, &part, &epoch);
+    if (rc) return rc;
     if (K > 1) {
       dim3 grid(col_tiles, (unsigned)ceil_div(K - 1, rpc));
-      launch_kernel(absmax_cols_partial_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, rpc, scratch);
+      launch_kernel(absmax_cols_partial_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, rpc, part, epoch);
     }
-    if (Wq == nullptr) {
+    if (Wq == nullptr)
       return (int)launch_kernel(absmax_cols_finalize_kernel<T>, dim3((unsigned)ceil_div(N, 256)), dim3(256), st, W, K, N,
-                                ldw, mode, scratch, Cw);
-    }
+                                ldw, mode, part, epoch, Cw);
   }
   dim3 grid(col_tiles, (unsigned)ceil_div(K, rpc));
-  return (int)launch_kernel(quant_cols_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode, rpc, scratch, sw, Wq,
-                            ldq, Cw);
+  return (int)launch_kernel(quant_cols_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode, rpc, part, epoch, sw,
+                            Wq, ldq, Cw);
 }
 
 }  // namespace

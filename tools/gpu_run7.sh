@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+tail -30 gpurun_out/pytest_gpu.log | cut -c1-250
+timeout 1200 python tools/gpu_perf.py --only quant_4096,quant_8192,full_4096_pdl,full_8192,full_2048_pdl > gpurun_out/perf.log 2>&1
+cat gpurun_out/perf.log | cut -c1-420
