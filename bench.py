@@ -233,6 +233,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    os.environ.pop("NCCL_DEBUG", None)  # NCCL's version banner goes to stdout and would precede the JSON line
     qg = importlib.import_module(PKG)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -251,23 +252,50 @@ def run_ours(args):
     Ws = [torch.rand((K, N), device=dev, generator=g) * 2 - 1 for _ in range(nset)]
     Os = [torch.empty((M, N), device=dev) for _ in range(nset)]
     gathered = torch.empty((world, M, N), device=dev) if world > 1 else None
+    # N > 1: the output gather is fused into the GEMM epilogue when symmetric (peer-mapped) memory is
+    # available -- every rank's [M, world*N] result buffer is written directly by all ranks' epilogues
+    exchange, symm_out, hdl, peer_ptrs = "none", None, None, []
+    if world > 1:
+        exchange = "nccl all_gather_into_tensor"
+        if os.environ.get("QG_BENCH_EXCHANGE", "fused") == "fused":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                symm_out = symm_mem.empty((M, N * world), dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(symm_out, dist.group.WORLD)
+                peer_ptrs = [int(hdl.buffer_ptrs[r]) + rank * N * 4 for r in range(world) if r != rank]
+                exchange = "fused: GEMM epilogue TMA-stores into every peer's result over NVLink (symmetric memory)"
+            except Exception as ex:  # no peer access on this box: fall back to the NCCL collective
+                exchange = f"nccl all_gather_into_tensor (symmetric memory unavailable: {str(ex)[:120]})"
+                symm_out, hdl, peer_ptrs = None, None, []
     Xq = torch.empty((M, K), dtype=torch.int8, device=dev)
     Wq = torch.empty((K, N), dtype=torch.int8, device=dev)
     Cx = torch.empty(M, device=dev)
     Cw = torch.empty(N, device=dev)
 
+    ws = torch.empty(qg.workspace_bytes(M, N, K), dtype=torch.uint8, device=dev)
+
     def step(i, ev=None):
-        # the three calls qg_quantized_mm makes, issued separately so that the dominant kernel can be
-        # bracketed by CUDA events inside the timed region
         s = i % nset
+        if ev is None and world == 1:
+            # the public call: one C-ABI entry, four PDL-chained launches
+            qg.op_quantized_mm(Xs[s], Ws[s], Os[s], 127.0, workspace=ws)
+            return
+        # the same launches issued one by one, so that the dominant kernel can be bracketed by CUDA events
+        # (instrumented pass) or given its peer destinations (N > 1)
         qg.absmax_quant_rows(Xs[s], 127.0, qg.MODE_REF_EXACT, Xq, Cx)
         qg.absmax_quant_cols(Ws[s], 127.0, qg.MODE_REF_EXACT, Wq, Cw)
         if ev is not None:
             ev[0].record()
-        qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, Os[s], 127.0)
+        if hdl is not None:
+            hdl.barrier(channel=0)  # peers have consumed the previous step's result
+            qg.gemm_s8_dequant_ex(Xq, Wq, False, Cx, Cw, symm_out[:, rank * N:(rank + 1) * N], peer_ptrs, 127.0)
+            hdl.barrier(channel=1)  # every rank's blocks have landed everywhere
+        else:
+            qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, Os[s], 127.0)
         if ev is not None:
             ev[1].record()
-        if world > 1:
+        if world > 1 and hdl is None:
             dist.all_gather_into_tensor(gathered, Os[s])
 
     for i in range(args.warmup):
@@ -286,10 +314,16 @@ def run_ours(args):
     qg.launch_count(reset=True)
     t_start.record()
     for i in range(args.steps):
-        step(i, evs[i])
+        step(i)
     t_end.record()
     torch.cuda.synchronize()
     launches = qg.launch_count()
+    # instrumented pass, immediately after and on the same buffers: the same K steps with a CUDA event
+    # pair around the dominant kernel (events between the launches would otherwise break the
+    # programmatic-dependent-launch overlap of the timed pass above)
+    for i in range(args.steps):
+        step(i, evs[i])
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -404,12 +438,14 @@ def run_ours(args):
                                + (f"; column-parallel over {world} GPUs + NCCL all-gather of the fp32 outputs" if world > 1 else ""),
                    "M": M, "N": N * world, "K": K, "mode": "REF_EXACT",
                    "l2": "2 rotating buffer sets, 384 MiB touched per 2 steps (> 126 MB L2); no explicit flush",
-                   "parallelism": f"column-parallel x{world}" if world > 1 else "single GPU"},
+                   "parallelism": f"column-parallel x{world}" if world > 1 else "single GPU", "exchange": exchange},
         "roofline": {"bound": "tensor", "kernel": "gemm_i8_tc_kernel (tcgen05 kind::i8 + fused dequantize epilogue)",
                      "achieved": gemm_tops, "peak": int8_peak, "unit": "TOP/s", "frac": gemm_tops / int8_peak,
                      "peak_note": f"2 x {peak_key} from MEASURED_PEAKS.json ({peaks['source']}); int8 dense "
                                   f"rate is 2x bf16; spec 4500 TOP/s -> frac_spec {gemm_tops / INT8_SPEC_TOPS:.3f}",
-                     "frac_spec": gemm_tops / INT8_SPEC_TOPS, "ms": gemm_ms, "traffic": None},
+                     "frac_spec": gemm_tops / INT8_SPEC_TOPS, "ms": gemm_ms, "traffic": None,
+                     "timing": "CUDA events around this launch in every step of an instrumented pass of the same K steps, "
+                               "run directly after the timed pass"},
         "stages": {
             "quant_rows": {"ms": rows_ms, "achieved": (M * K * 5 + 4 * M) / rows_ms / 1e6, "unit": "GB/s", "bound": "hbm",
                            "frac": (M * K * 5 + 4 * M) / rows_ms / 1e6 / peaks["hbm_gbs"]},

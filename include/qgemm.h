@@ -92,7 +92,8 @@ QG_API int qg_quantize_cols(const void *W, int dtype, int k, int n, int64_t ldw,
 /* replaces op_absmax + op_inv_divide + op_multiply at src/ops/op_mm.cuh:76-77,82-83,86-87 */
 QG_API int qg_absmax_quant_rows(const void *X, int dtype, int m, int k, int64_t ldx, float range,
                                 int mode, int8_t *Xq, int64_t ldq, float *Cx, qg_stream_t stream);
-/* replaces src/ops/op_mm.cuh:78-79,84-85,88-89.  scratch: N floats of device memory. */
+/* replaces src/ops/op_mm.cuh:78-79,84-85,88-89.  scratch: unused since the library keeps its own
+ * epoch-tagged column-max scratch (parameter kept for ABI stability; pass NULL). */
 QG_API int qg_absmax_quant_cols(const void *W, int dtype, int k, int n, int64_t ldw, float range,
                                 int mode, int8_t *Wq, int64_t ldq, float *Cw, float *scratch,
                                 qg_stream_t stream);
@@ -141,6 +142,24 @@ QG_API int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int
                              const float *Cw, const float *bias, void *Y, int64_t ldy, int out_dtype,
                              int m, int n, int k, float range, int mode, void *workspace,
                              size_t workspace_bytes, qg_stream_t stream);
+
+/* ---- column-parallel LinearLayer::forward with the output gather fused into the GEMM epilogue -- */
+/* Rank p owns output columns [lo, hi): Wt/Cw/bias are its shard (n = hi - lo).  Its [m, n] block is
+ * written to y_local and to y_peers[0..n_peers) -- the other GPUs' [m, N_total] output matrices,
+ * mapped into this process (CUDA IPC / symmetric memory), every pointer already offset by `lo`
+ * columns, common leading dimension ldy.  Peer stores are issued by the epilogue (TMA over NVLink)
+ * and overlap the main loop; the caller places a cross-GPU barrier before consuming the result. */
+QG_API int qg_linear_forward_multi(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt, int64_t ldwt,
+                                   const float *Cw, const float *bias, void *y_local, void *const *y_peers,
+                                   int n_peers, int64_t ldy, int out_dtype, int m, int n, int k, float range,
+                                   int mode, void *workspace, size_t workspace_bytes, qg_stream_t stream);
+
+/* General form of the fused GEMM (a5..a8, a10): B = Wq [K,N] (b_kmajor 0) or Wt [N,K] (1); the block is
+ * also written to peers[0..n_peers) (see qg_linear_forward_multi for the pointer convention). */
+QG_API int qg_gemm_s8_dequant_ex(const int8_t *Xq, int64_t ldxq, const int8_t *B, int64_t ldb, int b_kmajor,
+                                 const float *Cx, const float *Cw, const float *bias, int m, int n, int k,
+                                 float range, void *O, void *const *peers, int n_peers, int out_dtype,
+                                 int64_t ldo, qg_stream_t stream);
 
 /* ---- host-buffer form of a9 (pageable or pinned host pointers; H2D + compute + D2H) --------- */
 /* what a caller holding host tensors (Tensor<T>{h,w,false}, toDevice/toHost at

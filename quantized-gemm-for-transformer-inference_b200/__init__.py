@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_prepare_weights", "qg_gemm_s8t_dequant",
     "qg_linear_forward",
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
-    "qg_linear_forward_outlier", "qg_mm_f32",
+    "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_mm_f32",
 ]
 
 
@@ -208,11 +208,10 @@ def absmax_quant_cols(W: torch.Tensor, range_: float = 127.0, mode: int = MODE_R
         Wq = torch.empty((K, N), dtype=torch.int8, device=W.device)
     if Cw is None:
         Cw = torch.empty(N, dtype=torch.float32, device=W.device)
-    scratch = torch.empty(N, dtype=torch.float32, device=W.device)
     pw, ldw = _dev2d(W)
     pq, ldq = _dev2d(Wq)
     _check(lib().qg_absmax_quant_cols(pw, _dt(W), K, N, ldw, C.c_float(range_), mode, pq, ldq, _vec(Cw, N),
-                                      _vec(scratch, N), _stream()), "qg_absmax_quant_cols")
+                                      None, _stream()), "qg_absmax_quant_cols")
     return Wq, Cw
 
 
@@ -261,6 +260,23 @@ def gemm_s8t_dequant(Xq, Wt, Cx, Cw, out, range_: float = 127.0, bias=None) -> N
     pbias = None if bias is None else _vec(bias.reshape(-1), N)
     _check(lib().qg_gemm_s8t_dequant(pa, lda, pb, ldb, pcx, pcw, pbias, M, N, K, C.c_float(range_), po, od, ldo,
                                      _stream()), "qg_gemm_s8t_dequant")
+
+
+def gemm_s8_dequant_ex(Xq, B, b_kmajor: bool, Cx, Cw, out, peer_ptrs=(), range_: float = 127.0, bias=None) -> None:
+    """Fused GEMM with B in either layout; `out` ([M,n] view, possibly a column block of a wider matrix)
+    is also written at the device addresses `peer_ptrs` (ints: same block inside peers' matrices)."""
+    M, K = Xq.shape
+    N = B.shape[0] if b_kmajor else B.shape[1]
+    assert out.shape == (M, N)
+    pa, lda = _dev2d(Xq)
+    pb, ldb = _dev2d(B)
+    po, ldo = _dev2d(out)
+    pbias = None if bias is None else _vec(bias.reshape(-1), N)
+    n = len(peer_ptrs)
+    arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    _check(lib().qg_gemm_s8_dequant_ex(pa, lda, pb, ldb, 1 if b_kmajor else 0, _vec(Cx.reshape(-1), M),
+                                       _vec(Cw.reshape(-1), N), pbias, M, N, K, C.c_float(range_), po, arr, n, _dt(out),
+                                       ldo, _stream()), "qg_gemm_s8_dequant_ex")
 
 
 def workspace_bytes(M: int, N: int, K: int) -> int:

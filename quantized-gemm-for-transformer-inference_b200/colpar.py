@@ -97,3 +97,52 @@ class ColumnParallelLinear:
         if self.world == 1:
             return y
         return gather_columns(y, self.n, self.world, self.rank, self.group, self.align, out)
+
+
+class FusedColumnParallelLinear:
+    """Column-parallel linear whose output gather is fused into the GEMM epilogue: every rank's
+    [M, N] result lives in symmetric memory (torch.distributed._symmetric_memory: peer-mapped over
+    NVLink), and each rank's epilogue TMA-stores its column block into all of them while its main
+    loop is still running.  Two cross-GPU barriers bracket a forward (peers are done reading the
+    previous result / every block has landed)."""
+
+    def __init__(self, w_full: torch.Tensor, bias: Optional[torch.Tensor], rank: int, world: int, group=None,
+                 align: int = 16, range_: float = 127.0, mode: int = 0):
+        from . import prepare_weights
+
+        self.rank, self.world, self.align = rank, world, align
+        self.group = group if group is not None else dist.group.WORLD
+        self.k, self.n = w_full.shape
+        self.lo, self.hi = shard_bounds(self.n, world, rank, align)
+        self.w = w_full[:, self.lo:self.hi].contiguous()
+        self.b = None if bias is None else bias.reshape(-1)[self.lo:self.hi].contiguous().float()
+        self.range, self.mode = range_, mode
+        self.wt, self.cw = prepare_weights(self.w, range_, mode)
+        self.out = None
+        self.hdl = None
+        self._xq = self._cx = None
+
+    def _ensure_out(self, m: int, dtype, device):
+        if self.out is not None and self.out.shape[0] == m and self.out.dtype == dtype:
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.out = symm_mem.empty((m, self.n), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.out, self.group)
+        es = self.out.element_size()
+        self.peer_ptrs = [int(self.hdl.buffer_ptrs[r]) + self.lo * es for r in range(self.world) if r != self.rank]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import absmax_quant_rows, gemm_s8_dequant_ex
+
+        m = x.shape[0]
+        self._ensure_out(m, x.dtype, x.device)
+        if self._xq is None or self._xq.shape[0] != m:
+            self._xq = torch.empty((m, self.k), dtype=torch.int8, device=x.device)
+            self._cx = torch.empty(m, dtype=torch.float32, device=x.device)
+        absmax_quant_rows(x, self.range, self.mode, self._xq, self._cx)
+        self.hdl.barrier(channel=0)  # every peer has finished with the previous contents of its matrix
+        gemm_s8_dequant_ex(self._xq, self.wt, True, self._cx, self.cw, self.out[:, self.lo:self.hi], self.peer_ptrs,
+                           self.range, self.b)
+        self.hdl.barrier(channel=1)  # all blocks of all ranks have landed
+        return self.out

@@ -38,7 +38,7 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 void gemm_i8_tc_set_stats(long long *dev_ptr);
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               const SideArgs *side, int num_sms, cudaStream_t st);
+               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st);
 
 // ---- error state ----
 static thread_local char g_err[512] = "";
@@ -152,16 +152,22 @@ static Workspace carve(void *base, int M, int N, int K) {
 // b_kmajor == 0: B is the reference's [K,N] (MN-major tensor-core operand); 1: B is Wt [N,K]
 static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M,
                          int N, int K, void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw,
-                         const float *bias, float c, cudaStream_t st, const SideArgs *side = nullptr) {
+                         const float *bias, float c, cudaStream_t st, const SideArgs *side = nullptr,
+                         const MultiOut *multi = nullptr) {
   int variant = g_variant.load();
   const bool tc_ok = gemm_i8_tc_supported(A, lda, B, ldb);
   // the 2-SM tile (256x256 per CTA pair) halves the shared-memory traffic per MAC; one CTA row
   // of work is all a problem with M <= 128 has, so it takes the 1-SM kernel
   if (variant == QG_GEMM_AUTO) variant = !tc_ok ? QG_GEMM_SIMT : (M > 128 ? QG_GEMM_TC_2SM : QG_GEMM_TC_1SM);
-  if (variant == QG_GEMM_SIMT || !tc_ok)
+  if (variant == QG_GEMM_SIMT || !tc_ok) {
+    if (multi != nullptr && multi->n > 0) {
+      set_error("extra destinations need the tensor-core path (16-byte aligned operands)");
+      return QG_ENOTSUP;
+    }
     return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st);
+  }
   return gemm_i8_tc(variant == QG_GEMM_TC_2SM ? 2 : 1, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias,
-                    c, side, d->sm_count, st);
+                    c, side, multi, d->sm_count, st);
 }
 
 }  // namespace qg
@@ -479,6 +485,51 @@ int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, const vo
                        no_pad > 0 ? &side : nullptr);
 }
 
+/* Column-parallel LinearLayer::forward: this rank's [m, n] block (n = its share
+ * of the output columns, Wt/Cw/bias = its shard) is written into `y_local` and into the n_peers
+ * matrices `y_peers[]` -- peer GPUs' [m, N_total] outputs mapped into this process, every pointer
+ * already offset to this rank's first column, all with leading dimension ldy.  The GEMM epilogue
+ * issues the peer stores itself (TMA over NVLink), so the gather overlaps the main loop. */
+int qg_linear_forward_multi(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt, int64_t ldwt, const float *Cw,
+                            const float *bias, void *y_local, void *const *y_peers, int n_peers, int64_t ldy,
+                            int out_dtype, int M, int N, int K, float range, int mode, void *workspace,
+                            size_t workspace_bytes, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && Wt && Cw && y_local && M > 0 && N > 0 && K > 0 && ldx >= K && ldwt >= K && ldy >= N && valid_io(in_dtype) &&
+                 valid_io(out_dtype) && n_peers >= 0 && n_peers <= kMaxExtraOut && (n_peers == 0 || y_peers),
+             "qg_linear_forward_multi: bad arguments (n_peers=%d)", n_peers);
+  Workspace w;
+  rc = get_workspace(d, workspace, workspace_bytes, M, 1, K, &w);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
+  if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+  MultiOut mo = {};
+  mo.n = n_peers;
+  for (int i = 0; i < n_peers; i++) mo.dst[i] = y_peers[i];
+  return gemm_dispatch(d, w.Xq, w.ldxq, Wt, ldwt, 1, M, N, K, y_local, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range),
+                       st, nullptr, &mo);
+}
+
+/* General form of the fused GEMM: B in either layout, optional extra destinations for the epilogue. */
+int qg_gemm_s8_dequant_ex(const int8_t *Xq, int64_t ldxq, const int8_t *B, int64_t ldb, int b_kmajor, const float *Cx,
+                          const float *Cw, const float *bias, int M, int N, int K, float range, void *O,
+                          void *const *peers, int n_peers, int out_dtype, int64_t ldo, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(Xq && B && Cx && Cw && O && M > 0 && N > 0 && K > 0 && ldxq >= K && ldb >= (b_kmajor ? K : N) && ldo >= N &&
+                 valid_io(out_dtype) && n_peers >= 0 && n_peers <= kMaxExtraOut && (n_peers == 0 || peers),
+             "qg_gemm_s8_dequant_ex: bad arguments");
+  MultiOut mo = {};
+  mo.n = n_peers;
+  for (int i = 0; i < n_peers; i++) mo.dst[i] = peers[i];
+  return gemm_dispatch(d, Xq, ldxq, B, ldb, b_kmajor ? 1 : 0, M, N, K, O, ldo, out_dtype, Cx, Cw, bias, 1 / (range * range),
+                       (cudaStream_t)stream, nullptr, n_peers > 0 ? &mo : nullptr);
+}
+
 int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host, int M, int N, int K, float range,
                          int mode, const float *bias_host) {
   DeviceState *d;
@@ -542,7 +593,7 @@ QG_API int qg_test_gemm_s8_bt(int cg, const int8_t *A, int64_t lda, const int8_t
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
-  return gemm_i8_tc(cg, A, lda, Bt, ldbt, 1, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f, nullptr,
+  return gemm_i8_tc(cg, A, lda, Bt, ldbt, 1, M, N, K, C, ldc, QG_S32, nullptr, nullptr, nullptr, 0.0f, nullptr, nullptr,
                     d->sm_count, (cudaStream_t)stream);
 }
 

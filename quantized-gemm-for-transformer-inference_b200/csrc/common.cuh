@@ -64,6 +64,15 @@ struct SideArgs {
   int side_bf16;   // 0: fp16 operands, 1: bf16
 };
 
+// additional destinations of the GEMM epilogue: the same [M,N] block is also written (same leading
+// dimension and dtype) to these buffers -- peers' output matrices mapped over NVLink in the
+// column-parallel linear, so the all-gather rides inside the GEMM
+constexpr int kMaxExtraOut = 7;
+struct MultiOut {
+  void *dst[kMaxExtraOut];
+  int n;
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 static inline size_t dtype_size(int dt) { return dt == QG_F32 ? 4 : 2; }

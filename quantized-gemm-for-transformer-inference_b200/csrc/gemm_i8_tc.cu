@@ -54,6 +54,13 @@ struct GemmParams {
   const void *Xo, *Wo;
   int64_t ldxo, ldwo;
   int no_pad, side_bf16;
+  // extra destinations (peer GPUs): same block, same ldo; TMA maps in ExtraMaps, raw pointers here
+  int n_extra;
+  void *extra_out[kMaxExtraOut];
+};
+
+struct ExtraMaps {
+  CUtensorMap m[kMaxExtraOut];
 };
 
 constexpr int kSideMax = 16;  // outlier columns the fused epilogue can take
@@ -91,7 +98,7 @@ template <int CG, bool B_MN, int OUT, bool SIDE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_o,
-                  const GemmParams p) {
+                  const __grid_constant__ ExtraMaps xmaps, const GemmParams p) {
   using C = Cfg<CG, B_MN, SIDE>;
   using OT = OutTraits<OUT>;
   using OutT = typename OT::T;
@@ -421,10 +428,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&map_o, stage_u32, n_base + c0, m_base + q * 32);
+            for (int d = 0; d < p.n_extra; d++)  // peers' copies of the block, straight over NVLink
+              tma_store_2d(&xmaps.m[d], stage_u32, n_base + c0, m_base + q * 32);
             tma_store_commit();
           }
         } else if (row < p.M) {
-          OutT *dst = reinterpret_cast<OutT *>(p.out) + (int64_t)row * p.ldo + n_base + c0;
+         for (int d = -1; d < p.n_extra; d++) {  // local matrix, then the peers' copies
+          OutT *dst = reinterpret_cast<OutT *>(d < 0 ? p.out : p.extra_out[d]) + (int64_t)row * p.ldo + n_base + c0;
           const int ncols = min(OT::kCols, p.N - (n_base + c0));
           if (ncols == OT::kCols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
@@ -439,6 +449,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int j = 0; j < 64; j++)
               if (j < ncols) reinterpret_cast<uint16_t *>(dst)[j] = (uint16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
           }
+         }
         }
       }
       // accumulator stage is free for the MMA warp again
@@ -508,8 +519,8 @@ int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, size_t esize, const vo
 }
 
 template <int CG, bool B_MN, int OUT, bool SIDE = false>
-int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo, GemmParams p,
-           int num_sms, cudaStream_t st) {
+int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo,
+           const ExtraMaps &xm, GemmParams p, int num_sms, cudaStream_t st) {
   using C = Cfg<CG, B_MN, SIDE>;
   auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT, SIDE>;
   static bool configured = false;  // per instantiation
@@ -544,30 +555,30 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  QG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mbh, mo, p));
+  QG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mbh, mo, xm, p));
   count_launch();
   return QG_OK;
 }
 
 template <int CG, bool B_MN>
 int launch_out(int out_kind, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo,
-               const GemmParams &p, int num_sms, cudaStream_t st) {
+               const ExtraMaps &xm, const GemmParams &p, int num_sms, cudaStream_t st) {
   if (p.Xo != nullptr) {  // outlier side product: prepared (K-major) weights, floating-point output
     if constexpr (!B_MN) {
       switch (out_kind) {
-        case QG_F32: return launch<CG, false, QG_F32, true>(ma, mb, mbh, mo, p, num_sms, st);
-        case QG_F16: return launch<CG, false, QG_F16, true>(ma, mb, mbh, mo, p, num_sms, st);
-        case QG_BF16: return launch<CG, false, QG_BF16, true>(ma, mb, mbh, mo, p, num_sms, st);
+        case QG_F32: return launch<CG, false, QG_F32, true>(ma, mb, mbh, mo, xm, p, num_sms, st);
+        case QG_F16: return launch<CG, false, QG_F16, true>(ma, mb, mbh, mo, xm, p, num_sms, st);
+        case QG_BF16: return launch<CG, false, QG_BF16, true>(ma, mb, mbh, mo, xm, p, num_sms, st);
       }
     }
     set_error("gemm_i8_tc: the side product needs prepared weights and an f32/f16/bf16 output");
     return QG_ENOTSUP;
   }
   switch (out_kind) {
-    case QG_S32: return launch<CG, B_MN, QG_S32>(ma, mb, mbh, mo, p, num_sms, st);
-    case QG_F32: return launch<CG, B_MN, QG_F32>(ma, mb, mbh, mo, p, num_sms, st);
-    case QG_F16: return launch<CG, B_MN, QG_F16>(ma, mb, mbh, mo, p, num_sms, st);
-    case QG_BF16: return launch<CG, B_MN, QG_BF16>(ma, mb, mbh, mo, p, num_sms, st);
+    case QG_S32: return launch<CG, B_MN, QG_S32>(ma, mb, mbh, mo, xm, p, num_sms, st);
+    case QG_F32: return launch<CG, B_MN, QG_F32>(ma, mb, mbh, mo, xm, p, num_sms, st);
+    case QG_F16: return launch<CG, B_MN, QG_F16>(ma, mb, mbh, mo, xm, p, num_sms, st);
+    case QG_BF16: return launch<CG, B_MN, QG_BF16>(ma, mb, mbh, mo, xm, p, num_sms, st);
   }
   set_error("gemm_i8_tc: unsupported output kind %d", out_kind);
   return QG_ENOTSUP;
@@ -591,7 +602,7 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 // out_kind QG_S32 writes raw accumulators; otherwise the dequantize epilogue runs.
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               const SideArgs *side, int num_sms, cudaStream_t st) {
+               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st) {
   if (!gemm_i8_tc_supported(A, lda, B, ldb)) {
     set_error("gemm_i8_tc: operands must be 16-byte aligned with leading dimensions multiple of 16");
     return QG_EINVAL;
@@ -641,10 +652,31 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   } else {
     mo = ma;  // unused by the kernel
   }
-  if (cg == 1) return b_kmajor ? launch_out<1, false>(out_kind, ma, mb, mbh, mo, p, num_sms, st)
-                               : launch_out<1, true>(out_kind, ma, mb, mbh, mo, p, num_sms, st);
-  if (cg == 2) return b_kmajor ? launch_out<2, false>(out_kind, ma, mb, mbh, mo, p, num_sms, st)
-                               : launch_out<2, true>(out_kind, ma, mb, mbh, mo, p, num_sms, st);
+  static ExtraMaps xm_zero = {};
+  ExtraMaps xm = xm_zero;
+  if (multi != nullptr && multi->n > 0) {
+    if (multi->n > kMaxExtraOut || out_kind == QG_S32) {
+      set_error("gemm_i8_tc: at most %d extra destinations, floating-point output", kMaxExtraOut);
+      return QG_EINVAL;
+    }
+    p.n_extra = multi->n;
+    for (int d = 0; d < multi->n; d++) {
+      p.extra_out[d] = multi->dst[d];
+      if (p.tma_store && !aligned16(multi->dst[d])) p.tma_store = 0;
+    }
+    if (p.tma_store) {
+      CUtensorMapDataType odt = out_kind == QG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                : out_kind == QG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      for (int d = 0; d < multi->n; d++) {
+        rc = make_map_2d(&xm.m[d], odt, osz, multi->dst[d], M, N, ldo, 32, (uint32_t)(128 / osz));
+        if (rc) return rc;
+      }
+    }
+  }
+  if (cg == 1) return b_kmajor ? launch_out<1, false>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st)
+                               : launch_out<1, true>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st);
+  if (cg == 2) return b_kmajor ? launch_out<2, false>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st)
+                               : launch_out<2, true>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st);
   return QG_EINVAL;
 }
 

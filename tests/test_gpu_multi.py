@@ -60,3 +60,48 @@ def test_column_parallel_matches_single_gpu(shape, dt):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), shape, dt, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _worker_fused(rank, world, port, shape, dt, ret):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        sys.path.insert(0, ROOT)
+        qg = importlib.import_module(PKG)
+        cp = importlib.import_module(PKG + ".colpar")
+        M, N, K = shape
+        tdt = {"f32": torch.float32, "f16": torch.float16}[dt]
+        g = torch.Generator().manual_seed(11)
+        X = (torch.rand((M, K), generator=g) * 2 - 1).to(tdt).cuda()
+        W = (torch.rand((K, N), generator=g) * 2 - 1).to(tdt).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        layer = cp.FusedColumnParallelLinear(W, b, rank, world)
+        ok = True
+        for _ in range(3):  # repeated forwards reuse the symmetric buffer
+            y = layer.forward(X)
+            torch.cuda.synchronize()
+            full = torch.empty((M, N), dtype=tdt, device="cuda")
+            qg.op_quantized_mm(X, W, full, 127.0, bias=b)
+            torch.cuda.synchronize()
+            view = torch.int32 if dt == "f32" else torch.int16
+            ok = ok and bool(torch.equal(y.view(view), full.view(view)))
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,dt", [((512, 1024, 768), "f32"), ((300, 2048, 520), "f16"), ((4096, 4096, 1024), "f16")])
+def test_fused_epilogue_gather_matches_single_gpu(shape, dt):
+    """Same check with the gather fused into the GEMM epilogue (peer TMA stores over NVLink)."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_fused, args=(world, _free_port(), shape, dt, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
