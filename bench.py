@@ -270,6 +270,8 @@ def run_ours(args):
                 symm_out, hdl, peer_ptrs = None, None, []
     Xq = torch.empty((M, K), dtype=torch.int8, device=dev)
     Wq = torch.empty((K, N), dtype=torch.int8, device=dev)
+    Wt = torch.empty((N, K), dtype=torch.int8, device=dev)
+    kmajor = os.environ.get("QG_PERCALL_KMAJOR", "1") != "0"  # same switch the library reads
     Cx = torch.empty(M, device=dev)
     Cw = torch.empty(N, device=dev)
 
@@ -284,13 +286,19 @@ def run_ours(args):
         # the same launches issued one by one, so that the dominant kernel can be bracketed by CUDA events
         # (instrumented pass) or given its peer destinations (N > 1)
         qg.absmax_quant_rows(Xs[s], 127.0, qg.MODE_REF_EXACT, Xq, Cx)
-        qg.absmax_quant_cols(Ws[s], 127.0, qg.MODE_REF_EXACT, Wq, Cw)
+        if kmajor:  # weight codes transposed on the fly (what qg_quantized_mm does by default)
+            qg.prepare_weights(Ws[s], 127.0, qg.MODE_REF_EXACT, Wt, Cw)
+        else:
+            qg.absmax_quant_cols(Ws[s], 127.0, qg.MODE_REF_EXACT, Wq, Cw)
         if ev is not None:
             ev[0].record()
         if hdl is not None:
             hdl.barrier(channel=0)  # peers have consumed the previous step's result
-            qg.gemm_s8_dequant_ex(Xq, Wq, False, Cx, Cw, symm_out[:, rank * N:(rank + 1) * N], peer_ptrs, 127.0)
+            qg.gemm_s8_dequant_ex(Xq, Wt if kmajor else Wq, kmajor, Cx, Cw, symm_out[:, rank * N:(rank + 1) * N],
+                                  peer_ptrs, 127.0)
             hdl.barrier(channel=1)  # every rank's blocks have landed everywhere
+        elif kmajor:
+            qg.gemm_s8t_dequant(Xq, Wt, Cx, Cw, Os[s], 127.0)
         else:
             qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, Os[s], 127.0)
         if ev is not None:
@@ -353,7 +361,8 @@ def run_ours(args):
         return e0.elapsed_time(e1) / n
 
     rows_ms = stage_ms(lambda j: qg.absmax_quant_rows(Xs[j % nset], 127.0, qg.MODE_REF_EXACT, Xq, Cx))
-    cols_ms = stage_ms(lambda j: qg.absmax_quant_cols(Ws[j % nset], 127.0, qg.MODE_REF_EXACT, Wq, Cw))
+    cols_ms = stage_ms(lambda j: qg.prepare_weights(Ws[j % nset], 127.0, qg.MODE_REF_EXACT, Wt, Cw) if kmajor
+                       else qg.absmax_quant_cols(Ws[j % nset], 127.0, qg.MODE_REF_EXACT, Wq, Cw))
 
     if rank != 0:
         if world > 1:

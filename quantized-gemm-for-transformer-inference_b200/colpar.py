@@ -138,7 +138,8 @@ class FusedColumnParallelLinear:
         m = x.shape[0]
         self._ensure_out(m, x.dtype, x.device)
         if self._xq is None or self._xq.shape[0] != m:
-            self._xq = torch.empty((m, self.k), dtype=torch.int8, device=x.device)
+            ldk = (self.k + 15) // 16 * 16  # TMA wants 16-byte aligned rows
+            self._xq = torch.zeros((m, ldk), dtype=torch.int8, device=x.device)[:, : self.k]
             self._cx = torch.empty(m, dtype=torch.float32, device=x.device)
         absmax_quant_rows(x, self.range, self.mode, self._xq, self._cx)
         self.hdl.barrier(channel=0)  # every peer has finished with the previous contents of its matrix

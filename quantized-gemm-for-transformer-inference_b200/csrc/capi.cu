@@ -122,6 +122,15 @@ static int grow(void **p, size_t *have, size_t want) {
   return QG_OK;
 }
 
+// layout of the per-call weight codes: 1 = transposed (K-major GEMM operand), 0 = the reference's [K,N]
+static bool percall_kmajor() {
+  static const bool on = [] {
+    const char *e = getenv("QG_PERCALL_KMAJOR");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+
 static bool valid_io(int dt) { return dt == QG_F32 || dt == QG_F16 || dt == QG_BF16; }
 
 // layout of the scratch block shared by qg_quantized_mm / qg_linear_forward
@@ -137,7 +146,9 @@ static Workspace carve(void *base, int M, int N, int K) {
   w.ldwq = round_up(N, 16);  // per-call weight codes Wq [K, ldwq] (the reference's layout)
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = (size_t)round_up((int64_t)(off + n), 256); return o; };
-  const size_t oxq = take((size_t)M * w.ldxq), owq = take((size_t)K * w.ldwq);
+  // the weight-code region fits either layout: Wq [K, ceil16(N)] or Wt [N, ceil16(K)]
+  const size_t wq_bytes = (size_t)K * w.ldwq > (size_t)N * w.ldxq ? (size_t)K * w.ldwq : (size_t)N * w.ldxq;
+  const size_t oxq = take((size_t)M * w.ldxq), owq = take(wq_bytes);
   const size_t ocx = take(sizeof(float) * M), ocw = take(sizeof(float) * N), osc = take(sizeof(float) * N);
   char *b = reinterpret_cast<char *>(base);
   w.Xq = reinterpret_cast<int8_t *>(b + oxq);
@@ -338,12 +349,12 @@ int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ldw, int 
   cudaStream_t st = (cudaStream_t)stream;
   rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  // per-call weight quantization: row-major codes (two coalesced passes) feeding the GEMM as an MN-major
-  // operand beat transposed codes + K-major GEMM here; prepared weights (qg_prepare_weights) take the latter
-  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, false, st);
+  // per-call weight quantization; QG_PERCALL_KMAJOR=0 keeps the reference's [K,N] code layout (MN-major operand)
+  const bool kmajor = percall_kmajor();
+  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, kmajor ? w.ldxq : w.ldwq, w.Cw, w.scratch, kmajor, st);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 0, M, N, K, O, ldo, out_dtype, w.Cx, w.Cw, bias,
-                       1 / (range * range), st);
+  return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, kmajor ? w.ldxq : w.ldwq, kmajor ? 1 : 0, M, N, K, O, ldo, out_dtype, w.Cx,
+                       w.Cw, bias, 1 / (range * range), st);
 }
 
 int qg_prepare_weights(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, int8_t *Wt,

@@ -313,241 +313,93 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
   for (; k < k1; k += 8) emit(ldg16(base + (int64_t)k * ldw), k);
 }
 
-// ------------------------------------------------------------------------------------------
-// Columns, ONE launch and one HBM read of W: "decoupled" two-phase kernel.
-// W is cut into column panels (kPanelTiles tiles of 512 bytes of columns; 16 MB of fp32 at
-// K = 4096).  The block list interleaves the phases of neighbouring panels,
-//     P1(0) P1(1) P2(0) P1(2) P2(1) ... P2(last)
-// P1 blocks reduce |w| of a [32 rows x 512 B] patch into part[col] (atomicMax on fp32 bit
-// patterns) and then bump the panel's arrival counter; P2 blocks wait for that counter (they only
-// ever wait for blocks with a SMALLER block index, which the hardware dispatches first, so the wait
-// cannot deadlock), fold in the signed row 0, and re-read their patch -- fetched from HBM two
-// groups earlier, now an L2 hit -- to emit the codes.  The last P2 block of a panel resets part[]
-// and the counters, so the persistent scratch is clean for the next call.
-// kTranspose: codes go out as Wt[n][k] (K contiguous), the K-major operand layout the tensor-core
-// GEMM runs fastest on, staged through a word-swizzled smem tile so stores are 32-byte sectors
-// (neighbouring row chunks, which run concurrently, complete the 128-byte lines in L2).
-// (Two earlier designs were measured and dropped: a thread-block-cluster kernel that kept a
-// 128-byte-wide strip in registers -- one read, but narrow rows use HBM badly, 29 us at 4096^2 --
-// and a cluster kernel re-reading a 512-byte strip through L2 with a DSMEM max exchange -- too
-// few CTAs in flight, 34-40 us.  A first cut of this kernel with 128-row patches (16 loads and
-// ~110 registers per thread, 2 CTAs per SM) read W from HBM once, as intended, but was latency
-// bound at 35 us, and one-shot CTAs on 32-row patches were worse still (46 us: per-CTA start-up,
-// fence and wait latencies are not amortised).  Hence persistent CTAs with a register double buffer.
-// Three separate launches: 26 us.)
-// ------------------------------------------------------------------------------------------
-constexpr int kPanelTiles = 8;
-
-__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-struct ColqScratch {
-  float *part;    // [N] running maxima, -inf when idle
-  int *arrived;   // [panels] P1 blocks done
-  int *finished;  // [panels] P2 blocks done
-};
-
-constexpr int kPatchRows = 32;  // rows per work item: one row quad (4 rows) per warp
-
-// Work item i of the interleaved list -> (phase, panel, row chunk, column tile)
-struct ColqItem { int phase, panel, chunk, tile; };
-__device__ __forceinline__ ColqItem colq_decode(int i, int G, int panels) {
-  const int g = i / G, r = i - g * G;
-  ColqItem it;
-  if (g == 0) { it.phase = 1; it.panel = 0; }
-  else if (g == 2 * panels - 1) { it.phase = 2; it.panel = panels - 1; }
-  else if (g & 1) { it.phase = 1; it.panel = (g + 1) / 2; }
-  else { it.phase = 2; it.panel = g / 2 - 1; }
-  it.chunk = r / kPanelTiles;
-  it.tile = it.panel * kPanelTiles + r % kPanelTiles;
-  return it;
-}
-
-// Persistent CTAs walk the item list with stride gridDim.x, loading the next item's four row
-// vectors before working on the current one (register double buffer), so HBM/L2 latency overlaps
-// the reduction / quantization of the previous patch.  A CTA announces a panel's phase 1 once,
-// after its last phase-1 item of that panel; phase-2 items wait until `expected` CTAs have done so.
-// All CTAs are co-resident (the grid is sized from the occupancy), and every CTA meets its own
-// phase-1 items of a panel before any phase-2 item of it, so the wait always ends.
-template <typename T, bool kTranspose>
+// Pass 2 with transposed output: codes go out as Wt[n][k] (K contiguous), the K-major operand layout
+// the tensor-core GEMM runs fastest on.  A CTA walks its row chunk in patches of 32 rows (one row
+// quad per warp, next patch prefetched into registers), packs four k-consecutive codes per column
+// into a word, stages them in a bank-rotated smem tile and writes 32-byte sectors of Wt; the
+// neighbouring row chunks, which run concurrently, complete the 128-byte lines in L2.
+//
+// Single-launch designs were built and measured at 4096^2 fp32 before settling on two launches
+// (26 us row-major, ~29 us transposed): a thread-block-cluster kernel holding a 128-byte-wide strip
+// in registers with a DSMEM max exchange (one HBM read, but narrow rows: 29 us); a cluster kernel
+// re-reading a 512-byte strip through L2 (34-40 us, too few CTAs in flight); and a "decoupled"
+// kernel whose phase-2 blocks wait on per-panel arrival counters (ncu: 67 MB of DRAM reads, i.e. the
+// re-read did hit L2, yet 35-48 us in three variants -- fence, atomic and wait latency per patch).
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-quant_cols_decoupled_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int panels,
-                            int chunks, int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw, ColqScratch sc) {
+quant_cols_t_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int rows_per_cta,
+                    const unsigned long long *__restrict__ part, uint32_t epoch, int8_t *__restrict__ Wt, int64_t ldt,
+                    float *__restrict__ Cw) {
   constexpr int EPV = Unpack<T>::EPV;
-  constexpr int SC = 32 * EPV;  // columns per tile (512 bytes of input per row)
-  // phase 1: [8 warps][SC] partial maxima; phase 2 (transposed): [8 k-words][SC columns]
-  __shared__ uint32_t s_buf[(kThreads / 32) * SC];
-  __shared__ int s_last;
-  const int G = kPanelTiles * chunks;  // items per phase group
-  const int total = 2 * panels * G;
-  const int expected = min(G, (int)gridDim.x);  // CTAs that own at least one item of a group
+  constexpr int SC = 32 * EPV;  // columns per CTA
+  __shared__ uint32_t s_buf[(kThreads / 32) * SC];  // [8 k-words][SC columns]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  auto load = [&](const ColqItem &it, uint4 (&v)[4]) {
-    const int col = it.tile * SC + lane * EPV;
-    const int row0 = it.chunk * kPatchRows + 4 * warp;
-    const int r1 = min(K, (it.chunk + 1) * kPatchRows);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      v[i] = (col < N && row0 + i < r1) ? ldg16(W + (int64_t)(row0 + i) * ldw + col) : make_uint4(0, 0, 0, 0);
-  };
-
+  const int col = (blockIdx.x * 32 + lane) * EPV;
+  const bool col_ok = col < N;
+  const T *base = W + col;
   griddep_wait();
-  int i = blockIdx.x;
-  if (i >= total) return;
-  ColqItem cur = colq_decode(i, G, panels);
+  float s[EPV];
+  if (col_ok) {
+    float x0[EPV];
+    Unpack<T>::run(ldg16(base), x0);
+#pragma unroll
+    for (int e = 0; e < EPV; e++) {
+      float c;
+      if (fold_first(x0[e], part_value(part[col + e], epoch), mode, c)) {
+        for (int k = 1; k < K; k++) {
+          const float x = to_f32(base[(int64_t)k * ldw + e]);
+          if (x == x) { c = -x; break; }
+        }
+      }
+      if (blockIdx.y == 0 && warp == 0 && Cw != nullptr) Cw[col + e] = c;
+      s[e] = __fdiv_rn(range, c);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPV; e++) s[e] = 0.0f;
+  }
+  const int k0 = blockIdx.y * rows_per_cta, k1 = min(K, k0 + rows_per_cta);
+  auto load = [&](int rb, uint4 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int row = rb + 4 * warp + i;
+      v[i] = (col_ok && row < k1) ? ldg16(base + (int64_t)row * ldw) : make_uint4(0, 0, 0, 0);
+    }
+  };
   uint4 v[4], vn[4];
-  load(cur, v);
-  int waited_panel = -1;
-  for (; i < total; i += gridDim.x) {
-    const int inext = i + gridDim.x;
-    ColqItem nxt = cur;
-    const bool has_next = inext < total;
-    if (has_next) {
-      nxt = colq_decode(inext, G, panels);
-      load(nxt, vn);
+  load(k0, v);
+  for (int rb = k0; rb < k1; rb += 32) {
+    if (rb + 32 < k1) load(rb + 32, vn);
+    float f[4][EPV];
+#pragma unroll
+    for (int i = 0; i < 4; i++) Unpack<T>::run(v[i], f[i]);
+#pragma unroll
+    for (int e = 0; e < EPV; e++) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t code = (rb + 4 * warp + i < k1) ? quant_code_u8(f[i][e], s[e]) : 0u;  // rows past K: zeros
+        w |= code << (8 * i);
+      }
+      // a lane's EPV columns are rotated by lane / (32 / EPV): 32 lanes (same e) hit 32 different banks
+      s_buf[warp * SC + lane * EPV + ((e + lane / (32 / EPV)) & (EPV - 1))] = w;
     }
-    const int col = cur.tile * SC + lane * EPV;
-    const bool col_ok = col < N;
-    const int rb = cur.chunk * kPatchRows, r1 = min(K, rb + kPatchRows);
-    const int row0 = rb + 4 * warp;
-
-    if (cur.phase == 1) {
-      float m[EPV];
+    __syncthreads();
+    for (int t = threadIdx.x; t < SC * 2; t += kThreads) {  // a thread moves 16 of a column's 32 bytes
+      const int h = t / SC, c = t - h * SC;
+      const int gc = blockIdx.x * SC + c;
+      const int wl = c / EPV;
+      const int pos = wl * EPV + (((c & (EPV - 1)) + wl / (32 / EPV)) & (EPV - 1));
+      uint32_t w4[4];
 #pragma unroll
-      for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int row = row0 + q;
-        if (col_ok && row < r1 && row > 0) {  // row 0 is folded in signed, in phase 2
-          float f[EPV];
-          Unpack<T>::run(v[q], f);
-#pragma unroll
-          for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
-        }
-      }
-      float *s_red = reinterpret_cast<float *>(s_buf);
-#pragma unroll
-      for (int e = 0; e < EPV; e++) s_red[warp * SC + lane * EPV + e] = m[e];
-      __syncthreads();
-      for (int c = threadIdx.x; c < SC; c += kThreads) {
-        float mm = s_red[c];
-#pragma unroll
-        for (int w = 1; w < kThreads / 32; w++) mm = fmaxf(mm, s_red[w * SC + c]);
-        const int gc = cur.tile * SC + c;
-        if (gc < N && mm >= 0.0f) atomicMax(reinterpret_cast<int *>(sc.part) + gc, __float_as_int(mm));
-      }
-      const bool last_of_panel = !has_next || nxt.phase != 1 || nxt.panel != cur.panel;
-      if (last_of_panel) __threadfence();
-      __syncthreads();
-      if (last_of_panel && threadIdx.x == 0) atomicAdd(sc.arrived + cur.panel, 1);
-    } else {
-      if (waited_panel != cur.panel) {
-        if (threadIdx.x == 0) {
-          const long long t0 = clock64();
-          while (ld_acquire_gpu(sc.arrived + cur.panel) < expected) {
-            __nanosleep(64);
-            if (clock64() - t0 > 4000000000LL) {
-              printf("[qgemm] column quantizer: panel %d never completed phase 1\n", cur.panel);
-              __trap();
-            }
-          }
-        }
-        __syncthreads();
-        waited_panel = cur.panel;
-      }
-      float s[EPV];
-      if (col_ok) {
-        float x0[EPV];
-        Unpack<T>::run(ldg16(W + col), x0);
-#pragma unroll
-        for (int e = 0; e < EPV; e++) {
-          const float mm = __ldcg(sc.part + col + e);
-          float cw;
-          if (fold_first(x0[e], mm, mode, cw)) {
-            for (int k = 1; k < K; k++) {  // rare +-0 tie-break: sign of the first later non-NaN zero
-              const float x = to_f32(W[(int64_t)k * ldw + col + e]);
-              if (x == x) { cw = -x; break; }
-            }
-          }
-          if (cur.chunk == 0 && warp == 0 && Cw != nullptr) Cw[col + e] = cw;
-          s[e] = __fdiv_rn(range, cw);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < EPV; e++) s[e] = 0.0f;
-      }
-      if (Wq != nullptr) {
-        float f[4][EPV];
-#pragma unroll
-        for (int q = 0; q < 4; q++) Unpack<T>::run(v[q], f[q]);
-        if (kTranspose) {
-#pragma unroll
-          for (int e = 0; e < EPV; e++) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint32_t code = (row0 + q < r1) ? quant_code_u8(f[q][e], s[e]) : 0u;  // rows past K: zero padding
-              w |= code << (8 * q);
-            }
-            // [8 k-words][SC columns]; a lane's EPV columns are rotated by lane / (32 / EPV) so that
-            // the 32 lanes of a warp (same e) fall into 32 different banks
-            s_buf[warp * SC + lane * EPV + ((e + lane / (32 / EPV)) & (EPV - 1))] = w;
-          }
-          __syncthreads();
-          // SC columns x 32 bytes: a thread moves one 16-byte half of a column's 32-byte row of Wt
-          for (int t = threadIdx.x; t < SC * 2; t += kThreads) {
-            const int h = t / SC, c = t - h * SC;
-            const int gc = cur.tile * SC + c;
-            const int wl = c / EPV;  // lane that wrote this column
-            const int pos = wl * EPV + (((c & (EPV - 1)) + wl / (32 / EPV)) & (EPV - 1));
-            uint32_t w4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) w4[j] = s_buf[(4 * h + j) * SC + pos];
-            const int row = rb + 16 * h;
-            if (gc < N && row < r1)
-              *reinterpret_cast<uint4 *>(Wq + (int64_t)gc * ldq + row) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-          }
-          __syncthreads();
-        } else if (col_ok) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int row = row0 + q;
-            if (row < r1) {
-              uint32_t w[EPV / 4];
-#pragma unroll
-              for (int qq = 0; qq < EPV / 4; qq++)
-                w[qq] = quant_code_u8(f[q][4 * qq], s[4 * qq]) | (quant_code_u8(f[q][4 * qq + 1], s[4 * qq + 1]) << 8) |
-                        (quant_code_u8(f[q][4 * qq + 2], s[4 * qq + 2]) << 16) |
-                        (quant_code_u8(f[q][4 * qq + 3], s[4 * qq + 3]) << 24);
-              int8_t *dst = Wq + (int64_t)row * ldq + col;
-              if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
-              else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
-            }
-          }
-        }
-      }
-      // a CTA's last phase-2 item of the panel: the last CTA to get there cleans the scratch
-      const bool last_of_panel = !has_next || nxt.phase != 2 || nxt.panel != cur.panel;
-      if (last_of_panel) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(sc.finished + cur.panel, 1) == expected - 1);
-        __syncthreads();
-        if (s_last) {
-          for (int c = threadIdx.x; c < kPanelTiles * SC; c += kThreads) {
-            const int gc = cur.panel * kPanelTiles * SC + c;
-            if (gc < N) sc.part[gc] = -INFINITY;
-          }
-          if (threadIdx.x == 0) { sc.arrived[cur.panel] = 0; sc.finished[cur.panel] = 0; }
-        }
-      }
+      for (int j = 0; j < 4; j++) w4[j] = s_buf[(4 * h + j) * SC + pos];
+      const int row = rb + 16 * h;
+      if (gc < N && row < k1)
+        *reinterpret_cast<uint4 *>(Wt + (int64_t)gc * ldt + row) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
     }
-    cur = nxt;
+    __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; q++) v[q] = vn[q];
+    for (int i = 0; i < 4; i++) v[i] = vn[i];
   }
 }
 
@@ -605,13 +457,8 @@ __global__ void outlier_mask_kernel(const float *__restrict__ A, int M, int K, i
 
 inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-__global__ void colq_scratch_init_kernel(float *part, int n, int *counters, int nc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) part[i] = -INFINITY;
-  if (i < nc) counters[i] = 0;
-}
-
-// Epoch-tagged scratch of the two-launch column path: zero-initialised once, never reset.
+// Epoch-tagged column-max scratch: zero-initialised once, never reset (each call uses a fresh epoch).
+// One buffer per device, so calls that quantize weights are not re-entrant across streams.
 int twopass_scratch(int N, unsigned long long **part, uint32_t *epoch) {
   struct State { unsigned long long *part = nullptr; int n = 0; uint32_t epoch = 0; };
   static State state[16];
@@ -627,31 +474,6 @@ int twopass_scratch(int N, unsigned long long **part, uint32_t *epoch) {
   }
   *part = s.part;
   *epoch = ++s.epoch;  // 0 is never used, so zero-initialised entries never match
-  return 0;
-}
-
-// Persistent per-device scratch of the decoupled column quantizer: clean (-inf / 0) between calls,
-// because the kernel resets what it used.  Grown (and initialised on `st`) on demand.  Calls that
-// quantize weights are therefore not re-entrant across streams of one device.
-int colq_scratch(int N, int panels, ColqScratch *out, cudaStream_t st) {
-  struct State { float *part = nullptr; int *counters = nullptr; int n = 0, panels = 0; };
-  static State state[16];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  State &s = state[dev & 15];
-  if (s.n < N || s.panels < panels) {
-    if (s.part) { cudaDeviceSynchronize(); cudaFree(s.part); cudaFree(s.counters); }
-    s.n = (int)round_up(N < 16384 ? 16384 : N, 4096);
-    s.panels = (int)round_up(panels < 256 ? 256 : panels, 64);
-    if (cudaMalloc(&s.part, sizeof(float) * (size_t)s.n) != cudaSuccess) { s = State(); return (int)cudaGetLastError(); }
-    if (cudaMalloc(&s.counters, sizeof(int) * 2 * (size_t)s.panels) != cudaSuccess) { s = State(); return (int)cudaGetLastError(); }
-    const int total = s.n > 2 * s.panels ? s.n : 2 * s.panels;
-    colq_scratch_init_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(s.part, s.n, s.counters, 2 * s.panels);
-    count_launch();
-  }
-  out->part = s.part;
-  out->arrived = s.counters;
-  out->finished = s.counters + s.panels;
   return 0;
 }
 
@@ -711,7 +533,7 @@ template <typename T>
 int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, const float *sw, int8_t *Wq,
                   int64_t ldq, float *Cw, float *scratch, bool transpose, cudaStream_t st) {
   constexpr int EPV = Unpack<T>::EPV;
-  if (transpose && Wq != nullptr && !(aligned(Wq, 4) && ldq % 4 == 0))
+  if (transpose && Wq != nullptr && !(aligned(Wq, 16) && ldq % 16 == 0))
     return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   const bool vec_ok = (N % EPV == 0) && aligned(W, 16) && ((ldw * sizeof(T)) % 16 == 0) &&
@@ -720,33 +542,6 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
   if (!vec_ok) {
     return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
-  }
-  // transposed (K-major) codes: the single-launch decoupled kernel; row-major codes: two launches,
-  // which measured faster (26 us vs 34-45 us at 4096^2; QG_COLS_DECOUPLED=1 forces the former)
-  if (sw == nullptr && Wq != nullptr && (transpose || getenv("QG_COLS_DECOUPLED") != nullptr)) {
-    const int tiles = (int)ceil_div(N, 32 * EPV);
-    const int panels = (int)ceil_div(tiles, kPanelTiles);
-    const int chunks = (int)ceil_div(K, kPatchRows);
-    ColqScratch sc;
-    int rc = colq_scratch(N, panels, &sc, st);
-    if (rc) return rc;
-    const int64_t total = (int64_t)2 * panels * kPanelTiles * chunks;
-    static int resident[2] = {0, 0};  // co-resident CTAs per instantiation (the kernel's wait relies on it)
-    int &res = resident[transpose ? 1 : 0];
-    if (res == 0) {
-      int per_sm = 0, dev = 0, sms = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (transpose) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quant_cols_decoupled_kernel<T, true>, kThreads, 0);
-      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quant_cols_decoupled_kernel<T, false>, kThreads, 0);
-      res = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
-    }
-    const dim3 grid((unsigned)(total < res ? total : res));
-    if (transpose)
-      return (int)launch_kernel(quant_cols_decoupled_kernel<T, true>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode,
-                                panels, chunks, Wq, ldq, Cw, sc);
-    return (int)launch_kernel(quant_cols_decoupled_kernel<T, false>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode,
-                              panels, chunks, Wq, ldq, Cw, sc);
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
   const int rpc = cols_rows_per_cta(K, col_tiles);
@@ -764,6 +559,9 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
                                 ldw, mode, part, epoch, Cw);
   }
   dim3 grid(col_tiles, (unsigned)ceil_div(K, rpc));
+  if (transpose)
+    return (int)launch_kernel(quant_cols_t_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode, rpc, part, epoch,
+                              Wq, ldq, Cw);
   return (int)launch_kernel(quant_cols_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode, rpc, part, epoch, sw,
                             Wq, ldq, Cw);
 }
