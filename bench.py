@@ -314,16 +314,19 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sample_clocks = rank == 0 and os.environ.get("QG_BENCH_NO_CLOCKS") is None
+    if sample_clocks:
         sampler.start()
         time.sleep(0.25)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     qg.launch_count(reset=True)
+    t_host0 = time.perf_counter()
     t_start.record()
     for i in range(args.steps):
         step(i)
     t_end.record()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     torch.cuda.synchronize()
     launches = qg.launch_count()
     # instrumented pass, immediately after and on the same buffers: the same K steps with a CUDA event
@@ -335,7 +338,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sample_clocks else None
 
     total_ms = t_start.elapsed_time(t_end)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -467,6 +470,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": int(launches),
+        "host_enqueue_ms": host_enqueue_ms,
         "clocks": clocks,
     }
     print(json.dumps(line))

@@ -1,0 +1,101 @@
+"""Measurements for the BASELINE.json configs other than the headline one (which bench.py owns):
+
+  config 2  square sweep M=N=K in {1024, 2048, 4096, 8192}: quantized linear vs fp16 GEMM
+  config 4  OPT-6.7B-shaped decoder linears, T = 8 x 2048 tokens, fp16 in/out, 6 injected outlier
+            feature dims (x20), threshold 6.0: with / without the decomposition, error vs fp16 GEMM
+  config 5  OPT-66B-shaped FFN shards as one GPU sees them at P = 8 (multi-GPU runs: bench.py --gpus N)
+
+All timings: CUDA events, 3 warm-up + 10 timed calls, two rotating activation buffers.
+Writes gpurun_out/configs.json.
+"""
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+qg = importlib.import_module("quantized-gemm-for-transformer-inference_b200")
+DEV = "cuda"
+
+
+def timed(fn, iters=10, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def linear_case(name, M, K, N, dt=torch.float16, outliers=0, w_std=0.02, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    X = [torch.randn((M, K), device=DEV, generator=g).to(dt) for _ in range(2)]
+    idx = None
+    if outliers:
+        cols = torch.randperm(K, device=DEV, generator=g)[:outliers].sort().values
+        for x in X:
+            x[:, cols] *= 20
+        idx = cols.to(torch.int32)
+    lin = qg.LinearLayer(K, N, device=DEV, dtype=dt)
+    lin.w.normal_(0, w_std, generator=g)
+    lin.b.zero_()
+    lin.quantize_weights()
+    y = torch.empty((M, N), dtype=dt, device=DEV)
+    ops = 2.0 * M * N * K
+    res = {"name": name, "M": M, "K": K, "N": N, "dtype": str(dt).split(".")[-1], "outlier_dims": outliers}
+    us = timed(lambda i: lin.forward(X[i & 1], y))
+    res["int8_linear_us"], res["int8_linear_tops"] = us, ops / us / 1e6
+    ref = X[0].float() @ lin.w.float() if M * N <= 4096 * 16384 else None
+    if ref is not None:
+        lin.forward(X[0], y)
+        res["int8_mean_abs_err"] = (y.float() - ref).abs().mean().item()
+        res["ref_rms"] = ref.pow(2).mean().sqrt().item()
+    if idx is not None:
+        us = timed(lambda i: lin.forward_outlier(X[i & 1], y, idx))
+        res["int8_outlier_linear_us"], res["int8_outlier_linear_tops"] = us, ops / us / 1e6
+        found, n = qg.outlier_cols(X[0], 6.0)
+        res["outliers_detected"] = n
+        us = timed(lambda i: qg.outlier_cols(X[i & 1], 6.0))
+        res["outlier_detect_us"] = us
+        if ref is not None:
+            lin.forward_outlier(X[0], y, idx)
+            res["int8_outlier_mean_abs_err"] = (y.float() - ref).abs().mean().item()
+    w16 = lin.w.to(torch.float16)
+    x16 = [x.to(torch.float16) for x in X]
+    us = timed(lambda i: torch.matmul(x16[i & 1], w16))
+    res["fp16_gemm_us"], res["fp16_gemm_tflops"] = us, ops / us / 1e6
+    if ref is not None:
+        res["fp16_mean_abs_err"] = (torch.matmul(x16[0], w16).float() - ref).abs().mean().item()
+    res["speedup_vs_fp16"] = res["fp16_gemm_us"] / res["int8_linear_us"]
+    del lin, X, y, w16, x16
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    out = []
+    for n in (1024, 2048, 4096, 8192):  # config 2
+        out.append(linear_case(f"square_{n}_f16", n, n, n, torch.float16, w_std=1.0 / n ** 0.5))
+        out.append(linear_case(f"square_{n}_f32", n, n, n, torch.float32, w_std=1.0 / n ** 0.5))
+    T = 8 * 2048  # config 4
+    for name, K, N in (("opt6.7b_qkv", 4096, 12288), ("opt6.7b_out", 4096, 4096), ("opt6.7b_fc1", 4096, 16384),
+                       ("opt6.7b_fc2", 16384, 4096)):
+        out.append(linear_case(name, T, K, N, torch.float16, outliers=6))
+    for name, K, N in (("opt66b_fc1_shard_of_8", 9216, 36864 // 8), ("opt66b_fc2_shard_of_8", 36864, 9216 // 8)):  # config 5
+        out.append(linear_case(name, 4096, K, N, torch.float16))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    for r in out:
+        print(json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()}))
+
+
+if __name__ == "__main__":
+    main()
