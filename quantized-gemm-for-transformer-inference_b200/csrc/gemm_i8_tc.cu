@@ -38,6 +38,7 @@ struct GemmParams {
   // would fill at most half of the machine, each is cut into `tail_split` = 2 tiles of 128
   // columns so the last wave takes half as long (4096^3 on 74 CTA pairs: 3.5 rounds instead of 4).
   int full_tiles, total_tiles, tail_split;
+  uint32_t nstages;  // smem ring depth actually used (<= the compiled kStages)
   void *out;             // [M,N] of the epilogue's type
   int64_t ldo;           // elements
   const float *Cx, *Cw, *bias;
@@ -153,6 +154,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // preceding kernel; from here on its outputs (Xq, Wq, Cx, Cw) are read
   griddep_wait();
 
+  const uint32_t nstages = p.nstages;  // == kStages unless narrowed for a pipeline-depth experiment
   const int num_tiles = p.total_tiles;
   // tile index -> (row block, first column, width)
   auto tile_coords = [&](int t, int &m_blk, int &n0, int &bn) {
@@ -185,7 +187,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const bool half = bn != BN;  // only generated for K-major B (see host side)
         const uint32_t stage_tx = C::kABytes + (uint32_t)(bn / CG) * BK;
         for (int kb = 0; kb < num_kb; kb++, it++) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          const uint32_t s = it % nstages, ph = (it / nstages) & 1;
           if (p.stats) {
             const long long t0 = clock64();
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
@@ -245,7 +247,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tile_coords(t, m_blk, n0, bn);
         const uint32_t idesc = idesc_nofield | ((uint32_t)(bn >> 3) << 17);  // UMMA N of this tile
         for (int kb = 0; kb < num_kb; kb++, it++) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          const uint32_t s = it % nstages, ph = (it / nstages) & 1;
           if (p.stats) {
             const long long t0 = clock64();
             mbar_wait(smem_u32(&full_bar[s]), ph, 3);
@@ -496,9 +498,51 @@ EncodeFn encode_fn() {
   return fn;
 }
 
+// Encoding a tensor map costs a few microseconds of host time, which is what a small GEMM takes on
+// the device; inference calls come back with the same buffers, so the last maps are kept per thread.
+struct MapKey {
+  const void *base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  int dt;
+  bool operator==(const MapKey &o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && dt == o.dt;
+  }
+};
+struct MapCache {
+  static constexpr int kSlots = 64;
+  MapKey key[kSlots];
+  CUtensorMap map[kSlots];
+  bool used[kSlots] = {};
+  int next = 0;
+};
+
+int make_map_2d_uncached(CUtensorMap *map, CUtensorMapDataType dt, size_t esize, const void *base, uint64_t rows,
+                         uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+
 // 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols]
 int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, size_t esize, const void *base, uint64_t rows, uint64_t cols,
                 uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  static thread_local MapCache cache;
+  const MapKey k = {base, rows, cols, ld, box_rows, box_cols, (int)dt};
+  for (int i = 0; i < MapCache::kSlots; i++)
+    if (cache.used[i] && cache.key[i] == k) {
+      *map = cache.map[i];
+      return QG_OK;
+    }
+  int rc = make_map_2d_uncached(map, dt, esize, base, rows, cols, ld, box_rows, box_cols);
+  if (rc) return rc;
+  const int slot = cache.next;
+  cache.next = (cache.next + 1) % MapCache::kSlots;
+  cache.key[slot] = k;
+  cache.map[slot] = *map;
+  cache.used[slot] = true;
+  return QG_OK;
+}
+
+int make_map_2d_uncached(CUtensorMap *map, CUtensorMapDataType dt, size_t esize, const void *base, uint64_t rows,
+                         uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   EncodeFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -530,11 +574,18 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   }
   const int base_tiles = p.tiles_m * p.tiles_n;
   const int max_clusters = num_sms / CG;
+  p.nstages = C::kStages;
+  static const char *dbg_stages = getenv("QG_DBG_STAGES");
+  if (const char *e = dbg_stages) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= C::kStages) p.nstages = (uint32_t)v;
+  }
   p.full_tiles = base_tiles;
   p.total_tiles = base_tiles;
   p.tail_split = 1;
   const int rem = base_tiles % max_clusters;
-  if (!B_MN && base_tiles > max_clusters && rem > 0 && 2 * rem <= max_clusters && getenv("QG_NO_TAIL_SPLIT") == nullptr) {
+  static const bool no_tail_split = getenv("QG_NO_TAIL_SPLIT") != nullptr;
+  if (!B_MN && base_tiles > max_clusters && rem > 0 && 2 * rem <= max_clusters && !no_tail_split) {
     p.full_tiles = base_tiles - rem;
     p.tail_split = 2;
     p.total_tiles = p.full_tiles + 2 * rem;
@@ -614,7 +665,8 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   p.out = O; p.ldo = ldo; p.Cx = Cx; p.Cw = Cw; p.bias = bias; p.c = c;
   const size_t osz = (out_kind == QG_F16 || out_kind == QG_BF16) ? 2 : 4;
   p.tma_store = (aligned16(O) && (ldo * osz) % 16 == 0) ? 1 : 0;
-  if (getenv("QG_DBG_NO_TMA_STORE") != nullptr) p.tma_store = 0;
+  static const bool dbg_no_tma_store = getenv("QG_DBG_NO_TMA_STORE") != nullptr;
+  if (dbg_no_tma_store) p.tma_store = 0;
   p.stats = g_stats;
   if (side != nullptr && side->no_pad > 0) {
     if (side->no_pad > kSideMax || side->no_pad % 8 != 0 || (side->ldxo % 8) != 0 ||
@@ -626,9 +678,10 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
     p.no_pad = side->no_pad; p.side_bf16 = side->side_bf16;
   }
   p.b_kstep = UK * 128; p.b_lbo = BK * 128; p.b_sbo = 1024;
-  if (const char *e = getenv("QG_DBG_B_KSTEP")) p.b_kstep = (uint32_t)atoi(e);
-  if (const char *e = getenv("QG_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);
-  if (const char *e = getenv("QG_DBG_B_SBO")) p.b_sbo = (uint32_t)atoi(e);
+  static const char *dbg_kstep = getenv("QG_DBG_B_KSTEP"), *dbg_lbo = getenv("QG_DBG_B_LBO"), *dbg_sbo = getenv("QG_DBG_B_SBO");
+  if (dbg_kstep) p.b_kstep = (uint32_t)atoi(dbg_kstep);
+  if (dbg_lbo) p.b_lbo = (uint32_t)atoi(dbg_lbo);
+  if (dbg_sbo) p.b_sbo = (uint32_t)atoi(dbg_sbo);
 
   CUtensorMap ma, mb, mbh, mo;
   int rc = make_map_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A, M, K, lda, BM, BK);
