@@ -39,6 +39,7 @@ struct GemmParams {
   // columns so the last wave takes half as long (4096^3 on 74 CTA pairs: 3.5 rounds instead of 4).
   int full_tiles, total_tiles, tail_split;
   uint32_t nstages;  // smem ring depth actually used (<= the compiled kStages)
+  int dbg_noload;    // bring-up experiment: after the ring is filled once, signal 'full' without loading
   void *out;             // [M,N] of the epilogue's type
   int64_t ldo;           // elements
   const float *Cx, *Cw, *bias;
@@ -198,6 +199,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
           const int k0 = kb * BK;
+          if (p.dbg_noload && it >= nstages) {  // timing experiment only: stale operands, no TMA traffic
+            if (leader) mbar_arrive(smem_u32(&full_bar[s]));
+            continue;
+          }
           if (CG == 1) {
             const uint32_t fb = smem_u32(&full_bar[s]);
             mbar_arrive_expect_tx(fb, stage_tx);
@@ -575,6 +580,8 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   const int base_tiles = p.tiles_m * p.tiles_n;
   const int max_clusters = num_sms / CG;
   p.nstages = C::kStages;
+  static const bool dbg_noload = getenv("QG_DBG_NOLOAD") != nullptr, dbg_all_half = getenv("QG_DBG_ALL_HALF") != nullptr;
+  p.dbg_noload = dbg_noload ? 1 : 0;
   static const char *dbg_stages = getenv("QG_DBG_STAGES");
   if (const char *e = dbg_stages) {
     const int v = atoi(e);
@@ -589,6 +596,11 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
     p.full_tiles = base_tiles - rem;
     p.tail_split = 2;
     p.total_tiles = p.full_tiles + 2 * rem;
+  }
+  if (!B_MN && dbg_all_half) {  // experiment: every tile 128 columns wide
+    p.full_tiles = 0;
+    p.tail_split = 2;
+    p.total_tiles = 2 * base_tiles;
   }
   const int num_tiles = p.total_tiles;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
