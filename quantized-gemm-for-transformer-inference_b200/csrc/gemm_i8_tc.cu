@@ -121,7 +121,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t *tempty_bar = bars + 2 * kStages + 2; // [2]        epilogue -> MMA
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -174,43 +174,46 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int cluster_id = blockIdx.x / CG;
   const int num_kb = (p.K + BK - 1) / BK;
 
+  // The producer and MMA warps keep their control flow WARP-UNIFORM: all 32 lanes walk the loops and
+  // wait on the barriers, and only the instruction that must come from one thread is predicated with
+  // elect.sync.  (Running the role inside `if (lane == 0)` makes every operand of UTMALDG / UTCIMMA
+  // a per-thread value for the compiler, which then wraps each issue in an ELECT + 7x R2UR +
+  // BRA.U.ANY "waterfall" loop: ~200 cycles per MMA, more than the MMA itself takes.)
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      uint32_t it = 0;
-      long long w_empty = 0;
-      const long long t_begin = clock64();
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        int m_blk, n0, bn;
-        tile_coords(t, m_blk, n0, bn);
-        const int m_base = (m_blk * CG + (int)cta_rank) * BM;
-        const int n_base = n0 + (int)cta_rank * (bn / CG);
-        const bool half = bn != BN;  // only generated for K-major B (see host side)
-        const uint32_t stage_tx = C::kABytes + (uint32_t)(bn / CG) * BK;
-        for (int kb = 0; kb < num_kb; kb++, it++) {
-          const uint32_t s = it % nstages, ph = (it / nstages) & 1;
-          if (p.stats) {
-            const long long t0 = clock64();
-            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
-            w_empty += clock64() - t0;
-          } else {
-            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
-          }
-          const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
-          const uint32_t sb = sa + C::kABytes;
-          const int k0 = kb * BK;
+    uint32_t it = 0;
+    long long w_empty = 0;
+    const long long t_begin = clock64();
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int m_blk, n0, bn;
+      tile_coords(t, m_blk, n0, bn);
+      const int m_base = (m_blk * CG + (int)cta_rank) * BM;
+      const int n_base = n0 + (int)cta_rank * (bn / CG);
+      const bool half = bn != BN;  // only generated for K-major B (see host side)
+      const uint32_t stage_tx = C::kABytes + (uint32_t)(bn / CG) * BK;
+      for (int kb = 0; kb < num_kb; kb++, it++) {
+        const uint32_t s = it % nstages, ph = (it / nstages) & 1;
+        if (p.stats) {
+          const long long t0 = clock64();
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
+          w_empty += clock64() - t0;
+        } else {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, 1);
+        }
+        const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
+        const uint32_t sb = sa + C::kABytes;
+        const int k0 = kb * BK;
+        if (elect_one_sync()) {
           if (p.dbg_noload && it >= nstages) {  // timing experiment only: stale operands, no TMA traffic
             if (leader) mbar_arrive(smem_u32(&full_bar[s]));
-            continue;
-          }
-          if (CG == 1) {
+          } else if (CG == 1) {
             const uint32_t fb = smem_u32(&full_bar[s]);
             mbar_arrive_expect_tx(fb, stage_tx);
             tma_load_2d(sa, &map_a, fb, k0, m_base);
             if (B_MN) {  // two [128 k-rows x 128 n-bytes] boxes side by side
               tma_load_2d(sb, &map_b, fb, n_base, k0);
               tma_load_2d(sb + BK * 128, &map_b, fb, n_base + 128, k0);
-            } else {     // one [256 n-rows x 128 k-bytes] box
+            } else {     // one [256 (or 128) n-rows x 128 k-bytes] box
               tma_load_2d(sb, half ? &map_bh : &map_b, fb, k0, n_base);
             }
           } else {
@@ -223,17 +226,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             else tma_load_2d_2sm(sb, half ? &map_bh : &map_b, fb, k0, n_base);
           }
         }
-      }
-      if (p.stats) {
-        p.stats[blockIdx.x * 8 + 0] = w_empty;
-        p.stats[blockIdx.x * 8 + 1] = clock64() - t_begin;
+        __syncwarp();
       }
     }
-    __syncwarp();  // reconverge before the aligned teardown barrier
+    if (p.stats && lane == 0) {
+      p.stats[blockIdx.x * 8 + 0] = w_empty;
+      p.stats[blockIdx.x * 8 + 1] = clock64() - t_begin;
+    }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc_nofield = umma_idesc_i8(BM * CG, 0, 0, B_MN ? 1 : 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // tells the compiler it is warp-uniform
       uint32_t it = 0, acc_it = 0;
       long long w_full = 0, w_tempty = 0;
       const long long t_begin = clock64();
@@ -247,7 +251,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, 2);  // epilogue drained this accumulator
         }
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_u + as * BN;
         int m_blk, n0, bn;
         tile_coords(t, m_blk, n0, bn);
         const uint32_t idesc = idesc_nofield | ((uint32_t)(bn >> 3) << 17);  // UMMA N of this tile
@@ -263,30 +267,34 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; k++) {
-            // A: K-major, rows 128 B apart, 8-row groups 1024 B apart; +32 B per K step
-            const uint64_t adesc = umma_smem_desc_sw128(sa + k * UK, 16, 1024);
-            // B (MN-major): k-rows 128 B apart, 8-row groups 1024 B apart, next 128 columns
-            // BK*128 B further; +32 rows (4096 B) per K step.  B (K-major): like A.
-            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo)
-                                        : umma_smem_desc_sw128(sb + k * UK, 16, 1024);
-            umma_i8<CG>(tmem_d, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < BK / UK; k++) {
+              // A: K-major, rows 128 B apart, 8-row groups 1024 B apart; +32 B per K step
+              const uint64_t adesc = umma_smem_desc_sw128(sa + k * UK, 16, 1024);
+              // B (MN-major): k-rows 128 B apart, 8-row groups 1024 B apart, next 128 columns
+              // BK*128 B further; +32 rows (4096 B) per K step.  B (K-major): like A.
+              const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo)
+                                          : umma_smem_desc_sw128(sb + k * UK, 16, 1024);
+              umma_i8<CG>(tmem_d, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+            }
+            // frees the smem slot once the MMAs above have read it
+            if (CG == 1) umma_commit(smem_u32(&empty_bar[s]));
+            else umma_commit_2sm(smem_u32(&empty_bar[s]), 0x3);
+            if (kb == num_kb - 1) {  // accumulator complete: hand it to the epilogue
+              if (CG == 1) umma_commit(smem_u32(&tfull_bar[as]));
+              else umma_commit_2sm(smem_u32(&tfull_bar[as]), 0x3);
+            }
           }
-          // frees the smem slot once the MMAs above have read it
-          if (CG == 1) umma_commit(smem_u32(&empty_bar[s]));
-          else umma_commit_2sm(smem_u32(&empty_bar[s]), 0x3);
+          __syncwarp();
         }
-        if (CG == 1) umma_commit(smem_u32(&tfull_bar[as]));
-        else umma_commit_2sm(smem_u32(&tfull_bar[as]), 0x3);
       }
-      if (p.stats) {
+      if (p.stats && lane == 0) {
         p.stats[blockIdx.x * 8 + 2] = w_full;
         p.stats[blockIdx.x * 8 + 3] = w_tempty;
         p.stats[blockIdx.x * 8 + 4] = clock64() - t_begin;
       }
     }
-    __syncwarp();
   } else {
     // =============================== epilogue ===================================
     const int q = warp & 3;  // TMEM lane quarter this warp is allowed to read
@@ -433,7 +441,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0) {  // always lane 0: bulk async-groups are per thread
             tma_store_2d(&map_o, stage_u32, n_base + c0, m_base + q * 32);
             for (int d = 0; d < p.n_extra; d++)  // peers' copies of the block, straight over NVLink
               tma_store_2d(&xmaps.m[d], stage_u32, n_base + c0, m_base + q * 32);
