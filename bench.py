@@ -271,7 +271,7 @@ def run_ours(args):
     Xq = torch.empty((M, K), dtype=torch.int8, device=dev)
     Wq = torch.empty((K, N), dtype=torch.int8, device=dev)
     Wt = torch.empty((N, K), dtype=torch.int8, device=dev)
-    kmajor = os.environ.get("QG_PERCALL_KMAJOR", "1") != "0"  # same switch the library reads
+    kmajor = os.environ.get("QG_PERCALL_KMAJOR", "0") != "0"  # same switch the library reads
     Cx = torch.empty(M, device=dev)
     Cw = torch.empty(N, device=dev)
 
@@ -286,7 +286,7 @@ def run_ours(args):
         # the same launches issued one by one, so that the dominant kernel can be bracketed by CUDA events
         # (instrumented pass) or given its peer destinations (N > 1)
         qg.absmax_quant_rows(Xs[s], 127.0, qg.MODE_REF_EXACT, Xq, Cx)
-        if kmajor:  # weight codes transposed on the fly (what qg_quantized_mm does by default)
+        if kmajor:  # weight codes transposed on the fly (QG_PERCALL_KMAJOR=1)
             qg.prepare_weights(Ws[s], 127.0, qg.MODE_REF_EXACT, Wt, Cw)
         else:
             qg.absmax_quant_cols(Ws[s], 127.0, qg.MODE_REF_EXACT, Wq, Cw)

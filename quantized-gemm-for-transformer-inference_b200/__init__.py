@@ -16,7 +16,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqgemm.so")
+# QG_LIB selects an A/B build variant of the same library (build.py --tag); still in-tree, still CUDA only
+LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("QG_LIB", "libqgemm.so")))
 
 QG_F32, QG_F16, QG_BF16, QG_S32 = 0, 1, 2, 3
 MODE_REF_EXACT, MODE_TRUE_ABSMAX = 0, 1

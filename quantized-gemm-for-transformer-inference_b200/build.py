@@ -26,7 +26,12 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> str:
+def build_lib(force: bool = False, verbose: bool = False, tag: str = "", defines: tuple = ()) -> str:
+    """tag/defines: an A/B variant for experiments, built as libqgemm_<tag>.so with -D<define>...;
+    load it with QG_LIB=libqgemm_<tag>.so."""
+    OBJ = os.path.join(HERE, "build" + ("_" + tag if tag else ""))
+    LIB = os.path.join(HERE, "libqgemm" + ("_" + tag if tag else "") + ".so")
+    FLAGS = globals()["FLAGS"] + ["-D" + d for d in defines]
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "qgemm.h"))
@@ -52,11 +57,14 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for k, v in logs.items():
             sys.stderr.write(f"==== {k}\n{v}\n")
-    with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
+    with open(os.path.join(OBJ, "ptxas.log"), "w" if len(logs) == len(SOURCES) else "a") as f:
         for k, v in logs.items():
             f.write(f"==== {k}\n{v}\n")
     return LIB
 
 
 if __name__ == "__main__":
-    print(build_lib(force="--force" in sys.argv, verbose=True))
+    # python build.py [--force] [--tag NAME -DFOO -DBAR=1 ...]
+    tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else ""
+    print(build_lib(force="--force" in sys.argv, verbose=True, tag=tag,
+                    defines=tuple(a[2:] for a in sys.argv if a.startswith("-D"))))

@@ -122,11 +122,13 @@ static int grow(void **p, size_t *have, size_t want) {
   return QG_OK;
 }
 
-// layout of the per-call weight codes: 1 = transposed (K-major GEMM operand), 0 = the reference's [K,N]
+// layout of the per-call weight codes: 0 (default) = the reference's [K,N] (row-major quantizer pass,
+// MN-major GEMM operand), 1 = transposed (transposing quantizer pass, K-major operand).  Measured on
+// B200 at 4096^3 / 8192^3: 98.1 / 520.6 us against 100.3 / 524.5 us.
 static bool percall_kmajor() {
   static const bool on = [] {
     const char *e = getenv("QG_PERCALL_KMAJOR");
-    return e == nullptr || atoi(e) != 0;
+    return e != nullptr && atoi(e) != 0;
   }();
   return on;
 }

@@ -141,6 +141,25 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_r
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta_rank) : "memory");
 }
+// Same arrive without the release fence (MEMBAR.ALL + ERRBAR in SASS, ~1k cycles when bulk stores
+// are in flight).  Only for hand-offs whose payload is TMEM: the reads being handed back were
+// completed by tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta_rank) : "memory");
+}
+// explicit shared-window accesses (pointers rebuilt from an aligned uintptr_t are generic for nvcc)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -287,6 +306,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // in the stream start its prologue while this grid is still running.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Early trigger, issued right after griddep_wait(): the next kernel of the stream is launched as soon
+// as every CTA of this grid is running and then blocks in its own griddep_wait().  EXPERIMENT ONLY
+// (build.py --tag early -DQG_EARLY_TRIGGER): measured on B200 it is a loss -- op_quantized_mm
+// 4096^3 102.5 us against 95.7 us, 8192^3 531 against 513 us (profiles/r1_early_trigger_ab.json);
+// parked dependents cost the running grid more than the hidden launch latency returns.  The only
+// early trigger kept is the row quantizer's, on each CTA's last row block.
+__device__ __forceinline__ void griddep_trigger_early() {
+#ifdef QG_EARLY_TRIGGER
+  griddep_launch_dependents();
+#endif
+}
 
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

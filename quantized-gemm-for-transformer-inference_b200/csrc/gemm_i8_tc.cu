@@ -154,6 +154,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
   // preceding kernel; from here on its outputs (Xq, Wq, Cx, Cw) are read
   griddep_wait();
+  griddep_trigger_early();
 
   const uint32_t nstages = p.nstages;  // == kStages unless narrowed for a pipeline-depth experiment
   const int num_tiles = p.total_tiles;
@@ -386,59 +387,43 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-      const float *cw = cw_s + as * BN;
-      const float *bs = bias_s + as * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < bn; c0 += OT::kCols) {
-        if (n_base + c0 >= p.N) break;
-        uint32_t w[32];  // 128 bytes of output for this thread's row
-        if constexpr (OT::kCols == 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c0, r);
-          float sd[SIDE ? 32 : 1];
-          if constexpr (SIDE) side_chunk(c0, sd);  // CUDA-core work overlaps the TMEM load
-          tmem_ld_wait();
+      const uint32_t cw_u = smem_u32(cw_s + as * BN), bs_u = smem_u32(bias_s + as * BN);
+      const bool has_bias = p.bias != nullptr;
+      // v[j] = dequantized (+ side product, + bias) accumulator column cb + j of this thread's row
+      auto convert32 = [&](const uint32_t (&r)[32], int cb, const float *sd, float (&v)[32]) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            if (kDequant) {
-              float v = dequant_ref((int)r[j], cx, cw[c0 + j], p.c);
-              if constexpr (SIDE) { if (p.no_pad > 0) v = __fadd_rn(v, sd[j]); }
-              if (p.bias != nullptr) v = __fadd_rn(v, bs[c0 + j]);
-              w[j] = __float_as_uint(v);
-            } else {
-              w[j] = r[j];
-            }
-          }
-        } else {
+        for (int j4 = 0; j4 < 8; j4++) {
+          const float4 c4 = lds128(cw_u + (uint32_t)(cb + 4 * j4) * 4);
+          v[4 * j4] = dequant_ref((int)r[4 * j4], cx, c4.x, p.c);
+          v[4 * j4 + 1] = dequant_ref((int)r[4 * j4 + 1], cx, c4.y, p.c);
+          v[4 * j4 + 2] = dequant_ref((int)r[4 * j4 + 2], cx, c4.z, p.c);
+          v[4 * j4 + 3] = dequant_ref((int)r[4 * j4 + 3], cx, c4.w, p.c);
+        }
+        if constexpr (SIDE) {
+          if (p.no_pad > 0) {
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr + c0 + h * 32, r);
-            float sd[SIDE ? 32 : 1];
-            if constexpr (SIDE) side_chunk(c0 + h * 32, sd);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float v0 = dequant_ref((int)r[j], cx, cw[c0 + h * 32 + j], p.c);
-              float v1 = dequant_ref((int)r[j + 1], cx, cw[c0 + h * 32 + j + 1], p.c);
-              if constexpr (SIDE) {
-                if (p.no_pad > 0) { v0 = __fadd_rn(v0, sd[j]); v1 = __fadd_rn(v1, sd[j + 1]); }
-              }
-              if (p.bias != nullptr) {
-                v0 = __fadd_rn(v0, bs[c0 + h * 32 + j]);
-                v1 = __fadd_rn(v1, bs[c0 + h * 32 + j + 1]);
-              }
-              w[h * 16 + j / 2] = pack16(v0, v1, OutT());
-            }
+            for (int j = 0; j < 32; j++) v[j] = __fadd_rn(v[j], sd[j]);
           }
         }
+        if (has_bias) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++) {
+            const float4 b4 = lds128(bs_u + (uint32_t)(cb + 4 * j4) * 4);
+            v[4 * j4] = __fadd_rn(v[4 * j4], b4.x);
+            v[4 * j4 + 1] = __fadd_rn(v[4 * j4 + 1], b4.y);
+            v[4 * j4 + 2] = __fadd_rn(v[4 * j4 + 2], b4.z);
+            v[4 * j4 + 3] = __fadd_rn(v[4 * j4 + 3], b4.w);
+          }
+        }
+      };
+      // one 128-byte-per-row chunk (OT::kCols columns from c0) leaves for global memory
+      auto store_chunk = [&](const uint32_t (&w)[32], int c0) {
         if (p.tma_store) {
           if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading staging
           __syncwarp();
 #pragma unroll
           for (int j4 = 0; j4 < 8; j4++)  // 128B-swizzled rows: conflict-free 16 B stores
-            *reinterpret_cast<uint4 *>(stage + lane * 128 + ((j4 ^ (lane & 7)) << 4)) =
-                make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
+            sts128(stage_u32 + lane * 128 + ((j4 ^ (lane & 7)) << 4), w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {  // always lane 0: bulk async-groups are per thread
@@ -448,31 +433,78 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_store_commit();
           }
         } else if (row < p.M) {
-         for (int d = -1; d < p.n_extra; d++) {  // local matrix, then the peers' copies
-          OutT *dst = reinterpret_cast<OutT *>(d < 0 ? p.out : p.extra_out[d]) + (int64_t)row * p.ldo + n_base + c0;
-          const int ncols = min(OT::kCols, p.N - (n_base + c0));
-          if (ncols == OT::kCols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          for (int d = -1; d < p.n_extra; d++) {  // local matrix, then the peers' copies
+            OutT *dst = reinterpret_cast<OutT *>(d < 0 ? p.out : p.extra_out[d]) + (int64_t)row * p.ldo + n_base + c0;
+            const int ncols = min(OT::kCols, p.N - (n_base + c0));
+            if (ncols == OT::kCols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; j4++)
-              reinterpret_cast<uint4 *>(dst)[j4] = make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
-          } else if (sizeof(OutT) == 4) {  // ragged edge / unaligned rows: predicated scalar stores
+              for (int j4 = 0; j4 < 8; j4++)
+                reinterpret_cast<uint4 *>(dst)[j4] = make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
+            } else if (sizeof(OutT) == 4) {  // ragged edge / unaligned rows: predicated scalar stores
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (j < ncols) reinterpret_cast<uint32_t *>(dst)[j] = w[j];
+              for (int j = 0; j < 32; j++)
+                if (j < ncols) reinterpret_cast<uint32_t *>(dst)[j] = w[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; j++)
+                if (j < ncols) reinterpret_cast<uint16_t *>(dst)[j] = (uint16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+            }
+          }
+        }
+      };
+      // 64 accumulator columns per trip through two register sets: the TMEM load of the next 32
+      // columns is in flight while the CUDA cores convert the current 32
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll 1
+      for (int c0 = 0; c0 < bn; c0 += 64) {
+        if (n_base + c0 >= p.N) break;
+        uint32_t w[32];
+        float v[kDequant ? 32 : 1];
+        float sd[SIDE ? 32 : 1];
+        // ---- first half: columns c0 .. c0+31 (in ra) ----
+        if constexpr (SIDE) side_chunk(c0, sd);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(taddr + c0 + 32, rb);
+        if constexpr (!kDequant) {
+          store_chunk(ra, c0);
+        } else {
+          convert32(ra, c0, sd, v);
+          if constexpr (OT::kCols == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) w[j] = __float_as_uint(v[j]);
+            store_chunk(w, c0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 64; j++)
-              if (j < ncols) reinterpret_cast<uint16_t *>(dst)[j] = (uint16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+            for (int j = 0; j < 32; j += 2) w[j / 2] = pack16(v[j], v[j + 1], OutT());
           }
-         }
+        }
+        // ---- second half: columns c0+32 .. c0+63 (in rb) ----
+        if constexpr (SIDE) side_chunk(c0 + 32, sd);
+        tmem_ld_wait();
+        if (c0 + 64 < bn) tmem_ld_32x32b_x32(taddr + c0 + 64, ra);
+        if constexpr (!kDequant) {
+          if (n_base + c0 + 32 < p.N) store_chunk(rb, c0 + 32);
+        } else {
+          convert32(rb, c0 + 32, sd, v);
+          if constexpr (OT::kCols == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) w[j] = __float_as_uint(v[j]);
+            if (n_base + c0 + 32 < p.N) store_chunk(w, c0 + 32);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) w[16 + j / 2] = pack16(v[j], v[j + 1], OutT());
+            store_chunk(w, c0);
+          }
         }
       }
+      tmem_ld_wait();  // a prefetch may still be in flight when the loop leaves at the matrix edge
       // accumulator stage is free for the MMA warp again
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG == 1) mbar_arrive(smem_u32(&tempty_bar[as]));
-        else mbar_arrive_cluster(smem_u32(&tempty_bar[as]), 0);
+        else mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[as]), 0);
       }
     }
     if (p.tma_store && lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores

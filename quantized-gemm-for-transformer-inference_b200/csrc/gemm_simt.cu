@@ -28,6 +28,7 @@ gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__r
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   griddep_wait();
+  griddep_trigger_early();
   int acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -103,6 +104,7 @@ mm_f32_kernel(const float *__restrict__ A, int64_t sa_h, int64_t sa_w, const flo
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   griddep_wait();
+  griddep_trigger_early();
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -154,6 +156,7 @@ dequantize_kernel(const int32_t *__restrict__ acc, int64_t ldacc, const float *_
                   OutT *__restrict__ O, int64_t ldo) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
+  griddep_trigger_early();
   if (col >= N) return;
   const float cw = Cw[col];
   const float b = bias ? bias[col] : 0.0f;

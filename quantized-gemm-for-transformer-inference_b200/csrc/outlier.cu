@@ -29,6 +29,7 @@ outlier_detect_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float 
   const int col = (blockIdx.x * 32 + tx) * EPV;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   griddep_wait();
+  griddep_trigger_early();
   uint32_t bits = 0;
   if (col < K) {
     const T *base = X + col;
@@ -66,6 +67,7 @@ __global__ void outlier_detect_generic_kernel(const T *__restrict__ X, int M, in
                                               uint32_t *__restrict__ mask) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
+  griddep_trigger_early();
   if (k >= K) return;
   bool out = false;
   for (int i = 0; i < M; i++) {
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(1024)
 outlier_index_kernel(const uint32_t *__restrict__ mask, int K, int *__restrict__ idx, int max_idx,
                      int *__restrict__ count, int *__restrict__ wbase) {
   griddep_wait();
+  griddep_trigger_early();
   const int words = (K + 31) / 32;
   const int total = mask_prefix(mask, words, wbase);
   for (int w = threadIdx.x; w < words; w += 1024) {
@@ -138,6 +141,7 @@ __global__ void __launch_bounds__(1024)
 outlier_mask_from_idx_kernel(const int *__restrict__ idx, int n_idx, int K, uint32_t *__restrict__ mask,
                              int *__restrict__ wbase) {
   griddep_wait();
+  griddep_trigger_early();
   const int words = (K + 31) / 32;
   for (int w = threadIdx.x; w < words; w += 1024) mask[w] = 0;
   __syncthreads();
@@ -198,6 +202,7 @@ quant_rows_outlier_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, fl
   const int g = threadIdx.x;
   const int nvec = K / EPV;
   griddep_wait();
+  griddep_trigger_early();
   int it = 0;
   for (int row = blockIdx.x; row < M; row += gridDim.x, it++) {
     const T *xr = X + (int64_t)row * ldx;
@@ -287,6 +292,7 @@ quant_rows_outlier_generic_kernel(const T *__restrict__ X, int M, int K, int64_t
   const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   griddep_wait();
+  griddep_trigger_early();
   if (row >= M) return;
   const T *xr = X + (int64_t)row * ldx;
   auto is_out = [&](int j) { return ((__ldg(ro.mask + (j >> 5)) >> (j & 31)) & 1u) != 0; };
@@ -324,6 +330,7 @@ __global__ void gather_wo_kernel(const T *__restrict__ W, int64_t ldw, const int
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int o = blockIdx.y;
   griddep_wait();
+  griddep_trigger_early();
   if (j >= N) return;
   const float v = o < n_idx ? to_f32(W[(int64_t)idx[o] * ldw + j]) : 0.0f;
   if (side_bf16) reinterpret_cast<__nv_bfloat16 *>(Wo)[(int64_t)o * ldwo + j] = __float2bfloat16_rn(v);

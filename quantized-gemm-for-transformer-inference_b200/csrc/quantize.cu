@@ -53,6 +53,7 @@ quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float rang
   uint4 raw[NVC], nxt[NVC];
   int rb = blockIdx.x;
   griddep_wait();
+  griddep_trigger_early();
   if (NV > 0 && rb < nrb) load(raw, rb);
   for (int it = 0; rb < nrb; rb += gridDim.x, it++) {
     if (kPrefetch && rb + (int)gridDim.x < nrb) load(nxt, rb + gridDim.x);
@@ -152,6 +153,7 @@ quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, fl
   const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   griddep_wait();
+  griddep_trigger_early();
   if (row >= M) return;
   const T *xr = X + (int64_t)row * ldx;
   float scale;
@@ -202,6 +204,7 @@ absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, i
   const int k0 = 1 + blockIdx.y * rows_per_cta;
   const int k1 = min(K, k0 + rows_per_cta);
   griddep_wait();
+  griddep_trigger_early();
   float m[EPV];
 #pragma unroll
   for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
@@ -246,6 +249,7 @@ __global__ void absmax_cols_finalize_kernel(const T *__restrict__ W, int K, int 
                                             float *__restrict__ Cw) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
+  griddep_trigger_early();
   if (j >= N) return;
   float c;
   if (fold_first(to_f32(W[j]), part_value(part[j], epoch), mode, c)) {
@@ -266,6 +270,7 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * EPV;
   griddep_wait();
+  griddep_trigger_early();
   if (col >= N) return;
   const T *base = W + col;
   float s[EPV];
@@ -338,6 +343,7 @@ quant_cols_t_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float ra
   const bool col_ok = col < N;
   const T *base = W + col;
   griddep_wait();
+  griddep_trigger_early();
   float s[EPV];
   if (col_ok) {
     float x0[EPV];
@@ -411,6 +417,7 @@ quant_cols_generic_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, fl
                           float *__restrict__ Cw, bool transpose) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
+  griddep_trigger_early();
   if (j >= N) return;
   float scale;
   if (sw_in == nullptr) {
@@ -439,6 +446,7 @@ quant_cols_generic_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, fl
 __global__ void inv_divide_kernel(const float *__restrict__ a, int64_t n, float b, float *__restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
+  griddep_trigger_early();
   if (i < n) out[i] = __fdiv_rn(b, a[i]);
 }
 
@@ -447,6 +455,7 @@ __global__ void outlier_mask_kernel(const float *__restrict__ A, int M, int K, i
                                     float *__restrict__ mask, int64_t ldm) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   griddep_wait();
+  griddep_trigger_early();
   if (k >= K) return;
   for (int i = blockIdx.y; i < M; i += gridDim.y) {
     const float a = A[(int64_t)i * lda + k];
