@@ -309,15 +309,17 @@ def run_ours(args):
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sample_clocks = rank == 0 and os.environ.get("QG_BENCH_NO_CLOCKS") is None
     if sample_clocks:
         sampler.start()
         time.sleep(0.25)
+    # every rank enters the timed region together: rank 0's sampler start-up above must not show up
+    # as 250 ms of waiting inside the other ranks' first exchange
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     qg.launch_count(reset=True)
@@ -328,6 +330,9 @@ def run_ours(args):
     t_end.record()
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     launches = qg.launch_count()
     # instrumented pass, immediately after and on the same buffers: the same K steps with a CUDA event
     # pair around the dominant kernel (events between the launches would otherwise break the
@@ -349,7 +354,7 @@ def run_ours(args):
     ops = 2.0 * M * N * K
     value = world * ops / ms_per_step / 1e9  # TOPS, whole job
 
-    gemm_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    gemm_ms = statistics.median(e[0].elapsed_time(e[1]) for e in evs)
 
     # per-stage timings of the two HBM-bound quantizers, outside the timed region (same buffers)
     def stage_ms(fn, n=20):
