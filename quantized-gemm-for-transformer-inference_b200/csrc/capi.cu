@@ -2,6 +2,7 @@
 //
 // Argument checking, workspace carving and kernel selection live here; the kernels are in
 // quantize.cu (a1-a4), gemm_i8_tc.cu (a5-a8, a10 fused, tcgen05) and gemm_simt.cu (generic paths).
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdlib>
@@ -77,7 +78,10 @@ struct DeviceState {
   // host-buffer entry point
   void *hx = nullptr, *hw = nullptr, *ho = nullptr, *hb = nullptr;
   size_t hx_bytes = 0, hw_bytes = 0, ho_bytes = 0, hb_bytes = 0;
-  cudaStream_t hstream = nullptr;
+  // three streams: host->device copies, kernels, device->host copies (PCIe is full duplex)
+  cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
+  static constexpr int kHostChunks = 8;
+  cudaEvent_t ev_w = nullptr, ev_x[kHostChunks] = {}, ev_o[kHostChunks] = {};
 };
 static DeviceState g_dev[16];
 static std::mutex g_mu;
@@ -550,27 +554,61 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
   if (rc) return rc;
   QG_REQUIRE(X_host && W_host && O_host && M > 0 && N > 0 && K > 0, "qg_quantized_mm_host: bad arguments");
   std::lock_guard<std::mutex> lk(g_mu);
-  if (d->hstream == nullptr) QG_CUDA_OK(cudaStreamCreateWithFlags(&d->hstream, cudaStreamNonBlocking));
+  if (d->hstream == nullptr) {
+    QG_CUDA_OK(cudaStreamCreateWithFlags(&d->hstream, cudaStreamNonBlocking));
+    QG_CUDA_OK(cudaStreamCreateWithFlags(&d->hstream_in, cudaStreamNonBlocking));
+    QG_CUDA_OK(cudaStreamCreateWithFlags(&d->hstream_out, cudaStreamNonBlocking));
+    QG_CUDA_OK(cudaEventCreateWithFlags(&d->ev_w, cudaEventDisableTiming));
+    for (int i = 0; i < DeviceState::kHostChunks; i++) {
+      QG_CUDA_OK(cudaEventCreateWithFlags(&d->ev_x[i], cudaEventDisableTiming));
+      QG_CUDA_OK(cudaEventCreateWithFlags(&d->ev_o[i], cudaEventDisableTiming));
+    }
+  }
   const size_t xb = sizeof(float) * (size_t)M * K, wb = sizeof(float) * (size_t)K * N, ob = sizeof(float) * (size_t)M * N;
   if ((rc = grow(&d->hx, &d->hx_bytes, xb))) return rc;
   if ((rc = grow(&d->hw, &d->hw_bytes, wb))) return rc;
   if ((rc = grow(&d->ho, &d->ho_bytes, ob))) return rc;
   if (bias_host && (rc = grow(&d->hb, &d->hb_bytes, sizeof(float) * (size_t)N))) return rc;
   if ((rc = grow(&d->arena, &d->arena_bytes, carve(nullptr, M, N, K).bytes))) return rc;
-  cudaStream_t st = d->hstream;
-  QG_CUDA_OK(cudaMemcpyAsync(d->hx, X_host, xb, cudaMemcpyHostToDevice, st));
-  QG_CUDA_OK(cudaMemcpyAsync(d->hw, W_host, wb, cudaMemcpyHostToDevice, st));
-  if (bias_host) QG_CUDA_OK(cudaMemcpyAsync(d->hb, bias_host, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+  // The reference's toDevice() / toHost() round trip (tensor.cuh:77-119) as a three-stream pipeline:
+  //   in:      W, then X in row chunks                       (host -> device)
+  //   compute: column quantizer once W is in; per chunk row quantizer + GEMM/dequantize
+  //   out:     each finished row chunk of O                  (device -> host, concurrent with `in`)
+  // Row chunk r of O depends on row chunk r of X and all of W, so after W has landed the two PCIe
+  // directions run at the same time: about |W| + |X| + one chunk instead of |W| + |X| + |O|.
+  cudaStream_t s_in = d->hstream_in, s_k = d->hstream, s_out = d->hstream_out;
+  const float *bias_dev = bias_host ? (const float *)d->hb : nullptr;
   Workspace w = carve(d->arena, M, N, K);
-  rc = quant_rows(d->hx, QG_F32, M, K, K, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
-  if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, false, st);
+  if (bias_host) QG_CUDA_OK(cudaMemcpyAsync(d->hb, bias_host, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, s_in));
+  QG_CUDA_OK(cudaMemcpyAsync(d->hw, W_host, wb, cudaMemcpyHostToDevice, s_in));
+  QG_CUDA_OK(cudaEventRecord(d->ev_w, s_in));
+  QG_CUDA_OK(cudaStreamWaitEvent(s_k, d->ev_w, 0));
+  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, false, s_k);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  rc = gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, w.ldwq, 0, M, N, K, d->ho, N, QG_F32, w.Cx, w.Cw,
-                     bias_host ? (const float *)d->hb : nullptr, 1 / (range * range), st);
-  if (rc) return rc;
-  QG_CUDA_OK(cudaMemcpyAsync(O_host, d->ho, ob, cudaMemcpyDeviceToHost, st));
-  QG_CUDA_OK(cudaStreamSynchronize(st));
+  // row chunks: multiples of 256 rows (one 2-SM tile), at most kHostChunks of them
+  int rows_per = (M + DeviceState::kHostChunks - 1) / DeviceState::kHostChunks;
+  rows_per = ((rows_per + 255) / 256) * 256;
+  const float *Xd = (const float *)d->hx;
+  float *Od = (float *)d->ho;
+  int ci = 0;
+  for (int r0 = 0; r0 < M; r0 += rows_per, ci++) {
+    const int rows = std::min(rows_per, M - r0);
+    QG_CUDA_OK(cudaMemcpyAsync((void *)(Xd + (size_t)r0 * K), X_host + (size_t)r0 * K, sizeof(float) * (size_t)rows * K,
+                               cudaMemcpyHostToDevice, s_in));
+    QG_CUDA_OK(cudaEventRecord(d->ev_x[ci], s_in));
+    QG_CUDA_OK(cudaStreamWaitEvent(s_k, d->ev_x[ci], 0));
+    rc = quant_rows(Xd + (size_t)r0 * K, QG_F32, rows, K, K, range, mode, nullptr, w.Xq + (size_t)r0 * w.ldxq, w.ldxq,
+                    w.Cx + r0, s_k);
+    if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+    rc = gemm_dispatch(d, w.Xq + (size_t)r0 * w.ldxq, w.ldxq, w.Wq, w.ldwq, 0, rows, N, K, Od + (size_t)r0 * N, N, QG_F32,
+                       w.Cx + r0, w.Cw, bias_dev, 1 / (range * range), s_k);
+    if (rc) return rc;
+    QG_CUDA_OK(cudaEventRecord(d->ev_o[ci], s_k));
+    QG_CUDA_OK(cudaStreamWaitEvent(s_out, d->ev_o[ci], 0));
+    QG_CUDA_OK(cudaMemcpyAsync(O_host + (size_t)r0 * N, Od + (size_t)r0 * N, sizeof(float) * (size_t)rows * N,
+                               cudaMemcpyDeviceToHost, s_out));
+  }
+  QG_CUDA_OK(cudaStreamSynchronize(s_out));  // O_host is complete; `in` and `compute` finished before it
   return QG_OK;
 }
 

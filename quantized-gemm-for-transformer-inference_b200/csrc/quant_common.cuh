@@ -12,6 +12,24 @@ __device__ __forceinline__ uint4 ldg16(const void *p) {
   return __ldg(reinterpret_cast<const uint4 *>(p));
 }
 
+// 16-byte read-only load carrying an L2 eviction policy (createpolicy.fractional.*)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg16_hint(const void *p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+
 // unpack one 16-byte vector into fp32 lanes
 template <typename T> struct Unpack;
 template <> struct Unpack<float> {

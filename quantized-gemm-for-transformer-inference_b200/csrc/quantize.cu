@@ -205,6 +205,12 @@ absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, i
   const int k1 = min(K, k0 + rows_per_cta);
   griddep_wait();
   griddep_trigger_early();
+#ifndef QG_COLS_NO_L2_HINTS
+  const uint64_t pol = l2_policy_evict_last();
+#define QG_LD1(p) ldg16_hint(p, pol)
+#else
+#define QG_LD1(p) ldg16(p)
+#endif
   float m[EPV];
 #pragma unroll
   for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
@@ -214,7 +220,7 @@ absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, i
     for (; k + 24 < k1; k += 32) {  // 4 independent 16-byte loads in flight per thread
       uint4 r[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) r[u] = ldg16(base + (int64_t)(k + 8 * u) * ldw);
+      for (int u = 0; u < 4; u++) r[u] = QG_LD1(base + (int64_t)(k + 8 * u) * ldw);
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         float f[EPV];
@@ -225,7 +231,7 @@ absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, i
     }
     for (; k < k1; k += 8) {
       float f[EPV];
-      Unpack<T>::run(ldg16(base + (int64_t)k * ldw), f);
+      Unpack<T>::run(QG_LD1(base + (int64_t)k * ldw), f);
 #pragma unroll
       for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
     }
@@ -307,15 +313,27 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
     if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
     else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
   };
-  int k = k0 + ty;
-  for (; k + 24 < k1; k += 32) {
+#ifndef QG_COLS_NO_L2_HINTS
+  const uint64_t pol2 = l2_policy_evict_first();
+#define QG_LD2(p) ldg16_hint(p, pol2)
+#else
+#define QG_LD2(p) ldg16(p)
+#endif
+  // Bottom-up, with L1::no_allocate / L2 evict-first loads (pass 1: evict-last).  The hope was that
+  // the second pass would find in L2 what the first one had just streamed; it does not: with the
+  // caches left as the pipeline leaves them ncu still counts 67 MB of DRAM reads (0.6-17 % sector
+  // hits) in either walking order and with either eviction hint (W is 64 MiB at 4096^2; smaller
+  // panels showed the same per-byte cost).  The hinted loads are kept because they are ~7 % faster
+  // (24.1 -> 22.3 us for both passes), the order because it is free.
+  int k = k1 - 1 - ty;
+  for (; k - 24 >= k0; k -= 32) {
     uint4 r[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) r[u] = ldg16(base + (int64_t)(k + 8 * u) * ldw);
+    for (int u = 0; u < 4; u++) r[u] = QG_LD2(base + (int64_t)(k - 8 * u) * ldw);
 #pragma unroll
-    for (int u = 0; u < 4; u++) emit(r[u], k + 8 * u);
+    for (int u = 0; u < 4; u++) emit(r[u], k - 8 * u);
   }
-  for (; k < k1; k += 8) emit(ldg16(base + (int64_t)k * ldw), k);
+  for (; k >= k0; k -= 8) emit(QG_LD2(base + (int64_t)k * ldw), k);
 }
 
 // Pass 2 with transposed output: codes go out as Wt[n][k] (K contiguous), the K-major operand layout
@@ -373,9 +391,12 @@ quant_cols_t_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float ra
     }
   };
   uint4 v[4], vn[4];
-  load(k0, v);
-  for (int rb = k0; rb < k1; rb += 32) {
-    if (rb + 32 < k1) load(rb + 32, vn);
+  // bottom-up over the chunk's 32-row patches (see quant_cols_kernel: the rows pass 1 read last are
+  // the ones still in L2)
+  const int rb_last = k0 + ((k1 - k0 - 1) / 32) * 32;
+  load(rb_last, v);
+  for (int rb = rb_last; rb >= k0; rb -= 32) {
+    if (rb - 32 >= k0) load(rb - 32, vn);
     float f[4][EPV];
 #pragma unroll
     for (int i = 0; i < 4; i++) Unpack<T>::run(v[i], f[i]);
@@ -530,12 +551,23 @@ int rows_dispatch(const T *X, int M, int K, int64_t ldx, float range, int mode, 
 }
 
 // ---- column launcher ----
-inline int cols_rows_per_cta(int K, int col_tiles) {
-  // enough CTAs for ~4 waves of 148 SMs x 4 resident blocks, at least 32 rows per CTA
-  int64_t want = ceil_div((int64_t)148 * 16, col_tiles);
-  int64_t rows = ceil_div(K, want > 0 ? want : 1);
-  rows = round_up(rows < 32 ? 32 : rows, 32);
-  return (int)rows;
+inline int cols_rows_per_cta(int K, int col_tiles, int round) {
+  // One wave: every CTA of the grid is resident at once (6 blocks of 256 threads per SM), so all of
+  // them start together, stream the same number of rows and finish together.  Measured at 4096^2
+  // (both passes, us; fp32 / fp16 input): 4 per SM 23.5 / 17.5, 6: 24.1 / 17.5, 8: 25.7 / 20.5,
+  // ~14 (the earlier 2048 short blocks, 1.73 waves): 25.3 / 24.4; at 8192^2 fp32 4: 102.7, 6: 97.3,
+  // 8: 95.8, 16: 93.9.  QG_COLS_CTAS_PER_SM overrides the 6 for experiments.
+  static const int target = [] {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char *e = getenv("QG_COLS_CTAS_PER_SM");
+    const int per_sm = e != nullptr && atoi(e) > 0 ? atoi(e) : 6;
+    return (sms > 0 ? sms : 148) * per_sm;
+  }();
+  const int64_t chunks = target / col_tiles > 0 ? target / col_tiles : 1;
+  int64_t rows = round_up(ceil_div(K, chunks), round);
+  return (int)(rows < 32 ? 32 : rows);
 }
 
 template <typename T>
@@ -553,7 +585,7 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
-  const int rpc = cols_rows_per_cta(K, col_tiles);
+  const int rpc = cols_rows_per_cta(K, col_tiles, transpose ? 32 : 8);
   unsigned long long *part = nullptr;
   uint32_t epoch = 0;
   if (sw == nullptr) {

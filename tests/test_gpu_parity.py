@@ -388,6 +388,21 @@ def test_host_buffer_entry_point(qg, oracle):
     assert same_f32(out.numpy(), oracle.quantized_mm(X.numpy(), W.numpy()))
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_buffer_entry_point_row_chunk_pipeline(qg, oracle, pinned):
+    """M large enough for several row chunks of the copy/compute/copy pipeline, ragged last chunk, bias."""
+    rng = np.random.default_rng(19)
+    X = torch.from_numpy(make_edge_matrix(rng, 2200, 264))
+    W = torch.from_numpy(np.ascontiguousarray(make_edge_matrix(rng, 136, 264).T))
+    b = torch.from_numpy(rng.standard_normal(136).astype(np.float32))
+    if pinned:
+        X, W = X.pin_memory(), W.pin_memory()
+    expect = oracle.quantized_mm(X.numpy(), W.numpy(), 127.0, bias=b.numpy())
+    for _ in range(2):  # second call reuses the streams, events and device buffers
+        out = qg.quantized_mm_host(X, W, bias=b)
+        assert same_f32(out.numpy(), expect)
+
+
 def test_fp32_product_matches_reference_fma_order(qg, oracle):
     rng = np.random.default_rng(10)
     A = rng.standard_normal((70, 200)).astype(np.float32)
