@@ -446,6 +446,14 @@ def run_ours(args):
     at_max = bool(clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])
     peak_key = "bf16_tflops" if at_max or not (clocks and clocks.get("sm_mhz")) else "bf16_tflops_sustained"
     int8_peak = 2.0 * peaks[peak_key]
+    # dram__bytes_read.sum + dram__bytes_write.sum of the GEMM launch, from the committed ncu --set full capture
+    # of this same command (never measured in this run: nothing here runs under a profiler)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if world == 1 and (M, N, K) == (4096, 4096, 4096) and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
     gemm_tops = ops / gemm_ms / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "TOPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -460,7 +468,8 @@ def run_ours(args):
                      "achieved": gemm_tops, "peak": int8_peak, "unit": "TOP/s", "frac": gemm_tops / int8_peak,
                      "peak_note": f"2 x {peak_key} from MEASURED_PEAKS.json ({peaks['source']}); int8 dense "
                                   f"rate is 2x bf16; spec 4500 TOP/s -> frac_spec {gemm_tops / INT8_SPEC_TOPS:.3f}",
-                     "frac_spec": gemm_tops / INT8_SPEC_TOPS, "ms": gemm_ms, "traffic": None,
+                     "frac_spec": gemm_tops / INT8_SPEC_TOPS, "ms": gemm_ms, "traffic": traffic, "traffic_unit": "bytes per launch",
+                     "traffic_source": traffic_src,
                      "timing": "CUDA events around this launch in every step of an instrumented pass of the same K steps, "
                                "run directly after the timed pass"},
         "stages": {
