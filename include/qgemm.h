@@ -195,6 +195,30 @@ QG_API int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, c
 QG_API int qg_mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w,
                      int m, int n, int k, float *C, int64_t ldc, qg_stream_t stream);
 
+/* ---- op_multiply(A, scale, T); op_softmax(T, B)  src/modules/attention.cuh:62-68,
+ *      src/ops/op_elemwise.cuh:644-655, src/ops/op_softmax.cuh:6-41 ---------------------------- */
+/* Row softmax of fl(A * scale) with the reference kernel's arithmetic: max by strict '>' from column 0,
+ * e = expf(t - max), sum over ascending columns, e / sum (IEEE division).  scale = 1 gives plain
+ * op_softmax.  B may alias A.  (The reference sizes its grid from the width, op_softmax.cuh:38, and
+ * so skips rows beyond 256*ceil(w/256); every row is computed here.) */
+QG_API int qg_softmax_rows_f32(const float *A, int64_t lda, int m, int n, float scale, float *B, int64_t ldb,
+                               qg_stream_t stream);
+
+/* ---- AttentionLayer<float>::forward(X, output)  src/modules/attention.cuh:47-70, and the 3-argument
+ *      forward(Xq, Xkv, output) that src/transformer.cu:37,39,104,106,132 calls ------------------- */
+/* Scaled dot-product attention whose three projections (attention.cuh:54-56) go through the quantized
+ * linear path (qg_quantized_mm semantics, REF_EXACT arithmetic); Q K^T, the 1/sqrt(d_k) scaling, the
+ * softmax and P V keep the reference's fp32 arithmetic bit for bit.
+ *   Xq  [batch*sq,  d_model]  queries' input;  Xkv [batch*skv, d_model] keys'/values' input
+ *                             (Xq == Xkv, sq == skv: self-attention, one fused projection)
+ *   Wqkv [d_model, heads*(2*d_k + d_v)]: columns [ W_q of head 0..H-1 | W_k of head 0..H-1 | W_v ... ];
+ *        heads = 1 is the reference's AttentionLayer (W_q | W_k | W_v side by side)
+ *   out [batch*sq, heads*d_v]: head h in columns h*d_v .. (the concat of transformer.cu:43-50)
+ * batch sequences attend independently (the reference has no batch dimension: batch = 1). */
+QG_API int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq,
+                                int skv, int d_model, const float *Wqkv, int64_t ldw, int heads, int d_k, int d_v,
+                                float range, int mode, float *out, int64_t ldo, qg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

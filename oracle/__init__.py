@@ -282,3 +282,46 @@ def quantized_mm_outlier(X, W, thr, range_=127.0, mode=MODE_REF_EXACT, bias=None
         O = (O + _f32(bias).reshape(1, -1)).astype(np.float32)
     parts["outlier_idx"] = idx
     return O, parts
+
+
+# ---- attention: composition of the functions above -----------------------
+
+def softmax_rows(A, scale=1.0):
+    """op_multiply(A, scale) + op_softmax (attention.cuh:62-68, op_softmax.cuh:6-29) on the host."""
+    A = _f32(A)
+    M, N = A.shape
+    out = np.empty((M, N), np.float32)
+    lib().qo_softmax_rows_f32(_p(A), C.c_int64(N), C.c_int(M), C.c_int(N), C.c_float(scale), _p(out), C.c_int64(N))
+    return out
+
+
+def attention_forward(Xq, Xkv, Wq, Wk, Wv, range_=127.0, mode=MODE_REF_EXACT, return_parts=False):
+    """AttentionLayer::forward (attention.cuh:47-70), one head, one sequence, with the three
+    projections routed to op_quantized_mm (the re-pointing of SURVEY F2); Xq is Xkv for the
+    reference's 2-argument form."""
+    Q = quantized_mm(Xq, Wq, range_, mode)
+    K = quantized_mm(Xkv, Wk, range_, mode)
+    V = quantized_mm(Xkv, Wv, range_, mode)
+    S = gemm_f32_ref(Q, np.ascontiguousarray(K.T))                 # op_mm(Q, K.transpose(), QK_T)
+    d_k = Wq.shape[1]
+    P = softmax_rows(S, np.float32(1.0 / np.sqrt(np.float64(d_k))))  # T scale_factor = 1.0 / std::sqrt(d_k)
+    out = gemm_f32_ref(P, V)
+    if return_parts:
+        return {"Q": Q, "K": K, "V": V, "S": S, "P": P, "out": out}
+    return out
+
+
+def multi_head_attention(Xq, Xkv, Wqkv, heads, d_k, d_v, batch=1, range_=127.0, mode=MODE_REF_EXACT):
+    """The head loop + concat of transformer.cu:27-50 over `batch` independent sequences.
+    Wqkv columns: [W_q of every head | W_k of every head | W_v of every head]."""
+    Xq, Xkv, Wqkv = _f32(Xq), _f32(Xkv), _f32(Wqkv)
+    sq, skv = Xq.shape[0] // batch, Xkv.shape[0] // batch
+    out = np.empty((batch * sq, heads * d_v), np.float32)
+    for b in range(batch):
+        xq, xkv = Xq[b * sq:(b + 1) * sq], Xkv[b * skv:(b + 1) * skv]
+        for h in range(heads):
+            wq = Wqkv[:, h * d_k:(h + 1) * d_k]
+            wk = Wqkv[:, heads * d_k + h * d_k:heads * d_k + (h + 1) * d_k]
+            wv = Wqkv[:, 2 * heads * d_k + h * d_v:2 * heads * d_k + (h + 1) * d_v]
+            out[b * sq:(b + 1) * sq, h * d_v:(h + 1) * d_v] = attention_forward(xq, xkv, wq, wk, wv, range_, mode)
+    return out

@@ -16,6 +16,7 @@
 #undef N  // src/ops/op_elemwise.cuh:10 defines N as 256
 #include "ops/op_reduction.cuh"
 #include "ops/op_mm.cuh"
+#include "ops/op_softmax.cuh"
 
 unsigned long long randgen_seed = 0;  // the ops `extern` this (src/ops/op_elemwise.cuh:12)
 
@@ -200,6 +201,51 @@ int ref_time_quantized_mm_host(const float *X, const float *W, float *O, int m, 
   for (int i = 0; i < iters; i++) rc |= ref_op_quantized_mm(X, W, m, n, k, range, O);
   gettimeofday(&t1, NULL);
   *ms_wall = ((t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_usec - t0.tv_usec)) / 1e3 / iters;
+  return rc;
+}
+
+// op_softmax (src/ops/op_softmax.cuh:31-41).  Its grid covers rows 0 .. 256*ceil(w/256)-1 only
+// (op_softmax.cuh:38 sizes it from the width): callers keep h inside that.
+int ref_softmax(const float *A, int h, int w, float *B) {
+  Tensor<float> a{h, w, true}, b{h, w, true};
+  cudaMemcpy(a.rawp, A, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice);
+  op_softmax(a, b);
+  int rc = status();
+  d2h(B, b);
+  return rc;
+}
+
+// AttentionLayer<float>::forward (src/modules/attention.cuh:47-70) statement by statement, with the
+// three projections (:54-56) calling the reference's own op_quantized_mm instead of op_mm -- the
+// re-pointing of SURVEY.md F2 -- and queries / keys+values taken from two inputs as
+// src/transformer.cu:37 expects (pass the same X twice for the 2-argument form).  Every
+// intermediate can be read back.
+int ref_attention_quantized(const float *Xq, const float *Xkv, const float *Wq, const float *Wk, const float *Wv,
+                            int sq, int skv, int d_model, int d_k, int d_v, float range, float *Q_out, float *K_out,
+                            float *V_out, float *S_out, float *P_out, float *out) {
+  Tensor<float> xq{sq, d_model, true}, xkv{skv, d_model, true}, wq{d_model, d_k, true}, wk{d_model, d_k, true},
+      wv{d_model, d_v, true};
+  cudaMemcpy(xq.rawp, Xq, sizeof(float) * (size_t)sq * d_model, cudaMemcpyHostToDevice);
+  cudaMemcpy(xkv.rawp, Xkv, sizeof(float) * (size_t)skv * d_model, cudaMemcpyHostToDevice);
+  cudaMemcpy(wq.rawp, Wq, sizeof(float) * (size_t)d_model * d_k, cudaMemcpyHostToDevice);
+  cudaMemcpy(wk.rawp, Wk, sizeof(float) * (size_t)d_model * d_k, cudaMemcpyHostToDevice);
+  cudaMemcpy(wv.rawp, Wv, sizeof(float) * (size_t)d_model * d_v, cudaMemcpyHostToDevice);
+  Tensor<float> Q(sq, d_k, true), K(skv, d_k, true), V(skv, d_v, true);
+  op_quantized_mm(xq, wq, Q, range);
+  op_quantized_mm(xkv, wk, K, range);
+  op_quantized_mm(xkv, wv, V, range);
+  Tensor<float> K_transpose = K.transpose();
+  Tensor<float> QK_T(Q.h, K_transpose.w, true);
+  op_mm(Q, K_transpose, QK_T);
+  Tensor<float> scaled_QK_T(QK_T.h, QK_T.w, true);
+  float scale_factor = 1.0 / std::sqrt(d_k);
+  op_multiply(QK_T, scale_factor, scaled_QK_T);
+  Tensor<float> softmax_QK_T(QK_T.h, QK_T.w, true);
+  op_softmax(scaled_QK_T, softmax_QK_T);
+  Tensor<float> output(sq, d_v, true);
+  op_mm(softmax_QK_T, V, output);
+  int rc = status();
+  d2h(Q_out, Q); d2h(K_out, K); d2h(V_out, V); d2h(S_out, QK_T); d2h(P_out, softmax_QK_T); d2h(out, output);
   return rc;
 }
 

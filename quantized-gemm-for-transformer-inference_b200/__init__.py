@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "qg_linear_forward",
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
     "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_mm_f32",
+    "qg_softmax_rows_f32", "qg_attention_forward",
 ]
 
 
@@ -392,3 +393,83 @@ class LinearLayer:
                                        _dt(y), M, N, K, C.c_float(self.range), self.mode,
                                        C.c_void_p(self._ws.data_ptr()), C.c_size_t(self._ws.numel()), _stream()),
                "qg_linear_forward")
+
+
+def op_softmax(A: torch.Tensor, B: torch.Tensor, scale: float = 1.0) -> None:
+    """op_softmax (src/ops/op_softmax.cuh:31-41) of fl(A * scale), row-wise, fp32; B may be A."""
+    assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.shape == B.shape
+    pa, lda = _dev2d(A)
+    pb, ldb = _dev2d(B)
+    _check(lib().qg_softmax_rows_f32(pa, lda, A.shape[0], A.shape[1], C.c_float(scale), pb, ldb, _stream()),
+           "qg_softmax_rows_f32")
+
+
+def attention_forward(Xq: torch.Tensor, Xkv: torch.Tensor, Wqkv: torch.Tensor, out: torch.Tensor, heads: int, d_k: int,
+                      d_v: int, batch: int = 1, range_: float = 127.0, mode: int = MODE_REF_EXACT) -> None:
+    """qg_attention_forward: see include/qgemm.h.  Xq [batch*sq, d_model], Xkv [batch*skv, d_model],
+    Wqkv [d_model, heads*(2*d_k+d_v)] = [all W_q | all W_k | all W_v], out [batch*sq, heads*d_v]."""
+    assert all(t.dtype == torch.float32 and t.is_cuda for t in (Xq, Xkv, Wqkv, out))
+    assert Xq.shape[0] % batch == 0 and Xkv.shape[0] % batch == 0
+    sq, skv, d_model = Xq.shape[0] // batch, Xkv.shape[0] // batch, Xq.shape[1]
+    assert Xkv.shape[1] == d_model and Wqkv.shape == (d_model, heads * (2 * d_k + d_v))
+    assert out.shape == (batch * sq, heads * d_v)
+    pq, ldq = _dev2d(Xq)
+    pkv, ldkv = _dev2d(Xkv)
+    pw, ldw = _dev2d(Wqkv)
+    po, ldo = _dev2d(out)
+    _check(lib().qg_attention_forward(pq, ldq, pkv, ldkv, batch, sq, skv, d_model, pw, ldw, heads, d_k, d_v,
+                                      C.c_float(range_), mode, po, ldo, _stream()), "qg_attention_forward")
+
+
+class AttentionLayer:
+    """AttentionLayer<float> (src/modules/attention.cuh:10-70): single head, no bias, no mask.
+    W_q, W_k [d_model, d_k] and W_v [d_model, d_v] are views of one [d_model, 2*d_k+d_v] parameter, so
+    the three projections of forward() run as ONE quantized product (bit-identical to three).
+    forward(X, out) is the reference's; forward(Xq, Xkv, out) is the cross-attention form
+    src/transformer.cu:37,132 calls."""
+
+    def __init__(self, d_model: int, d_k: int, d_v: int, device="cuda", range_: float = 127.0, mode: int = MODE_REF_EXACT):
+        self.d_model, self.d_k, self.d_v, self.range, self.mode = d_model, d_k, d_v, range_, mode
+        self.W_qkv = torch.empty((d_model, 2 * d_k + d_v), dtype=torch.float32, device=device)
+        self.W_q = self.W_qkv[:, :d_k]
+        self.W_k = self.W_qkv[:, d_k:2 * d_k]
+        self.W_v = self.W_qkv[:, 2 * d_k:]
+
+    def parameters(self):  # attention.cuh:32-38
+        return [self.W_q, self.W_k, self.W_v]
+
+    def init_uniform(self, generator=None):  # attention.cuh:40-45
+        mx = 1.0 / (self.d_k ** 0.5)
+        self.W_qkv.uniform_(-mx, mx, generator=generator)
+
+    def forward(self, *args) -> None:
+        if len(args) == 2:
+            (X, out), Xkv = args, args[0]
+        else:
+            X, Xkv, out = args
+        attention_forward(X, Xkv, self.W_qkv, out, 1, self.d_k, self.d_v, 1, self.range, self.mode)
+
+
+class MultiHeadAttention:
+    """The per-head AttentionLayer loop + host-side concat of src/transformer.cu:27-50 as one call:
+    all heads' projections in one quantized product, scores / softmax / P V batched over
+    (sequence, head), heads written side by side.  `batch` independent sequences per call."""
+
+    def __init__(self, d_model: int, n_heads: int, device="cuda", range_: float = 127.0, mode: int = MODE_REF_EXACT):
+        assert d_model % n_heads == 0
+        self.d_model, self.n_heads, self.range, self.mode = d_model, n_heads, range_, mode
+        self.d_k = self.d_v = d_model // n_heads  # transformer.cu:21-22
+        self.W_qkv = torch.empty((d_model, n_heads * (2 * self.d_k + self.d_v)), dtype=torch.float32, device=device)
+
+    def head_weights(self, h: int):
+        """(W_q, W_k, W_v) views of head h, each [d_model, d_k]."""
+        H, dk, dv = self.n_heads, self.d_k, self.d_v
+        return (self.W_qkv[:, h * dk:(h + 1) * dk], self.W_qkv[:, H * dk + h * dk:H * dk + (h + 1) * dk],
+                self.W_qkv[:, 2 * H * dk + h * dv:2 * H * dk + (h + 1) * dv])
+
+    def init_uniform(self, generator=None):
+        mx = 1.0 / (self.d_k ** 0.5)
+        self.W_qkv.uniform_(-mx, mx, generator=generator)
+
+    def forward(self, Xq: torch.Tensor, Xkv: torch.Tensor, out: torch.Tensor, batch: int = 1) -> None:
+        attention_forward(Xq, Xkv, self.W_qkv, out, self.n_heads, self.d_k, self.d_v, batch, self.range, self.mode)

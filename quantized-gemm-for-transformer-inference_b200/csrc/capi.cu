@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -32,7 +33,8 @@ int quant_rows_outlier(const void *X, int dtype, int M, int K, int64_t ldx, floa
 int gather_wo(const void *W, int dtype, int64_t ldw, const int *idx, int n_idx, int no_pad, int N, void *Wo, int64_t ldwo,
               int side_bf16, cudaStream_t st);
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
-           float *C, int64_t ldc, cudaStream_t st);
+           float *C, int64_t ldc, cudaStream_t st, const MmBatch *batch = nullptr);
+int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st);
 int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
                    float c, void *O, int out_dtype, int64_t ldo, cudaStream_t st);
 bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb);
@@ -78,6 +80,8 @@ struct DeviceState {
   // host-buffer entry point
   void *hx = nullptr, *hw = nullptr, *ho = nullptr, *hb = nullptr;
   size_t hx_bytes = 0, hw_bytes = 0, ho_bytes = 0, hb_bytes = 0;
+  void *attn = nullptr;  // grow-only scratch of qg_attention_forward (projections, scores)
+  size_t attn_bytes = 0;
   // three streams: host->device copies, kernels, device->host copies (PCIe is full duplex)
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
   static constexpr int kHostChunks = 8;
@@ -628,6 +632,80 @@ int qg_mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_
   if (rc) return rc;
   QG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N, "qg_mm_f32: bad arguments");
   return mm_f32(A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc, (cudaStream_t)stream);
+}
+
+int qg_softmax_rows_f32(const float *A, int64_t lda, int m, int n, float scale, float *B, int64_t ldb,
+                        qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && B && m > 0 && n > 0 && lda >= n && ldb >= n, "qg_softmax_rows_f32: bad arguments");
+  return cuda_status((cudaError_t)softmax_rows(A, lda, m, n, scale, B, ldb, (cudaStream_t)stream), "softmax");
+}
+
+int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq, int skv,
+                         int d_model, const float *Wqkv, int64_t ldw, int heads, int d_k, int d_v, float range, int mode,
+                         float *out, int64_t ldo, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  const int nq = heads * d_k, nkv = heads * (d_k + d_v), ntot = nq + nkv;
+  QG_REQUIRE(Xq && Xkv && Wqkv && out && batch > 0 && sq > 0 && skv > 0 && d_model > 0 && heads > 0 && d_k > 0 && d_v > 0 &&
+                 ldxq >= d_model && ldxkv >= d_model && ldw >= ntot && ldo >= heads * d_v,
+             "qg_attention_forward: bad arguments");
+  const bool self = (Xq == Xkv) && sq == skv && ldxq == ldxkv;
+  const int64_t tq = (int64_t)batch * sq, tkv = (int64_t)batch * skv;
+  QG_REQUIRE(tq < (1 << 30) && tkv < (1 << 30) && (int64_t)batch * heads <= 65535, "qg_attention_forward: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch: projections [tq, nq] + [tkv, nkv] (one [tq, ntot] matrix for self-attention), scores [batch*heads*sq, skv]
+  const size_t proj_elems = self ? (size_t)tq * ntot : (size_t)tq * nq + (size_t)tkv * nkv;
+  const size_t score_elems = (size_t)batch * heads * sq * skv;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if ((rc = grow(&d->attn, &d->attn_bytes, sizeof(float) * (proj_elems + score_elems) + 512))) return rc;
+  }
+  float *proj = (float *)d->attn;
+  float *scores = proj + round_up((int64_t)proj_elems, 64);
+  // 1. projections through the quantized linear path (attention.cuh:54-56 re-pointed).  Row scales
+  //    depend only on X and column scales only on their own column, so one product against the
+  //    concatenated [W_q | W_k | W_v] of all heads is bit-identical to the separate ones.
+  const float *Q, *Kp, *Vp;
+  int64_t ldq_, ldkv;
+  if (self) {
+    rc = qg_quantized_mm(Xq, ldxq, Wqkv, ldw, QG_F32, proj, ntot, QG_F32, (int)tq, ntot, d_model, range, mode, nullptr,
+                         nullptr, 0, stream);
+    if (rc) return rc;
+    Q = proj; Kp = proj + nq; Vp = proj + nq + heads * d_k;
+    ldq_ = ldkv = ntot;
+  } else {  // the 3-argument form transformer.cu:37,132 expects: queries from Xq, keys / values from Xkv
+    float *pkv = proj + (size_t)tq * nq;
+    rc = qg_quantized_mm(Xq, ldxq, Wqkv, ldw, QG_F32, proj, nq, QG_F32, (int)tq, nq, d_model, range, mode, nullptr, nullptr,
+                         0, stream);
+    if (rc) return rc;
+    rc = qg_quantized_mm(Xkv, ldxkv, Wqkv + nq, ldw, QG_F32, pkv, nkv, QG_F32, (int)tkv, nkv, d_model, range, mode, nullptr,
+                         nullptr, 0, stream);
+    if (rc) return rc;
+    Q = proj; Kp = pkv; Vp = pkv + heads * d_k;
+    ldq_ = nq; ldkv = nkv;
+  }
+  // 2. scores = Q K^T per (sequence, head): fp32, k-ascending FMA chain like op_mm (attention.cuh:58-60)
+  MmBatch bt;
+  bt.n_outer = batch; bt.n_inner = heads;
+  bt.a_outer = (int64_t)sq * ldq_;  bt.a_inner = d_k;
+  bt.b_outer = (int64_t)skv * ldkv; bt.b_inner = d_k;
+  bt.c_outer = (int64_t)heads * sq * skv; bt.c_inner = (int64_t)sq * skv;
+  rc = mm_f32(Q, ldq_, 1, Kp, 1, ldkv, sq, skv, d_k, scores, skv, st, &bt);  // B = K^T: element (k, n) at K[n, k]
+  if (rc) return cuda_status((cudaError_t)rc, "scores");
+  // 3. softmax(scores / sqrt(d_k)) in place (attention.cuh:62-68)
+  const float scale = (float)(1.0 / std::sqrt((double)d_k));
+  rc = softmax_rows(scores, skv, batch * heads * sq, skv, scale, scores, skv, st);
+  if (rc) return cuda_status((cudaError_t)rc, "softmax");
+  // 4. out[:, h*d_v : (h+1)*d_v] = P V per (sequence, head) (attention.cuh:69; the head concat of transformer.cu:43-50)
+  bt.a_outer = (int64_t)heads * sq * skv; bt.a_inner = (int64_t)sq * skv;
+  bt.b_outer = (int64_t)skv * ldkv;       bt.b_inner = d_v;
+  bt.c_outer = (int64_t)sq * ldo;         bt.c_inner = d_v;
+  rc = mm_f32(scores, skv, 1, Vp, ldkv, 1, sq, d_v, skv, out, ldo, st, &bt);
+  return cuda_status((cudaError_t)rc, "P*V");
 }
 
 /* bring-up hook: device buffer (8 x int64 per CTA) that the tcgen05 GEMM fills with pipeline wait

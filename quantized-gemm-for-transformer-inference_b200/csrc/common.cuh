@@ -64,6 +64,13 @@ struct SideArgs {
   int side_bf16;   // 0: fp16 operands, 1: bf16
 };
 
+// batch geometry of the fp32 product: blockIdx.z = outer * n_inner + inner selects one independent
+// product; element offsets per operand (attention: outer = sequence, inner = head)
+struct MmBatch {
+  int n_outer, n_inner;
+  int64_t a_outer, a_inner, b_outer, b_inner, c_outer, c_inner;
+};
+
 // additional destinations of the GEMM epilogue: the same [M,N] block is also written (same leading
 // dimension and dtype) to these buffers -- peers' output matrices mapped over NVLink in the
 // column-parallel linear, so the all-gather rides inside the GEMM

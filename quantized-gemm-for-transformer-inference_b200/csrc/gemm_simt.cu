@@ -98,11 +98,17 @@ gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__r
 // 32-wide tile adds fma(0,0,res) steps, which only turn -0 into +0.
 __global__ void __launch_bounds__(256)
 mm_f32_kernel(const float *__restrict__ A, int64_t sa_h, int64_t sa_w, const float *__restrict__ B, int64_t sb_h,
-              int64_t sb_w, int M, int N, int K, float *__restrict__ C, int64_t ldc) {
+              int64_t sb_w, int M, int N, int K, float *__restrict__ C, int64_t ldc, MmBatch bt) {
   __shared__ float sA[TK][TM + 1];
   __shared__ float sB[TK][TN + 1];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  {  // blockIdx.z = outer * n_inner + inner: one independent product per (outer, inner) pair
+    const int zo = blockIdx.z / bt.n_inner, zi = blockIdx.z % bt.n_inner;
+    A += zo * bt.a_outer + zi * bt.a_inner;
+    B += zo * bt.b_outer + zi * bt.b_inner;
+    C += zo * bt.c_outer + zi * bt.c_inner;
+  }
   griddep_wait();
   griddep_trigger_early();
   float acc[4][4];
@@ -197,9 +203,89 @@ int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int
 }
 
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
-           float *C, int64_t ldc, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
-  launch_kernel(mm_f32_kernel, grid, dim3(256), st, A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc);
+           float *C, int64_t ldc, cudaStream_t st, const MmBatch *batch) {
+  MmBatch bt = {};
+  bt.n_outer = bt.n_inner = 1;
+  if (batch != nullptr) bt = *batch;
+  dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM), (unsigned)(bt.n_outer * bt.n_inner));
+  launch_kernel(mm_f32_kernel, grid, dim3(256), st, A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc, bt);
+  return (int)cudaGetLastError();
+}
+
+// op_multiply(A, scale, T) + op_softmax(T, B) (attention.cuh:62-68; op_softmax.cuh:6-29) in one pass
+// over the same arithmetic: t_j = fl(a_j * scale); max by strict '>' starting from column 0;
+// e_j = expf(t_j - max); the sum runs over ascending j; b_j = e_j / sum.  One thread per row, as in
+// the reference, because the ascending-order fp32 sum is part of the result; a CTA's rows are
+// staged through shared memory in 32-column tiles so that global accesses stay coalesced.
+constexpr int kSmRows = 128;
+__global__ void __launch_bounds__(kSmRows)
+softmax_rows_kernel(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb) {  // A may alias B
+  __shared__ float tile[kSmRows][33];
+  const int r0 = blockIdx.x * kSmRows;
+  const int rows = min(kSmRows, M - r0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_wait();
+  griddep_trigger_early();
+  // tile <- fl(A[r0.., c0..c0+31] * scale): warp w loads rows w, w+4, ... 32 consecutive floats at a time
+  auto load_tile = [&](const float *src, int64_t ld, int c0, bool mul) {
+    for (int r = warp; r < rows; r += kSmRows / 32) {
+      const int c = c0 + lane;
+      float v = 0.0f;
+      if (c < N) v = src[(int64_t)(r0 + r) * ld + c];
+      tile[r][lane] = mul ? __fmul_rn(v, scale) : v;
+    }
+  };
+  auto store_tile = [&](int c0) {
+    for (int r = warp; r < rows; r += kSmRows / 32) {
+      const int c = c0 + lane;
+      if (c < N) B[(int64_t)(r0 + r) * ldb + c] = tile[r][lane];
+    }
+  };
+  const int t = threadIdx.x;
+  float mx = 0.0f, sum = 0.0f;
+  for (int c0 = 0; c0 < N; c0 += 32) {  // pass 1: row max
+    __syncthreads();
+    load_tile(A, lda, c0, true);
+    __syncthreads();
+    if (t < rows) {
+      const int n = min(32, N - c0);
+      for (int j = 0; j < n; j++) {
+        const float v = tile[t][j];
+        if (c0 + j == 0) mx = v;
+        else if (v > mx) mx = v;
+      }
+    }
+  }
+  for (int c0 = 0; c0 < N; c0 += 32) {  // pass 2: e_j, running sum; e_j parked in B
+    __syncthreads();
+    load_tile(A, lda, c0, true);
+    __syncthreads();
+    if (t < rows) {
+      const int n = min(32, N - c0);
+      for (int j = 0; j < n; j++) {
+        const float e = expf(__fsub_rn(tile[t][j], mx));
+        tile[t][j] = e;
+        sum = __fadd_rn(sum, e);
+      }
+    }
+    __syncthreads();
+    store_tile(c0);
+  }
+  for (int c0 = 0; c0 < N; c0 += 32) {  // pass 3: divide
+    __syncthreads();
+    load_tile(B, ldb, c0, false);
+    __syncthreads();
+    if (t < rows) {
+      const int n = min(32, N - c0);
+      for (int j = 0; j < n; j++) tile[t][j] = __fdiv_rn(tile[t][j], sum);
+    }
+    __syncthreads();
+    store_tile(c0);
+  }
+}
+
+int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st) {
+  launch_kernel(softmax_rows_kernel, dim3((unsigned)ceil_div(M, kSmRows)), dim3(kSmRows), st, A, lda, M, N, scale, B, ldb);
   return (int)cudaGetLastError();
 }
 

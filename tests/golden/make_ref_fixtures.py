@@ -59,12 +59,56 @@ def cases(ref):
     yield "curand_seed0_32x16x64", X, W
 
 
+def run_ref_attention(ref, Xq, Xkv, Wq, Wk, Wv, range_=127.0):
+    """AttentionLayer::forward with the projections on op_quantized_mm, every intermediate kept."""
+    sq, d_model = Xq.shape
+    skv = Xkv.shape[0]
+    d_k, d_v = Wq.shape[1], Wv.shape[1]
+    Q, K, V = np.empty((sq, d_k), np.float32), np.empty((skv, d_k), np.float32), np.empty((skv, d_v), np.float32)
+    S, P, out = np.empty((sq, skv), np.float32), np.empty((sq, skv), np.float32), np.empty((sq, d_v), np.float32)
+    rc = ref.ref_attention_quantized(p(Xq), p(Xkv), p(Wq), p(Wk), p(Wv), sq, skv, d_model, d_k, d_v, C.c_float(range_),
+                                     p(Q), p(K), p(V), p(S), p(P), p(out))
+    assert rc == 0, rc
+    return dict(Xq=Xq, Xkv=Xkv, Wq=Wq, Wk=Wk, Wv=Wv, Q=Q, K=K, V=V, S=S, P=P, out=out)
+
+
+def attention_cases():
+    rng = np.random.default_rng(7)
+    u = lambda *s: (rng.random(s, dtype=np.float32) * 2 - 1)
+    # the shape of src/test_attn.cu:100-134 (seq 2, d_model 3, d_k 2, d_v 4) with its hard-coded weights' ranges
+    X = u(2, 3)
+    yield "attn_self_2x3_dk2_dv4", X, X, u(3, 2), u(3, 2), u(3, 4)
+    X = u(48, 64)
+    s = np.float32(1 / 8)
+    yield "attn_self_48x64_dk16_dv24", X, X, u(64, 16) * s, u(64, 16) * s, u(64, 24) * s
+    yield "attn_cross_40_72x96_dk32_dv32", u(40, 96), u(72, 96), u(96, 32) * s, u(96, 32) * s, u(96, 32) * s
+    X = rng.standard_normal((128, 512)).astype(np.float32)  # one head of BASELINE config 3
+    s = np.float32(1 / 64 ** 0.5)
+    yield "attn_self_128x512_dk64_dv64", X, X, u(512, 64) * s, u(512, 64) * s, u(512, 64) * s
+
+
+def softmax_cases():
+    rng = np.random.default_rng(8)
+    yield "softmax_1x3", np.array([[1.0, 2.0, 3.0]], np.float32)  # src/test_softmax.cu:30-66
+    A = (rng.standard_normal((200, 77)) * 4).astype(np.float32)
+    A[3, 5] = np.float32(88.0); A[4, :] = np.float32(-1e30); A[5, 0] = np.float32(-0.0)
+    yield "softmax_200x77", A
+
+
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(out, exist_ok=True)
     ref = load_ref()
     for name, X, W in cases(ref):
         np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), **run_ref(ref, X, W))
+        print("wrote", name)
+    for name, Xq, Xkv, Wq, Wk, Wv in attention_cases():
+        np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), **run_ref_attention(ref, Xq, Xkv, Wq, Wk, Wv))
+        print("wrote", name)
+    for name, A in softmax_cases():
+        B = np.empty_like(A)
+        assert ref.ref_softmax(p(A), A.shape[0], A.shape[1], p(B)) == 0
+        np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), A=A, B=B)
         print("wrote", name)
 
 

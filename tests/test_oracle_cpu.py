@@ -150,3 +150,26 @@ def test_oracle_matches_reference_kernel_outputs(oracle, name):
     assert _same_f32(O, r["O"])          # step-by-step pipeline (timing_quantize.cu:38-58)
     assert _same_f32(O, r["O_op"])       # the reference's op_quantized_mm itself (op_mm.cuh:67-101)
     assert _same_f32(oracle.gemm_f32_ref(r["X"], r["W"]), r["C_fp32"])
+
+
+# ---- attention widening: oracle against the reference kernels' outputs ----
+import glob as _glob  # noqa: E402
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(_glob.glob(os.path.join(_GOLDEN, "ref_softmax_*.npz"))))
+def test_oracle_softmax_vs_reference_kernel(oracle, path):
+    g = np.load(path)
+    # libm expf vs the device's expf (<= 2 ulp): tolerance, not bits
+    np.testing.assert_allclose(oracle.softmax_rows(g["A"]), g["B"], rtol=2e-6, atol=1e-37)
+
+
+@pytest.mark.parametrize("path", sorted(_glob.glob(os.path.join(_GOLDEN, "ref_attn_*.npz"))))
+def test_oracle_attention_vs_reference_kernels(oracle, path):
+    g = np.load(path)
+    o = oracle.attention_forward(g["Xq"], g["Xkv"], g["Wq"], g["Wk"], g["Wv"], return_parts=True)
+    for k in ("Q", "K", "V", "S"):  # quantized projections and the fp32 score product: bit-exact
+        assert np.array_equal(o[k].view(np.uint32), g[k].view(np.uint32)), k
+    np.testing.assert_allclose(o["P"], g["P"], rtol=2e-6, atol=1e-37)
+    np.testing.assert_allclose(o["out"], g["out"], rtol=1e-5, atol=2e-6)
