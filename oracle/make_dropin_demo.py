@@ -6,6 +6,7 @@ src/test_quantize.cu, compiled twice from a scratch copy of /root/reference/src 
                                     (src/ops/op_mm.cuh:67-101) replaced by the one-line call into
                                     qg_dropin.cuh / libqgemm.so that INTEGRATION.md describes
 
+(and likewise src/test_softmax.cu -> test_softmax_ref / test_softmax_dropin with op_softmax re-pointed).
 Both print the same three blocks (unquantized result, quantized result, mean error); the GPU test
 tests/test_gpu_dropin.py runs them and compares the text.  Nothing from the reference is written
 into this repository: the edited copy lives in /tmp, only the two binaries land in oracle/_ref/.
@@ -56,6 +57,18 @@ def main():
     open(path, "w").write(text)
     subprocess.run([NVCC, *FLAGS, "-I", src, "-I", os.path.join(PKG, "cpp"), os.path.join(src, "test_quantize.cu"), "-o",
                     os.path.join(OUT, "test_quantize_dropin"), "-lcurand", "-L", PKG, "-lqgemm",
+                    "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../quantized-gemm-for-transformer-inference_b200"],
+                   check=True)
+    # the same for op_softmax and the reference's own src/test_softmax.cu
+    subprocess.run([NVCC, *FLAGS, "-I", os.path.join(REF, "src"), os.path.join(REF, "src", "test_softmax.cu"), "-o",
+                    os.path.join(OUT, "test_softmax_ref")], check=True)
+    path = os.path.join(src, "ops", "op_softmax.cuh")
+    text = open(path).read()
+    text = text.replace("#pragma once", '#pragma once\n#include "qg_dropin.cuh"', 1)
+    text = replace_body(text, "op_softmax", "    qg_dropin::op_softmax(A, B);")
+    open(path, "w").write(text)
+    subprocess.run([NVCC, *FLAGS, "-I", src, "-I", os.path.join(PKG, "cpp"), os.path.join(src, "test_softmax.cu"), "-o",
+                    os.path.join(OUT, "test_softmax_dropin"), "-L", PKG, "-lqgemm",
                     "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../quantized-gemm-for-transformer-inference_b200"],
                    check=True)
     shutil.rmtree(tmp, ignore_errors=True)

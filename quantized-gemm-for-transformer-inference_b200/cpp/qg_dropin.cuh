@@ -124,6 +124,51 @@ void linear_forward(const TensorT &x, const TensorT &w, const TensorT &b, Tensor
                         x.w, range, mode, base_ptr(b), nullptr, 0, nullptr), "qg_quantized_mm(+bias)");
 }
 
+// op_softmax(A, B): src/ops/op_softmax.cuh:31-41 (contiguous columns, as every reference call site has)
+template <class TensorT>
+void op_softmax(const TensorT &A, TensorT &B) {
+  assert(A.h == B.h && A.w == B.w);
+  assert(A.on_device && B.on_device);
+  assert(A.stride_w == 1 && B.stride_w == 1);
+  check(qg_softmax_rows_f32(base_ptr(A), A.stride_h, A.h, A.w, 1.0f, base_ptr(B), B.stride_h, nullptr), "qg_softmax_rows_f32");
+}
+
+// AttentionLayer<T>::forward(X, output), src/modules/attention.cuh:47-70, and the (Xq, Xkv, output) form
+// src/transformer.cu:37,132 calls: the three projections on the quantized path, the rest in the
+// reference's fp32 arithmetic.  W_q / W_k / W_v are separate tensors in the reference; they are packed
+// side by side into one scratch matrix (3 strided device copies) so that the projections run as one
+// product.  A layer that keeps its weights packed calls qg_attention_forward directly.
+template <class TensorT>
+void attention_forward(const TensorT &Xq, const TensorT &Xkv, const TensorT &W_q, const TensorT &W_k, const TensorT &W_v,
+                       TensorT &output, float range = 127.0f, int mode = QG_MODE_REF_EXACT) {
+  const int d_model = Xq.w, d_k = W_q.w, d_v = W_v.w, ntot = 2 * d_k + d_v;
+  assert(Xkv.w == d_model && W_q.h == d_model && W_k.h == d_model && W_v.h == d_model && W_k.w == d_k);
+  assert(output.h == Xq.h && output.w == d_v);
+  assert(Xq.on_device && Xkv.on_device && W_q.on_device && W_k.on_device && W_v.on_device && output.on_device);
+  assert(Xq.stride_w == 1 && Xkv.stride_w == 1 && W_q.stride_w == 1 && W_k.stride_w == 1 && W_v.stride_w == 1);
+  float *packed = nullptr;
+  cudaError_t e = cudaMalloc(&packed, sizeof(float) * (size_t)d_model * ntot);
+  assert(e == cudaSuccess);
+  const TensorT *ws[3] = {&W_q, &W_k, &W_v};
+  int col = 0;
+  for (int i = 0; i < 3; i++) {
+    e = cudaMemcpy2DAsync(packed + col, sizeof(float) * ntot, base_ptr(*ws[i]), sizeof(float) * ws[i]->stride_h,
+                          sizeof(float) * ws[i]->w, d_model, cudaMemcpyDeviceToDevice, nullptr);
+    assert(e == cudaSuccess);
+    col += ws[i]->w;
+  }
+  (void)e;
+  const bool self = base_ptr(Xq) == base_ptr(Xkv) && Xq.h == Xkv.h;
+  check(qg_attention_forward(base_ptr(Xq), Xq.stride_h, self ? base_ptr(Xq) : base_ptr(Xkv), Xkv.stride_h, 1, Xq.h, Xkv.h,
+                             d_model, packed, ntot, 1, d_k, d_v, range, mode, base_ptr(output), output.stride_h, nullptr),
+        "qg_attention_forward");
+  cudaFree(packed);  // synchronises with the legacy stream the work above ran on
+}
+template <class TensorT>
+void attention_forward(const TensorT &X, const TensorT &W_q, const TensorT &W_k, const TensorT &W_v, TensorT &output) {
+  attention_forward(X, X, W_q, W_k, W_v, output);
+}
+
 // op_outlier_extractor(a, b, out): src/ops/op_elemwise.cuh:698-708
 template <class TensorT, typename T>
 void op_outlier_extractor(const TensorT &a, T b, TensorT &out) {

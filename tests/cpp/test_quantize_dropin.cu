@@ -83,6 +83,37 @@ int main() {
   Tensor<float> h1 = O1.toHost(), h2 = O2.toHost();
   for (int i = 0; i < M * N; i++)
     if (h1.rawp[i] != h2.rawp[i]) { bad++; break; }
+  // AttentionLayer::forward (src/modules/attention.cuh:47-70) re-pointed: the fused call must equal the
+  // statement-by-statement sequence run through the single drop-in ops, bit for bit
+  {
+    const int S = 40, DM = 64, DK = 16, DV = 24;
+    Tensor<float> Xa{S, DM}, Wq{DM, DK}, Wk{DM, DK}, Wv{DM, DV};
+    for (int i = 0; i < S * DM; i++) Xa.rawp[i] = (float)rand() / RAND_MAX * 2 - 1;
+    for (int i = 0; i < DM * DK; i++) { Wq.rawp[i] = ((float)rand() / RAND_MAX * 2 - 1) / 4; Wk.rawp[i] = ((float)rand() / RAND_MAX * 2 - 1) / 4; }
+    for (int i = 0; i < DM * DV; i++) Wv.rawp[i] = ((float)rand() / RAND_MAX * 2 - 1) / 4;
+    Tensor<float> dX = Xa.toDevice(), dWq = Wq.toDevice(), dWk = Wk.toDevice(), dWv = Wv.toDevice();
+    Tensor<float> fused{S, DV, true};
+    attention_forward(dX, dWq, dWk, dWv, fused);
+    Tensor<float> Qp{S, DK, true}, Kp{S, DK, true}, Vp{S, DV, true}, Sc{S, S, true}, Pr{S, S, true}, manual{S, DV, true};
+    op_quantized_mm(dX, dWq, Qp, 127.0f);
+    op_quantized_mm(dX, dWk, Kp, 127.0f);
+    op_quantized_mm(dX, dWv, Vp, 127.0f);
+    Tensor<float> Kt = Kp.transpose();
+    op_mm(Qp, Kt, Sc);
+    const float scale = (float)(1.0 / std::sqrt((double)DK));
+    if (qg_softmax_rows_f32(Sc.rawp, Sc.stride_h, S, S, scale, Pr.rawp, Pr.stride_h, nullptr) != 0) bad++;
+    op_mm(Pr, Vp, manual);
+    cudaDeviceSynchronize();
+    Tensor<float> fh = fused.toHost(), mh = manual.toHost(), ph = Pr.toHost();
+    for (int i = 0; i < S * DV; i++)
+      if (fh.rawp[i] != mh.rawp[i]) { printf("attention: fused != sequence at %d: %g vs %g\n", i, fh.rawp[i], mh.rawp[i]); bad++; break; }
+    for (int i = 0; i < S; i++) {
+      float sum = 0;
+      for (int j = 0; j < S; j++) sum += ph.at(i, j);
+      if (std::fabs(sum - 1.0f) > 1e-5f) { printf("softmax row %d sums to %g\n", i, sum); bad++; break; }
+    }
+    printf("attention (fused QKV) == op-by-op sequence: %s\n", bad ? "no" : "yes");
+  }
   printf(bad ? "FAILED (%d)\n" : "All tests completed successfully!\n", bad);
   return bad ? 1 : 0;
 }

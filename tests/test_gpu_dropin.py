@@ -26,6 +26,13 @@ def test_reference_driver_prints_identical_results_on_the_new_path():
     assert new == ref
 
 
+def test_reference_softmax_driver_prints_identical_results_on_the_new_path():
+    ref = run(os.path.join(ROOT, "oracle", "_ref", "test_softmax_ref"))
+    new = run(os.path.join(ROOT, "oracle", "_ref", "test_softmax_dropin"))
+    assert "Test passed." in ref
+    assert new == ref
+
+
 def test_cpp_driver_over_dropin_layer():
     out = run(os.path.join(ROOT, "tests", "cpp", "test_quantize_dropin"))
     assert "All tests completed successfully!" in out

@@ -79,6 +79,50 @@ def linear_case(name, M, K, N, dt=torch.float16, outliers=0, w_std=0.02, seed=0)
     return res
 
 
+def attention_case(batch=32, seq=128, d_model=512, heads=8):
+    """config 3 building block: multi-head self-attention over `batch` sequences, all projections int8.
+    fused = one qg_attention_forward call; looped = the reference's structure (transformer.cu:27-50):
+    one single-head AttentionLayer call per (sequence, head)."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    X = [torch.randn((batch * seq, d_model), device=DEV, generator=g) for _ in range(2)]
+    mha = qg.MultiHeadAttention(d_model, heads, device=DEV)
+    mha.init_uniform(g)
+    out = torch.empty((batch * seq, d_model), device=DEV)
+    res = {"name": f"mha_b{batch}_s{seq}_d{d_model}_h{heads}", "tokens": batch * seq}
+    us = timed(lambda i: mha.forward(X[i & 1], X[i & 1], out, batch=batch))
+    res["fused_us"], res["fused_tok_per_s"] = us, batch * seq / us * 1e6
+    d = d_model // heads
+    layers = []
+    for h in range(heads):
+        att = qg.AttentionLayer(d_model, d, d, device=DEV)
+        for dst, src in zip((att.W_q, att.W_k, att.W_v), mha.head_weights(h)):
+            dst.copy_(src)
+        layers.append(att)
+    o1 = torch.empty((seq, d), device=DEV)
+
+    def looped(i):
+        x = X[i & 1]
+        for b in range(batch):
+            xb = x[b * seq:(b + 1) * seq]
+            for att in layers:
+                att.forward(xb, o1)
+
+    us = timed(looped, iters=3, warm=1)
+    res["per_head_per_sequence_calls_us"] = us
+    res["speedup_fused_vs_looped"] = us / res["fused_us"]
+    # fp32 library attention for scale (not the same arithmetic: cuBLAS/SDPA, no quantization)
+    w = mha.W_qkv
+    def torch_ref(i):
+        qkv = X[i & 1] @ w
+        H, dk = heads, d
+        q = qkv[:, :H * dk].view(batch, seq, H, dk).transpose(1, 2)
+        k = qkv[:, H * dk:2 * H * dk].view(batch, seq, H, dk).transpose(1, 2)
+        v = qkv[:, 2 * H * dk:].view(batch, seq, H, dk).transpose(1, 2)
+        return torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    res["torch_fp32_sdpa_us"] = timed(torch_ref)
+    return res
+
+
 def main():
     out = []
     for n in (1024, 2048, 4096, 8192):  # config 2
@@ -90,6 +134,7 @@ def main():
         out.append(linear_case(name, T, K, N, torch.float16, outliers=6))
     for name, K, N in (("opt66b_fc1_shard_of_8", 9216, 36864 // 8), ("opt66b_fc2_shard_of_8", 36864, 9216 // 8)):  # config 5
         out.append(linear_case(name, 4096, K, N, torch.float16))
+    out.append(attention_case())  # config 3 building block
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w") as f:
         json.dump(out, f, indent=1)
