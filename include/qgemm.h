@@ -195,6 +195,23 @@ QG_API int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, c
 QG_API int qg_mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w,
                      int m, int n, int k, float *C, int64_t ldc, qg_stream_t stream);
 
+/* ---- LinearLayer::forward followed by op_relu  src/transformer.cu:65-67 (ll1.forward; op_relu) ---------- */
+/* qg_linear_forward with an activation applied after the bias add, inside the GEMM epilogue.
+ * QG_ACT_RELU is ReluFunc (src/ops/op_elemwise.cuh:181-195): x < 0 ? 0 : x (NaN and -0 pass through). */
+enum { QG_ACT_NONE = 0, QG_ACT_RELU = 1 };
+QG_API int qg_linear_forward_act(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt, int64_t ldwt,
+                                 const float *Cw, const float *bias, int act, void *Y, int64_t ldy, int out_dtype,
+                                 int m, int n, int k, float range, int mode, void *workspace, size_t workspace_bytes,
+                                 qg_stream_t stream);
+
+/* ---- op_add(A, R, T); op_layernorm(T, B)  src/transformer.cu:57-58,74-75, src/ops/op_layernorm.cuh:6-44 -- */
+/* The stack's "ADD & NORM" with the reference kernel's arithmetic: t = fl(a + r); mean and variance by
+ * ascending-order fp32 sums; b = (t - mean) / var  (the reference divides by the variance, no epsilon).
+ * R == NULL: plain op_layernorm.  B may alias A or R.  Every row is computed (the reference sizes its grid
+ * from the width, op_layernorm.cuh:41, and leaves rows beyond 256*ceil(w/256) untouched). */
+QG_API int qg_add_layernorm_f32(const float *A, int64_t lda, const float *R, int64_t ldr, int m, int n, float *B,
+                                int64_t ldb, qg_stream_t stream);
+
 /* ---- op_multiply(A, scale, T); op_softmax(T, B)  src/modules/attention.cuh:62-68,
  *      src/ops/op_elemwise.cuh:644-655, src/ops/op_softmax.cuh:6-41 ---------------------------- */
 /* Row softmax of fl(A * scale) with the reference kernel's arithmetic: max by strict '>' from column 0,

@@ -325,3 +325,36 @@ def multi_head_attention(Xq, Xkv, Wqkv, heads, d_k, d_v, batch=1, range_=127.0, 
             wv = Wqkv[:, 2 * heads * d_k + h * d_v:2 * heads * d_k + (h + 1) * d_v]
             out[b * sq:(b + 1) * sq, h * d_v:(h + 1) * d_v] = attention_forward(xq, xkv, wq, wk, wv, range_, mode)
     return out
+
+
+# ---- encoder block: src/transformer.cu:24-76 with persistent weights -----
+
+def add_layernorm(A, R=None):
+    """op_add(A, R) + op_layernorm (transformer.cu:57-58; op_layernorm.cuh:6-32) on the host."""
+    A = _f32(A)
+    M, N = A.shape
+    out = np.empty((M, N), np.float32)
+    if R is not None:
+        R = _f32(R)
+    lib().qo_add_layernorm_f32(_p(A), C.c_int64(N), _p(R) if R is not None else None, C.c_int64(N), C.c_int(M), C.c_int(N),
+                               _p(out), C.c_int64(N))
+    return out
+
+
+def relu(A):
+    """ReluFunc, src/ops/op_elemwise.cuh:181-195: x < 0 ? 0 : x (NaN and -0 pass through)."""
+    A = _f32(A)
+    return np.where(A < 0, np.float32(0), A).astype(np.float32)
+
+
+def encoder_block(X, Wqkv, W_O, W1, b1, W2, b2, heads, batch=1, range_=127.0, mode=MODE_REF_EXACT):
+    """One iteration of the Encoder loop (transformer.cu:24-76), every op_mm / LinearLayer on the quantized
+    path, the residual taken from the attention output exactly as the reference does (:57, :74)."""
+    d_model = X.shape[1]
+    d = d_model // heads
+    mh = multi_head_attention(X, X, Wqkv, heads, d, d, batch, range_, mode)        # :27-50
+    out = quantized_mm(mh, W_O, range_, mode)                                        # :54  op_mm(multiHeadOut, W_O, output)
+    out = add_layernorm(out, mh)                                                     # :57-58
+    ffn = relu(quantized_mm(out, W1, range_, mode, bias=b1))                         # :63-67
+    out = quantized_mm(ffn, W2, range_, mode, bias=b2)                               # :69-71
+    return add_layernorm(out, mh)                                                    # :74-75

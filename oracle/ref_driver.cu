@@ -17,6 +17,7 @@
 #include "ops/op_reduction.cuh"
 #include "ops/op_mm.cuh"
 #include "ops/op_softmax.cuh"
+#include "ops/op_layernorm.cuh"
 
 unsigned long long randgen_seed = 0;  // the ops `extern` this (src/ops/op_elemwise.cuh:12)
 
@@ -246,6 +247,72 @@ int ref_attention_quantized(const float *Xq, const float *Xkv, const float *Wq, 
   op_mm(softmax_QK_T, V, output);
   int rc = status();
   d2h(Q_out, Q); d2h(K_out, K); d2h(V_out, V); d2h(S_out, QK_T); d2h(P_out, softmax_QK_T); d2h(out, output);
+  return rc;
+}
+
+// op_add(a, r, a); op_layernorm(a, a) -- the in-place ADD & NORM of src/transformer.cu:57-58.  The
+// layernorm grid covers rows 0 .. 256*ceil(w/256)-1 only (op_layernorm.cuh:41); r == NULL skips the add.
+int ref_add_layernorm(const float *A, const float *R, int h, int w, float *B) {
+  Tensor<float> a{h, w, true}, r{h, w, true};
+  cudaMemcpy(a.rawp, A, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice);
+  if (R) {
+    cudaMemcpy(r.rawp, R, sizeof(float) * (size_t)h * w, cudaMemcpyHostToDevice);
+    op_add(a, r, a);
+  }
+  op_layernorm(a, a);
+  int rc = status();
+  d2h(B, a);
+  return rc;
+}
+
+// One iteration of the Encoder loop, src/transformer.cu:24-76, statement by statement on the reference's
+// own kernels, with: weights supplied by the caller instead of re-drawn (op_uniform_init) every call;
+// every op_mm on weights routed to op_quantized_mm; the per-head result copied into
+// its column block on the device instead of through the host (:43-50, same values); ffnOut sized
+// [h, d_ff] (the reference's [h, d_model] buffer only works for d_ff == d_model).
+// Wq/Wk/Wv: heads consecutive [d_model, d] matrices each.
+int ref_encoder_block(const float *X, int h, int d_model, int heads, int d_ff, const float *Wq, const float *Wk,
+                      const float *Wv, const float *W_O, const float *W1, const float *b1, const float *W2,
+                      const float *b2, float range, float *out) {
+  const int d = d_model / heads;
+  auto up = [](const float *src, int r, int c) {
+    Tensor<float> t{r, c, true};
+    cudaMemcpy(t.rawp, src, sizeof(float) * (size_t)r * c, cudaMemcpyHostToDevice);
+    return t;
+  };
+  Tensor<float> x = up(X, h, d_model), wo = up(W_O, d_model, d_model), w1 = up(W1, d_model, d_ff), bb1 = up(b1, 1, d_ff),
+                w2 = up(W2, d_ff, d_model), bb2 = up(b2, 1, d_model);
+  Tensor<float> multiHeadOut{h, d_model, true}, output{h, d_model, true};
+  for (int j = 0; j < heads; j++) {
+    Tensor<float> wq = up(Wq + (size_t)j * d_model * d, d_model, d), wk = up(Wk + (size_t)j * d_model * d, d_model, d),
+                  wv = up(Wv + (size_t)j * d_model * d, d_model, d);
+    Tensor<float> Q(h, d, true), K(h, d, true), V(h, d, true);
+    op_quantized_mm(x, wq, Q, range);
+    op_quantized_mm(x, wk, K, range);
+    op_quantized_mm(x, wv, V, range);
+    Tensor<float> K_transpose = K.transpose();
+    Tensor<float> QK_T(h, h, true), scaled(h, h, true), P(h, h, true), attnHeadOut(h, d, true);
+    op_mm(Q, K_transpose, QK_T);
+    float scale_factor = 1.0 / std::sqrt(d);
+    op_multiply(QK_T, scale_factor, scaled);
+    op_softmax(scaled, P);
+    op_mm(P, V, attnHeadOut);
+    cudaMemcpy2D(multiHeadOut.rawp + j * d, sizeof(float) * d_model, attnHeadOut.rawp, sizeof(float) * d, sizeof(float) * d, h,
+                 cudaMemcpyDeviceToDevice);
+  }
+  op_quantized_mm(multiHeadOut, wo, output, range);
+  op_add(output, multiHeadOut, output);
+  op_layernorm(output, output);
+  Tensor<float> ffnOut{h, d_ff, true};
+  op_quantized_mm(output, w1, ffnOut, range);  // LinearLayer::forward: op_mm + op_add(bias), linear.cuh:53-54
+  op_add(ffnOut, bb1, ffnOut);
+  op_relu(ffnOut, ffnOut);
+  op_quantized_mm(ffnOut, w2, output, range);
+  op_add(output, bb2, output);
+  op_add(output, multiHeadOut, output);
+  op_layernorm(output, output);
+  int rc = status();
+  d2h(out, output);
   return rc;
 }
 

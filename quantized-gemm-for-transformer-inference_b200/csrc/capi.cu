@@ -23,7 +23,7 @@ int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
                  int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c,
-                 const SideArgs *side, cudaStream_t st);
+                 const SideArgs *side, cudaStream_t st, int act = QG_ACT_NONE);
 int outlier_detect(const void *X, int dtype, int M, int K, int64_t ldx, float thr, uint32_t *mask, cudaStream_t st);
 int outlier_index(const uint32_t *mask, int K, int *idx, int max_idx, int *count, int *wbase, cudaStream_t st);
 int outlier_mask_from_idx(const int *idx, int n_idx, int K, uint32_t *mask, int *wbase, cudaStream_t st);
@@ -35,13 +35,15 @@ int gather_wo(const void *W, int dtype, int64_t ldw, const int *idx, int n_idx, 
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
            float *C, int64_t ldc, cudaStream_t st, const MmBatch *batch = nullptr);
 int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st);
+int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, float *B, int64_t ldb,
+                       cudaStream_t st);
 int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
                    float c, void *O, int out_dtype, int64_t ldo, cudaStream_t st);
 bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb);
 void gemm_i8_tc_set_stats(long long *dev_ptr);
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st);
+               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act = QG_ACT_NONE);
 
 // ---- error state ----
 static thread_local char g_err[512] = "";
@@ -84,8 +86,9 @@ struct DeviceState {
   size_t attn_bytes = 0;
   // three streams: host->device copies, kernels, device->host copies (PCIe is full duplex)
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
-  static constexpr int kHostChunks = 8;
-  cudaEvent_t ev_w = nullptr, ev_x[kHostChunks] = {}, ev_o[kHostChunks] = {};
+  static constexpr int kHostChunksMax = 32;
+  int host_chunks = 8;  // QG_HOST_CHUNKS
+  cudaEvent_t ev_w = nullptr, ev_x[kHostChunksMax] = {}, ev_o[kHostChunksMax] = {};
 };
 static DeviceState g_dev[16];
 static std::mutex g_mu;
@@ -174,7 +177,7 @@ static Workspace carve(void *base, int M, int N, int K) {
 static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M,
                          int N, int K, void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw,
                          const float *bias, float c, cudaStream_t st, const SideArgs *side = nullptr,
-                         const MultiOut *multi = nullptr) {
+                         const MultiOut *multi = nullptr, int act = QG_ACT_NONE) {
   int variant = g_variant.load();
   const bool tc_ok = gemm_i8_tc_supported(A, lda, B, ldb);
   // the 2-SM tile (256x256 per CTA pair) halves the shared-memory traffic per MAC; one CTA row
@@ -185,10 +188,10 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
       set_error("extra destinations need the tensor-core path (16-byte aligned operands)");
       return QG_ENOTSUP;
     }
-    return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st);
+    return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st, act);
   }
   return gemm_i8_tc(variant == QG_GEMM_TC_2SM ? 2 : 1, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias,
-                    c, side, multi, d->sm_count, st);
+                    c, side, multi, d->sm_count, st, act);
 }
 
 }  // namespace qg
@@ -392,19 +395,28 @@ int qg_gemm_s8t_dequant(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_
 int qg_linear_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt, int64_t ldwt, const float *Cw,
                       const float *bias, void *Y, int64_t ldy, int out_dtype, int M, int N, int K, float range, int mode,
                       void *workspace, size_t workspace_bytes, qg_stream_t stream) {
+  return qg_linear_forward_act(X, ldx, in_dtype, Wt, ldwt, Cw, bias, QG_ACT_NONE, Y, ldy, out_dtype, M, N, K, range, mode,
+                               workspace, workspace_bytes, stream);
+}
+
+int qg_linear_forward_act(const void *X, int64_t ldx, int in_dtype, const int8_t *Wt, int64_t ldwt, const float *Cw,
+                          const float *bias, int act, void *Y, int64_t ldy, int out_dtype, int M, int N, int K, float range,
+                          int mode, void *workspace, size_t workspace_bytes, qg_stream_t stream) {
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
   QG_REQUIRE(X && Wt && Cw && Y && M > 0 && N > 0 && K > 0 && ldx >= K && ldwt >= K && ldy >= N && valid_io(in_dtype) &&
                  valid_io(out_dtype),
              "qg_linear_forward: bad arguments (M=%d N=%d K=%d)", M, N, K);
+  QG_REQUIRE(act == QG_ACT_NONE || act == QG_ACT_RELU, "qg_linear_forward: unknown activation %d", act);
   Workspace w;
   rc = get_workspace(d, workspace, workspace_bytes, M, N, K, &w);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
-  return gemm_dispatch(d, w.Xq, w.ldxq, Wt, ldwt, 1, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st);
+  return gemm_dispatch(d, w.Xq, w.ldxq, Wt, ldwt, 1, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st,
+                       nullptr, nullptr, act);
 }
 
 // ---- outlier decomposition ------------------------------------------------------------------
@@ -563,7 +575,9 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
     QG_CUDA_OK(cudaStreamCreateWithFlags(&d->hstream_in, cudaStreamNonBlocking));
     QG_CUDA_OK(cudaStreamCreateWithFlags(&d->hstream_out, cudaStreamNonBlocking));
     QG_CUDA_OK(cudaEventCreateWithFlags(&d->ev_w, cudaEventDisableTiming));
-    for (int i = 0; i < DeviceState::kHostChunks; i++) {
+    const char *hc = getenv("QG_HOST_CHUNKS");
+    if (hc != nullptr && atoi(hc) >= 1 && atoi(hc) <= DeviceState::kHostChunksMax) d->host_chunks = atoi(hc);
+    for (int i = 0; i < DeviceState::kHostChunksMax; i++) {
       QG_CUDA_OK(cudaEventCreateWithFlags(&d->ev_x[i], cudaEventDisableTiming));
       QG_CUDA_OK(cudaEventCreateWithFlags(&d->ev_o[i], cudaEventDisableTiming));
     }
@@ -589,8 +603,8 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
   QG_CUDA_OK(cudaStreamWaitEvent(s_k, d->ev_w, 0));
   rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, false, s_k);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  // row chunks: multiples of 256 rows (one 2-SM tile), at most kHostChunks of them
-  int rows_per = (M + DeviceState::kHostChunks - 1) / DeviceState::kHostChunks;
+  // row chunks: multiples of 256 rows (one 2-SM tile), at most host_chunks of them
+  int rows_per = (M + d->host_chunks - 1) / d->host_chunks;
   rows_per = ((rows_per + 255) / 256) * 256;
   const float *Xd = (const float *)d->hx;
   float *Od = (float *)d->ho;
@@ -632,6 +646,15 @@ int qg_mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_
   if (rc) return rc;
   QG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N, "qg_mm_f32: bad arguments");
   return mm_f32(A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc, (cudaStream_t)stream);
+}
+
+int qg_add_layernorm_f32(const float *A, int64_t lda, const float *R, int64_t ldr, int m, int n, float *B, int64_t ldb,
+                         qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && B && m > 0 && n > 0 && lda >= n && ldb >= n && (R == nullptr || ldr >= n), "qg_add_layernorm_f32: bad arguments");
+  return cuda_status((cudaError_t)add_layernorm_rows(A, lda, R, ldr, m, n, B, ldb, (cudaStream_t)stream), "add + layernorm");
 }
 
 int qg_softmax_rows_f32(const float *A, int64_t lda, int m, int n, float scale, float *B, int64_t ldb,

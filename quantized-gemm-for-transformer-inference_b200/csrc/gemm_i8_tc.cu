@@ -44,6 +44,7 @@ struct GemmParams {
   int64_t ldo;           // elements
   const float *Cx, *Cw, *bias;
   float c;               // 1 / (range*range)
+  int relu;              // 1: ReluFunc (x < 0 ? 0 : x, op_elemwise.cuh:181-195) after the bias add
   int tma_store;         // 1: epilogue leaves through TMA; 0: direct global stores
   // MN-major B descriptor geometry (bytes).  Defaults: k-step 32 rows * 128 B, LBO = BK * 128 B
   // (next 128-column chunk), SBO = 8 rows * 128 B.  Overridable through QG_DBG_B_* for bring-up.
@@ -415,6 +416,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             v[4 * j4 + 3] = __fadd_rn(v[4 * j4 + 3], b4.w);
           }
         }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = v[j] < 0.0f ? 0.0f : v[j];
+        }
       };
       // one 128-byte-per-row chunk (OT::kCols columns from c0) leaves for global memory
       auto store_chunk = [&](const uint32_t (&w)[32], int c0) {
@@ -705,7 +710,7 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 // out_kind QG_S32 writes raw accumulators; otherwise the dequantize epilogue runs.
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st) {
+               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act) {
   if (!gemm_i8_tc_supported(A, lda, B, ldb)) {
     set_error("gemm_i8_tc: operands must be 16-byte aligned with leading dimensions multiple of 16");
     return QG_EINVAL;
@@ -715,6 +720,7 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   p.tiles_m = (int)ceil_div(M, BM * cg);
   p.tiles_n = (int)ceil_div(N, BN);
   p.out = O; p.ldo = ldo; p.Cx = Cx; p.Cw = Cw; p.bias = bias; p.c = c;
+  p.relu = (act == QG_ACT_RELU && out_kind != QG_S32) ? 1 : 0;
   const size_t osz = (out_kind == QG_F16 || out_kind == QG_BF16) ? 2 : 4;
   p.tma_store = (aligned16(O) && (ldo * osz) % 16 == 0) ? 1 : 0;
   static const bool dbg_no_tma_store = getenv("QG_DBG_NO_TMA_STORE") != nullptr;

@@ -22,7 +22,7 @@ template <bool kDequant, typename OutT>
 __global__ void __launch_bounds__(256)
 gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__restrict__ B, int64_t sb_k, int64_t sb_n,
                     int M, int N, int K, void *__restrict__ O, int64_t ldo, const float *__restrict__ Cx,
-                    const float *__restrict__ Cw, const float *__restrict__ bias, float c, SideArgs side) {
+                    const float *__restrict__ Cw, const float *__restrict__ bias, float c, SideArgs side, int relu) {
   __shared__ int8_t sA[TM][TK + 4];
   __shared__ int8_t sB[TK][TN + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -85,6 +85,7 @@ gemm_s8_simt_kernel(const int8_t *__restrict__ A, int64_t lda, const int8_t *__r
           v = __fadd_rn(v, sd);
         }
         if (bias != nullptr) v = __fadd_rn(v, bias[col]);
+        if (relu) v = v < 0.0f ? 0.0f : v;
         store_out<OutT>(O, ldo, r, col, v);
       } else {
         reinterpret_cast<int32_t *>(O)[(int64_t)r * ldo + col] = acc[i][j];
@@ -178,23 +179,23 @@ dequantize_kernel(const int32_t *__restrict__ acc, int64_t ldacc, const float *_
 // b_kmajor == 0: B is [K,N] with leading dimension ldb; 1: B is [N,K]
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
                  int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c,
-                 const SideArgs *side_in, cudaStream_t st) {
+                 const SideArgs *side_in, cudaStream_t st, int act) {
   const int64_t sb_k = b_kmajor ? 1 : ldb, sb_n = b_kmajor ? ldb : 1;
   SideArgs side = {};
   if (side_in != nullptr) side = *side_in;
   dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
   switch (out_dtype) {
     case QG_S32:
-      launch_kernel(gemm_s8_simt_kernel<false, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
+      launch_kernel(gemm_s8_simt_kernel<false, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side, act == QG_ACT_RELU ? 1 : 0);
       break;
     case QG_F32:
-      launch_kernel(gemm_s8_simt_kernel<true, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
+      launch_kernel(gemm_s8_simt_kernel<true, float>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side, act == QG_ACT_RELU ? 1 : 0);
       break;
     case QG_F16:
-      launch_kernel(gemm_s8_simt_kernel<true, __half>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
+      launch_kernel(gemm_s8_simt_kernel<true, __half>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side, act == QG_ACT_RELU ? 1 : 0);
       break;
     case QG_BF16:
-      launch_kernel(gemm_s8_simt_kernel<true, __nv_bfloat16>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side);
+      launch_kernel(gemm_s8_simt_kernel<true, __nv_bfloat16>, grid, dim3(256), st, A, lda, B, sb_k, sb_n, M, N, K, O, ldo, Cx, Cw, bias, c, side, act == QG_ACT_RELU ? 1 : 0);
       break;
     default:
       return QG_EINVAL;
@@ -217,38 +218,48 @@ int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t s
 // e_j = expf(t_j - max); the sum runs over ascending j; b_j = e_j / sum.  One thread per row, as in
 // the reference, because the ascending-order fp32 sum is part of the result; a CTA's rows are
 // staged through shared memory in 32-column tiles so that global accesses stay coalesced.
-constexpr int kSmRows = 128;
-__global__ void __launch_bounds__(kSmRows)
+// 128 threads stage ROWS x TW tiles (every load of a tile in flight at once: the tile loop is a chain of
+// global-latency round trips, so wide tiles matter); the first ROWS threads own one row each.
+// ROWS = 32 spreads a short matrix over four times as many SMs (the per-row work is serial either way).
+constexpr int kSmThreads = 128;
+template <int ROWS, int TW>
+__global__ void __launch_bounds__(kSmThreads)
 softmax_rows_kernel(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb) {  // A may alias B
-  __shared__ float tile[kSmRows][33];
-  const int r0 = blockIdx.x * kSmRows;
-  const int rows = min(kSmRows, M - r0);
+  __shared__ float tile[ROWS][TW + 1];
+  const int r0 = blockIdx.x * ROWS;
+  const int rows = min(ROWS, M - r0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   griddep_wait();
   griddep_trigger_early();
-  // tile <- fl(A[r0.., c0..c0+31] * scale): warp w loads rows w, w+4, ... 32 consecutive floats at a time
+  // tile <- fl(A[r0.., c0..c0+TW-1] * scale): warp w loads rows w, w+4, ..., 32 consecutive floats per load
   auto load_tile = [&](const float *src, int64_t ld, int c0, bool mul) {
-    for (int r = warp; r < rows; r += kSmRows / 32) {
-      const int c = c0 + lane;
-      float v = 0.0f;
-      if (c < N) v = src[(int64_t)(r0 + r) * ld + c];
-      tile[r][lane] = mul ? __fmul_rn(v, scale) : v;
+    for (int r = warp; r < rows; r += kSmThreads / 32) {
+#pragma unroll
+      for (int cc = lane; cc < TW; cc += 32) {
+        const int c = c0 + cc;
+        float v = 0.0f;
+        if (c < N) v = src[(int64_t)(r0 + r) * ld + c];
+        tile[r][cc] = mul ? __fmul_rn(v, scale) : v;
+      }
     }
   };
   auto store_tile = [&](int c0) {
-    for (int r = warp; r < rows; r += kSmRows / 32) {
-      const int c = c0 + lane;
-      if (c < N) B[(int64_t)(r0 + r) * ldb + c] = tile[r][lane];
+    for (int r = warp; r < rows; r += kSmThreads / 32) {
+#pragma unroll
+      for (int cc = lane; cc < TW; cc += 32) {
+        const int c = c0 + cc;
+        if (c < N) B[(int64_t)(r0 + r) * ldb + c] = tile[r][cc];
+      }
     }
   };
   const int t = threadIdx.x;
   float mx = 0.0f, sum = 0.0f;
-  for (int c0 = 0; c0 < N; c0 += 32) {  // pass 1: row max
+  for (int c0 = 0; c0 < N; c0 += TW) {  // pass 1: row max
     __syncthreads();
     load_tile(A, lda, c0, true);
     __syncthreads();
     if (t < rows) {
-      const int n = min(32, N - c0);
+      const int n = min(TW, N - c0);
       for (int j = 0; j < n; j++) {
         const float v = tile[t][j];
         if (c0 + j == 0) mx = v;
@@ -256,12 +267,12 @@ softmax_rows_kernel(const float *A, int64_t lda, int M, int N, float scale, floa
       }
     }
   }
-  for (int c0 = 0; c0 < N; c0 += 32) {  // pass 2: e_j, running sum; e_j parked in B
+  for (int c0 = 0; c0 < N; c0 += TW) {  // pass 2: e_j, running sum; e_j parked in B
     __syncthreads();
     load_tile(A, lda, c0, true);
     __syncthreads();
     if (t < rows) {
-      const int n = min(32, N - c0);
+      const int n = min(TW, N - c0);
       for (int j = 0; j < n; j++) {
         const float e = expf(__fsub_rn(tile[t][j], mx));
         tile[t][j] = e;
@@ -271,12 +282,12 @@ softmax_rows_kernel(const float *A, int64_t lda, int M, int N, float scale, floa
     __syncthreads();
     store_tile(c0);
   }
-  for (int c0 = 0; c0 < N; c0 += 32) {  // pass 3: divide
+  for (int c0 = 0; c0 < N; c0 += TW) {  // pass 3: divide
     __syncthreads();
     load_tile(B, ldb, c0, false);
     __syncthreads();
     if (t < rows) {
-      const int n = min(32, N - c0);
+      const int n = min(TW, N - c0);
       for (int j = 0; j < n; j++) tile[t][j] = __fdiv_rn(tile[t][j], sum);
     }
     __syncthreads();
@@ -284,8 +295,98 @@ softmax_rows_kernel(const float *A, int64_t lda, int M, int N, float scale, floa
   }
 }
 
+// op_add(A, R, T) + op_layernorm(T, B): the "ADD & NORM" of src/transformer.cu:57-58,74-75, arithmetic of
+// AddFunc (op_elemwise.cuh:57-65) and layernorm_kernel (src/ops/op_layernorm.cuh:6-32):
+//   t_j = fl(a_j + r_j);  mean = (sum of t_j, ascending j, from 0) / w;  var = (sum of pow(t_j - mean, 2)) / w;
+//   b_j = (t_j - mean) / var            -- divides by the variance, not its square root, and has no epsilon
+// One thread per row (ascending-order sums), rows staged through shared memory like the softmax.
+template <int ROWS, int TW>
+__global__ void __launch_bounds__(kSmThreads)
+add_layernorm_rows_kernel(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, float *B, int64_t ldb) {
+  __shared__ float tile[ROWS][TW + 1];
+  const int r0 = blockIdx.x * ROWS;
+  const int rows = min(ROWS, M - r0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_wait();
+  griddep_trigger_early();
+  auto load_tile = [&](int c0) {
+    for (int r = warp; r < rows; r += kSmThreads / 32) {
+#pragma unroll
+      for (int cc = lane; cc < TW; cc += 32) {
+        const int c = c0 + cc;
+        float v = 0.0f;
+        if (c < N) {
+          v = A[(int64_t)(r0 + r) * lda + c];
+          if (R != nullptr) v = __fadd_rn(v, R[(int64_t)(r0 + r) * ldr + c]);
+        }
+        tile[r][cc] = v;
+      }
+    }
+  };
+  const int t = threadIdx.x;
+  const int w = N;
+  float mean = 0.0;
+  float var = 0.0;
+  for (int c0 = 0; c0 < N; c0 += TW) {
+    __syncthreads();
+    load_tile(c0);
+    __syncthreads();
+    if (t < rows) {
+      const int n = min(TW, N - c0);
+      for (int j = 0; j < n; j++) mean += tile[t][j];
+    }
+  }
+  mean = mean / w;
+  for (int c0 = 0; c0 < N; c0 += TW) {
+    __syncthreads();
+    load_tile(c0);
+    __syncthreads();
+    if (t < rows) {
+      const int n = min(TW, N - c0);
+      for (int j = 0; j < n; j++) {
+        // the reference writes `var += pow(x - mean, 2)`: float base, int exponent -> the double overload,
+        // so every step adds an exact double square and rounds the running sum back to float
+        const double dd = (double)(tile[t][j] - mean);
+        var = (float)((double)var + dd * dd);
+      }
+    }
+  }
+  var = var / w;
+  // A (and R) are read for the last time in this pass, tile by tile, before the same tile of B is
+  // written: B may alias A or R (the reference normalises in place)
+  for (int c0 = 0; c0 < N; c0 += TW) {
+    __syncthreads();
+    load_tile(c0);
+    __syncthreads();
+    if (t < rows) {
+      const int n = min(TW, N - c0);
+      for (int j = 0; j < n; j++) tile[t][j] = (tile[t][j] - mean) / var;
+    }
+    __syncthreads();
+    for (int r = warp; r < rows; r += kSmThreads / 32) {
+#pragma unroll
+      for (int cc = lane; cc < TW; cc += 32) {
+        const int c = c0 + cc;
+        if (c < N) B[(int64_t)(r0 + r) * ldb + c] = tile[r][cc];
+      }
+    }
+  }
+}
+
+int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, float *B, int64_t ldb,
+                       cudaStream_t st) {
+  if (M >= 148 * 128)
+    launch_kernel(add_layernorm_rows_kernel<128, 64>, dim3((unsigned)ceil_div(M, 128)), dim3(kSmThreads), st, A, lda, R, ldr, M, N, B, ldb);
+  else
+    launch_kernel(add_layernorm_rows_kernel<32, 128>, dim3((unsigned)ceil_div(M, 32)), dim3(kSmThreads), st, A, lda, R, ldr, M, N, B, ldb);
+  return (int)cudaGetLastError();
+}
+
 int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st) {
-  launch_kernel(softmax_rows_kernel, dim3((unsigned)ceil_div(M, kSmRows)), dim3(kSmRows), st, A, lda, M, N, scale, B, ldb);
+  if (M >= 148 * 128)
+    launch_kernel(softmax_rows_kernel<128, 64>, dim3((unsigned)ceil_div(M, 128)), dim3(kSmThreads), st, A, lda, M, N, scale, B, ldb);
+  else
+    launch_kernel(softmax_rows_kernel<32, 128>, dim3((unsigned)ceil_div(M, 32)), dim3(kSmThreads), st, A, lda, M, N, scale, B, ldb);
   return (int)cudaGetLastError();
 }
 

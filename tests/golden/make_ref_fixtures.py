@@ -95,6 +95,43 @@ def softmax_cases():
     yield "softmax_200x77", A
 
 
+def run_ref_encoder_block(ref, X, heads, d_ff, Wq, Wk, Wv, W_O, W1, b1, W2, b2, range_=127.0):
+    """Wq/Wk/Wv: [heads, d_model, d] stacks.  One Encoder-loop iteration on the reference's kernels."""
+    h, d_model = X.shape
+    out = np.empty((h, d_model), np.float32)
+    rc = ref.ref_encoder_block(p(X), h, d_model, heads, d_ff, p(Wq), p(Wk), p(Wv), p(W_O), p(W1), p(b1), p(W2), p(b2),
+                               C.c_float(range_), p(out))
+    assert rc == 0, rc
+    return out
+
+
+def encoder_weights(rng, d_model, heads, d_ff):
+    d = d_model // heads
+    u = lambda lo, hi, *s: (rng.random(s, dtype=np.float32) * np.float32(hi - lo) + np.float32(lo))
+    a = 1 / d ** 0.5
+    Wq, Wk, Wv = u(-a, a, heads, d_model, d), u(-a, a, heads, d_model, d), u(-a, a, heads, d_model, d)
+    W_O = u(-1, 1, d_model, d_model)
+    a1, a2 = 1 / d_model ** 0.5, 1 / d_ff ** 0.5
+    return dict(Wq=Wq, Wk=Wk, Wv=Wv, W_O=W_O, W1=u(-a1, a1, d_model, d_ff), b1=u(-a1, a1, 1, d_ff),
+                W2=u(-a2, a2, d_ff, d_model), b2=u(-a2, a2, 1, d_model))
+
+
+def encoder_cases():
+    rng = np.random.default_rng(21)
+    # the shape of transformer.cu:170-185 (6 x 8 input, 4 heads, d_ff 8), then a wider one
+    for name, h, d_model, heads, d_ff in (("enc_6x8_h4_ff8", 6, 8, 4, 8), ("enc_48x64_h4_ff96", 48, 64, 4, 96)):
+        X = (rng.random((h, d_model), dtype=np.float32) * 2 - 1)
+        yield name, X, heads, d_ff, encoder_weights(rng, d_model, heads, d_ff)
+
+
+def addnorm_cases():
+    rng = np.random.default_rng(22)
+    A = rng.standard_normal((200, 77)).astype(np.float32)
+    R = rng.standard_normal((200, 77)).astype(np.float32)
+    yield "addnorm_200x77", A, R
+    yield "addnorm_6x8_noadd", rng.standard_normal((6, 8)).astype(np.float32), None
+
+
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(out, exist_ok=True)
@@ -104,6 +141,15 @@ def main():
         print("wrote", name)
     for name, Xq, Xkv, Wq, Wk, Wv in attention_cases():
         np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), **run_ref_attention(ref, Xq, Xkv, Wq, Wk, Wv))
+        print("wrote", name)
+    for name, X, heads, d_ff, w in encoder_cases():
+        o = run_ref_encoder_block(ref, X, heads, d_ff, **w)
+        np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), X=X, heads=heads, d_ff=d_ff, out=o, **w)
+        print("wrote", name)
+    for name, A, R in addnorm_cases():
+        B = np.empty_like(A)
+        assert ref.ref_add_layernorm(p(A), p(R) if R is not None else None, A.shape[0], A.shape[1], p(B)) == 0
+        np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), A=A, B=B, **({"R": R} if R is not None else {}))
         print("wrote", name)
     for name, A in softmax_cases():
         B = np.empty_like(A)

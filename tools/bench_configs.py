@@ -123,6 +123,29 @@ def attention_case(batch=32, seq=128, d_model=512, heads=8):
     return res
 
 
+def transformer_case(batch=32, seq=128, d_model=512, heads=8, d_ff=2048, n_blocks=6):
+    """BASELINE config 3: encoder + decoder stack, 6 + 6 blocks, all projections int8, 32 x 128 tokens."""
+    tf = importlib.import_module(qg.__name__ + ".transformer")
+    g = torch.Generator(device=DEV).manual_seed(0)
+    T = batch * seq
+    enc, dec = tf.Encoder(d_model, heads, n_blocks, d_ff, DEV), tf.Decoder(d_model, heads, n_blocks, d_ff, DEV)
+    enc.init_uniform(g); dec.init_uniform(g)
+    X = [torch.randn((T, d_model), device=DEV, generator=g) for _ in range(2)]
+    Y = [torch.randn((T, d_model), device=DEV, generator=g) for _ in range(2)]
+    eo, do = torch.empty((T, d_model), device=DEV), torch.empty((T, d_model), device=DEV)
+
+    def step(i):
+        enc.forward(X[i & 1], eo, batch)
+        dec.forward(Y[i & 1], eo, do, batch)
+
+    us = timed(step, iters=5, warm=2)
+    res = {"name": f"transformer_enc{n_blocks}_dec{n_blocks}_b{batch}_s{seq}_d{d_model}_h{heads}_ff{d_ff}", "tokens": T,
+           "stack_us": us, "tok_per_s": T / us * 1e6, "finite": bool(torch.isfinite(do).all().item())}
+    res["encoder_block_us"] = timed(lambda i: enc.blocks[0].forward(X[i & 1], eo, batch))
+    res["decoder_block_us"] = timed(lambda i: dec.blocks[0].forward(Y[i & 1], eo, do, batch))
+    return res
+
+
 def main():
     out = []
     for n in (1024, 2048, 4096, 8192):  # config 2
@@ -135,6 +158,7 @@ def main():
     for name, K, N in (("opt66b_fc1_shard_of_8", 9216, 36864 // 8), ("opt66b_fc2_shard_of_8", 36864, 9216 // 8)):  # config 5
         out.append(linear_case(name, 4096, K, N, torch.float16))
     out.append(attention_case())  # config 3 building block
+    out.append(transformer_case())  # config 3
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w") as f:
         json.dump(out, f, indent=1)
