@@ -118,12 +118,14 @@ mm_f32_kernel(const float *__restrict__ A, int64_t sa_h, int64_t sa_w, const flo
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
   for (int k0 = 0; k0 < K; k0 += TK) {
+    // consecutive threads walk whichever index is contiguous in memory (a transposed view, e.g. the
+    // K^T of attention.cuh:58-60, has its unit stride along k)
     for (int e = threadIdx.x; e < TM * TK; e += 256) {
-      const int r = e / TK, kk = e % TK;
+      const int r = sa_w == 1 ? e / TK : e % TM, kk = sa_w == 1 ? e % TK : e / TM;
       sA[kk][r] = (m0 + r < M && k0 + kk < K) ? A[(int64_t)(m0 + r) * sa_h + (int64_t)(k0 + kk) * sa_w] : 0.0f;
     }
     for (int e = threadIdx.x; e < TK * TN; e += 256) {
-      const int kk = e / TN, cidx = e % TN;
+      const int kk = sb_w == 1 ? e / TN : e % TK, cidx = sb_w == 1 ? e % TN : e / TK;
       sB[kk][cidx] = (k0 + kk < K && n0 + cidx < N) ? B[(int64_t)(k0 + kk) * sb_h + (int64_t)(n0 + cidx) * sb_w] : 0.0f;
     }
     __syncthreads();
@@ -149,6 +151,89 @@ mm_f32_kernel(const float *__restrict__ A, int64_t sa_h, int64_t sa_w, const flo
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      C[(int64_t)r * ldc + col] = pad ? __fadd_rn(acc[i][j], 0.0f) : acc[i][j];
+    }
+  }
+}
+
+
+// The same product on 128 x 128 block tiles, 8 x 8 outputs per thread, with the next k-tile's global
+// loads issued into registers before the current tile is multiplied.  The 64 x 64 kernel above
+// exposes one DRAM round trip per k-tile and spends half its issue slots on shared-memory loads
+// (ncu: long-scoreboard stalls at the tile stores, short-scoreboard at the FFMAs; 46 us for the 256
+// [128 x 64] x [64 x 128] score products of an attention call).  Same k-ascending fma chain per output.
+constexpr int BM2 = 128, BN2 = 128, BK2 = 16;
+__global__ void __launch_bounds__(256)
+mm_f32_128_kernel(const float *__restrict__ A, int64_t sa_h, int64_t sa_w, const float *__restrict__ B, int64_t sb_h,
+                  int64_t sb_w, int M, int N, int K, float *__restrict__ C, int64_t ldc, MmBatch bt) {
+  __shared__ float sA[BK2][BM2 + 1];
+  __shared__ float sB[BK2][BN2 + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * BM2, n0 = blockIdx.x * BN2;
+  {
+    const int zo = blockIdx.z / bt.n_inner, zi = blockIdx.z % bt.n_inner;
+    A += zo * bt.a_outer + zi * bt.a_inner;
+    B += zo * bt.b_outer + zi * bt.b_inner;
+    C += zo * bt.c_outer + zi * bt.c_inner;
+  }
+  griddep_wait();
+  griddep_trigger_early();
+  constexpr int PER = BM2 * BK2 / 256;  // 8 elements of each operand tile per thread
+  float ra[PER], rb[PER];
+  // consecutive threads walk whichever index is contiguous in memory
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int e = threadIdx.x + u * 256;
+      const int r = sa_w == 1 ? e / BK2 : e % BM2, kk = sa_w == 1 ? e % BK2 : e / BM2;
+      ra[u] = (m0 + r < M && k0 + kk < K) ? A[(int64_t)(m0 + r) * sa_h + (int64_t)(k0 + kk) * sa_w] : 0.0f;
+      const int kb = sb_w == 1 ? e / BN2 : e % BK2, c = sb_w == 1 ? e % BN2 : e / BK2;
+      rb[u] = (k0 + kb < K && n0 + c < N) ? B[(int64_t)(k0 + kb) * sb_h + (int64_t)(n0 + c) * sb_w] : 0.0f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int e = threadIdx.x + u * 256;
+      const int r = sa_w == 1 ? e / BK2 : e % BM2, kk = sa_w == 1 ? e % BK2 : e / BM2;
+      sA[kk][r] = ra[u];
+      const int kb = sb_w == 1 ? e / BN2 : e % BK2, c = sb_w == 1 ? e % BN2 : e / BK2;
+      sB[kb][c] = rb[u];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += BK2) {
+    stash();
+    __syncthreads();
+    if (k0 + BK2 < K) fetch(k0 + BK2);
+    const int kmax = min(BK2, K - k0);
+    for (int kk = 0; kk < kmax; kk++) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = sA[kk][ty + 16 * i];  // rows ty, ty+16, ...: conflict-free across ty
+#pragma unroll
+      for (int j = 0; j < 8; j++) b[j] = sB[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool pad = (K % 32) != 0;  // the reference's 32-wide k-tile, zero padded: fma(0,0,res) turns -0 into +0
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int r = m0 + ty + 16 * i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int col = n0 + tx + 16 * j;
       if (col >= N) continue;
       C[(int64_t)r * ldc + col] = pad ? __fadd_rn(acc[i][j], 0.0f) : acc[i][j];
     }
@@ -208,6 +293,11 @@ int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t s
   MmBatch bt = {};
   bt.n_outer = bt.n_inner = 1;
   if (batch != nullptr) bt = *batch;
+  if (M >= 96 && N >= 96) {
+    dim3 grid((unsigned)ceil_div(N, BN2), (unsigned)ceil_div(M, BM2), (unsigned)(bt.n_outer * bt.n_inner));
+    launch_kernel(mm_f32_128_kernel, grid, dim3(256), st, A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc, bt);
+    return (int)cudaGetLastError();
+  }
   dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM), (unsigned)(bt.n_outer * bt.n_inner));
   launch_kernel(mm_f32_kernel, grid, dim3(256), st, A, sa_h, sa_w, B, sb_h, sb_w, M, N, K, C, ldc, bt);
   return (int)cudaGetLastError();
@@ -373,8 +463,205 @@ add_layernorm_rows_kernel(const float *A, int64_t lda, const float *R, int64_t l
   }
 }
 
+
+// ---- warp-per-row forms (rows up to kWarpRowMaxN columns) ----------------------------------------------
+// The order-dependent part of both ops is one fp32 (softmax) or fp32/fp64 (layernorm) running sum per
+// row; everything else -- loads, expf, squares, divisions, stores -- is independent per element.  A warp
+// owns a row: all lanes do the independent work on a shared-memory copy of the row, lane 0 walks the
+// sums in ascending column order.  4096 x 512 ADD & NORM: 73 us with one thread per row -> see DESIGN.md.
+constexpr int kRowWarps = 4;
+constexpr int kWarpRowMaxN = 4096;
+
+__device__ __forceinline__ float warp_max_f32(float m) {  // fmaxf drops NaNs
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return m;
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+softmax_warp_rows_kernel(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb) {  // A may alias B
+  extern __shared__ float sm_rows[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *row = sm_rows + (size_t)warp * N;
+  griddep_wait();
+  griddep_trigger_early();
+  for (int r = blockIdx.x * kRowWarps + warp; r < M; r += gridDim.x * kRowWarps) {
+    const float *a = A + (int64_t)r * lda;
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+      const float t = __fmul_rn(a[j], scale);
+      row[j] = t;
+      m = fmaxf(m, t);  // NaNs are skipped, as `t > max` skips them
+    }
+    m = warp_max_f32(m);
+    __syncwarp();
+    const float t0 = row[0];
+    const float mx = (t0 != t0) ? t0 : m;  // max starts AT column 0: a NaN there is never replaced
+    for (int j = lane; j < N; j += 32) row[j] = expf(__fsub_rn(row[j], mx));
+    __syncwarp();
+    float sum = 0.0f;
+    if (lane == 0) {
+#pragma unroll 8
+      for (int j = 0; j < N; j++) sum = __fadd_rn(sum, row[j]);
+    }
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    float *b = B + (int64_t)r * ldb;
+    for (int j = lane; j < N; j += 32) b[j] = __fdiv_rn(row[j], sum);
+    __syncwarp();
+  }
+}
+
+// ADD & NORM.  The reference's `var += pow(x - mean, 2)` is, per element, v <- RN32(v + d*d) with d*d
+// exact: a double add stored back to float.  Done literally that is F2F.F64 -> DADD -> F2F.F32 in a
+// dependent chain, ~176 cycles per element on this part (47 us for 4096 x 512).  Here the running
+// sum stays in a double register and the store-to-float is done on its bit pattern (round to nearest
+// even at bit 29: add 0x0fffffff + lsb, clear the low 29 bits), which leaves DADD + four integer
+// instructions on the chain.  Valid while every partial sum is a normal float: rows with a non-zero
+// square below 2^-100, a square above 1e30, or inf / NaN take the literal chain.  (An fp32-only
+// chain -- error-free square + round-to-odd 3-sum, Boldo & Melquiond 2008 -- was bit-exact too but
+// slower: 68 us.)
+// Serial sums go one row per THREAD (warp 0 of the CTA owns up to 32 rows) while all 128 threads do
+// the independent work -- loads, a + r, exact double squares, the final divisions, stores -- on a
+// shared-memory copy of the CTA's rows.  Rows per CTA shrink with N so that rows + squares fit.
+constexpr int kLnThreads = 256;
+
+__global__ void __launch_bounds__(kLnThreads)
+add_layernorm_cta_rows_kernel(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, int rows_per_cta,
+                              float *B, int64_t ldb) {  // B may alias A or R
+  extern __shared__ double sm_rows_d[];
+  const int ldsq = N + 1, ldrow = N + 1;  // odd strides: 32 threads walking 32 rows hit 32 banks
+  double *sq = sm_rows_d;                                                   // [rows_per_cta][N+1] exact squares
+  __shared__ int s_slow[32];
+  float *row = reinterpret_cast<float *>(sm_rows_d + (size_t)rows_per_cta * ldsq);  // [rows_per_cta][N+1] t = a + r
+  __shared__ float s_mean[32], s_var[32];
+  const int t = threadIdx.x;
+  griddep_wait();
+  griddep_trigger_early();
+  const int w = N;
+  for (int r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
+    const int rows = min(rows_per_cta, M - r0);
+    if (t < 32) s_slow[t] = 0;
+    // eight independent loads per thread in flight (a plain loop here is a chain of DRAM round trips:
+    // that, not the serial sums, was most of the first version's 73 us)
+    for (int e0 = t; e0 < rows * N; e0 += kLnThreads * 4) {
+      float va[4], vr[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * kLnThreads;
+        const int r = e / N, j = e - r * N;
+        va[u] = vr[u] = 0.0f;
+        if (e < rows * N) {
+          va[u] = A[(int64_t)(r0 + r) * lda + j];
+          if (R != nullptr) vr[u] = R[(int64_t)(r0 + r) * ldr + j];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * kLnThreads;
+        const int r = e / N, j = e - r * N;
+        if (e < rows * N) row[r * ldrow + j] = R != nullptr ? __fadd_rn(va[u], vr[u]) : va[u];
+      }
+    }
+    __syncthreads();
+    if (t < rows) {
+      float mean = 0.0f;
+      const float *x = row + t * ldrow;
+#pragma unroll 8
+      for (int j = 0; j < N; j++) mean += x[j];
+      s_mean[t] = mean / w;
+    }
+    __syncthreads();
+    for (int e = t; e < rows * N; e += kLnThreads) {
+      const int r = e / N, j = e - r * N;
+      const double dd = (double)(row[r * ldrow + j] - s_mean[r]);
+      const double q = dd * dd;  // exact: 24-bit x 24-bit
+      sq[r * ldsq + j] = q;
+      // the bit-pattern rounding needs every partial sum to be zero or a normal, finite float
+      if ((q != 0.0 && q < 7.888609052210118e-31) || !(q < 1e30)) s_slow[r] = 1;  // 2^-100
+    }
+    __syncthreads();
+    if (t < rows) {
+      float var = 0.0f;
+      const double *q = sq + t * ldsq;
+      if (!s_slow[t] && N <= 4096) {
+        double v = 0.0;  // always exactly a float value
+#pragma unroll 8
+        for (int j = 0; j < N; j++) {
+          long long b = __double_as_longlong(v + q[j]);
+          b += 0x0fffffffLL + ((b >> 29) & 1);
+          v = __longlong_as_double(b & ~0x1fffffffLL);
+        }
+        var = (float)v;
+      } else {  // `var += pow(x - mean, 2)` literally: double add, float store
+        const float *x = row + t * ldrow;
+        const float mean = s_mean[t];
+        for (int j = 0; j < N; j++) {
+          const double dd = (double)(x[j] - mean);
+          var = (float)((double)var + dd * dd);
+        }
+      }
+      s_var[t] = var / w;
+    }
+    __syncthreads();
+    for (int e = t; e < rows * N; e += kLnThreads) {
+      const int r = e / N, j = e - r * N;
+      B[(int64_t)(r0 + r) * ldb + j] = (row[r * ldrow + j] - s_mean[r]) / s_var[r];
+    }
+    __syncthreads();
+  }
+}
+
+// dynamic shared memory above 48 KB needs the opt-in once per kernel
+template <typename... KArgs, typename... Args>
+static void warp_rows_launch(void (*kern)(KArgs...), size_t smem, int M, cudaStream_t st, Args &&...args) {
+  static size_t allowed = 48 << 10;
+  if (smem > allowed) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
+    allowed = 200 << 10;
+  }
+  const int64_t ctas = ceil_div(M, kRowWarps);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ctas < 148 * 16 ? ctas : 148 * 16));
+  cfg.blockDim = dim3(kRowWarps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, float *B, int64_t ldb,
                        cudaStream_t st) {
+  if (N <= kWarpRowMaxN) {
+    // rows + squares of a CTA's rows in at most 192 KB of shared memory, at most 32 rows (one warp of serial sums)
+    int rpc = (int)((192 << 10) / ((size_t)(N + 1) * 12));
+    rpc = rpc > 32 ? 32 : rpc;
+    while (rpc > 1 && ceil_div(M, rpc) < 148) rpc >>= 1;  // short matrices: spread over the SMs first
+    const size_t smem = (size_t)rpc * (N + 1) * 12;
+    static bool opted = false;
+    if (!opted) {
+      cudaFuncSetAttribute(add_layernorm_cta_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
+      opted = true;
+    }
+    const int64_t ctas = ceil_div(M, rpc);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctas < 148 * 8 ? ctas : 148 * 8));
+    cfg.blockDim = dim3(kLnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    count_launch();
+    cudaLaunchKernelEx(&cfg, add_layernorm_cta_rows_kernel, A, lda, R, ldr, M, N, rpc, B, ldb);
+    return (int)cudaGetLastError();
+  }
   if (M >= 148 * 128)
     launch_kernel(add_layernorm_rows_kernel<128, 64>, dim3((unsigned)ceil_div(M, 128)), dim3(kSmThreads), st, A, lda, R, ldr, M, N, B, ldb);
   else
@@ -383,6 +670,10 @@ int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr,
 }
 
 int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st) {
+  if (N <= kWarpRowMaxN) {
+    warp_rows_launch(softmax_warp_rows_kernel, (size_t)kRowWarps * N * 4, M, st, A, lda, M, N, scale, B, ldb);
+    return (int)cudaGetLastError();
+  }
   if (M >= 148 * 128)
     launch_kernel(softmax_rows_kernel<128, 64>, dim3((unsigned)ceil_div(M, 128)), dim3(kSmThreads), st, A, lda, M, N, scale, B, ldb);
   else

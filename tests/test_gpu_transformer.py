@@ -74,6 +74,33 @@ def test_add_layernorm_vs_oracle_and_live_reference(tf, oracle, ref, shape):
     assert same_f32(got[:covered], Bref[:covered])
 
 
+def test_add_layernorm_edge_rows_vs_oracle(tf, oracle):
+    """Rows that leave the fp32 3-sum chain (tiny deviations, overflowing squares, inf, NaN), rows of very
+    different magnitudes, and a wide row (rows-per-CTA shrinks) -- all bit-exact against the oracle's
+    literal double-add / float-store restatement."""
+    rng = np.random.default_rng(77)
+    N = 300
+    A = rng.standard_normal((40, N)).astype(np.float32)
+    A[1] *= np.float32(1e-20); A[2] *= np.float32(1e18); A[3] *= np.float32(3e19)   # tiny / large / overflowing squares
+    A[4] = np.float32(1.0); A[4, 7] = np.float32(1.0 + 2.0 ** -23)                   # deviations near 1e-7
+    A[5] = np.float32(0.0)                                                           # var = 0 -> 0/0
+    A[6, 5] = np.inf; A[7, 9] = np.nan; A[8] = np.float32(1e-30)
+    A[9] = (rng.standard_normal(N) * 1e-12).astype(np.float32)
+    for scale_row in range(10, 40):
+        A[scale_row] *= np.float32(2.0 ** rng.integers(-30, 30))
+    B = torch.empty((40, N), device="cuda")
+    tf.add_layernorm(to_dev(A), None, B)
+    assert same_f32(B.cpu().numpy(), oracle.add_layernorm(A))
+    wide = rng.standard_normal((9, 3000)).astype(np.float32)
+    Bw = torch.empty((9, 3000), device="cuda")
+    tf.add_layernorm(to_dev(wide), to_dev(wide[::-1].copy()), Bw)
+    assert same_f32(Bw.cpu().numpy(), oracle.add_layernorm(wide, wide[::-1].copy()))
+    big = (rng.standard_normal((2000, 512)) * 3).astype(np.float32)
+    Bb = torch.empty((2000, 512), device="cuda")
+    tf.add_layernorm(to_dev(big), None, Bb)
+    assert same_f32(Bb.cpu().numpy(), oracle.add_layernorm(big))
+
+
 @pytest.mark.parametrize("shape", [(5, 7, 9), (200, 136, 264), (512, 768, 1024)])
 def test_relu_epilogue(qg, tf, oracle, shape):
     M, N, K = shape
