@@ -1,0 +1,16 @@
+"""Prepared-weight linear (fp16 in/out) on a few shapes, 3 repeats each: same-box A/B of scheduler switches."""
+import importlib, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tools.bench_configs import timed
+qg = importlib.import_module("quantized-gemm-for-transformer-inference_b200")
+shapes = [("fc1_shard", 4096, 9216, 4608), ("fc2_shard", 4096, 36864, 1152), ("sq4096", 4096, 4096, 4096), ("n1152_k4096", 4096, 4096, 1152),
+          ("opt_out", 16384, 4096, 4096)]
+res = {}
+for name, M, K, N in shapes:
+    lin = qg.LinearLayer(K, N, device="cuda", dtype=torch.float16); lin.w.normal_(0, 0.02); lin.b.zero_(); lin.quantize_weights()
+    X = [torch.randn((M, K), device="cuda", dtype=torch.float16) for _ in range(2)]
+    y = torch.empty((M, N), device="cuda", dtype=torch.float16)
+    res[name] = [round(timed(lambda i: lin.forward(X[i & 1], y)), 1) for _ in range(3)]
+    del lin, X, y; torch.cuda.empty_cache()
+print(json.dumps({"snake": os.environ.get("QG_NO_SNAKE") is None, "split": os.environ.get("QG_NO_TAIL_SPLIT") is None, **res}))
