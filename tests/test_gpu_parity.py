@@ -341,6 +341,43 @@ def test_op_quantized_mm_bit_exact(qg, oracle, shape, variant):
     assert same_f32(O.cpu().numpy(), expect)
 
 
+@pytest.mark.parametrize("size", [4096, 8192])
+def test_op_quantized_mm_full_size_properties(qg, oracle, size):
+    """BASELINE's headline shape (and 8192^3) at full size, through properties that do not need a full CPU
+    product: exact scales, sampled rows bit-exact against the oracle, and the independence structure of the
+    op -- rows of X are quantized independently (row permutation commutes with the op, bit for bit),
+    columns of W independently (a column block of W gives the same block of O), repeat calls identical."""
+    M = N = K = size
+    g = torch.Generator(device=DEV).manual_seed(size)
+    X = torch.rand((M, K), device=DEV, generator=g) * 2 - 1
+    W = torch.rand((K, N), device=DEV, generator=g) * 2 - 1
+    O = torch.empty((M, N), device=DEV)
+    qg.op_quantized_mm(X, W, O, 127.0)
+    Xh, Wh = X.cpu().numpy(), W.cpu().numpy()
+    # scales of the whole problem
+    Xq = torch.empty((M, K), dtype=torch.int8, device=DEV); Cx = torch.empty(M, device=DEV)
+    Wq = torch.empty((K, N), dtype=torch.int8, device=DEV); Cw = torch.empty(N, device=DEV)
+    qg.absmax_quant_rows(X, 127.0, qg.MODE_REF_EXACT, Xq, Cx)
+    qg.absmax_quant_cols(W, 127.0, qg.MODE_REF_EXACT, Wq, Cw)
+    assert same_f32(Cx.cpu().numpy(), oracle.absmax_rows(Xh)) and same_f32(Cw.cpu().numpy(), oracle.absmax_cols(Wh))
+    # sampled rows, bit-exact (the oracle quantizes all of W, and only these rows of X)
+    rows = np.sort(np.random.default_rng(size).choice(M, 24, replace=False))
+    assert same_f32(O[torch.from_numpy(rows).to(DEV)].cpu().numpy(), oracle.quantized_mm(Xh[rows], Wh))
+    # row permutation commutes with the op
+    perm = torch.randperm(M, device=DEV, generator=g)
+    O2 = torch.empty_like(O)
+    qg.op_quantized_mm(X[perm].contiguous(), W, O2, 127.0)
+    assert torch.equal(O2.view(torch.int32), O[perm].view(torch.int32))
+    # a column block of W gives the same block of O (strided W view, narrower N)
+    nb = N // 4 + 16
+    O3 = torch.empty((M, nb), device=DEV)
+    qg.op_quantized_mm(X, W[:, 256:256 + nb], O3, 127.0)
+    assert torch.equal(O3.view(torch.int32), O[:, 256:256 + nb].contiguous().view(torch.int32))
+    # repeat call: identical bits
+    qg.op_quantized_mm(X, W, O2, 127.0)
+    assert torch.equal(O2.view(torch.int32), O.view(torch.int32))
+
+
 def test_op_quantized_mm_uniform_2048_error_stats(qg, oracle):
     """timing_quantize's default shape and distribution: report-level error figures
     (BASELINE.md: signed-mean ~1e-4, mean-abs ~0.17, max-abs ~1.1 for 2048^3)."""
