@@ -516,6 +516,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (p.stats && warp == 2 && lane == 0) {
       p.stats[blockIdx.x * 8 + 5] = w_tfull;
       p.stats[blockIdx.x * 8 + 6] = clock64() - t_begin;
+      unsigned long long now_ns;  // when this CTA's last tile left: spread over the grid = launch skew + imbalance
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now_ns));
+      p.stats[blockIdx.x * 8 + 7] = (long long)now_ns;
     }
   }
 

@@ -70,6 +70,19 @@ def gemm_stats(variant, size, out="f32", kmajor=True):
     used = s[:, 4] > 0 if variant == "TC_1SM" else s[:, 1] > 0
     names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tempty", "mma_total", "epi_wait_tfull", "epi_total"]
     res = {"us": us, "us_with_stats": us_stats, "tops": 2.0 * M * N * K / us / 1e6}
+    # end-of-work wall clock per CTA (ns) and its start (end - loop cycles / 1.965 GHz): skew across the grid
+    end_ns = s[:, 7]
+    live = end_ns > 0
+    if live.any():
+        start_ns = end_ns - s[:, 6] / 1.965
+        res["end_spread_us"] = float((end_ns[live].max() - end_ns[live].min()) / 1e3)
+        res["start_spread_us"] = float((start_ns[live].max() - start_ns[live].min()) / 1e3)
+        res["first_start_to_last_end_us"] = float((end_ns[live].max() - start_ns[live].min()) / 1e3)
+        # per-cluster finish offsets relative to the first finisher (us), leader CTAs only, in cluster order
+        raw = stats.cpu()[:, 7]
+        lead_ns = raw[::2] if variant == "TC_2SM" else raw
+        lead_ns = lead_ns[lead_ns > 0]
+        res["end_offsets_us"] = [round(float(v - lead_ns.min()) / 1e3, 1) for v in lead_ns]
     lead = s[s[:, 4] > 0]
     for i, n in enumerate(names):
         col = s[:, i]
