@@ -18,7 +18,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <math.h>
+#include <string.h>
+
 #include <memory>
+#include <vector>
 #include <type_traits>
 
 #include "../../include/qgemm.h"
@@ -231,6 +235,99 @@ class Tensor {
     for (int i = 0; i < h; i++)
       for (int j = 0; j < w; j++) s += at(i, j);
     return s / (h * w);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// The reference's module classes on the quantized path (inference side): same names, members and
+// call signatures as src/modules/param.cuh, linear.cuh:7-72 and attention.cuh:10-70, templated on the
+// tensor type so that they work with the reference's Tensor<T> as well as the one above.
+//   LinearLayer:    forward(x, y) = x @ w + b with the int8 codes of w prepared on first use
+//                   (qg_prepare_weights -> qg_linear_forward), optional ReLU (transformer.cu:65-67)
+//   AttentionLayer: forward(X, out) and the forward(Xq, Xkv, out) of transformer.cu:37,132
+// Weights are plain public members; call invalidate() after changing them.  backward(), SGD and the
+// loss stay with the reference (training is out of scope).
+// ------------------------------------------------------------------------------------------
+template <typename T, template <typename> class TensorT = Tensor>
+class Parameter {
+ public:
+  Parameter() = default;
+  Parameter(int t_h, int t_w, bool gpu) : t(t_h, t_w, gpu), dt(t_h, t_w, gpu) {}
+  TensorT<T> t, dt;
+};
+
+// U(lo, hi) from a 64-bit LCG (the reference draws with cuRAND, op_elemwise.cuh:12-47; any values do)
+template <class TensorT>
+void uniform_init(TensorT &t, float lo, float hi, uint64_t seed) {
+  std::vector<float> h((size_t)t.h * t.w);
+  uint64_t s = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+  for (float &v : h) {
+    s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+    v = lo + (hi - lo) * (float)((s >> 40) & 0xffffff) / 16777216.0f;
+  }
+  assert(t.stride_w == 1 && t.stride_h == t.w);
+  if (t.on_device) cudaMemcpy(base_ptr(t), h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice);
+  else memcpy(base_ptr(t), h.data(), sizeof(float) * h.size());
+}
+
+template <typename T, template <typename> class TensorT = Tensor>
+class LinearLayer {
+ public:
+  int in_dim = 0, out_dim = 0;
+  Parameter<T, TensorT> w, b;
+
+  LinearLayer() = default;
+  LinearLayer(int in_dim_, int out_dim_, bool gpu) : in_dim(in_dim_), out_dim(out_dim_), w(in_dim_, out_dim_, gpu), b(1, out_dim_, gpu) {
+    assert(gpu);
+  }
+  std::vector<Parameter<T, TensorT> *> parameters() { return {&w, &b}; }
+  void init_uniform(uint64_t seed = 1) {  // linear.cuh:33-39
+    const float mx = 1.0f / std::sqrt((float)in_dim);
+    uniform_init(w.t, -mx, mx, seed);
+    uniform_init(b.t, -mx, mx, seed + 1);
+    invalidate();
+  }
+  void invalidate() { prepared_ = false; }
+  void forward(const TensorT<T> &x, TensorT<T> &y, int act = QG_ACT_NONE) {  // linear.cuh:49-56
+    assert(x.w == in_dim && y.h == x.h && y.w == out_dim && x.on_device && y.on_device);
+    if (!prepared_) {
+      wt_ = TensorT<int8_t>(out_dim, (in_dim + 15) / 16 * 16, true);
+      cw_ = TensorT<float>(1, out_dim, true);
+      check(qg_prepare_weights(base_ptr(w.t), QG_F32, in_dim, out_dim, w.t.stride_h, 127.0f, QG_MODE_REF_EXACT, wt_.rawp,
+                               wt_.stride_h, cw_.rawp, nullptr), "qg_prepare_weights");
+      prepared_ = true;
+    }
+    check(qg_linear_forward_act(base_ptr(x), x.stride_h, QG_F32, wt_.rawp, wt_.stride_h, cw_.rawp, base_ptr(b.t), act,
+                                base_ptr(y), y.stride_h, QG_F32, x.h, out_dim, in_dim, 127.0f, QG_MODE_REF_EXACT, nullptr, 0,
+                                nullptr), "qg_linear_forward_act");
+  }
+
+ private:
+  TensorT<int8_t> wt_;
+  TensorT<float> cw_;
+  bool prepared_ = false;
+};
+
+template <typename T, template <typename> class TensorT = Tensor>
+class AttentionLayer {
+ public:
+  int d_model, d_k, d_v;
+  Parameter<T, TensorT> W_q, W_k, W_v;
+
+  AttentionLayer(int d_model_, int d_k_, int d_v_, bool gpu)
+      : d_model(d_model_), d_k(d_k_), d_v(d_v_), W_q(d_model_, d_k_, gpu), W_k(d_model_, d_k_, gpu), W_v(d_model_, d_v_, gpu) {
+    assert(gpu);
+  }
+  std::vector<Parameter<T, TensorT> *> parameters() { return {&W_q, &W_k, &W_v}; }
+  void init_uniform(uint64_t seed = 1) {  // attention.cuh:40-45
+    const float mx = 1.0f / std::sqrt((float)d_k);
+    uniform_init(W_q.t, -mx, mx, seed);
+    uniform_init(W_k.t, -mx, mx, seed + 1);
+    uniform_init(W_v.t, -mx, mx, seed + 2);
+  }
+  void forward(const TensorT<T> &X, TensorT<T> &output) { attention_forward(X, X, W_q.t, W_k.t, W_v.t, output); }
+  void forward(const TensorT<T> &Xq, const TensorT<T> &Xkv, TensorT<T> &output) {
+    attention_forward(Xq, Xkv, W_q.t, W_k.t, W_v.t, output);
   }
 };
 

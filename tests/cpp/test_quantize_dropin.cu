@@ -113,6 +113,31 @@ int main() {
       if (std::fabs(sum - 1.0f) > 1e-5f) { printf("softmax row %d sums to %g\n", i, sum); bad++; break; }
     }
     printf("attention (fused QKV) == op-by-op sequence: %s\n", bad ? "no" : "yes");
+
+    // the module classes (reference names and signatures): LinearLayer with prepared weights must equal the
+    // per-call op + bias, AttentionLayer::forward the function form above
+    LinearLayer<float> lin{DM, DV, true};
+    lin.init_uniform(7);
+    Tensor<float> y1{S, DV, true}, y2{S, DV, true}, yr{S, DV, true};
+    lin.forward(dX, y1);
+    linear_forward(dX, lin.w.t, lin.b.t, y2);
+    lin.forward(dX, yr, QG_ACT_RELU);
+    AttentionLayer<float> att{DM, DK, DV, true};
+    cudaMemcpy(att.W_q.t.rawp, dWq.rawp, sizeof(float) * DM * DK, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(att.W_k.t.rawp, dWk.rawp, sizeof(float) * DM * DK, cudaMemcpyDeviceToDevice);
+    cudaMemcpy(att.W_v.t.rawp, dWv.rawp, sizeof(float) * DM * DV, cudaMemcpyDeviceToDevice);
+    Tensor<float> a1{S, DV, true};
+    att.forward(dX, a1);
+    cudaDeviceSynchronize();
+    Tensor<float> y1h = y1.toHost(), y2h = y2.toHost(), yrh = yr.toHost(), a1h = a1.toHost();
+    int bad_mod = 0;
+    for (int i = 0; i < S * DV; i++) {
+      if (y1h.rawp[i] != y2h.rawp[i]) bad_mod++;
+      if (yrh.rawp[i] != (y1h.rawp[i] < 0.0f ? 0.0f : y1h.rawp[i])) bad_mod++;
+      if (a1h.rawp[i] != fh.rawp[i]) bad_mod++;
+    }
+    printf("LinearLayer / AttentionLayer classes == function forms: %s\n", bad_mod ? "no" : "yes");
+    bad += bad_mod;
   }
   printf(bad ? "FAILED (%d)\n" : "All tests completed successfully!\n", bad);
   return bad ? 1 : 0;
