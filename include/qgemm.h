@@ -22,6 +22,13 @@
  *   - every launch goes to `stream` (a cudaStream_t; NULL = the legacy default stream the
  *     reference uses).  No call synchronises the device; no call allocates unless stated.
  *   - there is no CPU fallback: without an sm_100 device every compute call fails.
+ *   - re-entrancy: like the reference (everything on the legacy default stream) the library assumes
+ *     one stream of calls per device at a time.  Entry points that quantize weight columns
+ *     (qg_absmax_cols, qg_quantize_cols without given scales, qg_absmax_quant_cols, qg_prepare_weights,
+ *     qg_quantized_mm*) share a per-device column-maximum scratch; entry points called with
+ *     workspace == NULL, qg_quantized_mm_host and qg_attention_forward share grow-only per-device
+ *     buffers.  Calls on different devices, and calls that pass their own workspace and prepared
+ *     weights (qg_linear_forward*), are independent.
  */
 #ifndef QGEMM_H_
 #define QGEMM_H_
