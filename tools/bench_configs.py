@@ -146,8 +146,47 @@ def transformer_case(batch=32, seq=128, d_model=512, heads=8, d_ff=2048, n_block
     return res
 
 
+def timing_quantize_case(M=2048, N=512, K=512):
+    """BASELINE config 0: the shape of src/timing_quantize.cu (README: 0.31954 ms fp32 vs 1.33682 ms quantized,
+    hardware not stated): our op_quantized_mm and fp32 op_mm, the reference's own kernels on this GPU, and the
+    CPU oracle on the host cores."""
+    import ctypes as C
+    import time
+
+    import numpy as np
+
+    X = torch.rand((M, K), device=DEV) * 2 - 1
+    W = torch.rand((K, N), device=DEV) * 2 - 1
+    O = torch.empty((M, N), device=DEV)
+    res = {"name": f"timing_quantize_{M}x{N}x{K}"}
+    res["ours_quantized_us"] = timed(lambda i: qg.op_quantized_mm(X, W, O, 127.0))
+    res["ours_fp32_op_mm_us"] = timed(lambda i: qg.op_mm(X, W, O))
+    res["torch_fp32_matmul_us"] = timed(lambda i: torch.matmul(X, W, out=O))
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_qmm.so")
+    if os.path.exists(so):
+        ref = C.CDLL(so)
+        ev, wall, fp = C.c_double(), C.c_double(), C.c_double()
+        ref.ref_time_quantized_mm_dev(C.c_void_p(X.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(O.data_ptr()), M, N, K,
+                                      C.c_float(127.0), 3, 10, C.byref(ev), C.byref(wall))
+        ref.ref_time_mm_f32_dev(C.c_void_p(X.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(O.data_ptr()), M, N, K, 3, 10,
+                                C.byref(fp))
+        res["reference_quantized_kernels_us"] = ev.value * 1e3
+        res["reference_quantized_call_us"] = wall.value * 1e3  # with its 9 cudaMalloc/cudaFree per call
+        res["reference_fp32_op_mm_us"] = fp.value * 1e3
+    sys.path.insert(0, ROOT)
+    oracle = importlib.import_module("oracle")
+    Xh, Wh = X.cpu().numpy(), W.cpu().numpy()
+    oracle.quantized_mm(Xh[:64], Wh)
+    t0 = time.perf_counter()
+    oracle.quantized_mm(Xh, Wh)
+    res["cpu_oracle_us"] = (time.perf_counter() - t0) * 1e6
+    res["cpu_threads"] = oracle.num_threads()
+    return res
+
+
 def main():
     out = []
+    out.append(timing_quantize_case())  # config 0
     for n in (1024, 2048, 4096, 8192):  # config 2
         out.append(linear_case(f"square_{n}_f16", n, n, n, torch.float16, w_std=1.0 / n ** 0.5))
         out.append(linear_case(f"square_{n}_f32", n, n, n, torch.float32, w_std=1.0 / n ** 0.5))
