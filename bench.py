@@ -147,6 +147,17 @@ class ClockSampler:
         return out
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_tops(M, N, K, sample_rows, repeats=1):
     """The CPU oracle (port of the reference arithmetic, oracle/qoracle.c) on the host cores.
     Bounded sample: W is quantized in full, the activation side runs on `sample_rows` rows of X;
@@ -191,7 +202,7 @@ def run_reference_cpu(args):
         "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8 x int8 -> int32, fp32 scales", "data": "synthetic U(-1,1)",
         "config": {"workload": f"op_quantized_mm {M}x{N}x{K} fp32 in/out, W re-quantized every step", "M": M, "N": N, "K": K},
-        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample, "cpu": cpu_model()},
         "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -440,7 +451,7 @@ def run_ours(args):
         cpu = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port",
                "sample": f"full {K}x{N} W column-quantized once + rows 0..{args.cpu_sample_rows - 1} of X through "
                          f"quantize/int8 GEMM/dequantize; full-step time = t_W + ({M}/{args.cpu_sample_rows}) * t_rows "
-                         f"= {est:.2f} s"}
+                         f"= {est:.2f} s", "cpu": cpu_model()}
 
     # burst peak when the SM clock stayed at its maximum during the (short) timed region, else sustained
     at_max = bool(clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])

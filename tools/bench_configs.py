@@ -74,6 +74,20 @@ def linear_case(name, M, K, N, dt=torch.float16, outliers=0, w_std=0.02, seed=0)
     if ref is not None:
         res["fp16_mean_abs_err"] = (torch.matmul(x16[0], w16).float() - ref).abs().mean().item()
     res["speedup_vs_fp16"] = res["fp16_gemm_us"] / res["int8_linear_us"]
+    if not outliers and M == N == K:  # config 2: the three views SURVEY 8(d) asks for, plus the library int8 GEMM
+        Wt, Cw = lin.quantize_weights()
+        Xq = torch.empty((M, K), dtype=torch.int8, device=DEV)
+        Cx = torch.empty(M, device=DEV)
+        qg.absmax_quant_rows(X[0], 127.0, qg.MODE_REF_EXACT, Xq, Cx)
+        us = timed(lambda i: qg.gemm_s8t_dequant(Xq, Wt, Cx, Cw, y))
+        res["gemm_only_us"], res["gemm_only_tops"] = us, ops / us / 1e6
+        us = timed(lambda i: qg.op_quantized_mm(X[i & 1], lin.w, y, 127.0))
+        res["full_op_requantizing_w_us"], res["full_op_tops"] = us, ops / us / 1e6
+        a8 = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=DEV)
+        b8 = torch.randint(-127, 128, (K, N), dtype=torch.int8, device=DEV)
+        us = timed(lambda i: torch._int_mm(a8, b8))
+        res["cublaslt_int8_gemm_us"], res["cublaslt_int8_tops"] = us, ops / us / 1e6
+        del a8, b8, Xq
     del lin, X, y, w16, x16
     torch.cuda.empty_cache()
     return res
@@ -181,12 +195,17 @@ def timing_quantize_case(M=2048, N=512, K=512):
     oracle.quantized_mm(Xh, Wh)
     res["cpu_oracle_us"] = (time.perf_counter() - t0) * 1e6
     res["cpu_threads"] = oracle.num_threads()
+    # error of the quantized result against the fp32 product (README: signed mean 4.58e-5, shape not stated)
+    qg.op_quantized_mm(X, W, O, 127.0)
+    err = (X.double() @ W.double()) - O.double()
+    res["err_signed_mean"], res["err_mean_abs"], res["err_max_abs"] = err.mean().item(), err.abs().mean().item(), err.abs().max().item()
     return res
 
 
 def main():
     out = []
-    out.append(timing_quantize_case())  # config 0
+    out.append(timing_quantize_case())  # config 0: both shapes found in the reference's timing driver
+    out.append(timing_quantize_case(2048, 2048, 2048))
     for n in (1024, 2048, 4096, 8192):  # config 2
         out.append(linear_case(f"square_{n}_f16", n, n, n, torch.float16, w_std=1.0 / n ** 0.5))
         out.append(linear_case(f"square_{n}_f32", n, n, n, torch.float32, w_std=1.0 / n ** 0.5))
