@@ -66,6 +66,21 @@ def test_softmax_vs_oracle_and_in_place(qg, oracle, shape, scale):
     assert same_f32(dA.cpu().numpy(), got)
 
 
+def test_softmax_and_layernorm_wide_rows_take_the_tiled_kernels(qg, oracle):
+    """More than 4096 columns: the warp-per-row / CTA-rows kernels hand over to the tiled thread-per-row ones."""
+    import importlib
+
+    tf = importlib.import_module(qg.__name__ + ".transformer")
+    rng = np.random.default_rng(41)
+    A = (rng.standard_normal((70, 5000)) * 3).astype(np.float32)
+    B = torch.empty((70, 5000), device="cuda")
+    qg.op_softmax(to_dev(A), B, 0.5)
+    np.testing.assert_allclose(B.cpu().numpy(), oracle.softmax_rows(A, 0.5), rtol=SOFTMAX_RTOL, atol=SOFTMAX_ATOL)
+    R = rng.standard_normal((70, 5000)).astype(np.float32)
+    tf.add_layernorm(to_dev(A), to_dev(R), B)
+    assert same_f32(B.cpu().numpy(), oracle.add_layernorm(A, R))
+
+
 def test_softmax_strided_views_and_rows_the_reference_grid_skips(qg, ref):
     """300 rows x 40 columns: the reference's grid (ceil(40/256) = 1 block of 256 threads, op_softmax.cuh:38)
     leaves rows 256.. untouched; ours computes them.  Rows 0..255 agree bit for bit."""
