@@ -317,8 +317,9 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 // as every CTA of this grid is running and then blocks in its own griddep_wait().  EXPERIMENT ONLY
 // (build.py --tag early -DQG_EARLY_TRIGGER): measured on B200 it is a loss -- op_quantized_mm
 // 4096^3 102.5 us against 95.7 us, 8192^3 531 against 513 us (profiles/r1_early_trigger_ab.json);
-// parked dependents cost the running grid more than the hidden launch latency returns.  The only
-// early trigger kept is the row quantizer's, on each CTA's last row block.
+// parked dependents cost the running grid more than the hidden launch latency returns.  Two targeted
+// triggers are kept because they measured as gains: the row quantizer's, on each CTA's last row
+// block, and the column quantizer's second pass (quant_cols_kernel), whose dependent is the GEMM.
 __device__ __forceinline__ void griddep_trigger_early() {
 #ifdef QG_EARLY_TRIGGER
   griddep_launch_dependents();
