@@ -43,7 +43,10 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 void gemm_i8_tc_set_stats(long long *dev_ptr);
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act = QG_ACT_NONE);
+               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act = QG_ACT_NONE,
+               int split_k = 1);
+int splitk_reduce(const int32_t *parts, int64_t slice_stride, int slices, int64_t ldp, const float *Cx, const float *Cw,
+                  const float *bias, int M, int N, float c, int act, void *O, int out_dtype, int64_t ldo, cudaStream_t st);
 
 // ---- error state ----
 static thread_local char g_err[512] = "";
@@ -84,6 +87,8 @@ struct DeviceState {
   size_t hx_bytes = 0, hw_bytes = 0, ho_bytes = 0, hb_bytes = 0;
   void *attn = nullptr;  // grow-only scratch of qg_attention_forward (projections, scores)
   size_t attn_bytes = 0;
+  void *splitk = nullptr;  // grow-only scratch: int32 partial sums of split-K products
+  size_t splitk_bytes = 0;
   // three streams: host->device copies, kernels, device->host copies (PCIe is full duplex)
   cudaStream_t hstream = nullptr, hstream_in = nullptr, hstream_out = nullptr;
   static constexpr int kHostChunksMax = 32;
@@ -173,6 +178,36 @@ static Workspace carve(void *base, int M, int N, int K) {
   return w;
 }
 
+// Split-K factor for tile-starved shapes.  Tiles are (128*cg) x 256; with T tiles on P clusters a product
+// takes ceil(T/P) rounds however few clusters the last one fills.  Cutting K into s slices gives
+// ceil(T*s/P) shorter rounds plus a reduce pass over s int32 matrices.  Time model (us, measured on
+// B200): a tile costs 11.5 per 4096 of K plus 1.5; the reduce pass 3 + bytes / 5 TB/s.  Taken only when
+// the model promises more than 25 % (it pays for few tiles and long K -- M <= 256 against K >= 8192:
+// 59.5 -> 31.5 us at 128 x 4096 x 16384 -- and loses elsewhere: 4096 x 1152 x 4096 went 38 -> 63 us
+// under a rounds-only model).  QG_SPLIT_K=n forces n (1 = off).
+static int choose_split_k(DeviceState *d, int cg, int M, int N, int K, int out_kind) {
+  static const int forced = [] { const char *e = getenv("QG_SPLIT_K"); return e ? atoi(e) : 0; }();
+  const int num_kb = (int)ceil_div(K, 128);
+  if (forced >= 1) return (forced <= num_kb && forced <= kMaxExtraOut + 1 && (forced - 1) * (int)ceil_div(num_kb, forced) < num_kb) ? forced : 1;
+  const int64_t T = ceil_div(M, 128 * cg) * ceil_div(N, 256);
+  const int P = d->sm_count / cg;
+  const double osz = (out_kind == QG_F16 || out_kind == QG_BF16) ? 2.0 : 4.0;
+  auto cost = [&](int s) {
+    const double gemm = (double)ceil_div(T * s, P) * (11.5 * K / s / 4096.0 + 1.5);
+    const double reduce = s == 1 ? 0.0 : 3.0 + ((double)M * N * (8.0 * s + osz)) / 5e6;
+    return gemm + reduce;
+  };
+  const double base = cost(1);
+  double best = base;
+  int pick = 1;
+  for (int s = 2; s <= 4; s++) {
+    if (num_kb / s < 8) break;
+    const double c = cost(s);
+    if (c < best) { best = c; pick = s; }
+  }
+  return best < 0.75 * base ? pick : 1;
+}
+
 // b_kmajor == 0: B is the reference's [K,N] (MN-major tensor-core operand); 1: B is Wt [N,K]
 static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M,
                          int N, int K, void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw,
@@ -190,8 +225,28 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
     }
     return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st, act);
   }
-  return gemm_i8_tc(variant == QG_GEMM_TC_2SM ? 2 : 1, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias,
-                    c, side, multi, d->sm_count, st, act);
+  const int cg = variant == QG_GEMM_TC_2SM ? 2 : 1;
+  const int sk = (side == nullptr && (multi == nullptr || multi->n == 0)) ? choose_split_k(d, cg, M, N, K, out_kind) : 1;
+  if (sk > 1) {
+    // split-K: int32 partial sums of every k-slice, then one pass that adds them and runs the epilogue
+    const int64_t ldp = round_up(N, 4);
+    const size_t slice = (size_t)M * ldp;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      int rc = grow(&d->splitk, &d->splitk_bytes, sizeof(int32_t) * slice * sk);
+      if (rc) return rc;
+    }
+    int32_t *parts = (int32_t *)d->splitk;
+    MultiOut slices = {};
+    slices.n = sk - 1;
+    for (int i = 1; i < sk; i++) slices.dst[i - 1] = parts + (size_t)i * slice;
+    int rc = gemm_i8_tc(cg, A, lda, B, ldb, b_kmajor, M, N, K, parts, ldp, QG_S32, nullptr, nullptr, nullptr, 0.0f, nullptr,
+                        &slices, d->sm_count, st, QG_ACT_NONE, sk);
+    if (rc) return rc;
+    return cuda_status((cudaError_t)splitk_reduce(parts, (int64_t)slice, sk, ldp, Cx, Cw, bias, M, N, c, act, O, out_kind, ldo, st),
+                       "split-K reduce");
+  }
+  return gemm_i8_tc(cg, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, multi, d->sm_count, st, act);
 }
 
 }  // namespace qg

@@ -38,6 +38,10 @@ struct GemmParams {
   // would fill at most half of the machine, each is cut into `tail_split` = 2 tiles of 128
   // columns so the last wave takes half as long (4096^3 on 74 CTA pairs: 3.5 rounds instead of 4).
   int full_tiles, total_tiles, tail_split;
+  // Split-K for tile-starved shapes: every tile is cut into `split_k` k-slices of kb_per_slice k-blocks;
+  // slice s writes raw int32 partial sums into its own [M, ldo] matrix (slice 0: `out`, slice s > 0:
+  // extra_out[s-1] / the matching ExtraMaps entry); a second kernel adds the slices and dequantizes.
+  int split_k, kb_per_slice;
   uint32_t nstages;  // smem ring depth actually used (<= the compiled kStages)
   int dbg_noload;    // bring-up experiment: after the ring is filled once, signal 'full' without loading
   void *out;             // [M,N] of the epilogue's type
@@ -160,7 +164,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t nstages = p.nstages;  // == kStages unless narrowed for a pipeline-depth experiment
   const int num_tiles = p.total_tiles;
   // tile index -> (row block, first column, width)
+  int cur_slice = 0;  // set by tile_coords
   auto tile_coords = [&](int t, int &m_blk, int &n0, int &bn) {
+    cur_slice = 0;
+    if (p.split_k > 1) {  // slices of one tile are neighbours in the tile order
+      cur_slice = t % p.split_k;
+      t /= p.split_k;
+    }
     int ft = t, part = 0;
     bn = BN;
     if (t >= p.full_tiles) {
@@ -174,7 +184,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   };
   const int num_clusters = gridDim.x / CG;
   const int cluster_id = blockIdx.x / CG;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  // k-blocks [kb_first(slice), kb_first + kb_count) belong to a slice (the whole K without split-K)
+  auto kb_first = [&](int slice) { return p.split_k > 1 ? slice * p.kb_per_slice : 0; };
+  auto kb_count = [&](int slice) {
+    return p.split_k > 1 ? min(p.kb_per_slice, num_kb_total - slice * p.kb_per_slice) : num_kb_total;
+  };
 
   // The producer and MMA warps keep their control flow WARP-UNIFORM: all 32 lanes walk the loops and
   // wait on the barriers, and only the instruction that must come from one thread is predicated with
@@ -193,6 +208,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int n_base = n0 + (int)cta_rank * (bn / CG);
       const bool half = bn != BN;  // only generated for K-major B (see host side)
       const uint32_t stage_tx = C::kABytes + (uint32_t)(bn / CG) * BK;
+      const int kb0 = kb_first(cur_slice), num_kb = kb_count(cur_slice);
       for (int kb = 0; kb < num_kb; kb++, it++) {
         const uint32_t s = it % nstages, ph = (it / nstages) & 1;
         if (p.stats) {
@@ -204,7 +220,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         const uint32_t sa = smem_u32(smem + s * C::kStageBytes);
         const uint32_t sb = sa + C::kABytes;
-        const int k0 = kb * BK;
+        const int k0 = (kb0 + kb) * BK;
         if (elect_one_sync()) {
           if (p.dbg_noload && it >= nstages) {  // timing experiment only: stale operands, no TMA traffic
             if (leader) mbar_arrive(smem_u32(&full_bar[s]));
@@ -257,6 +273,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int m_blk, n0, bn;
         tile_coords(t, m_blk, n0, bn);
         const uint32_t idesc = idesc_nofield | ((uint32_t)(bn >> 3) << 17);  // UMMA N of this tile
+        const int num_kb = kb_count(cur_slice);
         for (int kb = 0; kb < num_kb; kb++, it++) {
           const uint32_t s = it % nstages, ph = (it / nstages) & 1;
           if (p.stats) {
@@ -432,13 +449,19 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {  // always lane 0: bulk async-groups are per thread
-            tma_store_2d(&map_o, stage_u32, n_base + c0, m_base + q * 32);
-            for (int d = 0; d < p.n_extra; d++)  // peers' copies of the block, straight over NVLink
-              tma_store_2d(&xmaps.m[d], stage_u32, n_base + c0, m_base + q * 32);
+            if (p.split_k > 1) {  // this k-slice's partial sums
+              tma_store_2d(cur_slice > 0 ? &xmaps.m[cur_slice - 1] : &map_o, stage_u32, n_base + c0, m_base + q * 32);
+            } else {
+              tma_store_2d(&map_o, stage_u32, n_base + c0, m_base + q * 32);
+              for (int d = 0; d < p.n_extra; d++)  // peers' copies of the block, straight over NVLink
+                tma_store_2d(&xmaps.m[d], stage_u32, n_base + c0, m_base + q * 32);
+            }
             tma_store_commit();
           }
         } else if (row < p.M) {
-          for (int d = -1; d < p.n_extra; d++) {  // local matrix, then the peers' copies
+          const int d_first = (p.split_k > 1 && cur_slice > 0) ? cur_slice - 1 : -1;  // split-K: one destination, the slice's
+          const int d_end = p.split_k > 1 ? d_first + 1 : p.n_extra;
+          for (int d = d_first; d < d_end; d++) {  // local matrix, then the peers' copies
             OutT *dst = reinterpret_cast<OutT *>(d < 0 ? p.out : p.extra_out[d]) + (int64_t)row * p.ldo + n_base + c0;
             const int ncols = min(OT::kCols, p.N - (n_base + c0));
             if (ncols == OT::kCols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -640,12 +663,14 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   p.tail_split = 1;
   const int rem = base_tiles % max_clusters;
   static const bool no_tail_split = getenv("QG_NO_TAIL_SPLIT") != nullptr;
-  if (!B_MN && base_tiles > max_clusters && rem > 0 && 2 * rem <= max_clusters && !no_tail_split) {
+  if (p.split_k > 1) {
+    p.total_tiles = base_tiles * p.split_k;  // tile_coords divides the index by split_k first
+  } else if (!B_MN && base_tiles > max_clusters && rem > 0 && 2 * rem <= max_clusters && !no_tail_split) {
     p.full_tiles = base_tiles - rem;
     p.tail_split = 2;
     p.total_tiles = p.full_tiles + 2 * rem;
   }
-  if (!B_MN && dbg_all_half) {  // experiment: every tile 128 columns wide
+  if (!B_MN && dbg_all_half && p.split_k == 1) {  // experiment: every tile 128 columns wide
     p.full_tiles = 0;
     p.tail_split = 2;
     p.total_tiles = 2 * base_tiles;
@@ -713,7 +738,7 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 // out_kind QG_S32 writes raw accumulators; otherwise the dequantize epilogue runs.
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act) {
+               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act, int split_k) {
   if (!gemm_i8_tc_supported(A, lda, B, ldb)) {
     set_error("gemm_i8_tc: operands must be 16-byte aligned with leading dimensions multiple of 16");
     return QG_EINVAL;
@@ -724,6 +749,20 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   p.tiles_n = (int)ceil_div(N, BN);
   p.out = O; p.ldo = ldo; p.Cx = Cx; p.Cw = Cw; p.bias = bias; p.c = c;
   p.relu = (act == QG_ACT_RELU && out_kind != QG_S32) ? 1 : 0;
+  p.split_k = 1;
+  if (split_k > 1) {  // raw partial sums: `O` and multi->dst[] are the split_k int32 slice matrices (capi.cu)
+    const int num_kb = (int)ceil_div(K, BK);
+    if (out_kind != QG_S32 || side != nullptr || multi == nullptr || multi->n != split_k - 1 || split_k > num_kb) {
+      set_error("gemm_i8_tc: split-K needs int32 output and split_k - 1 extra slice matrices");
+      return QG_EINVAL;
+    }
+    p.split_k = split_k;
+    p.kb_per_slice = (int)ceil_div(num_kb, split_k);
+    if ((split_k - 1) * p.kb_per_slice >= num_kb) {
+      set_error("gemm_i8_tc: split-K leaves an empty slice (K=%d, split_k=%d)", K, split_k);
+      return QG_EINVAL;
+    }
+  }
   const size_t osz = (out_kind == QG_F16 || out_kind == QG_BF16) ? 2 : 4;
   p.tma_store = (aligned16(O) && (ldo * osz) % 16 == 0) ? 1 : 0;
   static const bool dbg_no_tma_store = getenv("QG_DBG_NO_TMA_STORE") != nullptr;
@@ -769,7 +808,7 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   static ExtraMaps xm_zero = {};
   ExtraMaps xm = xm_zero;
   if (multi != nullptr && multi->n > 0) {
-    if (multi->n > kMaxExtraOut || out_kind == QG_S32) {
+    if (multi->n > kMaxExtraOut || (out_kind == QG_S32 && p.split_k == 1)) {
       set_error("gemm_i8_tc: at most %d extra destinations, floating-point output", kMaxExtraOut);
       return QG_EINVAL;
     }
@@ -779,8 +818,10 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
       if (p.tma_store && !aligned16(multi->dst[d])) p.tma_store = 0;
     }
     if (p.tma_store) {
-      CUtensorMapDataType odt = out_kind == QG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                : out_kind == QG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      CUtensorMapDataType odt = out_kind == QG_S32   ? CU_TENSOR_MAP_DATA_TYPE_INT32
+                                : out_kind == QG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                : out_kind == QG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
       for (int d = 0; d < multi->n; d++) {
         rc = make_map_2d(&xm.m[d], odt, osz, multi->dst[d], M, N, ldo, 32, (uint32_t)(128 / osz));
         if (rc) return rc;

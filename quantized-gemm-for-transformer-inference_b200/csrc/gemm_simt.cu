@@ -259,7 +259,50 @@ dequantize_kernel(const int32_t *__restrict__ acc, int64_t ldacc, const float *_
   }
 }
 
+// Second half of a split-K product: adds the `slices` int32 partial matrices (exact, any order) and runs
+// the same epilogue as the fused GEMM -- dequantize, bias, ReLU, cast -- or stores the int32 sum (kRaw).
+template <bool kRaw, typename OutT>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const int32_t *__restrict__ parts, int64_t slice_stride, int slices, int64_t ldp,
+                     const float *__restrict__ Cx, const float *__restrict__ Cw, const float *__restrict__ bias, int M, int N,
+                     float c, int relu, void *__restrict__ O, int64_t ldo) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
+  griddep_trigger_early();
+  if (col >= N) return;
+  const float cw = kRaw ? 0.0f : Cw[col];
+  const float b = (!kRaw && bias) ? bias[col] : 0.0f;
+  for (int r = blockIdx.y; r < M; r += gridDim.y) {
+    int acc = 0;
+    for (int sl = 0; sl < slices; sl++) acc += parts[sl * slice_stride + (int64_t)r * ldp + col];
+    if (kRaw) {
+      reinterpret_cast<int32_t *>(O)[(int64_t)r * ldo + col] = acc;
+    } else {
+      float v = dequant_ref(acc, Cx[r], cw, c);
+      if (bias != nullptr) v = __fadd_rn(v, b);
+      if (relu) v = v < 0.0f ? 0.0f : v;
+      store_out<OutT>(O, ldo, r, col, v);
+    }
+  }
+}
+
 }  // namespace
+
+int splitk_reduce(const int32_t *parts, int64_t slice_stride, int slices, int64_t ldp, const float *Cx, const float *Cw,
+                  const float *bias, int M, int N, float c, int act, void *O, int out_dtype, int64_t ldo, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)(M < 4096 ? M : 4096));
+  const int relu = act == QG_ACT_RELU ? 1 : 0;
+#define QG_SPLITK(RAW, T) launch_kernel(splitk_reduce_kernel<RAW, T>, grid, dim3(256), st, parts, slice_stride, slices, ldp, Cx, Cw, bias, M, N, c, relu, O, ldo)
+  switch (out_dtype) {
+    case QG_S32: QG_SPLITK(true, float); break;
+    case QG_F32: QG_SPLITK(false, float); break;
+    case QG_F16: QG_SPLITK(false, __half); break;
+    case QG_BF16: QG_SPLITK(false, __nv_bfloat16); break;
+    default: return QG_EINVAL;
+  }
+#undef QG_SPLITK
+  return (int)cudaGetLastError();
+}
 
 // b_kmajor == 0: B is [K,N] with leading dimension ldb; 1: B is [N,K]
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,

@@ -241,6 +241,34 @@ def test_gemm_s8s8s32_bit_exact(qg, oracle, shape, variant):
     assert np.array_equal(out.cpu().numpy(), oracle.gemm_s8s8s32(A, B))
 
 
+@pytest.mark.parametrize("shape", [(256, 2048, 4096), (128, 1024, 8192), (300, 1000, 6144), (512, 520, 4096),
+                                   (4096, 512, 2048)])
+def test_gemm_split_k_shapes(qg, oracle, shape):
+    """Few tiles, long K: the dispatcher cuts K into 2-4 slices (int32 partial sums, then one reduce + epilogue
+    pass).  Integer partial sums add exactly, so every output must still be bit-exact: raw accumulators, the
+    dequantized fp32 / fp16 result with bias, and the prepared-weight linear with ReLU."""
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape))
+    A, B = codes(rng, M, K), codes(rng, K, N)
+    dA, dB = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
+    acc = torch.empty((M, N), dtype=torch.int32, device=DEV)
+    qg.op_mm(dA, dB, acc)
+    exp_acc = oracle.gemm_s8s8s32(A, B)
+    assert np.array_equal(acc.cpu().numpy(), exp_acc)
+    Cx = rng.random(M).astype(np.float32) + 0.5
+    Cw = rng.random(N).astype(np.float32) + 0.5
+    bias = rng.standard_normal(N).astype(np.float32)
+    exp = oracle.dequant(exp_acc, Cx, Cw, 127.0, bias)
+    Bt = torch.from_numpy(np.ascontiguousarray(B.T)).to(DEV)
+    for dt in ("f32", "f16"):
+        out = torch.empty((M, N), dtype=TORCH_DT[dt], device=DEV)
+        qg.gemm_s8t_dequant(dA, Bt, to_dev(Cx), to_dev(Cw), out, 127.0, bias=to_dev(bias))
+        if dt == "f32":
+            assert same_f32(out.cpu().numpy(), exp)
+        else:
+            assert torch.equal(out.cpu(), torch.from_numpy(exp).to(torch.float16))
+
+
 @pytest.mark.parametrize("variant", ["TC_1SM", "TC_2SM"])
 def test_gemm_large_sampled_rows(qg, oracle, variant):
     """4096^3 (BASELINE target shape): full result against torch._int_mm is not the bar -- the
