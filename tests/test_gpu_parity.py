@@ -241,8 +241,8 @@ def test_gemm_s8s8s32_bit_exact(qg, oracle, shape, variant):
     assert np.array_equal(out.cpu().numpy(), oracle.gemm_s8s8s32(A, B))
 
 
-@pytest.mark.parametrize("shape", [(256, 2048, 4096), (128, 1024, 8192), (300, 1000, 6144), (512, 520, 4096),
-                                   (4096, 512, 2048)])
+@pytest.mark.parametrize("shape", [(256, 2048, 4096), (128, 1024, 8192), (300, 1000, 6144), (64, 512, 16384),
+                                   (256, 768, 12288), (4096, 512, 2048)])
 def test_gemm_split_k_shapes(qg, oracle, shape):
     """Few tiles, long K: the dispatcher cuts K into 2-4 slices (int32 partial sums, then one reduce + epilogue
     pass).  Integer partial sums add exactly, so every output must still be bit-exact: raw accumulators, the
@@ -267,6 +267,18 @@ def test_gemm_split_k_shapes(qg, oracle, shape):
             assert same_f32(out.cpu().numpy(), exp)
         else:
             assert torch.equal(out.cpu(), torch.from_numpy(exp).to(torch.float16))
+
+
+@pytest.mark.parametrize("split", [2, 3, 4])
+def test_forced_split_k(split):
+    """Every tensor-core product cut into `split` k-slices (QG_SPLIT_K, read once per process -> subprocess)."""
+    import subprocess
+    import sys as _sys
+
+    env = dict(os.environ, QG_SPLIT_K=str(split))
+    r = subprocess.run([_sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "splitk_check.py")],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("variant", ["TC_1SM", "TC_2SM"])
