@@ -2,7 +2,7 @@
  * qgemm.h -- C ABI of the B200-native quantized-linear hot path (libqgemm.so).
  *
  * Drop-in boundary for the reference's operator layer (header-only C++ templates over
- * Tensor<T>, /root/reference/src/ops/*.cuh).  Each entry point names the reference interface it
+ * Tensor<T>, the .cuh files under /root/reference/src/ops).  Each entry point names the reference interface it
  * replaces (file:line relative to /root/reference).  The reference-shaped C++ templates
  * (op_quantized_mm, op_mm, op_absmax, ... over a Tensor<T> view) that forward to these
  * functions live in quantized-gemm-for-transformer-inference_b200/cpp/; INTEGRATION.md shows

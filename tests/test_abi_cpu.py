@@ -57,3 +57,18 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 for needle in ("import oracle", "from oracle", "libqoracle", "oracle/_ref", '#include "qoracle'):
                     assert needle not in text, (f, needle)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/qgemm.h is the FFI surface: it must compile as C99 (and C++) with no warnings and no CUDA headers."""
+    import shutil
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text('#include "qgemm.h"\nint main(void) { return qg_version() > 0 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        exe = shutil.which(cc) or "/usr/bin/" + cc
+        r = subprocess.run([exe, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", "-x",
+                            "c" if cc == "gcc" else "c++", str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
