@@ -81,3 +81,28 @@ def test_sharded_result_is_bit_identical(world, shape, align):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), shape, align, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (the CPU arm): one JSON line with the contract's keys; under torchrun only
+    rank 0 prints and the other ranks exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    small = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--size", "256", "--cpu-sample-rows", "16"]
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), *small], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "TOPS" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29613", os.path.join(root, "bench.py"), "--gpus", "2", *small],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
