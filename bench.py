@@ -2,6 +2,7 @@
 """bench.py -- headline measurement of the quantized-linear hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu]
+                    [-m M] [-n N] [-k K] [-s SEED]      (the flags of src/timing_quantize.cu:83-101)
 
 A step is one pass of the hot path over one batch of synthetic input: the reference's whole
 `op_quantized_mm` (row absmax-quantize X, column absmax-quantize W, int8 GEMM, dequantize) at
@@ -11,10 +12,15 @@ Nothing is cached between steps (W is re-quantized every step, as the reference 
   value     whole-job TOPS (2*M*N*K per GPU-step / device time), inputs resident in HBM
   e2e       same op through the host-buffer C-ABI call (H2D of X and W, D2H of O inside the timing)
   roofline  the dominant kernel (tcgen05 int8 GEMM + fused dequantize), CUDA-event timed per step
-  cpu_baseline  the CPU oracle (port of the reference math) on this box's host cores, bounded sample
+  cpu_baseline  the CPU port of the reference math (oracle/qfast.c: OpenMP + AVX-512 VNNI) on this box's
+                host cores: WHOLE steps on the same inputs, whose output also checks the GPU result bit for bit
+  sustained     the same step back to back for >= 2 s (clocks recorded), against the sustained tensor peak
 
 N > 1: column-parallel linear -- rank p owns W[:, p*N:(p+1)*N] (N = 4096 columns per GPU, weak
-scaling), quantizes the replicated X locally, and the fp32 outputs are all-gathered with NCCL.
+scaling), quantizes the replicated X locally, and the fp32 outputs are gathered by the GEMM epilogue's
+peer stores (NCCL all-gather when peer memory is unavailable).  After the timed loop every rank
+recomputes the full [M, N*P] product on its own GPU and compares its gathered copy bit for bit
+("parity_checked"); a mismatch fails the run.
 """
 from __future__ import annotations
 
@@ -158,54 +164,79 @@ def cpu_model() -> str:
     return "unknown"
 
 
-def cpu_reference_tops(M, N, K, sample_rows, repeats=1):
-    """The CPU oracle (port of the reference arithmetic, oracle/qoracle.c) on the host cores.
-    Bounded sample: W is quantized in full, the activation side runs on `sample_rows` rows of X;
-    the full-step time is t_W + (M / sample_rows) * t_rows."""
+def bench_config(M, N, K, world):
+    """The `config` object both arms print (identical for the same command line)."""
+    return {
+        "workload": f"op_quantized_mm {M}x{N}x{K} fp32 in / fp32 out per GPU, W re-quantized every step",
+        "M": M, "N": N * world, "K": K, "mode": "REF_EXACT",
+        "l2": "2 rotating buffer sets, 384 MiB touched per 2 steps at 4096^3 (> 126 MB L2); no explicit flush",
+        "parallelism": f"column-parallel x{world}" if world > 1 else "single GPU",
+        "exchange": ("output blocks gathered to every GPU (GEMM-epilogue peer stores over NVLink; NCCL all-gather "
+                     "when peer memory is unavailable)") if world > 1 else "none",
+    }
+
+
+def synth_inputs(M, N, K, seed, block):
+    """Deterministic host inputs: X is shared by every column block (it is replicated across GPUs),
+    W depends on the block (= rank).  U(-1, 1), the distribution of src/timing_quantize.cu:17-20."""
     import numpy as np
 
+    X = np.random.default_rng([seed, 0]).random((M, K), dtype=np.float32) * 2 - 1
+    W = np.random.default_rng([seed, 1 + block]).random((K, N), dtype=np.float32) * 2 - 1
+    return X, W
+
+
+def cpu_step_seconds(X, Ws, O, repeats=1):
+    """One whole step of the CPU port per column block: quantize X rows, quantize W columns, int8 GEMM,
+    dequantize (oracle/qfast.c: qf_quantized_mm_f32, scratch allocated per call like the reference)."""
     import oracle
 
-    rng = np.random.default_rng(0)
-    X = rng.random((sample_rows, K), dtype=np.float32) * 2 - 1
-    W = rng.random((K, N), dtype=np.float32) * 2 - 1
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        Wq, Cw = oracle.absmax_quant_cols(W)
-        t1 = time.perf_counter()
-        Xq, Cx = oracle.absmax_quant_rows(X)
-        acc = oracle.gemm_s8s8s32(Xq, Wq)
-        oracle.dequant(acc, Cx, Cw)
-        t2 = time.perf_counter()
-        est = (t1 - t0) + (M / sample_rows) * (t2 - t1)
-        best = est if best is None else min(best, est)
-    return 2.0 * M * N * K / best / 1e12, best, oracle.num_threads()
+        for W in Ws:
+            oracle.fast_quantized_mm(X, W, out=O)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
 
 
 def run_reference_cpu(args):
     """--impl reference: the reference has no CPU implementation of its own (every op asserts
-    off-device, src/ops/op_elemwise.cuh:459-463), so the CPU arm is the oracle port."""
-    M = N = K = args.size
-    rows = args.cpu_sample_rows
-    vals = []
+    off-device, src/ops/op_elemwise.cuh:459-463), so the CPU arm is the port under oracle/ (qfast.c),
+    run on every host core this process may use.  Each step is one WHOLE op_quantized_mm per GPU of the
+    repo arm's workload (world column blocks), nothing extrapolated."""
+    import numpy as np
+
+    import oracle
+
+    M, N, K = args.m, args.n, args.k
+    world = max(1, args.gpus)
+    cores = oracle.fast_set_threads()  # torchrun pins OMP_NUM_THREADS=1; ask for the cores we may use
+    X, _ = synth_inputs(M, N, K, args.seed, 0)
+    Ws = [synth_inputs(M, N, K, args.seed, b)[1] for b in range(world)]
+    O = np.empty((M, N), np.float32)
+    times = []
+    t_wall0 = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        tops, est, cores = cpu_reference_tops(M, N, K, rows)
+        dt = cpu_step_seconds(X, Ws, O)
         if i >= args.warmup:
-            vals.append((tops, est))
-    tops = statistics.mean(v[0] for v in vals)
-    est = statistics.mean(v[1] for v in vals)
-    sample = (f"each step: column-quantize the full {K}x{N} W, then quantize/GEMM/dequantize rows 0..{rows - 1} of X; "
-              f"full-step time = t_W + ({M}/{rows}) * t_rows")
+            times.append(dt)
+    wall = time.perf_counter() - t_wall0
+    sec = statistics.mean(times)
+    tops = world * 2.0 * M * N * K / sec / 1e12
+    sample = (f"every step: the whole op on the full {M}x{K} X and {world} x {K}x{N} W (row + column absmax quantize, "
+              f"int8 GEMM [{oracle.fast_kernel_name()}], dequantize); {args.warmup}+{args.steps} steps ran in {wall:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": tops, "unit": "TOPS", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int8 x int8 -> int32, fp32 scales", "data": "synthetic U(-1,1)",
-        "config": {"workload": f"op_quantized_mm {M}x{N}x{K} fp32 in/out, W re-quantized every step", "M": M, "N": N, "K": K},
-        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample, "cpu": cpu_model()},
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8 x int8 -> int32, fp32 scales and output (CPU: vpdpbusd)", "data": f"synthetic U(-1,1), seed {args.seed}",
+        "config": bench_config(M, N, K, world), "extrapolated": False,
+        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample,
+                         "cpu": cpu_model(), "nproc": os.cpu_count()},
         "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def run_reference_gpu(args):
@@ -220,7 +251,7 @@ def run_reference_gpu(args):
         print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/libref_qmm.so not built"}))
         return
     ref = C.CDLL(so)
-    M = N = K = args.size
+    M, N, K = args.m, args.n, args.k
     X = torch.rand((M, K), device="cuda") * 2 - 1
     W = torch.rand((K, N), device="cuda") * 2 - 1
     O = torch.empty((M, N), device="cuda")
@@ -240,11 +271,42 @@ def run_reference_gpu(args):
     }))
 
 
+def pcie_rates(dev, nbytes=64 << 20, reps=4):
+    """Pinned-host copy rates of this box, both directions at once (the e2e pipeline runs them concurrently):
+    GB/s host->device and device->host.  CUDA events on the two copy streams."""
+    import torch
+
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = [0.0, 0.0]
+    for _ in range(reps + 1):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            e[0].record()
+            d_in.copy_(h_in, non_blocking=True)
+            e[1].record()
+        with torch.cuda.stream(s2):
+            e[2].record()
+            h_out.copy_(d_out, non_blocking=True)
+            e[3].record()
+        torch.cuda.synchronize()
+        best[0] = max(best[0], nbytes / e[0].elapsed_time(e[1]) / 1e6)
+        best[1] = max(best[1], nbytes / e[2].elapsed_time(e[3]) / 1e6)
+    return best
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
-    os.environ.pop("NCCL_DEBUG", None)  # NCCL's version banner goes to stdout and would precede the JSON line
+    # NCCL's INFO log (the driver counts ranks from it) goes to stderr so that stdout carries only the JSON line
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     qg = importlib.import_module(PKG)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,32 +315,41 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    M = N = K = args.size
+    M, N, K = args.m, args.n, args.k
     peaks = measured_peaks()
 
-    # two rotating buffer sets: 2 x (X 64 MiB + W 64 MiB + O 64 MiB) = 384 MiB >> 126 MB L2
+    # two rotating buffer sets: 2 x (X 64 MiB + W 64 MiB + O 64 MiB) = 384 MiB >> 126 MB L2.
+    # Set 0 is the seeded host data both arms use (X shared by all ranks, W per rank); set 1 is drawn on the device.
     nset = 2
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    Xs = [torch.rand((M, K), device=dev, generator=g) * 2 - 1 for _ in range(nset)]
-    Ws = [torch.rand((K, N), device=dev, generator=g) * 2 - 1 for _ in range(nset)]
+    Xh0, Wh0 = synth_inputs(M, N, K, args.seed, rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + args.seed)
+    Xs = [torch.from_numpy(Xh0).to(dev), torch.rand((M, K), device=dev, generator=g) * 2 - 1]
+    g.manual_seed(4321 + args.seed + rank)
+    Ws = [torch.from_numpy(Wh0).to(dev), torch.rand((K, N), device=dev, generator=g) * 2 - 1]
     Os = [torch.empty((M, N), device=dev) for _ in range(nset)]
     gathered = torch.empty((world, M, N), device=dev) if world > 1 else None
     # N > 1: the output gather is fused into the GEMM epilogue when symmetric (peer-mapped) memory is
-    # available -- every rank's [M, world*N] result buffer is written directly by all ranks' epilogues
-    exchange, symm_out, hdl, peer_ptrs = "none", None, None, []
+    # available -- every rank's [M, world*N] result buffer is written directly by all ranks' epilogues.
+    # Two result buffers alternate, so ONE cross-GPU barrier per step (after the product: "every block has
+    # landed everywhere") also orders the reuse of a buffer two steps later.
+    exchange, symm, hdls, peer_ptrs = "none", [], [], []
     if world > 1:
         exchange = "nccl all_gather_into_tensor"
         if os.environ.get("QG_BENCH_EXCHANGE", "fused") == "fused":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
 
-                symm_out = symm_mem.empty((M, N * world), dtype=torch.float32, device=dev)
-                hdl = symm_mem.rendezvous(symm_out, dist.group.WORLD)
-                peer_ptrs = [int(hdl.buffer_ptrs[r]) + rank * N * 4 for r in range(world) if r != rank]
+                for _ in range(nset):
+                    buf = symm_mem.empty((M, N * world), dtype=torch.float32, device=dev)
+                    h = symm_mem.rendezvous(buf, dist.group.WORLD)
+                    symm.append(buf)
+                    hdls.append(h)
+                    peer_ptrs.append([int(h.buffer_ptrs[r]) + rank * N * 4 for r in range(world) if r != rank])
                 exchange = "fused: GEMM epilogue TMA-stores into every peer's result over NVLink (symmetric memory)"
             except Exception as ex:  # no peer access on this box: fall back to the NCCL collective
                 exchange = f"nccl all_gather_into_tensor (symmetric memory unavailable: {str(ex)[:120]})"
-                symm_out, hdl, peer_ptrs = None, None, []
+                symm, hdls, peer_ptrs = [], [], []
+    fused = bool(symm)
     Xq = torch.empty((M, K), dtype=torch.int8, device=dev)
     Wq = torch.empty((K, N), dtype=torch.int8, device=dev)
     Wt = torch.empty((N, K), dtype=torch.int8, device=dev)
@@ -291,7 +362,7 @@ def run_ours(args):
     def step(i, ev=None):
         s = i % nset
         if ev is None and world == 1:
-            # the public call: one C-ABI entry, four PDL-chained launches
+            # the public call: one C-ABI entry, PDL-chained launches
             qg.op_quantized_mm(Xs[s], Ws[s], Os[s], 127.0, workspace=ws)
             return
         # the same launches issued one by one, so that the dominant kernel can be bracketed by CUDA events
@@ -303,18 +374,17 @@ def run_ours(args):
             qg.absmax_quant_cols(Ws[s], 127.0, qg.MODE_REF_EXACT, Wq, Cw)
         if ev is not None:
             ev[0].record()
-        if hdl is not None:
-            hdl.barrier(channel=0)  # peers have consumed the previous step's result
-            qg.gemm_s8_dequant_ex(Xq, Wt if kmajor else Wq, kmajor, Cx, Cw, symm_out[:, rank * N:(rank + 1) * N],
-                                  peer_ptrs, 127.0)
-            hdl.barrier(channel=1)  # every rank's blocks have landed everywhere
+        if fused:
+            qg.gemm_s8_dequant_ex(Xq, Wt if kmajor else Wq, kmajor, Cx, Cw, symm[s][:, rank * N:(rank + 1) * N],
+                                  peer_ptrs[s], 127.0)
+            hdls[s].barrier(channel=0)  # every rank's blocks of this step have landed everywhere
         elif kmajor:
             qg.gemm_s8t_dequant(Xq, Wt, Cx, Cw, Os[s], 127.0)
         else:
             qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, Os[s], 127.0)
         if ev is not None:
             ev[1].record()
-        if world > 1 and hdl is None:
+        if world > 1 and not fused:
             dist.all_gather_into_tensor(gathered, Os[s])
 
     for i in range(args.warmup):
@@ -345,6 +415,7 @@ def run_ours(args):
         dist.barrier()
         torch.cuda.synchronize()
     launches = qg.launch_count()
+    clocks = sampler.stop() if sample_clocks else None
     # instrumented pass, immediately after and on the same buffers: the same K steps with a CUDA event
     # pair around the dominant kernel (events between the launches would otherwise break the
     # programmatic-dependent-launch overlap of the timed pass above)
@@ -354,7 +425,6 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if sample_clocks else None
 
     total_ms = t_start.elapsed_time(t_end)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -366,6 +436,27 @@ def run_ours(args):
     value = world * ops / ms_per_step / 1e9  # TOPS, whole job
 
     gemm_ms = statistics.median(e[0].elapsed_time(e[1]) for e in evs)
+
+    # ---- N > 1 parity: this rank's gathered [M, N*P] result of set 0 against the same product computed here,
+    # on one GPU, from the gathered weights (column blocks are independent, so the two must agree bit for bit)
+    parity = None
+    if world > 1:
+        step(0)  # set 0 once more, so the buffers hold a known step
+        torch.cuda.synchronize()
+        dist.barrier()
+        Wall = torch.empty((world, K, N), device=dev)
+        dist.all_gather_into_tensor(Wall, Ws[0])
+        Wfull = Wall.permute(1, 0, 2).reshape(K, world * N).contiguous()
+        Ofull = torch.empty((M, world * N), device=dev)
+        qg.op_quantized_mm(Xs[0], Wfull, Ofull, 127.0)
+        got = symm[0] if fused else gathered.permute(1, 0, 2).reshape(M, world * N)
+        ok = bool(torch.equal(got.view(torch.int32), Ofull.view(torch.int32)))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"checked": True, "ok": bool(flag.item() == 1),
+                  "how": "every rank: gathered [M, N*P] output == op_quantized_mm(X, all-gathered W) on one GPU, all bits"}
+        del Wall, Wfull, Ofull
+        torch.cuda.synchronize()
 
     # per-stage timings of the two HBM-bound quantizers, outside the timed region (same buffers)
     def stage_ms(fn, n=20):
@@ -386,7 +477,43 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if parity is not None and not parity["ok"]:
+            sys.exit(3)
         return
+
+    # ---- sustained leg (N = 1): the same step back to back for >= `--sustained-seconds`, clocks sampled ----
+    sustained = None
+    if world == 1 and args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds / (ms_per_step * 1e-3)))
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        time.sleep(0.05)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_sus):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        c2 = s2.stop()
+        sus_total_ms = e0.elapsed_time(e1)
+        sus_ms = sus_total_ms / n_sus
+        # the GEMM alone, back to back, for ~1/3 of that time: its fraction of the SUSTAINED tensor peak
+        n_g = max(10, int(args.sustained_seconds / 3 / (gemm_ms * 1e-3)))
+        s3 = ClockSampler(local_rank)
+        s3.start()
+        e0.record()
+        for i in range(n_g):
+            qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, Os[i % nset], 127.0)
+        e1.record()
+        torch.cuda.synchronize()
+        c3 = s3.stop()
+        g_ms = e0.elapsed_time(e1) / n_g
+        sustained = {"steps": n_sus, "seconds": sus_total_ms / 1e3, "ms_per_step": sus_ms,
+                     "value": ops / sus_ms / 1e9, "unit": "TOPS", "clocks": c2,
+                     "gemm": {"launches": n_g, "ms": g_ms, "tops": ops / g_ms / 1e9,
+                              "peak": 2.0 * peaks["bf16_tflops_sustained"],
+                              "frac": ops / g_ms / 1e9 / (2.0 * peaks["bf16_tflops_sustained"]),
+                              "peak_note": "2 x bf16_tflops_sustained (" + peaks["source"] + ")", "clocks": c3}}
 
     # ---- e2e: host buffers through the C-ABI host call (H2D X, W; compute; D2H O) ----
     e2e = None
@@ -403,9 +530,18 @@ def run_ours(args):
         for _ in range(n_e2e):
             qg.quantized_mm_host(Xh, Wh, out=Oh)  # blocks until Oh is written
         e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        h2d_b, d2h_b = (M * K + K * N) * 4, M * N * 4
+        h2d_gbs, d2h_gbs = pcie_rates(dev)
+        floor_ms = max(h2d_b / h2d_gbs, d2h_b / d2h_gbs) / 1e6
         e2e = {"value": ops / e2e_ms / 1e9, "unit": "TOPS", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": (M * K + K * N) * 4, "d2h_bytes_per_step": M * N * 4,
-               "api": "qg_quantized_mm_host (pinned host X, W -> host O)"}
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "api": "qg_quantized_mm_host (pinned host X, W -> host O)",
+               "parity_vs_device_path": bool(torch.equal(Oh.to(dev).view(torch.int32), _device_result(qg, Xs[0], Ws[0], ws).view(torch.int32))),
+               "roofline": {"bound": "pcie", "achieved": h2d_b / e2e_ms / 1e6, "peak": h2d_gbs, "unit": "GB/s",
+                            "frac": floor_ms / e2e_ms,
+                            "note": f"pinned copies measured on this box, both directions concurrently: H2D {h2d_gbs:.1f} GB/s, "
+                                    f"D2H {d2h_gbs:.1f} GB/s; floor = max(h2d_bytes/H2D, d2h_bytes/D2H) = {floor_ms:.3f} ms; "
+                                    "frac = floor / measured"}}
     else:
         e2e = {"value": None, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "host-buffer call measured at N=1 only"}
@@ -444,14 +580,23 @@ def run_ours(args):
     except Exception as ex:  # context only
         lib["error"] = str(ex)[:200]
 
-    # ---- CPU baseline: oracle port on the host cores, bounded sample ----
+    # ---- CPU baseline: the CPU port on the host cores, whole steps on the inputs of buffer set 0; its output
+    # doubles as the checker of the GPU result (N = 1 parity: every bit of the 4096 x 4096 output) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        tops, est, cores = cpu_reference_tops(M, N, K, args.cpu_sample_rows)
-        cpu = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port",
-               "sample": f"full {K}x{N} W column-quantized once + rows 0..{args.cpu_sample_rows - 1} of X through "
-                         f"quantize/int8 GEMM/dequantize; full-step time = t_W + ({M}/{args.cpu_sample_rows}) * t_rows "
-                         f"= {est:.2f} s", "cpu": cpu_model()}
+        import oracle
+
+        cores = oracle.fast_set_threads()
+        Ocpu = np.empty((M, N), np.float32)
+        t_w0 = time.perf_counter()
+        sec = cpu_step_seconds(Xh0, [Wh0], Ocpu, repeats=3 if M * N * K <= 4096 ** 3 else 1)
+        cpu = {"value": ops / sec / 1e12, "unit": "TOPS", "cores": cores, "kind": "port", "cpu": cpu_model(), "nproc": os.cpu_count(),
+               "sample": f"whole {M}x{N}x{K} steps (best of 3) on the inputs of buffer set 0: row + column absmax quantize, int8 GEMM "
+                         f"[{oracle.fast_kernel_name()}], dequantize; {time.perf_counter() - t_w0:.1f} s of CPU work",
+               "ms_per_step": sec * 1e3}
+        got = _device_result(qg, Xs[0], Ws[0], ws).cpu().numpy()
+        parity = {"checked": True, "ok": bool(np.array_equal(got.view(np.int32), Ocpu.view(np.int32))),
+                  "how": "op_quantized_mm output of buffer set 0 == the CPU port's output on the same inputs, all bits"}
 
     # burst peak when the SM clock stayed at its maximum during the (short) timed region, else sustained
     at_max = bool(clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])
@@ -460,21 +605,21 @@ def run_ours(args):
     # dram__bytes_read.sum + dram__bytes_write.sum of the GEMM launch, from the committed ncu --set full capture
     # of this same command (never measured in this run: nothing here runs under a profiler)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    if world == 1 and (M, N, K) == (4096, 4096, 4096) and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+    for tname in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if world == 1 and (M, N, K) == (4096, 4096, 4096) and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+            break
     gemm_tops = ops / gemm_ms / 1e9
+    cfg = bench_config(M, N, K, world)
     line = {
         "metric": METRIC, "value": value, "unit": "TOPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), fp32 scales and output", "data": "synthetic U(-1,1), seeded",
-        "config": {"workload": f"op_quantized_mm {M}x{N}x{K} fp32 in / fp32 out per GPU, W re-quantized every step"
-                               + (f"; column-parallel over {world} GPUs + NCCL all-gather of the fp32 outputs" if world > 1 else ""),
-                   "M": M, "N": N * world, "K": K, "mode": "REF_EXACT",
-                   "l2": "2 rotating buffer sets, 384 MiB touched per 2 steps (> 126 MB L2); no explicit flush",
-                   "parallelism": f"column-parallel x{world}" if world > 1 else "single GPU", "exchange": exchange},
+        "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), fp32 scales and output", "data": f"synthetic U(-1,1), seed {args.seed}",
+        "config": cfg, "exchange_used": exchange,
+        "parity_checked": bool(parity and parity["ok"]), "parity": parity,
         "roofline": {"bound": "tensor", "kernel": "gemm_i8_tc_kernel (tcgen05 kind::i8 + fused dequantize epilogue)",
                      "achieved": gemm_tops, "peak": int8_peak, "unit": "TOP/s", "frac": gemm_tops / int8_peak,
                      "peak_note": f"2 x {peak_key} from MEASURED_PEAKS.json ({peaks['source']}); int8 dense "
@@ -490,6 +635,7 @@ def run_ours(args):
                            "frac": (K * N * 5 + 4 * N) / cols_ms / 1e6 / peaks["hbm_gbs"]},
             "gemm_dequant": {"ms": gemm_ms, "tops": gemm_tops},
         },
+        "sustained": sustained,
         "linear_prepared_weights": cached,
         "library_context": lib,
         "cpu_baseline": cpu,
@@ -498,9 +644,28 @@ def run_ours(args):
         "host_enqueue_ms": host_enqueue_ms,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    if world > 1:
+        # exchange roofline: bytes every GPU must RECEIVE per step over NVLink against the measured peer bandwidth
+        rx = (world - 1) * M * N * 4
+        line["exchange_roofline"] = {"bound": "nvlink ingress", "bytes_received_per_gpu": rx,
+                                     "achieved": rx / ms_per_step / 1e6, "peak": 770.0, "unit": "GB/s",
+                                     "frac": rx / ms_per_step / 1e6 / 770.0,
+                                     "peak_note": "measured peer copy per direction per GPU (B200_PROFILING.md); nominal 900"}
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY MISMATCH\n")
+        sys.exit(3)
+
+
+def _device_result(qg, X, W, ws):
+    import torch
+
+    O = torch.empty((X.shape[0], W.shape[1]), device=X.device)
+    qg.op_quantized_mm(X, W, O, 127.0, workspace=ws)
+    torch.cuda.synchronize()
+    return O
 
 
 def main():
@@ -509,10 +674,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
-    ap.add_argument("--size", type=int, default=4096, help="M = N = K")
-    ap.add_argument("--cpu-sample-rows", type=int, default=64)
+    ap.add_argument("--size", type=int, default=4096, help="M = N = K (overridden by -m / -n / -k)")
+    # the flags of the reference's timing driver, src/timing_quantize.cu:83-101
+    ap.add_argument("-m", type=int, default=None, help="rows of X")
+    ap.add_argument("-n", type=int, default=None, help="columns of W (per GPU)")
+    ap.add_argument("-k", type=int, default=None, help="inner dimension")
+    ap.add_argument("-s", "--seed", type=int, default=0, help="random seed (randgen_seed)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.m = args.m or args.size
+    args.n = args.n or args.size
+    args.k = args.k or args.size
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

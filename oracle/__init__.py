@@ -358,3 +358,74 @@ def encoder_block(X, Wqkv, W_O, W1, b1, W2, b2, heads, batch=1, range_=127.0, mo
     ffn = relu(quantized_mm(out, W1, range_, mode, bias=b1))                         # :63-67
     out = quantized_mm(ffn, W2, range_, mode, bias=b2)                               # :69-71
     return add_layernorm(out, mh)                                                    # :74-75
+
+
+# ---------------------------------------------------------------------------------------------
+# Timed CPU baseline (oracle/qfast.c): the same pipeline, threaded and vectorised (AVX-512 VNNI
+# int8 GEMM behind a run-time check).  Used by bench.py's cpu_baseline / --impl reference legs;
+# tests/test_oracle_cpu.py checks it against the functions above bit for bit.
+# ---------------------------------------------------------------------------------------------
+_SO_FAST = os.path.join(_HERE, "libqfast.so")
+_fast = None
+
+
+def fast_lib() -> C.CDLL:
+    global _fast
+    if _fast is None:
+        src = os.path.join(_HERE, "qfast.c")
+        if not os.path.exists(_SO_FAST) or (os.path.exists(src) and os.path.getmtime(_SO_FAST) < os.path.getmtime(src)):
+            subprocess.run(["make", "-C", _HERE, "libqfast.so"], check=True, capture_output=True)
+        _fast = C.CDLL(_SO_FAST)
+        _fast.qf_num_threads.restype = C.c_int
+        _fast.qf_gemm_kernel.restype = C.c_int
+        _fast.qf_gemm_s8s8s32.restype = C.c_int
+        _fast.qf_quantized_mm_f32.restype = C.c_int
+    return _fast
+
+
+def fast_set_threads(n: int | None = None) -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm asks for the cores it may actually use."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    fast_lib().qf_set_threads(C.c_int(int(n)))
+    return int(fast_lib().qf_num_threads())
+
+
+def fast_kernel_name() -> str:
+    return {2: "avx512_vnni vpdpbusd 6x64 register block", 0: "portable blocked int32 (compiler-vectorised)"}[
+        int(fast_lib().qf_gemm_kernel())]
+
+
+def fast_gemm_s8s8s32(A, B):
+    A = np.ascontiguousarray(A, np.int8)
+    B = np.ascontiguousarray(B, np.int8)
+    M, K = A.shape
+    _, N = B.shape
+    out = np.empty((M, N), np.int32)
+    rc = fast_lib().qf_gemm_s8s8s32(_p(A), _p(B), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int64(K), C.c_int64(N), _p(out),
+                                    C.c_int64(N))
+    if rc != 0:
+        raise MemoryError("qf_gemm_s8s8s32")
+    return out
+
+
+def fast_quantized_mm(X, W, range_=127.0, mode=MODE_REF_EXACT, bias=None, return_parts=False, out=None):
+    X = _f32(X)
+    W = _f32(W)
+    M, K = X.shape
+    _, N = W.shape
+    O = np.empty((M, N), np.float32) if out is None else out
+    b = None if bias is None else _f32(bias).reshape(-1)
+    if return_parts:
+        Cx, Cw = np.empty(M, np.float32), np.empty(N, np.float32)
+        Xq, Wq, acc = np.empty((M, K), np.int8), np.empty((K, N), np.int8), np.empty((M, N), np.int32)
+    else:
+        Cx = Cw = Xq = Wq = acc = None
+    rc = fast_lib().qf_quantized_mm_f32(_p(X), _p(W), _p(O), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int64(K), C.c_int64(N),
+                                        C.c_int64(N), C.c_float(range_), C.c_int(mode), _p(b), _p(Cx), _p(Cw), _p(Xq),
+                                        _p(Wq), _p(acc))
+    if rc != 0:
+        raise MemoryError("qf_quantized_mm_f32")
+    if return_parts:
+        return O, dict(Cx=Cx, Cw=Cw, Xq=Xq, Wq=Wq, acc=acc)
+    return O

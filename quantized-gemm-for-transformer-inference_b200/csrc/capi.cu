@@ -18,7 +18,7 @@ namespace qg {
 int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, const float *sx,
                int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st);
 int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
-               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, bool transpose, cudaStream_t st);
+               int8_t *Wq, int64_t ldq, float *Cw, bool transpose, cudaStream_t st);
 int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
@@ -154,10 +154,13 @@ static bool valid_io(int dt) { return dt == QG_F32 || dt == QG_F16 || dt == QG_B
 // layout of the scratch block shared by qg_quantized_mm / qg_linear_forward
 struct Workspace {
   int8_t *Xq, *Wq;
-  float *Cx, *Cw, *scratch;
+  float *Cx, *Cw;
   int64_t ldxq, ldwq;
+  void *splitk;         // int32 partial sums of a split-K product (NULL when this shape never splits)
+  size_t splitk_bytes;
   size_t bytes;
 };
+static size_t splitk_need(int M, int N, int K);
 static Workspace carve(void *base, int M, int N, int K) {
   Workspace w;
   w.ldxq = round_up(K, 16);  // TMA: leading dimensions are multiples of 16 bytes
@@ -167,13 +170,15 @@ static Workspace carve(void *base, int M, int N, int K) {
   // the weight-code region fits either layout: Wq [K, ceil16(N)] or Wt [N, ceil16(K)]
   const size_t wq_bytes = (size_t)K * w.ldwq > (size_t)N * w.ldxq ? (size_t)K * w.ldwq : (size_t)N * w.ldxq;
   const size_t oxq = take((size_t)M * w.ldxq), owq = take(wq_bytes);
-  const size_t ocx = take(sizeof(float) * M), ocw = take(sizeof(float) * N), osc = take(sizeof(float) * N);
+  const size_t ocx = take(sizeof(float) * M), ocw = take(sizeof(float) * N);
+  w.splitk_bytes = splitk_need(M, N, K);
+  const size_t osk = take(w.splitk_bytes);
   char *b = reinterpret_cast<char *>(base);
   w.Xq = reinterpret_cast<int8_t *>(b + oxq);
   w.Wq = reinterpret_cast<int8_t *>(b + owq);
   w.Cx = reinterpret_cast<float *>(b + ocx);
   w.Cw = reinterpret_cast<float *>(b + ocw);
-  w.scratch = reinterpret_cast<float *>(b + osc);
+  w.splitk = w.splitk_bytes ? b + osk : nullptr;
   w.bytes = off;
   return w;
 }
@@ -185,12 +190,12 @@ static Workspace carve(void *base, int M, int N, int K) {
 // the model promises more than 25 % (it pays for few tiles and long K -- M <= 256 against K >= 8192:
 // 59.5 -> 31.5 us at 128 x 4096 x 16384 -- and loses elsewhere: 4096 x 1152 x 4096 went 38 -> 63 us
 // under a rounds-only model).  QG_SPLIT_K=n forces n (1 = off).
-static int choose_split_k(DeviceState *d, int cg, int M, int N, int K, int out_kind) {
+static int choose_split_k(int sm_count, int cg, int M, int N, int K, int out_kind) {
   static const int forced = [] { const char *e = getenv("QG_SPLIT_K"); return e ? atoi(e) : 0; }();
   const int num_kb = (int)ceil_div(K, 128);
   if (forced >= 1) return (forced <= num_kb && forced <= kMaxExtraOut + 1 && (forced - 1) * (int)ceil_div(num_kb, forced) < num_kb) ? forced : 1;
   const int64_t T = ceil_div(M, 128 * cg) * ceil_div(N, 256);
-  const int P = d->sm_count / cg;
+  const int P = sm_count / cg;
   const double osz = (out_kind == QG_F16 || out_kind == QG_BF16) ? 2.0 : 4.0;
   auto cost = [&](int s) {
     const double gemm = (double)ceil_div(T * s, P) * (11.5 * K / s / 4096.0 + 1.5);
@@ -208,11 +213,28 @@ static int choose_split_k(DeviceState *d, int cg, int M, int N, int K, int out_k
   return best < 0.75 * base ? pick : 1;
 }
 
+// Bytes of int32 slice matrices the split-K form of an M x N x K product may ask for (0: it never splits).
+// The split factor depends on the SM count (148 on every B200; the current device is asked when there is
+// one) and, weakly, on the output width, so the larger of the fp32 / 16-bit answers is reserved.
+static size_t splitk_need(int M, int N, int K) {
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+  } else {
+    cudaGetLastError();
+  }
+  const int cg = M > 128 ? 2 : 1;
+  const int sk = std::max(choose_split_k(sms, cg, M, N, K, QG_F32), choose_split_k(sms, cg, M, N, K, QG_F16));
+  return sk > 1 ? sizeof(int32_t) * (size_t)sk * M * (size_t)round_up(N, 4) : 0;
+}
+
 // b_kmajor == 0: B is the reference's [K,N] (MN-major tensor-core operand); 1: B is Wt [N,K]
 static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M,
                          int N, int K, void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw,
                          const float *bias, float c, cudaStream_t st, const SideArgs *side = nullptr,
-                         const MultiOut *multi = nullptr, int act = QG_ACT_NONE) {
+                         const MultiOut *multi = nullptr, int act = QG_ACT_NONE, void *sk_buf = nullptr,
+                         size_t sk_bytes = 0, bool sk_arena = true) {
   int variant = g_variant.load();
   const bool tc_ok = gemm_i8_tc_supported(A, lda, B, ldb);
   // the 2-SM tile (256x256 per CTA pair) halves the shared-memory traffic per MAC; one CTA row
@@ -226,17 +248,29 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
     return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st, act);
   }
   const int cg = variant == QG_GEMM_TC_2SM ? 2 : 1;
-  const int sk = (side == nullptr && (multi == nullptr || multi->n == 0)) ? choose_split_k(d, cg, M, N, K, out_kind) : 1;
+  int sk = (side == nullptr && (multi == nullptr || multi->n == 0)) ? choose_split_k(d->sm_count, cg, M, N, K, out_kind) : 1;
+  // split-K: int32 partial sums of every k-slice, then one pass that adds them and runs the epilogue.
+  // The slices live in the caller's workspace (qg_workspace_bytes reserves them); entry points without a
+  // workspace argument use a grow-only per-device buffer (sk_arena; documented as shared in qgemm.h).  A
+  // caller-provided block that is too small simply does not split.
+  const int64_t ldp = round_up(N, 4);
+  const size_t slice = (size_t)M * ldp;
+  int32_t *parts = nullptr;
   if (sk > 1) {
-    // split-K: int32 partial sums of every k-slice, then one pass that adds them and runs the epilogue
-    const int64_t ldp = round_up(N, 4);
-    const size_t slice = (size_t)M * ldp;
-    {
+    if (sk_buf != nullptr) {
+      while (sk > 1 && sizeof(int32_t) * slice * sk > sk_bytes) sk--;
+      if (sk > 1 && (sk - 1) * (int)ceil_div(ceil_div(K, 128), sk) >= (int)ceil_div(K, 128)) sk = 1;  // an empty slice
+      parts = (int32_t *)sk_buf;
+    } else if (sk_arena) {
       std::lock_guard<std::mutex> lk(g_mu);
       int rc = grow(&d->splitk, &d->splitk_bytes, sizeof(int32_t) * slice * sk);
       if (rc) return rc;
+      parts = (int32_t *)d->splitk;
+    } else {
+      sk = 1;
     }
-    int32_t *parts = (int32_t *)d->splitk;
+  }
+  if (sk > 1) {
     MultiOut slices = {};
     slices.n = sk - 1;
     for (int i = 1; i < sk; i++) slices.dst[i - 1] = parts + (size_t)i * slice;
@@ -291,13 +325,7 @@ int qg_absmax_cols(const void *W, int dtype, int K, int N, int64_t ldw, int mode
   int rc = device_state(&d);
   if (rc) return rc;
   QG_REQUIRE(W && Cw && K > 0 && N > 0 && ldw >= N && valid_io(dtype), "qg_absmax_cols: bad arguments");
-  float *scratch = nullptr;  // N floats for the cross-CTA partial maxima, from the library arena
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if ((rc = grow(&d->arena, &d->arena_bytes, sizeof(float) * (size_t)N))) return rc;
-    scratch = reinterpret_cast<float *>(d->arena);
-  }
-  return quant_cols(W, dtype, K, N, ldw, 127.0f, mode, nullptr, nullptr, 0, Cw, scratch, false, (cudaStream_t)stream);
+  return quant_cols(W, dtype, K, N, ldw, 127.0f, mode, nullptr, nullptr, 0, Cw, false, (cudaStream_t)stream);
 }
 
 int qg_inv_divide_f32(const float *a, int64_t n, float b, float *out, qg_stream_t stream) {
@@ -323,7 +351,7 @@ int qg_quantize_cols(const void *W, int dtype, int K, int N, int64_t ldw, const 
   int rc = device_state(&d);
   if (rc) return rc;
   QG_REQUIRE(W && sw && Wq && K > 0 && N > 0 && ldw >= N && ldq >= N && valid_io(dtype), "qg_quantize_cols: bad arguments");
-  return quant_cols(W, dtype, K, N, ldw, 127.0f, 0, sw, Wq, ldq, nullptr, nullptr, false, (cudaStream_t)stream);
+  return quant_cols(W, dtype, K, N, ldw, 127.0f, 0, sw, Wq, ldq, nullptr, false, (cudaStream_t)stream);
 }
 
 int qg_absmax_quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq,
@@ -343,7 +371,8 @@ int qg_absmax_quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, fl
   if (rc) return rc;
   QG_REQUIRE(W && Wq && Cw && K > 0 && N > 0 && ldw >= N && ldq >= N && valid_io(dtype),
              "qg_absmax_quant_cols: bad arguments");
-  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wq, ldq, Cw, scratch, false, (cudaStream_t)stream);
+  (void)scratch;  // kept in the ABI; the library owns the column-maximum scratch (per device and stream)
+  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wq, ldq, Cw, false, (cudaStream_t)stream);
 }
 
 int qg_gemm_s8s8s32(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int M, int N, int K, int32_t *C,
@@ -419,10 +448,10 @@ int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ldw, int 
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
   // per-call weight quantization; QG_PERCALL_KMAJOR=0 keeps the reference's [K,N] code layout (MN-major operand)
   const bool kmajor = percall_kmajor();
-  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, kmajor ? w.ldxq : w.ldwq, w.Cw, w.scratch, kmajor, st);
+  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, kmajor ? w.ldxq : w.ldwq, w.Cw, kmajor, st);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
   return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, kmajor ? w.ldxq : w.ldwq, kmajor ? 1 : 0, M, N, K, O, ldo, out_dtype, w.Cx,
-                       w.Cw, bias, 1 / (range * range), st);
+                       w.Cw, bias, 1 / (range * range), st, nullptr, nullptr, QG_ACT_NONE, w.splitk, w.splitk_bytes, false);
 }
 
 int qg_prepare_weights(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, int8_t *Wt,
@@ -431,7 +460,7 @@ int qg_prepare_weights(const void *W, int dtype, int K, int N, int64_t ldw, floa
   int rc = device_state(&d);
   if (rc) return rc;
   QG_REQUIRE(W && Wt && Cw && K > 0 && N > 0 && ldw >= N && ldwt >= K && valid_io(dtype), "qg_prepare_weights: bad arguments");
-  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wt, ldwt, Cw, nullptr, true, (cudaStream_t)stream);
+  return quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wt, ldwt, Cw, true, (cudaStream_t)stream);
 }
 
 int qg_gemm_s8t_dequant(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_t ldwt, const float *Cx, const float *Cw,
@@ -471,7 +500,7 @@ int qg_linear_forward_act(const void *X, int64_t ldx, int in_dtype, const int8_t
   rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
   return gemm_dispatch(d, w.Xq, w.ldxq, Wt, ldwt, 1, M, N, K, Y, ldy, out_dtype, w.Cx, Cw, bias, 1 / (range * range), st,
-                       nullptr, nullptr, act);
+                       nullptr, nullptr, act, w.splitk, w.splitk_bytes, false);
 }
 
 // ---- outlier decomposition ------------------------------------------------------------------
@@ -643,6 +672,13 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
   if ((rc = grow(&d->ho, &d->ho_bytes, ob))) return rc;
   if (bias_host && (rc = grow(&d->hb, &d->hb_bytes, sizeof(float) * (size_t)N))) return rc;
   if ((rc = grow(&d->arena, &d->arena_bytes, carve(nullptr, M, N, K).bytes))) return rc;
+  // row chunks: multiples of 256 rows (one 2-SM tile), at most host_chunks of them.  A chunk's product may be
+  // tile-starved enough to split K: its slice matrices are grown here, under the lock this function
+  // already holds (gemm_dispatch must not take g_mu again), and handed over explicitly.
+  int rows_per = (M + d->host_chunks - 1) / d->host_chunks;
+  rows_per = ((rows_per + 255) / 256) * 256;
+  const size_t sk_need = std::max(splitk_need(std::min(rows_per, M), N, K), splitk_need(M % rows_per ? M % rows_per : 1, N, K));
+  if (sk_need && (rc = grow(&d->splitk, &d->splitk_bytes, sk_need))) return rc;
   // The reference's toDevice() / toHost() round trip (tensor.cuh:77-119) as a three-stream pipeline:
   //   in:      W, then X in row chunks                       (host -> device)
   //   compute: column quantizer once W is in; per chunk row quantizer + GEMM/dequantize
@@ -656,11 +692,8 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
   QG_CUDA_OK(cudaMemcpyAsync(d->hw, W_host, wb, cudaMemcpyHostToDevice, s_in));
   QG_CUDA_OK(cudaEventRecord(d->ev_w, s_in));
   QG_CUDA_OK(cudaStreamWaitEvent(s_k, d->ev_w, 0));
-  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, w.scratch, false, s_k);
+  rc = quant_cols(d->hw, QG_F32, K, N, N, range, mode, nullptr, w.Wq, w.ldwq, w.Cw, false, s_k);
   if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
-  // row chunks: multiples of 256 rows (one 2-SM tile), at most host_chunks of them
-  int rows_per = (M + d->host_chunks - 1) / d->host_chunks;
-  rows_per = ((rows_per + 255) / 256) * 256;
   const float *Xd = (const float *)d->hx;
   float *Od = (float *)d->ho;
   int ci = 0;
@@ -674,7 +707,8 @@ int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host
                     w.Cx + r0, s_k);
     if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
     rc = gemm_dispatch(d, w.Xq + (size_t)r0 * w.ldxq, w.ldxq, w.Wq, w.ldwq, 0, rows, N, K, Od + (size_t)r0 * N, N, QG_F32,
-                       w.Cx + r0, w.Cw, bias_dev, 1 / (range * range), s_k);
+                       w.Cx + r0, w.Cw, bias_dev, 1 / (range * range), s_k, nullptr, nullptr, QG_ACT_NONE,
+                       sk_need ? d->splitk : nullptr, sk_need ? d->splitk_bytes : 0, false);
     if (rc) return rc;
     QG_CUDA_OK(cudaEventRecord(d->ev_o[ci], s_k));
     QG_CUDA_OK(cudaStreamWaitEvent(s_out, d->ev_o[ci], 0));

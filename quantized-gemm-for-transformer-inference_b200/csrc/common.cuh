@@ -35,6 +35,21 @@ int cuda_status(cudaError_t e, const char *what);
 void count_launch(int n = 1);
 bool pdl_enabled();
 
+// cudaFuncSetAttribute acts on the CURRENT device only, so the opt-in for more than 48 KB of dynamic shared
+// memory is remembered per (kernel instantiation, device): `done` is a function-static array at the call site.
+constexpr int kMaxDevices = 16;
+template <typename Kern>
+inline cudaError_t smem_optin(Kern kern, int bytes, bool (&done)[kMaxDevices]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev] = true;
+  return e;
+}
+
 // Launch through cudaLaunchKernelEx so that consecutive kernels of one call can overlap their
 // launch latency and prologue (programmatic stream serialization); every kernel of this library
 // executes griddep_wait() before touching global memory.

@@ -44,6 +44,8 @@ struct GemmParams {
   int split_k, kb_per_slice;
   uint32_t nstages;  // smem ring depth actually used (<= the compiled kStages)
   int dbg_noload;    // bring-up experiment: after the ring is filled once, signal 'full' without loading
+  int dbg_noepi;     // bring-up experiment: the epilogue hands the accumulator back without reading it
+  int last_ring;     // 1: a cluster's LAST tile stages its output in the (by then idle) operand ring
   void *out;             // [M,N] of the epilogue's type
   int64_t ldo;           // elements
   const float *Cx, *Cw, *bias;
@@ -319,7 +321,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int q = warp & 3;  // TMEM lane quarter this warp is allowed to read
     const int epi_tid = (warp - 2) * 32 + lane;
     uint8_t *stage = smem_out + q * kStageOutBytes;
-    const uint32_t stage_u32 = smem_u32(stage);
+    const uint32_t stage_u32_own = smem_u32(stage);
     uint32_t acc_it = 0;
     long long w_tfull = 0;
     const long long t_begin = clock64();
@@ -406,6 +408,21 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       const uint32_t cw_u = smem_u32(cw_s + as * BN), bs_u = smem_u32(bias_s + as * BN);
+      if (p.dbg_noepi) {  // timing experiment: main loop alone
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 1) mbar_arrive(smem_u32(&tempty_bar[as]));
+          else mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[as]), 0);
+        }
+        continue;
+      }
+      // This cluster's last tile: every operand load has landed and every MMA has retired (tfull), in both
+      // CTAs of a pair, so the operand ring is idle.  Each warp takes 32 KB of it as eight staging chunks and
+      // never waits for a bulk store to drain its buffer -- the one epilogue no main loop hides.
+      const bool ring_stage = p.last_ring && p.tma_store && (t + num_clusters >= num_tiles);
+      const uint32_t ring_u32 = smem_u32(smem) + (uint32_t)q * (8u * kStageOutBytes);
+      uint32_t chunk_no = 0;
       const bool has_bias = p.bias != nullptr;
       // v[j] = dequantized (+ side product, + bias) accumulator column cb + j of this thread's row
       auto convert32 = [&](const uint32_t (&r)[32], int cb, const float *sd, float (&v)[32]) {
@@ -441,8 +458,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // one 128-byte-per-row chunk (OT::kCols columns from c0) leaves for global memory
       auto store_chunk = [&](const uint32_t (&w)[32], int c0) {
         if (p.tma_store) {
-          if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading staging
-          __syncwarp();
+          uint32_t stage_u32 = stage_u32_own;
+          if (ring_stage) {
+            stage_u32 = ring_u32 + (chunk_no++ & 7u) * kStageOutBytes;
+          } else {
+            if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading staging
+            __syncwarp();
+          }
 #pragma unroll
           for (int j4 = 0; j4 < 8; j4++)  // 128B-swizzled rows: conflict-free 16 B stores
             sts128(stage_u32 + lane * 128 + ((j4 ^ (lane & 7)) << 4), w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
@@ -643,16 +665,17 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
            const ExtraMaps &xm, GemmParams p, int num_sms, cudaStream_t st) {
   using C = Cfg<CG, B_MN, SIDE>;
   auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT, SIDE>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    QG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
-  }
+  static bool configured[kMaxDevices] = {};  // per instantiation and device
+  QG_CUDA_OK(smem_optin(kern, C::kSmemBytes, configured));
   const int base_tiles = p.tiles_m * p.tiles_n;
   const int max_clusters = num_sms / CG;
   p.nstages = C::kStages;
   static const bool dbg_noload = getenv("QG_DBG_NOLOAD") != nullptr, dbg_all_half = getenv("QG_DBG_ALL_HALF") != nullptr;
   p.dbg_noload = dbg_noload ? 1 : 0;
+  static const bool dbg_noepi = getenv("QG_DBG_NOEPI") != nullptr, no_last_ring = getenv("QG_NO_LAST_RING") != nullptr;
+  p.dbg_noepi = dbg_noepi ? 1 : 0;
+  // the ring must hold 4 warps x 8 chunks x 4 KB = 128 KB (it does in every configuration: >= 144 KB)
+  p.last_ring = (!no_last_ring && C::kStages * C::kStageBytes >= 4 * 8 * kStageOutBytes) ? 1 : 0;
   static const char *dbg_stages = getenv("QG_DBG_STAGES");
   if (const char *e = dbg_stages) {
     const int v = atoi(e);

@@ -8,6 +8,9 @@
 // write packed int8 codes plus the fp32 absmax.  The arithmetic (and its quirks: signed first
 // element, IEEE 127/x, truncate-and-wrap cast) is reproduced exactly; see oracle/qoracle.c.
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "quant_common.cuh"
 
@@ -188,7 +191,8 @@ quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, fl
 // Thread layout: 32 x 8; a thread owns one 16-byte vector of columns and walks rows with stride 8.
 // ------------------------------------------------------------------------------------------
 // part[j] = (epoch << 32) | fp32 bits of the running maximum; every call uses a fresh epoch, so stale
-// entries lose every atomicMax and nothing has to be initialised between calls
+// entries lose every atomicMax and nothing has to be initialised between calls (twopass_scratch clears
+// the buffer when the epoch wraps)
 __device__ __forceinline__ float part_value(unsigned long long v, uint32_t epoch) {
   return (uint32_t)(v >> 32) == epoch ? __uint_as_float((uint32_t)v) : -INFINITY;
 }
@@ -492,22 +496,36 @@ __global__ void outlier_mask_kernel(const float *__restrict__ A, int M, int K, i
 inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // Epoch-tagged column-max scratch: zero-initialised once, never reset (each call uses a fresh epoch).
-// One buffer per device, so calls that quantize weights are not re-entrant across streams.
-int twopass_scratch(int N, unsigned long long **part, uint32_t *epoch) {
-  struct State { unsigned long long *part = nullptr; int n = 0; uint32_t epoch = 0; };
-  static State state[16];
+// One buffer per (device, stream): calls that quantize weights on different streams do not share it.
+// Epoch 0 is never used (zero-initialised entries never match); when the 32-bit epoch wraps the buffer
+// is cleared on the stream and the count restarts at 1, so stale tags can never win an atomicMax.
+struct ColScratch {
+  unsigned long long *part = nullptr;
+  int n = 0;
+  uint32_t epoch = 0;
+};
+int twopass_scratch(int N, cudaStream_t st, unsigned long long **part, uint32_t *epoch) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, ColScratch> states;
   int dev = 0;
-  cudaGetDevice(&dev);
-  State &s = state[dev & 15];
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(mu);
+  ColScratch &s = states[std::make_pair(dev, st)];
   if (s.n < N) {
-    if (s.part) { cudaDeviceSynchronize(); cudaFree(s.part); }
+    if (s.part) { cudaStreamSynchronize(st); cudaFree(s.part); s.part = nullptr; }
     s.n = (int)round_up(N < 16384 ? 16384 : N, 4096);
-    if (cudaMalloc(&s.part, sizeof(unsigned long long) * (size_t)s.n) != cudaSuccess) { s = State(); return (int)cudaGetLastError(); }
-    if (cudaMemset(s.part, 0, sizeof(unsigned long long) * (size_t)s.n) != cudaSuccess) return (int)cudaGetLastError();
+    if ((e = cudaMalloc(&s.part, sizeof(unsigned long long) * (size_t)s.n)) != cudaSuccess) { s = ColScratch(); return (int)e; }
+    if ((e = cudaMemsetAsync(s.part, 0, sizeof(unsigned long long) * (size_t)s.n, st)) != cudaSuccess) return (int)e;
     s.epoch = 0;
   }
+  if (++s.epoch == 0) {  // wrapped after 2^32 calls: forget every old tag
+    if ((e = cudaMemsetAsync(s.part, 0, sizeof(unsigned long long) * (size_t)s.n, st)) != cudaSuccess) return (int)e;
+    s.epoch = 1;
+  }
   *part = s.part;
-  *epoch = ++s.epoch;  // 0 is never used, so zero-initialised entries never match
+  *epoch = s.epoch;
   return 0;
 }
 
@@ -576,7 +594,7 @@ inline int cols_rows_per_cta(int K, int col_tiles, int round) {
 
 template <typename T>
 int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, const float *sw, int8_t *Wq,
-                  int64_t ldq, float *Cw, float *scratch, bool transpose, cudaStream_t st) {
+                  int64_t ldq, float *Cw, bool transpose, cudaStream_t st) {
   constexpr int EPV = Unpack<T>::EPV;
   if (transpose && Wq != nullptr && !(aligned(Wq, 16) && ldq % 16 == 0))
     return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
@@ -593,7 +611,7 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
   unsigned long long *part = nullptr;
   uint32_t epoch = 0;
   if (sw == nullptr) {
-    int rc = twopass_scratch(N, &part, &epoch);
+    int rc = twopass_scratch(N, st, &part, &epoch);
     if (rc) return rc;
     if (K > 1) {
       dim3 grid(col_tiles, (unsigned)ceil_div(K - 1, rpc));
@@ -626,12 +644,12 @@ int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range,
 
 // transpose: codes are written as Wt[n][k] with leading dimension ldq (K-major operand layout)
 int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
-               int8_t *Wq, int64_t ldq, float *Cw, float *scratch, bool transpose, cudaStream_t st) {
+               int8_t *Wq, int64_t ldq, float *Cw, bool transpose, cudaStream_t st) {
   switch (dtype) {
-    case QG_F32: return cols_dispatch((const float *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, transpose, st);
-    case QG_F16: return cols_dispatch((const __half *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, transpose, st);
+    case QG_F32: return cols_dispatch((const float *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, transpose, st);
+    case QG_F16: return cols_dispatch((const __half *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, transpose, st);
     case QG_BF16:
-      return cols_dispatch((const __nv_bfloat16 *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, scratch, transpose, st);
+      return cols_dispatch((const __nv_bfloat16 *)W, K, N, ldw, range, mode, sw, Wq, ldq, Cw, transpose, st);
   }
   return QG_EINVAL;
 }

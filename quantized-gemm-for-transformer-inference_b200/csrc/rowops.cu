@@ -317,11 +317,8 @@ add_layernorm_cta_rows_kernel(const float *A, int64_t lda, const float *R, int64
 // dynamic shared memory above 48 KB needs the opt-in once per kernel
 template <typename... KArgs, typename... Args>
 static void warp_rows_launch(void (*kern)(KArgs...), size_t smem, int M, cudaStream_t st, Args &&...args) {
-  static size_t allowed = 48 << 10;
-  if (smem > allowed) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
-    allowed = 200 << 10;
-  }
+  static bool opted[kMaxDevices] = {};  // per kernel (template instantiation of this launcher) and device
+  if (smem > (48 << 10)) smem_optin(kern, 200 << 10, opted);
   const int64_t ctas = ceil_div(M, kRowWarps);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ctas < 148 * 16 ? ctas : 148 * 16));
@@ -345,11 +342,8 @@ int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr,
     rpc = rpc > 32 ? 32 : rpc;
     while (rpc > 1 && ceil_div(M, rpc) < 148) rpc >>= 1;  // short matrices: spread over the SMs first
     const size_t smem = (size_t)rpc * (N + 1) * 12;
-    static bool opted = false;
-    if (!opted) {
-      cudaFuncSetAttribute(add_layernorm_cta_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
-      opted = true;
-    }
+    static bool opted[kMaxDevices] = {};
+    smem_optin(add_layernorm_cta_rows_kernel, 200 << 10, opted);
     const int64_t ctas = ceil_div(M, rpc);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ctas < 148 * 8 ? ctas : 148 * 8));

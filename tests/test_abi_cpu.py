@@ -41,9 +41,11 @@ def test_no_gpu_means_loud_failure_not_fallback(qg):
 
 def test_workspace_bytes_is_pure_host_logic(qg):
     wb = qg.workspace_bytes(4096, 4096, 4096)
-    # int8 copies of X and W, three fp32 vectors, 256-byte aligned pieces
-    assert wb >= 2 * 4096 * 4096 + 3 * 4 * 4096
-    assert wb < 2 * 4096 * 4096 + 3 * 4 * 4096 + 5 * 256 + 1
+    # int8 copies of X and W, two fp32 vectors, 256-byte aligned pieces (this shape never splits K)
+    assert wb >= 2 * 4096 * 4096 + 2 * 4 * 4096
+    assert wb < 2 * 4096 * 4096 + 2 * 4 * 4096 + 5 * 256 + 1
+    # a tile-starved shape reserves the int32 slice matrices of its split-K form in the same block
+    assert qg.workspace_bytes(128, 4096, 16384) >= 128 * 16384 + 4096 * 16384 + 2 * 4 * 128 * 4096
     assert qg.workspace_bytes(3, 2, 3) > 0 and qg.workspace_bytes(0, 1, 1) == 0
     # odd sizes are padded to the 16-byte leading dimensions TMA needs
     assert qg.workspace_bytes(3, 2, 3) >= 3 * 16 + 3 * 16

@@ -91,7 +91,7 @@ def test_bench_reference_arm_contract(tmp_path):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    small = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--size", "256", "--cpu-sample-rows", "16"]
+    small = ["--impl", "reference", "--steps", "1", "--warmup", "0", "-m", "256", "-n", "128", "-k", "192", "-s", "3"]
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), *small], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-1500:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -100,9 +100,20 @@ def test_bench_reference_arm_contract(tmp_path):
     assert line["impl"] == "reference" and line["unit"] == "TOPS" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["extrapolated"] is False and "seed 3" in line["data"]
+    # both arms print the SAME config object for the same command line (the driver compares them)
+    sys.path.insert(0, root)
+    import bench
+
+    assert line["config"] == bench.bench_config(256, 128, 192, 1)
+    assert (line["config"]["M"], line["config"]["N"], line["config"]["K"]) == (256, 128, 192)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29613", os.path.join(root, "bench.py"), "--gpus", "2", *small],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
+    assert len(lines) == 1
+    line2 = json.loads(lines[0])
+    assert line2["n_gpus"] == 2 and line2["config"] == bench.bench_config(256, 128, 192, 2)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use the cores it may use
+    assert line2["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))

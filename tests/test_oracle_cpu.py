@@ -190,3 +190,52 @@ def test_oracle_encoder_block_vs_reference_kernels(oracle, path):
     err = np.abs(o - g["out"])
     # libm vs device expf differ in the last bits and a 1-ulp change can move an int8 code downstream
     assert np.median(err) <= 1e-4 * max(1.0, np.abs(g["out"]).max())
+
+
+# ---- the timed CPU baseline (oracle/qfast.c) must be the same function as the oracle ----------------------
+
+def _edge_inputs(rng, M, K, N):
+    X = (rng.random((M, K), dtype=np.float32) * 2 - 1)
+    W = (rng.random((K, N), dtype=np.float32) * 2 - 1)
+    X[0, :] = 0.0                                  # all-zero row: 127/0 = inf, 0*inf = NaN -> code 0
+    if M > 1:
+        X[1, 0], X[1, 1:] = -5.0, 0.0              # negative first element, zeros after: the maximum is a zero
+    if M > 2:
+        X[2, 0], X[2, 1:] = -3.0, -0.0             # ... whose SIGN depends on the visiting order
+        X[2, min(5, K - 1)] = np.nan
+    if M > 3:
+        X[3, 0] = -2.5                             # largest magnitude negative and first: wrapped codes
+    W[:, 0] = 0.0
+    if N > 1:
+        W[0, 1], W[1:, 1] = -4.0, 0.0
+    if N > 2:
+        W[min(3, K - 1), 2] = np.inf
+    return X, W
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 2), (7, 70, 5), (70, 257, 130), (130, 96, 200), (260, 1000, 77)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fast_cpu_baseline_equals_oracle(oracle, shape, mode):
+    M, K, N = shape
+    rng = np.random.default_rng(M * 1000 + N)
+    X, W = _edge_inputs(rng, M, K, N)
+    b = rng.random(N, dtype=np.float32)
+    oracle.fast_set_threads(4)
+    O1, p1 = oracle.quantized_mm(X, W, 127.0, mode, bias=b, return_parts=True)
+    O2, p2 = oracle.fast_quantized_mm(X, W, 127.0, mode, bias=b, return_parts=True)
+    for key in ("Cx", "Cw"):
+        assert np.array_equal(p1[key].view(np.uint32), p2[key].view(np.uint32)), key
+    for key in ("Xq", "Wq", "acc"):
+        assert np.array_equal(p1[key], p2[key]), key
+    assert np.array_equal(O1.view(np.uint32), O2.view(np.uint32))
+
+
+def test_fast_cpu_gemm_extreme_codes(oracle):
+    """+-127 / -128 codes and K not a multiple of 4: the +128 bias trick of the VNNI kernel stays exact."""
+    rng = np.random.default_rng(9)
+    A = rng.integers(-128, 128, (37, 1030), dtype=np.int8)
+    B = rng.integers(-128, 128, (1030, 75), dtype=np.int8)
+    A[0, :], B[:, 0] = -128, -128
+    A[1, :], B[:, 1] = 127, -128
+    assert np.array_equal(oracle.fast_gemm_s8s8s32(A, B), oracle.gemm_s8s8s32(A, B))
+    assert np.array_equal(oracle.fast_gemm_s8s8s32(A, B), A.astype(np.int64) @ B.astype(np.int64))
