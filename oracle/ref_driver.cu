@@ -316,4 +316,66 @@ int ref_encoder_block(const float *X, int h, int d_model, int heads, int d_ff, c
   return rc;
 }
 
+// One iteration of the Decoder loop, src/transformer.cu:91-166, statement by statement on the reference's own
+// kernels, under the same conventions as ref_encoder_block (weights supplied, every product on weights through
+// op_quantized_mm, heads concatenated on the device, ffnOut sized [h, d_ff]).  The 3-argument
+// attn.forward(Xq, Xkv, out) the reference calls (:104,106,132) does not exist in attention.cuh;
+// it is spelt here as the op sequence of AttentionLayer::forward (attention.cuh:51-70) with the queries
+// projected from the first argument and the keys / values from the second.
+// X [h, d_model] decoder input, E [h_enc, d_model] encoder output.  Wq1/Wk1/Wv1, Wq2/Wk2/Wv2: heads consecutive
+// [d_model, d] matrices (self- and cross-attention); W_O1, W_O2 [d_model, d_model].
+int ref_decoder_block(const float *X, const float *E, int h, int h_enc, int d_model, int heads, int d_ff,
+                      const float *Wq1, const float *Wk1, const float *Wv1, const float *W_O1, const float *Wq2,
+                      const float *Wk2, const float *Wv2, const float *W_O2, const float *W1, const float *b1,
+                      const float *W2, const float *b2, float range, float *out) {
+  const int d = d_model / heads;
+  auto up = [](const float *src, int r, int c) {
+    Tensor<float> t{r, c, true};
+    cudaMemcpy(t.rawp, src, sizeof(float) * (size_t)r * c, cudaMemcpyHostToDevice);
+    return t;
+  };
+  Tensor<float> x = up(X, h, d_model), enc_output = up(E, h_enc, d_model), wo1 = up(W_O1, d_model, d_model),
+                wo2 = up(W_O2, d_model, d_model), w1 = up(W1, d_model, d_ff), bb1 = up(b1, 1, d_ff),
+                w2 = up(W2, d_ff, d_model), bb2 = up(b2, 1, d_model);
+  Tensor<float> multiHeadOut{h, d_model, true}, output{h, d_model, true};
+  // attention.cuh:51-70 with separate query and key/value inputs; result into column block j of multiHeadOut
+  auto head = [&](const Tensor<float> &xq, const Tensor<float> &xkv, const float *Wq, const float *Wk, const float *Wv, int j) {
+    Tensor<float> wq = up(Wq + (size_t)j * d_model * d, d_model, d), wk = up(Wk + (size_t)j * d_model * d, d_model, d),
+                  wv = up(Wv + (size_t)j * d_model * d, d_model, d);
+    Tensor<float> Q(xq.h, d, true), K(xkv.h, d, true), V(xkv.h, d, true);
+    op_quantized_mm(xq, wq, Q, range);
+    op_quantized_mm(xkv, wk, K, range);
+    op_quantized_mm(xkv, wv, V, range);
+    Tensor<float> K_transpose = K.transpose();
+    Tensor<float> QK_T(Q.h, K_transpose.w, true), scaled(Q.h, K_transpose.w, true), P(Q.h, K_transpose.w, true),
+        attnHeadOut(Q.h, d, true);
+    op_mm(Q, K_transpose, QK_T);
+    float scale_factor = 1.0 / std::sqrt(d);
+    op_multiply(QK_T, scale_factor, scaled);
+    op_softmax(scaled, P);
+    op_mm(P, V, attnHeadOut);
+    cudaMemcpy2D(multiHeadOut.rawp + j * d, sizeof(float) * d_model, attnHeadOut.rawp, sizeof(float) * d, sizeof(float) * d,
+                 Q.h, cudaMemcpyDeviceToDevice);
+  };
+  for (int j = 0; j < heads; j++) head(x, x, Wq1, Wk1, Wv1, j);           // :97-116 (the reference applies no causal mask)
+  op_quantized_mm(multiHeadOut, wo1, output, range);                         // :117-119
+  op_add(output, multiHeadOut, output);                                      // :123
+  op_layernorm(output, output);                                              // :124
+  for (int j = 0; j < heads; j++) head(output, enc_output, Wq2, Wk2, Wv2, j);  // :127-140
+  op_quantized_mm(multiHeadOut, wo2, output, range);                         // :143-144
+  op_add(output, multiHeadOut, output);                                      // :148
+  op_layernorm(output, output);                                              // :149
+  Tensor<float> ffnOut{h, d_ff, true};
+  op_quantized_mm(output, w1, ffnOut, range);                                // :154-156 (LinearLayer::forward)
+  op_add(ffnOut, bb1, ffnOut);
+  op_relu(ffnOut, ffnOut);                                                   // :157
+  op_quantized_mm(ffnOut, w2, output, range);                                // :159-161
+  op_add(output, bb2, output);
+  op_add(output, multiHeadOut, output);                                      // :165
+  op_layernorm(output, output);                                              // :166
+  int rc = status();
+  d2h(out, output);
+  return rc;
+}
+
 }  // extern "C"

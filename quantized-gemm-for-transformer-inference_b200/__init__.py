@@ -302,6 +302,22 @@ def op_quantized_mm(X: torch.Tensor, W: torch.Tensor, O: torch.Tensor, range_: f
                                  ws_p, C.c_size_t(ws_n), _stream()), "qg_quantized_mm")
 
 
+def linear_forward(X: torch.Tensor, Wt: torch.Tensor, Cw: torch.Tensor, bias, Y: torch.Tensor, range_: float = 127.0,
+                   mode: int = MODE_REF_EXACT, act: int = 0, workspace: torch.Tensor | None = None) -> None:
+    """LinearLayer::forward on prepared weights (qg_linear_forward_act): y = act(x @ w + b); the caller's
+    workspace (workspace_bytes(M, N, K)) holds every temporary of the call, split-K slices included."""
+    M, K = X.shape
+    N = Wt.shape[0]
+    assert Wt.shape[1] == K and Y.shape == (M, N)
+    px, ldx = _dev2d(X)
+    pq, ldq = _dev2d(Wt)
+    py, ldy = _dev2d(Y)
+    pb = None if bias is None else _vec(bias.reshape(-1), N)
+    ws_p, ws_n = (None, 0) if workspace is None else (C.c_void_p(workspace.data_ptr()), workspace.numel())
+    _check(lib().qg_linear_forward_act(px, ldx, _dt(X), pq, ldq, _vec(Cw, N), pb, act, py, ldy, _dt(Y), M, N, K,
+                                       C.c_float(range_), mode, ws_p, C.c_size_t(ws_n), _stream()), "qg_linear_forward_act")
+
+
 def quantized_mm_host(X, W, range_: float = 127.0, mode: int = MODE_REF_EXACT, bias=None, out=None):
     """Host-buffer form: X, W (and out) are CPU float32 tensors (pinned for full PCIe rate)."""
     assert not X.is_cuda and not W.is_cuda and X.dtype == torch.float32 and W.dtype == torch.float32

@@ -124,6 +124,41 @@ def encoder_cases():
         yield name, X, heads, d_ff, encoder_weights(rng, d_model, heads, d_ff)
 
 
+def run_ref_decoder_block(ref, X, E, heads, d_ff, sa, ca, W1, b1, W2, b2, range_=127.0):
+    """One Decoder-loop iteration (src/transformer.cu:91-166) on the reference's kernels.  sa / ca: dicts with
+    Wq, Wk, Wv ([heads, d_model, d] stacks) and W_O of the self- and the cross-attention."""
+    h, d_model = X.shape
+    out = np.empty((h, d_model), np.float32)
+    rc = ref.ref_decoder_block(p(X), p(E), h, E.shape[0], d_model, heads, d_ff, p(sa["Wq"]), p(sa["Wk"]), p(sa["Wv"]),
+                               p(sa["W_O"]), p(ca["Wq"]), p(ca["Wk"]), p(ca["Wv"]), p(ca["W_O"]), p(W1), p(b1), p(W2), p(b2),
+                               C.c_float(range_), p(out))
+    assert rc == 0, rc
+    return out
+
+
+def decoder_weights(rng, d_model, heads, d_ff):
+    sa = encoder_weights(rng, d_model, heads, d_ff)
+    ca = encoder_weights(rng, d_model, heads, d_ff)
+    return dict(sa={k: sa[k] for k in ("Wq", "Wk", "Wv", "W_O")}, ca={k: ca[k] for k in ("Wq", "Wk", "Wv", "W_O")},
+                W1=ca["W1"], b1=ca["b1"], W2=ca["W2"], b2=ca["b2"])
+
+
+def decoder_cases():
+    rng = np.random.default_rng(23)
+    # transformer.cu:170-185 shape (6 x 8, 4 heads, d_ff 8) with a 6-row encoder output; then a wider one whose
+    # encoder sequence is longer than the decoder's (cross-attention scores are not square)
+    for name, h, h_enc, d_model, heads, d_ff in (("dec_6x8_h4_ff8_enc6", 6, 6, 8, 4, 8), ("dec_40x64_h4_ff96_enc56", 40, 56, 64, 4, 96)):
+        X = (rng.random((h, d_model), dtype=np.float32) * 2 - 1)
+        E = (rng.random((h_enc, d_model), dtype=np.float32) * 2 - 1)
+        yield name, X, E, heads, d_ff, decoder_weights(rng, d_model, heads, d_ff)
+
+
+def save_decoder_case(path, X, E, heads, d_ff, w, out):
+    flat = {f"sa_{k}": v for k, v in w["sa"].items()}
+    flat.update({f"ca_{k}": v for k, v in w["ca"].items()})
+    np.savez_compressed(path, X=X, E=E, heads=heads, d_ff=d_ff, out=out, W1=w["W1"], b1=w["b1"], W2=w["W2"], b2=w["b2"], **flat)
+
+
 def addnorm_cases():
     rng = np.random.default_rng(22)
     A = rng.standard_normal((200, 77)).astype(np.float32)
@@ -145,6 +180,10 @@ def main():
     for name, X, heads, d_ff, w in encoder_cases():
         o = run_ref_encoder_block(ref, X, heads, d_ff, **w)
         np.savez_compressed(os.path.join(out, f"ref_{name}.npz"), X=X, heads=heads, d_ff=d_ff, out=o, **w)
+        print("wrote", name)
+    for name, X, E, heads, d_ff, w in decoder_cases():
+        o = run_ref_decoder_block(ref, X, E, heads, d_ff, **w)
+        save_decoder_case(os.path.join(out, f"ref_{name}.npz"), X, E, heads, d_ff, w, o)
         print("wrote", name)
     for name, A, R in addnorm_cases():
         B = np.empty_like(A)

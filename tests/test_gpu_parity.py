@@ -502,3 +502,138 @@ def test_argument_errors_are_reported(qg):
         qg.op_quantized_mm(X, W, O)
     rc = qg.lib().qg_gemm_s8s8s32(None, C.c_int64(8), None, C.c_int64(8), 4, 4, 8, None, C.c_int64(4), None)
     assert rc == -22 and b"bad arguments" in qg.lib().qg_last_error()
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE configs 4 / 5 at full size (OPT-6.7B linears at T = 16384, OPT-66B FFN shards at T = 4096, P = 8)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("shape", [(16384, 16384, 4096), (16384, 4096, 16384), (4096, 4608, 9216), (4096, 1152, 36864)],
+                         ids=["opt6.7b_fc1", "opt6.7b_fc2", "opt66b_fc1_shard", "opt66b_fc2_shard"])
+def test_baseline_config_shapes_full_size(qg, oracle, shape):
+    """fp16 in / fp16 out LinearLayer::forward with prepared weights at the shapes BASELINE.json times
+    (M, N, K): N(0,1) activations with six outlier feature columns scaled by 20, N(0, 0.02^2) weights.
+    Bars: column / row scales exact; sampled rows bit-exact against the oracle (int8 codes, int32 accumulators,
+    fp16 output); every partial sum of the sampled rows below 2^24 (the reference's fp32 accumulator is then
+    the exact integer); row and column checksums of ALL int32 accumulators against int64 arithmetic."""
+    M, N, K = shape
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    X = torch.randn((M, K), device=DEV, generator=g)
+    cols = torch.randperm(K, device=DEV, generator=g)[:6]
+    X[:, cols] *= 20.0
+    X = X.half()
+    W = (torch.randn((K, N), device=DEV, generator=g) * 0.02).half()
+    bias = torch.randn(N, device=DEV, generator=g)
+    Wt, Cw = qg.prepare_weights(W, 127.0, qg.MODE_REF_EXACT)
+    Y = torch.empty((M, N), dtype=torch.float16, device=DEV)
+    lin = qg.LinearLayer(K, N, device=DEV, dtype=torch.float16)
+    lin.w, lin.b = W, bias.reshape(1, N)
+    lin.quantize_weights()
+    lin.forward(X, Y)
+    torch.cuda.synchronize()
+    Xh, Wh = X.float().cpu().numpy(), W.float().cpu().numpy()
+    # scales and codes of the whole problem
+    Xq = torch.empty((M, K), dtype=torch.int8, device=DEV); Cx = torch.empty(M, device=DEV)
+    qg.absmax_quant_rows(X, 127.0, qg.MODE_REF_EXACT, Xq, Cx)
+    Wq_e, Cw_e = oracle.absmax_quant_cols(Wh)
+    assert same_f32(Cw.cpu().numpy(), Cw_e)
+    assert np.array_equal(Wt.cpu().numpy()[:, :K], Wq_e.T)
+    assert same_f32(Cx.cpu().numpy(), oracle.absmax_rows(Xh))
+    # sampled rows: codes, accumulators (exact int32 == the reference's fp32 chain), fp16 output
+    rows = np.sort(np.random.default_rng(M ^ N).choice(M, 12, replace=False))
+    Xq_e, Cx_e = oracle.absmax_quant_rows(Xh[rows])
+    assert np.array_equal(Xq.cpu().numpy()[rows], Xq_e)
+    assert oracle.max_partial_sum(Xq_e, Wq_e) < 2 ** 24
+    acc_e = oracle.gemm_s8s8s32(Xq_e, Wq_e)
+    y_e = oracle.dequant(acc_e, Cx_e, Cw_e, 127.0, bias.cpu().numpy())
+    assert torch.equal(Y[torch.from_numpy(rows).to(DEV)].cpu(), torch.from_numpy(y_e).to(torch.float16))
+    # all accumulators: row and column checksums in int64
+    acc = torch.empty((M, N), dtype=torch.int32, device=DEV)
+    qg.gemm_s8t_dequant(Xq, Wt, None, None, acc, 127.0)
+    torch.cuda.synchronize()
+    assert np.array_equal(acc.cpu().numpy()[rows], acc_e)
+    A64, B64 = Xq.cpu().numpy().astype(np.int64), Wq_e.astype(np.int64)
+    assert np.array_equal(acc.sum(dim=1, dtype=torch.int64).cpu().numpy(), A64 @ B64.sum(axis=1))
+    assert np.array_equal(acc.sum(dim=0, dtype=torch.int64).cpu().numpy(), A64.sum(axis=0) @ B64)
+
+
+# ------------------------------------------------------------------------------------------
+# robustness: host path on tile-starved chunks, two streams, two devices in one process
+# ------------------------------------------------------------------------------------------
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("shape", [(16, 4096, 4096), (64, 4096, 4096), (1, 4096, 4096), (256, 1024, 8192), (700, 512, 4352)])
+def test_host_buffer_entry_point_split_k_shapes(qg, oracle, shape):
+    """Host-buffer call whose per-chunk product is tile-starved enough for split-K (M <= 64 against K >= 4096 ...):
+    this used to self-deadlock on the library mutex (the split-K scratch grew under a lock the host call already held)."""
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape))
+    X = torch.from_numpy(rng.random((M, K), dtype=np.float32) * 2 - 1).pin_memory()
+    W = torch.from_numpy(rng.random((K, N), dtype=np.float32) * 2 - 1).pin_memory()
+    b = torch.from_numpy(rng.standard_normal(N).astype(np.float32))
+    out = qg.quantized_mm_host(X, W, bias=b)
+    assert same_f32(out.numpy(), oracle.quantized_mm(X.numpy(), W.numpy(), 127.0, bias=b.numpy()))
+
+
+def test_split_k_slices_live_in_the_callers_workspace(qg, oracle):
+    """Two streams running the same decode-shaped linear (split-K) with their OWN workspaces must not share
+    scratch: results equal the oracle on both, many times over."""
+    M, N, K = 128, 2048, 16384
+    rng = np.random.default_rng(5)
+    Wh = (rng.random((K, N), dtype=np.float32) * 2 - 1)
+    Wt, Cw = qg.prepare_weights(to_dev(Wh), 127.0, qg.MODE_REF_EXACT)
+    assert qg.workspace_bytes(M, N, K) > M * K + 4 * (M + N) + 2 * 4 * M * N  # the slices are part of the block
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    Xs = [rng.random((M, K), dtype=np.float32) * 2 - 1 for _ in range(2)]
+    exp = [oracle.quantized_mm(x, Wh) for x in Xs]
+    dX = [to_dev(x) for x in Xs]
+    Ys = [torch.empty((M, N), device=DEV) for _ in range(2)]
+    wss = [torch.empty(qg.workspace_bytes(M, N, K), dtype=torch.uint8, device=DEV) for _ in range(2)]
+    torch.cuda.synchronize()
+    for _ in range(20):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                qg.linear_forward(dX[i], Wt, Cw, None, Ys[i], workspace=wss[i])
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert same_f32(Ys[i].cpu().numpy(), exp[i])
+
+
+def test_weight_quantization_on_two_streams(qg, oracle):
+    """The column-maximum scratch is per (device, stream): concurrent per-call weight quantizations on two
+    streams give the same bits as sequential ones."""
+    rng = np.random.default_rng(6)
+    Ws = [make_edge_matrix(rng, 1500, 2048).T.copy() for _ in range(2)]  # [2048, 1500]
+    exp = [oracle.absmax_quant_cols(w) for w in Ws]
+    dW = [to_dev(w) for w in Ws]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [(torch.empty(w.shape, dtype=torch.int8, device=DEV), torch.empty(w.shape[1], device=DEV)) for w in Ws]
+    torch.cuda.synchronize()
+    for _ in range(10):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                qg.absmax_quant_cols(dW[i], 127.0, qg.MODE_REF_EXACT, outs[i][0], outs[i][1])
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert np.array_equal(outs[i][0].cpu().numpy(), exp[i][0]) and same_f32(outs[i][1].cpu().numpy(), exp[i][1])
+
+
+def test_second_device_in_one_process(qg, oracle):
+    """cudaFuncSetAttribute (the > 48 KB shared-memory opt-in) is per device: the tcgen05 GEMM, the softmax and
+    the ADD & NORM kernels must launch on device 1 after device 0 has used them, in the same process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs in one process")
+    rng = np.random.default_rng(8)
+    X = rng.random((300, 640), dtype=np.float32) * 2 - 1
+    W = rng.random((640, 512), dtype=np.float32) * 2 - 1
+    exp = oracle.quantized_mm(X, W)
+    S = rng.standard_normal((64, 600)).astype(np.float32)
+    for d in (0, 1, 0):
+        with torch.cuda.device(d):
+            dev = f"cuda:{d}"
+            O = torch.empty((300, 512), device=dev)
+            qg.op_quantized_mm(torch.from_numpy(X).to(dev), torch.from_numpy(W).to(dev), O, 127.0)
+            P = torch.empty((64, 600), device=dev)
+            qg.op_softmax(torch.from_numpy(S).to(dev), P)
+            torch.cuda.synchronize()
+            assert same_f32(O.cpu().numpy(), exp)
+            np.testing.assert_allclose(P.cpu().numpy(), oracle.softmax_rows(S), rtol=2e-6)

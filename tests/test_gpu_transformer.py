@@ -152,22 +152,53 @@ def test_encoder_block_matches_live_reference_and_batches(tf, ref, oracle, h, d_
         assert np.median(err) <= 1e-4 * max(1.0, np.abs(expect).max())
 
 
-def test_decoder_block_batched_equals_per_sequence(tf):
-    """No reference composite for the decoder (transformer.cu does not compile): its pieces are the
-    pinned ones; here the batched call must equal per-sequence calls bit for bit, in place included."""
-    g = torch.Generator(device="cuda").manual_seed(5)
-    d_model, heads, d_ff, s, s_enc = 64, 4, 96, 24, 40
-    blk = tf.DecoderBlock(d_model, heads, d_ff)
-    blk.init_uniform(g)
-    x = torch.rand((2 * s, d_model), device="cuda", generator=g) * 2 - 1
-    enc = torch.rand((2 * s_enc, d_model), device="cuda", generator=g) * 2 - 1
-    both = torch.empty_like(x)
-    blk.forward(x, enc, both, batch=2)
-    for b in range(2):
-        one = torch.empty((s, d_model), device="cuda")
-        blk.forward(x[b * s:(b + 1) * s], enc[b * s_enc:(b + 1) * s_enc], one)
-        assert torch.equal(one.view(torch.int32), both[b * s:(b + 1) * s].view(torch.int32))
-    xin = x.clone()
-    blk.forward(xin, enc, xin, batch=2)  # in place, as later loop iterations run (transformer.cu:104-106)
+def load_decoder_block(tf, X, heads, d_ff, sa, ca, W1, b1, W2, b2):
+    """DecoderBlock with the given weights ([heads, d_model, d] stacks -> the fused column layout)."""
+    blk = tf.DecoderBlock(X.shape[1], int(heads), int(d_ff))
+    for attn, wo, w in ((blk.self_attn, blk.W_O1, sa), (blk.cross_attn, blk.W_O2, ca)):
+        W = np.concatenate([np.concatenate(list(w[k]), axis=1) for k in ("Wq", "Wk", "Wv")], axis=1)
+        attn.W_qkv.copy_(to_dev(np.ascontiguousarray(W)))
+        wo.w.copy_(to_dev(w["W_O"]))
+    blk.ll1.w.copy_(to_dev(W1)); blk.ll1.b.copy_(to_dev(b1))
+    blk.ll2.w.copy_(to_dev(W2)); blk.ll2.b.copy_(to_dev(b2))
+    return blk
+
+
+def _unflatten_decoder_fixture(g):
+    sa = {k: g[f"sa_{k}"] for k in ("Wq", "Wk", "Wv", "W_O")}
+    ca = {k: g[f"ca_{k}"] for k in ("Wq", "Wk", "Wv", "W_O")}
+    return dict(sa=sa, ca=ca, W1=g["W1"], b1=g["b1"], W2=g["W2"], b2=g["b2"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_dec_*.npz"))))
+def test_decoder_block_matches_reference_fixture_bit_for_bit(tf, path):
+    """One Decoder-loop iteration (transformer.cu:91-166) composed from the REFERENCE's kernels on a B200
+    (oracle/ref_driver.cu: ref_decoder_block), committed as a fixture."""
+    g = np.load(path)
+    blk = load_decoder_block(tf, g["X"], g["heads"], g["d_ff"], **_unflatten_decoder_fixture(g))
+    out = torch.empty(g["X"].shape, device="cuda")
+    blk.forward(to_dev(g["X"]), to_dev(g["E"]), out)
+    assert same_f32(out.cpu().numpy(), g["out"])
+
+
+@pytest.mark.parametrize("h,h_enc,d_model,heads,d_ff", [(6, 6, 8, 4, 8), (24, 40, 64, 4, 96), (128, 96, 128, 8, 256)])
+def test_decoder_block_matches_live_reference_and_batches(tf, ref, h, h_enc, d_model, heads, d_ff):
+    """The same composite run live beside the new path: bit-exact; a batched call equals per-sequence reference
+    runs; an in-place call (later loop iterations, transformer.cu:104-106) equals the out-of-place one."""
+    from make_ref_fixtures import decoder_weights, run_ref_decoder_block
+
+    rng = np.random.default_rng(h * 17 + d_model)
+    w = decoder_weights(rng, d_model, heads, d_ff)
+    X = [(rng.random((h, d_model), dtype=np.float32) * 2 - 1) for _ in range(2)]
+    E = [(rng.random((h_enc, d_model), dtype=np.float32) * 2 - 1) for _ in range(2)]
+    expect = [run_ref_decoder_block(ref, X[b], E[b], heads, d_ff, **w) for b in range(2)]
+    blk = load_decoder_block(tf, X[0], heads, d_ff, **w)
+    out = torch.empty((h, d_model), device="cuda")
+    blk.forward(to_dev(X[0]), to_dev(E[0]), out)
+    assert same_f32(out.cpu().numpy(), expect[0])
+    both = torch.empty((2 * h, d_model), device="cuda")
+    blk.forward(to_dev(np.concatenate(X)), to_dev(np.concatenate(E)), both, batch=2)
+    assert same_f32(both[:h].cpu().numpy(), expect[0]) and same_f32(both[h:].cpu().numpy(), expect[1])
+    xin = to_dev(np.concatenate(X))
+    blk.forward(xin, to_dev(np.concatenate(E)), xin, batch=2)
     assert torch.equal(xin.view(torch.int32), both.view(torch.int32))
-    assert torch.isfinite(both).all()

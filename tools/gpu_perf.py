@@ -203,6 +203,37 @@ def lib_ref(size):
     return {"cublaslt_int8_us": u8, "cublaslt_int8_tops": ops / u8 / 1e6, "cublas_fp16_us": u16, "cublas_fp16_tflops": ops / u16 / 1e6}
 
 
+def gemm_inop(size, out="f32"):
+    """The GEMM launch bracketed by CUDA events INSIDE the op sequence (rows quantizer, columns quantizer, GEMM),
+    as bench.py's instrumented pass times it: start-to-end of one launch, not a back-to-back average."""
+    import statistics
+
+    import torch
+
+    qg = pkg()
+    M = N = K = size
+    X = [torch.rand((M, K), device="cuda") * 2 - 1 for _ in range(2)]
+    W = [torch.rand((K, N), device="cuda") * 2 - 1 for _ in range(2)]
+    O = [torch.empty((M, N), dtype=torch.float32 if out == "f32" else torch.float16, device="cuda") for _ in range(2)]
+    Xq = torch.empty((M, K), dtype=torch.int8, device="cuda")
+    Wq = torch.empty((K, N), dtype=torch.int8, device="cuda")
+    Cx, Cw = torch.empty(M, device="cuda"), torch.empty(N, device="cuda")
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(30)]
+    for i in range(35):
+        e = evs[max(0, i - 5)]
+        e[0].record()
+        qg.absmax_quant_rows(X[i & 1], 127.0, 0, Xq, Cx)
+        e[1].record()
+        qg.absmax_quant_cols(W[i & 1], 127.0, 0, Wq, Cw)
+        e[2].record()
+        qg.gemm_s8_dequant(Xq, Wq, Cx, Cw, O[i & 1], 127.0)
+        e[3].record()
+    torch.cuda.synchronize()
+    med = lambda a, b: statistics.median(e[a].elapsed_time(e[b]) for e in evs) * 1e3
+    return {"rows_us": med(0, 1), "cols_us": med(1, 2), "gemm_us": med(2, 3), "total_us": med(0, 3),
+            "gemm_tops": 2.0 * M * N * K / med(2, 3) / 1e6}
+
+
 EXPERIMENTS = {
     # name: (function, args, env)
     "lib_4096": (lib_ref, (4096,), {}),
@@ -221,6 +252,19 @@ EXPERIMENTS = {
     "stats_1sm_2048_f32": (gemm_stats, ("TC_1SM", 2048, "f32"), {}),
     "stats_2sm_1024_f32": (gemm_stats, ("TC_2SM", 1024, "f32"), {}),
     "stats_1sm_1024_f32": (gemm_stats, ("TC_1SM", 1024, "f32"), {}),
+    "r2_stats_2sm_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {}),
+    "r2_stats_2sm_4096_f32_noring": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_NO_LAST_RING": "1"}),
+    "r2_stats_2sm_4096_f32_noepi": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_NOEPI": "1"}),
+    "r2_stats_2sm_4096_f32_noepi_noload": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_NOEPI": "1", "QG_DBG_NOLOAD": "1"}),
+    "r2_stats_2sm_4096_f32_mn": (gemm_stats, ("TC_2SM", 4096, "f32", False), {}),
+    "r2_stats_2sm_4096_f32_mn_noring": (gemm_stats, ("TC_2SM", 4096, "f32", False), {"QG_NO_LAST_RING": "1"}),
+    "r2_stats_2sm_8192_f32": (gemm_stats, ("TC_2SM", 8192, "f32"), {}),
+    "r2_stats_2sm_8192_f32_noepi": (gemm_stats, ("TC_2SM", 8192, "f32"), {"QG_DBG_NOEPI": "1"}),
+    "r2_stats_2sm_2048_f32": (gemm_stats, ("TC_2SM", 2048, "f32"), {}),
+    "r2_inop_4096": (gemm_inop, (4096,), {}),
+    "r2_inop_4096_noring": (gemm_inop, (4096,), {"QG_NO_LAST_RING": "1"}),
+    "r2_inop_4096_f16": (gemm_inop, (4096, "f16"), {}),
+    "r2_inop_8192": (gemm_inop, (8192,), {}),
     "quant_4096": (quantizers, (4096,), {}),
     "quant_4096_twopass": (quantizers, (4096,), {"QG_COLS_TWO_PASS": "1"}),
     "quant_4096_f16": (quantizers, (4096, "f16"), {}),
