@@ -429,3 +429,17 @@ def fast_quantized_mm(X, W, range_=127.0, mode=MODE_REF_EXACT, bias=None, return
     if return_parts:
         return O, dict(Cx=Cx, Cw=Cw, Xq=Xq, Wq=Wq, acc=acc)
     return O
+
+
+def decoder_block(X, E, sa_Wqkv, sa_W_O, ca_Wqkv, ca_W_O, W1, b1, W2, b2, heads, batch=1, range_=127.0, mode=MODE_REF_EXACT):
+    """One iteration of the Decoder loop (transformer.cu:91-166): self-attention, ADD & NORM, cross-attention
+    (queries from the decoder stream, keys / values from the encoder output E), ADD & NORM, FFN, ADD & NORM --
+    every product on weights through op_quantized_mm, residuals taken from the attention outputs (:123,148,165)."""
+    d = X.shape[1] // heads
+    mh = multi_head_attention(X, X, sa_Wqkv, heads, d, d, batch, range_, mode)      # :97-116
+    out = add_layernorm(quantized_mm(mh, sa_W_O, range_, mode), mh)                  # :117-124
+    mh = multi_head_attention(out, E, ca_Wqkv, heads, d, d, batch, range_, mode)    # :127-141
+    out = add_layernorm(quantized_mm(mh, ca_W_O, range_, mode), mh)                  # :142-149
+    ffn = relu(quantized_mm(out, W1, range_, mode, bias=b1))                         # :152-157
+    out = quantized_mm(ffn, W2, range_, mode, bias=b2)                               # :159-161
+    return add_layernorm(out, mh)                                                    # :165-166

@@ -229,6 +229,19 @@ __device__ __forceinline__ void tma_store_2d(const void *desc, uint32_t src, int
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(desc), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// the same store carrying an L2 eviction policy (createpolicy.fractional.L2::*): output tiles are written once
+// and not read again by the kernel that produces them
+__device__ __forceinline__ void tma_store_2d_hint(const void *desc, uint32_t src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(desc), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 1: evict_first, 2: evict_last, else evict_normal
+  uint64_t pol;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");

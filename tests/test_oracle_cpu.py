@@ -239,3 +239,19 @@ def test_fast_cpu_gemm_extreme_codes(oracle):
     A[1, :], B[:, 1] = 127, -128
     assert np.array_equal(oracle.fast_gemm_s8s8s32(A, B), oracle.gemm_s8s8s32(A, B))
     assert np.array_equal(oracle.fast_gemm_s8s8s32(A, B), A.astype(np.int64) @ B.astype(np.int64))
+
+
+@pytest.mark.parametrize("path", sorted(_glob.glob(os.path.join(_GOLDEN, "ref_dec_*.npz"))))
+def test_oracle_decoder_block_vs_reference_kernels(oracle, path):
+    """The decoder composite of the reference's kernels (oracle/ref_driver.cu: ref_decoder_block, run on a B200)
+    against the CPU restatement.  libm's expf is not the device's, and a last-bit difference in a softmax can move
+    an int8 code downstream, so the bound is statistical (as for the encoder); the bit-exact check of the CUDA path
+    against this fixture is tests/test_gpu_transformer.py."""
+    g = np.load(path)
+    cat = lambda pre: np.ascontiguousarray(np.concatenate(
+        [np.concatenate(list(g[f"{pre}_{k}"]), axis=1) for k in ("Wq", "Wk", "Wv")], axis=1))
+    o = oracle.decoder_block(g["X"], g["E"], cat("sa"), g["sa_W_O"], cat("ca"), g["ca_W_O"], g["W1"], g["b1"], g["W2"], g["b2"],
+                             int(g["heads"]))
+    assert o.shape == g["out"].shape
+    err = np.abs(o - g["out"])
+    assert np.median(err) <= 1e-4 * max(1.0, np.abs(g["out"]).max())

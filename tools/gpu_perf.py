@@ -261,6 +261,23 @@ EXPERIMENTS = {
     "r2_stats_2sm_8192_f32": (gemm_stats, ("TC_2SM", 8192, "f32"), {}),
     "r2_stats_2sm_8192_f32_noepi": (gemm_stats, ("TC_2SM", 8192, "f32"), {"QG_DBG_NOEPI": "1"}),
     "r2_stats_2sm_2048_f32": (gemm_stats, ("TC_2SM", 2048, "f32"), {}),
+    "r2_clusters74_noepi_noload": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_NOEPI": "1", "QG_DBG_NOLOAD": "1", "QG_NO_TAIL_SPLIT": "1"}),
+    "r2_clusters64_noepi_noload": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_NOEPI": "1", "QG_DBG_NOLOAD": "1", "QG_DBG_MAX_CLUSTERS": "64", "QG_NO_TAIL_SPLIT": "1"}),
+    "r2_clusters32_noepi_noload": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_NOEPI": "1", "QG_DBG_NOLOAD": "1", "QG_DBG_MAX_CLUSTERS": "32", "QG_NO_TAIL_SPLIT": "1"}),
+    "r2_clusters8_noepi_noload": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_NOEPI": "1", "QG_DBG_NOLOAD": "1", "QG_DBG_MAX_CLUSTERS": "8", "QG_NO_TAIL_SPLIT": "1"}),
+    "r2_clusters8_full": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_MAX_CLUSTERS": "8", "QG_NO_TAIL_SPLIT": "1"}),
+    "r2_epi1_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_EPI_LEVEL": "1"}),
+    "r2_epi1_4096_s32": (gemm_stats, ("TC_2SM", 4096, "s32"), {"QG_DBG_EPI_LEVEL": "1"}),
+    "r2_epi2_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_EPI_LEVEL": "2"}),
+    "r2_epi2_4096_s32": (gemm_stats, ("TC_2SM", 4096, "s32"), {"QG_DBG_EPI_LEVEL": "2"}),
+    "r2_epi0_4096_s32": (gemm_stats, ("TC_2SM", 4096, "s32"), {}),
+    "r2_epi0_4096_f16": (gemm_stats, ("TC_2SM", 4096, "f16"), {}),
+    "r2_epi0_4096_f32_nostore_tma": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_DBG_NO_TMA_STORE": "1"}),
+    "r2_hint0_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {}),
+    "r2_hint1_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_STORE_HINT": "1"}),
+    "r2_hint2_4096_f32": (gemm_stats, ("TC_2SM", 4096, "f32"), {"QG_STORE_HINT": "2"}),
+    "r2_hint1_8192_f32": (gemm_stats, ("TC_2SM", 8192, "f32"), {"QG_STORE_HINT": "1"}),
+    "r2_hint0_8192_f32": (gemm_stats, ("TC_2SM", 8192, "f32"), {}),
     "r2_inop_4096": (gemm_inop, (4096,), {}),
     "r2_inop_4096_noring": (gemm_inop, (4096,), {"QG_NO_LAST_RING": "1"}),
     "r2_inop_4096_f16": (gemm_inop, (4096, "f16"), {}),
