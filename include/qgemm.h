@@ -22,13 +22,14 @@
  *   - every launch goes to `stream` (a cudaStream_t; NULL = the legacy default stream the
  *     reference uses).  No call synchronises the device; no call allocates unless stated.
  *   - there is no CPU fallback: without an sm_100 device every compute call fails.
- *   - re-entrancy: like the reference (everything on the legacy default stream) the library assumes
- *     one stream of calls per device at a time.  Entry points that quantize weight columns
- *     (qg_absmax_cols, qg_quantize_cols without given scales, qg_absmax_quant_cols, qg_prepare_weights,
- *     qg_quantized_mm*) share a per-device column-maximum scratch; entry points called with
- *     workspace == NULL, qg_quantized_mm_host and qg_attention_forward share grow-only per-device
- *     buffers.  Calls on different devices, and calls that pass their own workspace and prepared
- *     weights (qg_linear_forward*), are independent.
+ *   - re-entrancy: calls on different devices are independent, and so are calls on different streams of
+ *     one device as long as each passes its OWN workspace (qg_workspace_bytes covers every temporary of
+ *     qg_quantized_mm / qg_linear_forward*, the int32 slice matrices of a split-K product included) and its
+ *     own prepared weights.  The column-maximum scratch of the weight quantizers is kept per (device,
+ *     stream).  What IS shared per device, as in the reference (everything on the legacy default stream):
+ *     the grow-only buffers behind workspace == NULL, qg_quantized_mm_host and qg_attention_forward, and the
+ *     split-K slices of the entry points that take no workspace argument (qg_gemm_s8*); growing one of those
+ *     buffers allocates and synchronises the device once.
  */
 #ifndef QGEMM_H_
 #define QGEMM_H_
@@ -242,6 +243,31 @@ QG_API int qg_softmax_rows_f32(const float *A, int64_t lda, int m, int n, float 
 QG_API int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq,
                                 int skv, int d_model, const float *Wqkv, int64_t ldw, int heads, int d_k, int d_v,
                                 float range, int mode, float *out, int64_t ldo, qg_stream_t stream);
+
+/* ---- the elementwise tail of the pipeline, op by op ------------------------------------------------
+ * The fused epilogue makes these unnecessary on the fast path; they let the reference's step-by-step
+ * sequence (src/timing_quantize.cu:38-58,67-70) be re-pointed one call at a time with identical bits.
+ * B is [b_rows, b_cols]: the same shape as A, [1, n] (repeated down the rows) or [m, 1] (across the
+ * columns) -- the broadcast rule of op_elemwise_binary_w_bcast_kernel, src/ops/op_elemwise.cuh:404-424.
+ * O may alias A. */
+/* op_add(a, b, out)  src/ops/op_elemwise.cuh:501-512 (AddFunc :57-65) */
+QG_API int qg_add_f32(const float *A, int64_t lda, const float *B, int64_t ldb, int b_rows, int b_cols, float *O,
+                      int64_t ldo, int m, int n, qg_stream_t stream);
+/* op_subtract(a, b, out)  src/ops/op_elemwise.cuh:531-542 (timing_quantize.cu:68: C - qC) */
+QG_API int qg_subtract_f32(const float *A, int64_t lda, const float *B, int64_t ldb, int b_rows, int b_cols, float *O,
+                           int64_t ldo, int m, int n, qg_stream_t stream);
+/* op_multiply(a, b, out) with T == OutT == float  src/ops/op_elemwise.cuh:629-640 (MultiplyFunc :81-91) */
+QG_API int qg_multiply_f32(const float *A, int64_t lda, const float *B, int64_t ldb, int b_rows, int b_cols, float *O,
+                           int64_t ldo, int m, int n, qg_stream_t stream);
+/* op_multiply(a, T b, out)  src/ops/op_elemwise.cuh:644-654 (MultiplyConstFunc :118-129; op_mm.cuh:99) */
+QG_API int qg_multiply_const_f32(const float *A, int64_t lda, float c, float *O, int64_t ldo, int m, int n,
+                                 qg_stream_t stream);
+/* op_relu(t, out)  src/ops/op_elemwise.cuh:454-465 (ReluFunc :181-195: x < 0 ? 0 : x) */
+QG_API int qg_relu_f32(const float *A, int64_t lda, float *O, int64_t ldo, int m, int n, qg_stream_t stream);
+/* op_dequantize(a, b, out)  src/ops/op_elemwise.cuh:614-625 (DequantizeFunc :93-103): out = (float)acc * outer,
+ * over a MATERIALISED outer-product matrix, exactly as op_mm.cuh:96-98 spells it */
+QG_API int qg_dequantize_outer_f32(const int32_t *acc, int64_t ldacc, const float *outer, int64_t ldouter, float *O,
+                                   int64_t ldo, int m, int n, qg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
     "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_mm_f32",
     "qg_softmax_rows_f32", "qg_attention_forward", "qg_linear_forward_act", "qg_add_layernorm_f32",
+    "qg_add_f32", "qg_subtract_f32", "qg_multiply_f32", "qg_multiply_const_f32", "qg_relu_f32", "qg_dequantize_outer_f32",
 ]
 
 

@@ -76,19 +76,83 @@ void op_inv_divide(const TensorT &a, T b, TensorT &out) {
   check(qg_inv_divide_f32(base_ptr(a), (int64_t)a.h * a.w, (float)b, base_ptr(out), nullptr), "qg_inv_divide_f32");
 }
 
-// op_multiply<T,int8_t>(a, scale, out): src/ops/op_elemwise.cuh:629-640
+// rows of a [h,w] view as a leading dimension the C ABI accepts (a size-1 dimension may carry any stride)
+template <class TensorT>
+int64_t ld_of(const TensorT &t) { return t.h > 1 ? t.stride_h : (t.stride_h >= t.w ? t.stride_h : t.w); }
+
+// op_multiply<T,OutT>(a, b, out): src/ops/op_elemwise.cuh:629-640.  OutT == int8_t is the quantizing cast with a
+// broadcast scale vector (a4 of the hot path); OutT == T is the plain elementwise product (:598-610).
 template <class TensorA, class TensorQ>
 void op_multiply(const TensorA &a, const TensorA &b, TensorQ &out) {
-  static_assert(sizeof(*out.rawp) == 1, "quantizing overload: out must be int8");
   assert(out.h == a.h && out.w == a.w);
-  assert((a.h == b.h && b.w == 1) || (a.w == b.w && b.h == 1));
+  assert((a.h == b.h && a.w == b.w) || (a.h == b.h && b.w == 1) || (a.w == b.w && b.h == 1));
   assert(a.on_device && b.on_device && out.on_device);
-  if (b.w == 1 && a.h == b.h && a.w != b.w)
-    check(qg_quantize_rows(base_ptr(a), QG_F32, a.h, a.w, a.stride_h, base_ptr(b), base_ptr(out), out.stride_h, nullptr),
-          "qg_quantize_rows");
-  else
-    check(qg_quantize_cols(base_ptr(a), QG_F32, a.h, a.w, a.stride_h, base_ptr(b), base_ptr(out), out.stride_h, nullptr),
-          "qg_quantize_cols");
+  assert(unit_inner(a) && unit_inner(out));
+  if (sizeof(*out.rawp) == 1) {
+    assert((a.h == b.h && b.w == 1) || (a.w == b.w && b.h == 1));
+    if (b.w == 1 && a.h == b.h && a.w != b.w)
+      check(qg_quantize_rows(base_ptr(a), QG_F32, a.h, a.w, ld_of(a), (const float *)base_ptr(b), (int8_t *)base_ptr(out),
+                             ld_of(out), nullptr), "qg_quantize_rows");
+    else
+      check(qg_quantize_cols(base_ptr(a), QG_F32, a.h, a.w, ld_of(a), (const float *)base_ptr(b), (int8_t *)base_ptr(out),
+                             ld_of(out), nullptr), "qg_quantize_cols");
+  } else {
+    check(qg_multiply_f32((const float *)base_ptr(a), ld_of(a), (const float *)base_ptr(b), ld_of(b), b.h, b.w,
+                          (float *)base_ptr(out), ld_of(out), a.h, a.w, nullptr), "qg_multiply_f32");
+  }
+}
+
+// op_multiply(a, T b, out): src/ops/op_elemwise.cuh:644-654 (the 1/range^2 step of op_mm.cuh:99)
+template <class TensorT, typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
+void op_multiply(const TensorT &a, T b, TensorT &out) {
+  assert(out.h == a.h && out.w == a.w);
+  assert(a.on_device && out.on_device && unit_inner(a) && unit_inner(out));
+  check(qg_multiply_const_f32(base_ptr(a), ld_of(a), (float)b, base_ptr(out), ld_of(out), a.h, a.w, nullptr),
+        "qg_multiply_const_f32");
+}
+
+// op_dequantize(a, b, out): src/ops/op_elemwise.cuh:614-625 -- out = (float)a * b over a materialised b
+template <class TensorI, class TensorF>
+void op_dequantize(const TensorI &a, const TensorF &b, TensorF &out) {
+  assert(out.h == a.h && out.w == a.w);
+  assert(a.h == b.h && a.w == b.w);  // the pipeline's call site (op_mm.cuh:98) passes the full outer product
+  assert(a.on_device && b.on_device && out.on_device && unit_inner(a) && unit_inner(b) && unit_inner(out));
+  check(qg_dequantize_outer_f32((const int32_t *)base_ptr(a), ld_of(a), base_ptr(b), ld_of(b), base_ptr(out), ld_of(out), a.h,
+                                a.w, nullptr), "qg_dequantize_outer_f32");
+}
+
+// op_add(a, b, out) / op_subtract(a, b, out): src/ops/op_elemwise.cuh:501-512, 531-542 (broadcast rule :410-421)
+template <class TensorT>
+void op_add(const TensorT &a, const TensorT &b, TensorT &out) {
+  assert(out.h == a.h && out.w == a.w);
+  assert((a.h == b.h && a.w == b.w) || (a.h == b.h && b.w == 1) || (a.w == b.w && b.h == 1));
+  assert(a.on_device && b.on_device && out.on_device && unit_inner(a) && unit_inner(b) && unit_inner(out));
+  check(qg_add_f32(base_ptr(a), ld_of(a), base_ptr(b), ld_of(b), b.h, b.w, base_ptr(out), ld_of(out), a.h, a.w, nullptr),
+        "qg_add_f32");
+}
+template <class TensorT>
+void op_subtract(const TensorT &a, const TensorT &b, TensorT &out) {
+  assert(out.h == a.h && out.w == a.w);
+  assert((a.h == b.h && a.w == b.w) || (a.h == b.h && b.w == 1) || (a.w == b.w && b.h == 1));
+  assert(a.on_device && b.on_device && out.on_device && unit_inner(a) && unit_inner(b) && unit_inner(out));
+  check(qg_subtract_f32(base_ptr(a), ld_of(a), base_ptr(b), ld_of(b), b.h, b.w, base_ptr(out), ld_of(out), a.h, a.w, nullptr),
+        "qg_subtract_f32");
+}
+
+// op_relu(t, out): src/ops/op_elemwise.cuh:454-465
+template <class TensorT>
+void op_relu(const TensorT &t, TensorT &out) {
+  assert(out.h == t.h && out.w == t.w);
+  assert(t.on_device && out.on_device && unit_inner(t) && unit_inner(out));
+  check(qg_relu_f32(base_ptr(t), ld_of(t), base_ptr(out), ld_of(out), t.h, t.w, nullptr), "qg_relu_f32");
+}
+
+// op_layernorm(A, B): src/ops/op_layernorm.cuh:34-44 -- (x - mean) / var with ascending-order sums; every row
+template <class TensorT>
+void op_layernorm(const TensorT &A, TensorT &B) {
+  assert(A.h == B.h && A.w == B.w);
+  assert(A.on_device && B.on_device && unit_inner(A) && unit_inner(B));
+  check(qg_add_layernorm_f32(base_ptr(A), ld_of(A), nullptr, 0, A.h, A.w, base_ptr(B), ld_of(B), nullptr), "qg_add_layernorm_f32");
 }
 
 // op_mm<T,OutT>(A, B, C): src/ops/op_mm.cuh:49-65
@@ -238,6 +302,16 @@ class Tensor {
   }
 };
 
+// non-owning view over any tensor type with the reference's public fields
+template <class AnyTensor>
+Tensor<float> view_of(const AnyTensor &t) {
+  Tensor<float> v;
+  v.h = t.h; v.w = t.w; v.stride_h = t.stride_h; v.stride_w = t.stride_w; v.offset = t.offset;
+  v.rawp = const_cast<float *>(reinterpret_cast<const float *>(t.rawp));
+  v.on_device = t.on_device;
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------
 // The reference's module classes on the quantized path (inference side): same names, members and
 // call signatures as src/modules/param.cuh, linear.cuh:7-72 and attention.cuh:10-70, templated on the
@@ -330,5 +404,165 @@ class AttentionLayer {
     attention_forward(Xq, Xkv, W_q.t, W_k.t, W_v.t, output);
   }
 };
+
+// ------------------------------------------------------------------------------------------
+// Encoder / Decoder of src/transformer.cu:14-168 on the quantized path.
+//
+// The reference functions re-draw every weight (op_uniform_init) inside every call, run one single-head
+// AttentionLayer per head and concatenate the heads through the host.  Here a block owns its weights (drawn once,
+// int8 codes prepared on first use); all heads' projections are one quantized product (qg_attention_forward with
+// heads > 1, W_q | W_k | W_v of all heads packed side by side); W_O and the FFN go through qg_linear_forward_act
+// (ReLU inside the GEMM epilogue); ADD & NORM is qg_add_layernorm_f32.  Every step keeps the reference's
+// arithmetic, including its quirks: the residual added is the attention output (:57,74,123,148,165), W_O is drawn
+// from U(-1, 1) (:53), the "layernorm" divides by the variance.  `batch` independent sequences per call (the
+// reference has none: batch = 1).  The free functions Encoder(...) / Decoder(...) keep the reference's
+// signatures and its "fresh random weights on every call" behaviour.
+// ------------------------------------------------------------------------------------------
+template <template <typename> class TensorT = Tensor>
+class PreparedLinear {  // y = act(x @ w [+ b]); bias optional (W_O is a bare product, transformer.cu:52-54)
+ public:
+  int in_dim = 0, out_dim = 0;
+  TensorT<float> w, b;
+  bool has_bias = true;
+  PreparedLinear() = default;
+  PreparedLinear(int in_dim_, int out_dim_, bool bias) : in_dim(in_dim_), out_dim(out_dim_), w(in_dim_, out_dim_, true),
+                                                         b(1, out_dim_, true), has_bias(bias) {}
+  void init_uniform(uint64_t seed, float lo = 0.0f, float hi = 0.0f) {
+    const float mx = 1.0f / std::sqrt((float)in_dim);  // linear.cuh:33-39
+    uniform_init(w, lo == hi ? -mx : lo, lo == hi ? mx : hi, seed);
+    uniform_init(b, -mx, mx, seed + 1);
+    prepared_ = false;
+  }
+  void invalidate() { prepared_ = false; }
+  void forward(const TensorT<float> &x, TensorT<float> &y, int act = QG_ACT_NONE) {
+    assert(x.w == in_dim && y.h == x.h && y.w == out_dim && x.on_device && y.on_device);
+    if (!prepared_) {
+      wt_ = TensorT<int8_t>(out_dim, (in_dim + 15) / 16 * 16, true);
+      cw_ = TensorT<float>(1, out_dim, true);
+      check(qg_prepare_weights(base_ptr(w), QG_F32, in_dim, out_dim, w.stride_h, 127.0f, QG_MODE_REF_EXACT, wt_.rawp,
+                               wt_.stride_h, cw_.rawp, nullptr), "qg_prepare_weights");
+      prepared_ = true;
+    }
+    check(qg_linear_forward_act(base_ptr(x), ld_of(x), QG_F32, wt_.rawp, wt_.stride_h, cw_.rawp, has_bias ? base_ptr(b) : nullptr,
+                                act, base_ptr(y), ld_of(y), QG_F32, x.h, out_dim, in_dim, 127.0f, QG_MODE_REF_EXACT, nullptr, 0,
+                                nullptr), "qg_linear_forward_act");
+  }
+
+ private:
+  TensorT<int8_t> wt_;
+  TensorT<float> cw_;
+  bool prepared_ = false;
+};
+
+// all heads of one attention sub-layer: W_qkv [d_model, heads * (2 d_k + d_v)] = [ W_q of every head | W_k ... | W_v ... ]
+template <template <typename> class TensorT = Tensor>
+class MultiHeadAttention {
+ public:
+  int d_model = 0, heads = 0, d_k = 0, d_v = 0;
+  TensorT<float> W_qkv;
+  MultiHeadAttention() = default;
+  MultiHeadAttention(int d_model_, int heads_) : d_model(d_model_), heads(heads_), d_k(d_model_ / heads_), d_v(d_model_ / heads_),
+                                                 W_qkv(d_model_, heads_ * 3 * (d_model_ / heads_), true) {}
+  void init_uniform(uint64_t seed) {  // attention.cuh:40-45, every head
+    const float mx = 1.0f / std::sqrt((float)d_k);
+    uniform_init(W_qkv, -mx, mx, seed);
+  }
+  // queries from xq, keys / values from xkv (the same tensor for self-attention); out [rows, heads * d_v]
+  void forward(const TensorT<float> &xq, const TensorT<float> &xkv, TensorT<float> &out, int batch = 1) {
+    assert(xq.w == d_model && xkv.w == d_model && out.h == xq.h && out.w == heads * d_v);
+    assert(xq.h % batch == 0 && xkv.h % batch == 0);
+    check(qg_attention_forward(base_ptr(xq), ld_of(xq), base_ptr(xkv), ld_of(xkv), batch, xq.h / batch, xkv.h / batch, d_model,
+                               base_ptr(W_qkv), W_qkv.stride_h, heads, d_k, d_v, 127.0f, QG_MODE_REF_EXACT, base_ptr(out),
+                               ld_of(out), nullptr), "qg_attention_forward");
+  }
+};
+
+template <class TensorF>
+void add_layernorm(const TensorF &a, const TensorF &r, TensorF &out) {  // op_add(a, r, out); op_layernorm(out, out)
+  check(qg_add_layernorm_f32(base_ptr(a), ld_of(a), base_ptr(r), ld_of(r), a.h, a.w, base_ptr(out), ld_of(out), nullptr),
+        "qg_add_layernorm_f32");
+}
+
+template <template <typename> class TensorT = Tensor>
+class EncoderBlock {  // one iteration of the loop at transformer.cu:24-76
+ public:
+  int d_model, heads, d_ff;
+  MultiHeadAttention<TensorT> attn;
+  PreparedLinear<TensorT> W_O, ll1, ll2;
+  EncoderBlock(int d_model_, int heads_, int d_ff_)
+      : d_model(d_model_), heads(heads_), d_ff(d_ff_), attn(d_model_, heads_), W_O(d_model_, d_model_, false),
+        ll1(d_model_, d_ff_, true), ll2(d_ff_, d_model_, true) {}
+  void init_uniform(uint64_t seed) {
+    attn.init_uniform(seed);
+    W_O.init_uniform(seed + 10, -1.0f, 1.0f);  // transformer.cu:53
+    ll1.init_uniform(seed + 20);
+    ll2.init_uniform(seed + 30);
+  }
+  void forward(const TensorT<float> &x, TensorT<float> &out, int batch = 1) {
+    TensorT<float> mh(x.h, d_model, true), ffn(x.h, d_ff, true);
+    attn.forward(x, x, mh, batch);       // :27-50
+    W_O.forward(mh, out);                // :52-54
+    add_layernorm(out, mh, out);         // :57-58
+    ll1.forward(out, ffn, QG_ACT_RELU);  // :63-67
+    ll2.forward(ffn, out);               // :69-71
+    add_layernorm(out, mh, out);         // :74-75
+    cudaStreamSynchronize(nullptr);      // the scratch tensors above are freed on return
+  }
+};
+
+template <template <typename> class TensorT = Tensor>
+class DecoderBlock {  // one iteration of the loop at transformer.cu:91-166
+ public:
+  int d_model, heads, d_ff;
+  MultiHeadAttention<TensorT> self_attn, cross_attn;
+  PreparedLinear<TensorT> W_O1, W_O2, ll1, ll2;
+  DecoderBlock(int d_model_, int heads_, int d_ff_)
+      : d_model(d_model_), heads(heads_), d_ff(d_ff_), self_attn(d_model_, heads_), cross_attn(d_model_, heads_),
+        W_O1(d_model_, d_model_, false), W_O2(d_model_, d_model_, false), ll1(d_model_, d_ff_, true), ll2(d_ff_, d_model_, true) {}
+  void init_uniform(uint64_t seed) {
+    self_attn.init_uniform(seed);
+    cross_attn.init_uniform(seed + 5);
+    W_O1.init_uniform(seed + 10, -1.0f, 1.0f);  // transformer.cu:117-118
+    W_O2.init_uniform(seed + 15, -1.0f, 1.0f);  // transformer.cu:143
+    ll1.init_uniform(seed + 20);
+    ll2.init_uniform(seed + 30);
+  }
+  void forward(const TensorT<float> &x, const TensorT<float> &enc_output, TensorT<float> &out, int batch = 1) {
+    TensorT<float> mh(x.h, d_model, true), ffn(x.h, d_ff, true);
+    self_attn.forward(x, x, mh, batch);              // :97-116
+    W_O1.forward(mh, out);                           // :117-119
+    add_layernorm(out, mh, out);                     // :123-124
+    cross_attn.forward(out, enc_output, mh, batch);  // :127-141 (queries: decoder stream; keys / values: encoder output)
+    W_O2.forward(mh, out);                           // :143-144
+    add_layernorm(out, mh, out);                     // :148-149
+    ll1.forward(out, ffn, QG_ACT_RELU);              // :152-157
+    ll2.forward(ffn, out);                           // :159-161
+    add_layernorm(out, mh, out);                     // :165-166
+    cudaStreamSynchronize(nullptr);
+  }
+};
+
+// void Encoder(const Tensor<float> &X, Tensor<float> &output, int n_heads, int n_blocks, int d_ff)  transformer.cu:14
+template <class TensorF>
+void Encoder(const TensorF &X, TensorF &output, int n_heads, int n_blocks, int d_ff, uint64_t seed = 0) {
+  assert(X.h == output.h && X.w == output.w && X.w % n_heads == 0);
+  for (int i = 0; i < n_blocks; i++) {
+    EncoderBlock<Tensor> blk(X.w, n_heads, d_ff);
+    blk.init_uniform(seed + 100 * (uint64_t)i);  // fresh weights per block and call, as the reference draws them
+    Tensor<float> in = view_of(i == 0 ? X : output), out = view_of(output);
+    blk.forward(in, out);  // block 0 reads X, later blocks the running output (:35-39); in place is safe (see transformer.py)
+  }
+}
+// void Decoder(const Tensor<float> &X, Tensor<float> &enc_output, Tensor<float> &output, ...)  transformer.cu:79-80
+template <class TensorF>
+void Decoder(const TensorF &X, TensorF &enc_output, TensorF &output, int n_heads, int n_blocks, int d_ff, uint64_t seed = 0) {
+  assert(X.h == output.h && X.w == output.w && enc_output.w == X.w && X.w % n_heads == 0);
+  for (int i = 0; i < n_blocks; i++) {
+    DecoderBlock<Tensor> blk(X.w, n_heads, d_ff);
+    blk.init_uniform(seed + 100 * (uint64_t)i);
+    Tensor<float> in = view_of(i == 0 ? X : output), enc = view_of(enc_output), out = view_of(output);
+    blk.forward(in, enc, out);
+  }
+}
 
 }  // namespace qg_dropin

@@ -45,6 +45,8 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
                const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act = QG_ACT_NONE,
                int split_k = 1);
+int elemwise(int op, const void *A, int64_t lda, const float *B, int64_t ldb, int bmode, float c, float *O, int64_t ldo, int M,
+             int N, cudaStream_t st);
 int splitk_reduce(const int32_t *parts, int64_t slice_stride, int slices, int64_t ldp, const float *Cx, const float *Cw,
                   const float *bias, int M, int N, float c, int act, void *O, int out_dtype, int64_t ldo, cudaStream_t st);
 
@@ -818,6 +820,60 @@ int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_
   bt.c_outer = (int64_t)sq * ldo;         bt.c_inner = d_v;
   rc = mm_f32(scores, skv, 1, Vp, ldkv, 1, sq, d_v, skv, out, ldo, st, &bt);
   return cuda_status((cudaError_t)rc, "P*V");
+}
+
+/* ---- the elementwise tail of the pipeline, op by op (src/ops/op_elemwise.cuh) ---- */
+static int bcast_mode(int b_rows, int b_cols, int m, int n) {
+  // the reference's rule (op_elemwise.cuh:410-421): [1,n] repeats down the rows, [m,1] across the columns
+  if (b_rows == 1 && b_cols == n && m != 1) return 1;
+  if (b_cols == 1 && b_rows == m && n != 1) return 2;
+  if (b_rows == m && b_cols == n) return 0;
+  return -1;
+}
+static int binary_op(int op, const char *name, const float *A, int64_t lda, const float *B, int64_t ldb, int b_rows, int b_cols,
+                     float *O, int64_t ldo, int m, int n, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  const int bm = bcast_mode(b_rows, b_cols, m, n);
+  QG_REQUIRE(A && B && O && m > 0 && n > 0 && lda >= n && ldo >= n && bm >= 0 && (bm != 0 || ldb >= n) && (bm != 2 || ldb >= 1),
+             "%s: bad arguments (b is %d x %d against %d x %d)", name, b_rows, b_cols, m, n);
+  return cuda_status((cudaError_t)elemwise(op, A, lda, B, ldb, bm, 0.0f, O, ldo, m, n, (cudaStream_t)stream), name);
+}
+int qg_add_f32(const float *A, int64_t lda, const float *B, int64_t ldb, int b_rows, int b_cols, float *O, int64_t ldo, int m,
+               int n, qg_stream_t stream) {
+  return binary_op(0, "qg_add_f32", A, lda, B, ldb, b_rows, b_cols, O, ldo, m, n, stream);
+}
+int qg_subtract_f32(const float *A, int64_t lda, const float *B, int64_t ldb, int b_rows, int b_cols, float *O, int64_t ldo,
+                    int m, int n, qg_stream_t stream) {
+  return binary_op(1, "qg_subtract_f32", A, lda, B, ldb, b_rows, b_cols, O, ldo, m, n, stream);
+}
+int qg_multiply_f32(const float *A, int64_t lda, const float *B, int64_t ldb, int b_rows, int b_cols, float *O, int64_t ldo,
+                    int m, int n, qg_stream_t stream) {
+  return binary_op(2, "qg_multiply_f32", A, lda, B, ldb, b_rows, b_cols, O, ldo, m, n, stream);
+}
+int qg_multiply_const_f32(const float *A, int64_t lda, float c, float *O, int64_t ldo, int m, int n, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && O && m > 0 && n > 0 && lda >= n && ldo >= n, "qg_multiply_const_f32: bad arguments");
+  return cuda_status((cudaError_t)elemwise(4, A, lda, nullptr, 0, 3, c, O, ldo, m, n, (cudaStream_t)stream), "qg_multiply_const_f32");
+}
+int qg_relu_f32(const float *A, int64_t lda, float *O, int64_t ldo, int m, int n, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && O && m > 0 && n > 0 && lda >= n && ldo >= n, "qg_relu_f32: bad arguments");
+  return cuda_status((cudaError_t)elemwise(5, A, lda, nullptr, 0, 3, 0.0f, O, ldo, m, n, (cudaStream_t)stream), "qg_relu_f32");
+}
+int qg_dequantize_outer_f32(const int32_t *acc, int64_t ldacc, const float *outer, int64_t ldouter, float *O, int64_t ldo, int m,
+                            int n, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(acc && outer && O && m > 0 && n > 0 && ldacc >= n && ldouter >= n && ldo >= n, "qg_dequantize_outer_f32: bad arguments");
+  return cuda_status((cudaError_t)elemwise(3, acc, ldacc, outer, ldouter, 0, 0.0f, O, ldo, m, n, (cudaStream_t)stream),
+                     "qg_dequantize_outer_f32");
 }
 
 /* bring-up hook: device buffer (8 x int64 per CTA) that the tcgen05 GEMM fills with pipeline wait

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "qg_dropin.cuh"
@@ -69,6 +70,49 @@ int main() {
   const int expect_acc[6] = {-8128, 0, -10668, -5461, 16129, 16129};
   for (int i = 0; i < 6; i++)
     if (acch.rawp[i] != expect_acc[i]) { printf("acc[%d] = %d, expected %d\n", i, acch.rawp[i], expect_acc[i]); bad++; }
+
+  // ... and the tail of the sequence op by op, as src/timing_quantize.cu:52-58,67-70 spells it:
+  // outer product through op_mm (K = 1), op_dequantize over the materialised outer product, op_multiply by
+  // 1/range^2 in place, op_subtract for the error -- must equal the one-call op bit for bit
+  {
+    Tensor<float> Outer{m, n, true}, qC{m, n, true}, Qerr{m, n, true};
+    op_mm(Cx, Cw, Outer);
+    op_dequantize(acc, Outer, qC);
+    const float range = 127.0f;
+    op_multiply(qC, 1 / (range * range), qC);
+    op_subtract(uQ, qC, Qerr);
+    cudaDeviceSynchronize();
+    Tensor<float> qCh = qC.toHost(), Qe = Qerr.toHost();
+    for (int i = 0; i < m * n; i++)
+      if (memcmp(&qCh.rawp[i], &Qh.rawp[i], 4) != 0) { printf("op-by-op tail differs from op_quantized_mm at %d\n", i); bad++; }
+    if (Qe.mean() != err.mean()) { printf("op_subtract mean %g != %g\n", Qe.mean(), err.mean()); bad++; }
+    // op_add with the [1,n] broadcast of LinearLayer::forward (linear.cuh:54), op_relu, op_layernorm
+    Tensor<float> bh{1, n}, y{m, n, true}, r{m, n, true}, ln{m, n, true};
+    bh.rawp[0] = 0.5f; bh.rawp[1] = -3.0f;
+    Tensor<float> bd = bh.toDevice();
+    op_add(qC, bd, y);
+    op_relu(y, r);
+    op_layernorm(y, ln);
+    cudaDeviceSynchronize();
+    Tensor<float> yh = y.toHost(), rh = r.toHost(), lh = ln.toHost();
+    for (int i = 0; i < m; i++) {
+      float mean = 0, var = 0;
+      for (int j = 0; j < n; j++) {
+        const float e = qCh.at(i, j) + bh.rawp[j];
+        if (yh.at(i, j) != e) { printf("op_add mismatch\n"); bad++; }
+        if (rh.at(i, j) != (e < 0 ? 0.0f : e)) { printf("op_relu mismatch\n"); bad++; }
+        mean += e;
+      }
+      mean = mean / n;
+      for (int j = 0; j < n; j++) var = (float)((double)var + (double)(yh.at(i, j) - mean) * (double)(yh.at(i, j) - mean));
+      var = var / n;
+      for (int j = 0; j < n; j++) {
+        const float e = (yh.at(i, j) - mean) / var;
+        if (memcmp(&e, &lh.at(i, j), 4) != 0 && !(e != e && lh.at(i, j) != lh.at(i, j))) { printf("op_layernorm mismatch %g %g\n", e, lh.at(i, j)); bad++; }
+      }
+    }
+    printf("op-by-op tail (op_mm outer, op_dequantize, op_multiply const, op_subtract, op_add, op_relu, op_layernorm): %s\n", bad ? "no" : "yes");
+  }
 
   // a larger shape, called twice: results must be identical
   const int M = 512, N = 768, K = 1024;
