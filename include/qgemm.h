@@ -244,6 +244,37 @@ QG_API int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv,
                                 int skv, int d_model, const float *Wqkv, int64_t ldw, int heads, int d_k, int d_v,
                                 float range, int mode, float *out, int64_t ldo, qg_stream_t stream);
 
+/* ---- quantization carried across layers (the FFN of src/transformer.cu:63-71) -----
+ * The reference's stack runs ll1.forward -> op_relu -> ll2.forward; on the quantized path every linear starts with
+ * a row quantizer pass over its input (reduce every row, then quantize it).  Here the producing GEMM's epilogue
+ * already knows the row maxima of what it writes, and the ADD & NORM kernel holds whole rows on chip:
+ *   - qg_linear_forward_q: LinearLayer::forward (+ activation) on activations that are ALREADY int8 codes + Cx;
+ *     with y_rowmax != NULL the epilogue also leaves max_{j>=1} |y[i,j]| (of the values as stored) in y_rowmax[i];
+ *   - qg_quantize_rows_given_max: the next layer's quantizer without its reduction: the scale comes from
+ *     (Y[i,0], y_rowmax[i]) with the reference's signed-first-element rule, then the codes -- same bits as
+ *     qg_absmax_quant_rows on Y;
+ *   - qg_ffn_forward: the whole ll1 -> relu -> ll2 chain in one call (X given as floats, or as codes + Cx);
+ *   - qg_add_layernorm_quant_f32: ADD & NORM (qg_add_layernorm_f32) that also emits the codes + Cx of its result,
+ *     for the linear layer that consumes it.
+ * Results are bit-identical to the unfused sequence (LinearLayer::forward calls one after the other). */
+QG_API int qg_linear_forward_q(const int8_t *Xq, int64_t ldxq, const float *Cx, const int8_t *Wt, int64_t ldwt,
+                               const float *Cw, const float *bias, int act, void *Y, int64_t ldy, int out_dtype, int m,
+                               int n, int k, float range, float *y_rowmax, void *workspace, size_t workspace_bytes,
+                               qg_stream_t stream);
+QG_API int qg_quantize_rows_given_max(const void *Y, int dtype, int m, int k, int64_t ldy, float range, int mode,
+                                      const float *rowmax, int8_t *Xq, int64_t ldq, float *Cx, qg_stream_t stream);
+QG_API size_t qg_ffn_workspace_bytes(int m, int d_in, int d_ff, int d_out);
+/* H [m, d_ff] = relu(x @ W1 + b1) (h_dtype), Y [m, d_out] = H @ W2 + b2.  Either X (floats, in_dtype) or
+ * Xq_in + Cx_in (codes from qg_add_layernorm_quant_f32 / qg_absmax_quant_rows; X may then be NULL). */
+QG_API int qg_ffn_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in, int64_t ldxq_in,
+                          const float *Cx_in, const int8_t *W1t, int64_t ldw1t, const float *Cw1, const float *b1,
+                          const int8_t *W2t, int64_t ldw2t, const float *Cw2, const float *b2, void *H, int64_t ldh,
+                          int h_dtype, void *Y, int64_t ldy, int out_dtype, int m, int d_in, int d_ff, int d_out,
+                          float range, int mode, void *workspace, size_t workspace_bytes, qg_stream_t stream);
+QG_API int qg_add_layernorm_quant_f32(const float *A, int64_t lda, const float *R, int64_t ldr, int m, int n, float *B,
+                                      int64_t ldb, float range, int mode, int8_t *Xq, int64_t ldq, float *Cx,
+                                      qg_stream_t stream);
+
 /* ---- the elementwise tail of the pipeline, op by op ------------------------------------------------
  * The fused epilogue makes these unnecessary on the fast path; they let the reference's step-by-step
  * sequence (src/timing_quantize.cu:38-58,67-70) be re-pointed one call at a time with identical bits.

@@ -33,6 +33,8 @@ ABI_SYMBOLS = [
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
     "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_mm_f32",
     "qg_softmax_rows_f32", "qg_attention_forward", "qg_linear_forward_act", "qg_add_layernorm_f32",
+    "qg_linear_forward_q", "qg_quantize_rows_given_max", "qg_ffn_workspace_bytes", "qg_ffn_forward",
+    "qg_add_layernorm_quant_f32",
     "qg_add_f32", "qg_subtract_f32", "qg_multiply_f32", "qg_multiply_const_f32", "qg_relu_f32", "qg_dequantize_outer_f32",
 ]
 
@@ -56,6 +58,7 @@ def lib() -> C.CDLL:
         L.qg_workspace_bytes.restype = C.c_size_t
         L.qg_outlier_workspace_bytes.restype = C.c_size_t
         L.qg_launch_count.restype = C.c_int64
+        L.qg_ffn_workspace_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -317,6 +320,71 @@ def linear_forward(X: torch.Tensor, Wt: torch.Tensor, Cw: torch.Tensor, bias, Y:
     ws_p, ws_n = (None, 0) if workspace is None else (C.c_void_p(workspace.data_ptr()), workspace.numel())
     _check(lib().qg_linear_forward_act(px, ldx, _dt(X), pq, ldq, _vec(Cw, N), pb, act, py, ldy, _dt(Y), M, N, K,
                                        C.c_float(range_), mode, ws_p, C.c_size_t(ws_n), _stream()), "qg_linear_forward_act")
+
+
+def linear_forward_q(Xq: torch.Tensor, Cx: torch.Tensor, Wt: torch.Tensor, Cw: torch.Tensor, bias, Y: torch.Tensor,
+                     range_: float = 127.0, act: int = 0, y_rowmax: torch.Tensor | None = None) -> None:
+    """LinearLayer::forward on activations that are already int8 codes + Cx; optional row maxima of Y for the
+    next layer's quantizer (qg_linear_forward_q)."""
+    M, K = Xq.shape
+    N = Wt.shape[0]
+    assert Wt.shape[1] == K and Y.shape == (M, N)
+    pa, lda = _dev2d(Xq)
+    pq, ldq = _dev2d(Wt)
+    py, ldy = _dev2d(Y)
+    pb = None if bias is None else _vec(bias.reshape(-1), N)
+    prm = None if y_rowmax is None else _vec(y_rowmax, M)
+    _check(lib().qg_linear_forward_q(pa, lda, _vec(Cx.reshape(-1), M), pq, ldq, _vec(Cw, N), pb, act, py, ldy, _dt(Y), M, N, K,
+                                     C.c_float(range_), prm, None, C.c_size_t(0), _stream()), "qg_linear_forward_q")
+
+
+def quantize_rows_given_max(Y: torch.Tensor, rowmax: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT):
+    """The row quantizer without its reduction: scale from (Y[i,0], rowmax[i]); returns (Xq, Cx)."""
+    M, K = Y.shape
+    Xq = torch.empty((M, K), dtype=torch.int8, device=Y.device)
+    Cx = torch.empty(M, dtype=torch.float32, device=Y.device)
+    py, ldy = _dev2d(Y)
+    pq, ldq = _dev2d(Xq)
+    _check(lib().qg_quantize_rows_given_max(py, _dt(Y), M, K, ldy, C.c_float(range_), mode, _vec(rowmax, M), pq, ldq, _vec(Cx, M),
+                                            _stream()), "qg_quantize_rows_given_max")
+    return Xq, Cx
+
+
+def ffn_forward(X, W1t, Cw1, b1, W2t, Cw2, b2, H: torch.Tensor, Y: torch.Tensor, range_: float = 127.0,
+                mode: int = MODE_REF_EXACT, Xq: torch.Tensor | None = None, Cx: torch.Tensor | None = None,
+                workspace: torch.Tensor | None = None) -> None:
+    """ll1.forward -> op_relu -> ll2.forward (transformer.cu:63-71) in one call (qg_ffn_forward): H = relu(x W1 + b1),
+    Y = H W2 + b2; the hidden activation's row maxima come out of the first GEMM's epilogue.  Pass Xq / Cx instead of
+    X when the input is already quantized (add_layernorm_quant)."""
+    M = (Xq if Xq is not None else X).shape[0]
+    d_in, d_ff, d_out = W1t.shape[1], W1t.shape[0], W2t.shape[0]
+    assert W2t.shape[1] == d_ff and H.shape == (M, d_ff) and Y.shape == (M, d_out)
+    px, ldx, dtx = (None, C.c_int64(0), QG_F32) if X is None else (*_dev2d(X), _dt(X))
+    pxq, ldxq = (None, C.c_int64(0)) if Xq is None else _dev2d(Xq)
+    pcx = None if Cx is None else _vec(Cx.reshape(-1), M)
+    p1, ld1 = _dev2d(W1t)
+    p2, ld2 = _dev2d(W2t)
+    ph, ldh = _dev2d(H)
+    py, ldy = _dev2d(Y)
+    ws_p, ws_n = (None, 0) if workspace is None else (C.c_void_p(workspace.data_ptr()), workspace.numel())
+    _check(lib().qg_ffn_forward(px, ldx, dtx, pxq, ldxq, pcx, p1, ld1, _vec(Cw1, d_ff), None if b1 is None else _vec(b1.reshape(-1), d_ff),
+                                p2, ld2, _vec(Cw2, d_out), None if b2 is None else _vec(b2.reshape(-1), d_out), ph, ldh, _dt(H),
+                                py, ldy, _dt(Y), M, d_in, d_ff, d_out, C.c_float(range_), mode, ws_p, C.c_size_t(ws_n), _stream()),
+           "qg_ffn_forward")
+
+
+def add_layernorm_quant(A: torch.Tensor, R, B: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT):
+    """ADD & NORM (transformer.cu:57-58) that also returns the int8 codes + Cx of its result (qg_add_layernorm_quant_f32)."""
+    M, N = A.shape
+    Xq = torch.zeros((M, (N + 15) // 16 * 16), dtype=torch.int8, device=A.device)[:, :N]
+    Cx = torch.empty(M, dtype=torch.float32, device=A.device)
+    pa, lda = _dev2d(A)
+    pb, ldb = _dev2d(B)
+    pr, ldr = _dev2d(R) if R is not None else (None, C.c_int64(0))
+    pq, ldq = _dev2d(Xq)
+    _check(lib().qg_add_layernorm_quant_f32(pa, lda, pr, ldr, M, N, pb, ldb, C.c_float(range_), mode, pq, ldq, _vec(Cx, M),
+                                            _stream()), "qg_add_layernorm_quant_f32")
+    return Xq, Cx
 
 
 def quantized_mm_host(X, W, range_: float = 127.0, mode: int = MODE_REF_EXACT, bias=None, out=None):

@@ -16,7 +16,7 @@ namespace qg {
 
 // ---- kernels / launchers defined in the other translation units ----
 int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, const float *sx,
-               int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st);
+               int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st, RowMaxIo io = RowMaxIo());
 int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
                int8_t *Wq, int64_t ldq, float *Cw, bool transpose, cudaStream_t st);
 int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
@@ -36,7 +36,8 @@ int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t s
            float *C, int64_t ldc, cudaStream_t st, const MmBatch *batch = nullptr);
 int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st);
 int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, float *B, int64_t ldb,
-                       cudaStream_t st);
+                       cudaStream_t st, int8_t *Xq = nullptr, int64_t ldq = 0, float *Cx = nullptr, float range = 127.0f,
+                       int mode = QG_MODE_REF_EXACT);
 int dequantize_s32(const int32_t *acc, int64_t ldacc, const float *Cx, const float *Cw, const float *bias, int M, int N,
                    float c, void *O, int out_dtype, int64_t ldo, cudaStream_t st);
 bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb);
@@ -44,7 +45,7 @@ void gemm_i8_tc_set_stats(long long *dev_ptr);
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
                const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act = QG_ACT_NONE,
-               int split_k = 1);
+               int split_k = 1, float *rowmax = nullptr);
 int elemwise(int op, const void *A, int64_t lda, const float *B, int64_t ldb, int bmode, float c, float *O, int64_t ldo, int M,
              int N, cudaStream_t st);
 int splitk_reduce(const int32_t *parts, int64_t slice_stride, int slices, int64_t ldp, const float *Cx, const float *Cw,
@@ -236,7 +237,10 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
                          int N, int K, void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw,
                          const float *bias, float c, cudaStream_t st, const SideArgs *side = nullptr,
                          const MultiOut *multi = nullptr, int act = QG_ACT_NONE, void *sk_buf = nullptr,
-                         size_t sk_bytes = 0, bool sk_arena = true) {
+                         size_t sk_bytes = 0, bool sk_arena = true, float *rowmax = nullptr, bool *rowmax_done = nullptr) {
+  // rowmax (optional): the tensor-core epilogue raises rowmax[i] to max_{j>=1} |y[i,j]| (RowMaxIo); *rowmax_done tells
+  // the caller whether this path did it (the CUDA-core and split-K forms do not)
+  if (rowmax_done) *rowmax_done = false;
   int variant = g_variant.load();
   const bool tc_ok = gemm_i8_tc_supported(A, lda, B, ldb);
   // the 2-SM tile (256x256 per CTA pair) halves the shared-memory traffic per MAC; one CTA row
@@ -282,7 +286,9 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
     return cuda_status((cudaError_t)splitk_reduce(parts, (int64_t)slice, sk, ldp, Cx, Cw, bias, M, N, c, act, O, out_kind, ldo, st),
                        "split-K reduce");
   }
-  return gemm_i8_tc(cg, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, multi, d->sm_count, st, act);
+  if (rowmax_done) *rowmax_done = rowmax != nullptr && out_kind != QG_S32;
+  return gemm_i8_tc(cg, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, multi, d->sm_count, st, act, 1,
+                    rowmax);
 }
 
 }  // namespace qg
@@ -820,6 +826,159 @@ int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_
   bt.c_outer = (int64_t)sq * ldo;         bt.c_inner = d_v;
   rc = mm_f32(scores, skv, 1, Vp, ldkv, 1, sq, d_v, skv, out, ldo, st, &bt);
   return cuda_status((cudaError_t)rc, "P*V");
+}
+
+/* ---- quantization carried across layers ---- */
+namespace qg {
+__global__ void fill_f32_kernel(float *p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_wait();
+  if (i < n) p[i] = v;
+}
+}  // namespace qg
+
+int qg_quantize_rows_given_max(const void *Y, int dtype, int M, int K, int64_t ldy, float range, int mode,
+                               const float *rowmax, int8_t *Xq, int64_t ldq, float *Cx, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(Y && rowmax && Xq && Cx && M > 0 && K > 0 && ldy >= K && ldq >= K && valid_io(dtype),
+             "qg_quantize_rows_given_max: bad arguments");
+  RowMaxIo io;
+  io.m_in = rowmax;
+  return quant_rows(Y, dtype, M, K, ldy, range, mode, nullptr, Xq, ldq, Cx, (cudaStream_t)stream, io);
+}
+
+int qg_linear_forward_q(const int8_t *Xq, int64_t ldxq, const float *Cx, const int8_t *Wt, int64_t ldwt, const float *Cw,
+                        const float *bias, int act, void *Y, int64_t ldy, int out_dtype, int M, int N, int K, float range,
+                        float *y_rowmax, void *workspace, size_t workspace_bytes, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(Xq && Cx && Wt && Cw && Y && M > 0 && N > 0 && K > 0 && ldxq >= K && ldwt >= K && ldy >= N && valid_io(out_dtype) &&
+                 (act == QG_ACT_NONE || act == QG_ACT_RELU),
+             "qg_linear_forward_q: bad arguments (M=%d N=%d K=%d)", M, N, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  void *sk = nullptr;
+  size_t sk_bytes = 0;
+  if (workspace != nullptr) {  // only the split-K slices of a tile-starved shape live there
+    QG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "qg_linear_forward_q: workspace must be 256-byte aligned");
+    sk = workspace;
+    sk_bytes = workspace_bytes;
+  }
+  if (y_rowmax != nullptr)
+    QG_CUDA_OK(launch_kernel(fill_f32_kernel, dim3((unsigned)ceil_div(M, 256)), dim3(256), st, y_rowmax, M, -INFINITY));
+  bool done = false;
+  rc = gemm_dispatch(d, Xq, ldxq, Wt, ldwt, 1, M, N, K, Y, ldy, out_dtype, Cx, Cw, bias, 1 / (range * range), st, nullptr, nullptr,
+                     act, sk, sk_bytes, workspace == nullptr, y_rowmax, &done);
+  if (rc) return rc;
+  if (y_rowmax != nullptr && !done) {  // CUDA-core or split-K form: one reduction pass over Y instead
+    RowMaxIo io;
+    io.m_out = y_rowmax;
+    rc = quant_rows(Y, out_dtype, M, N, ldy, range, QG_MODE_REF_EXACT, nullptr, nullptr, 0, nullptr, st, io);
+    if (rc) return cuda_status((cudaError_t)rc, "row maxima");
+  }
+  return QG_OK;
+}
+
+struct FfnWs {
+  int8_t *Xq1, *Xq2;
+  float *Cx1, *Cx2, *rowmax;
+  int64_t ldq1, ldq2;
+  void *sk;
+  size_t sk_bytes, bytes;
+};
+static FfnWs carve_ffn(void *base, int M, int d_in, int d_ff, int d_out) {
+  FfnWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (size_t)round_up((int64_t)(off + n), 256); return o; };
+  w.ldq1 = round_up(d_in, 16);
+  w.ldq2 = round_up(d_ff, 16);
+  const size_t o1 = take((size_t)M * w.ldq1), o2 = take((size_t)M * w.ldq2), c1 = take(4 * (size_t)M), c2 = take(4 * (size_t)M),
+               rm = take(4 * (size_t)M);
+  w.sk_bytes = std::max(splitk_need(M, d_ff, d_in), splitk_need(M, d_out, d_ff));
+  const size_t osk = take(w.sk_bytes);
+  char *b = reinterpret_cast<char *>(base);
+  w.Xq1 = reinterpret_cast<int8_t *>(b + o1); w.Xq2 = reinterpret_cast<int8_t *>(b + o2);
+  w.Cx1 = reinterpret_cast<float *>(b + c1); w.Cx2 = reinterpret_cast<float *>(b + c2); w.rowmax = reinterpret_cast<float *>(b + rm);
+  w.sk = w.sk_bytes ? b + osk : nullptr;
+  w.bytes = off;
+  return w;
+}
+size_t qg_ffn_workspace_bytes(int M, int d_in, int d_ff, int d_out) {
+  if (M <= 0 || d_in <= 0 || d_ff <= 0 || d_out <= 0) return 0;
+  return carve_ffn(nullptr, M, d_in, d_ff, d_out).bytes;
+}
+
+int qg_ffn_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in, int64_t ldxq_in, const float *Cx_in,
+                   const int8_t *W1t, int64_t ldw1t, const float *Cw1, const float *b1, const int8_t *W2t, int64_t ldw2t,
+                   const float *Cw2, const float *b2, void *H, int64_t ldh, int h_dtype, void *Y, int64_t ldy, int out_dtype,
+                   int M, int d_in, int d_ff, int d_out, float range, int mode, void *workspace, size_t workspace_bytes,
+                   qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  const bool preq = Xq_in != nullptr;
+  QG_REQUIRE((preq ? (Cx_in != nullptr && ldxq_in >= d_in) : (X != nullptr && ldx >= d_in && valid_io(in_dtype))) && W1t && Cw1 &&
+                 W2t && Cw2 && H && Y && M > 0 && d_in > 0 && d_ff > 0 && d_out > 0 && ldw1t >= d_in && ldw2t >= d_ff &&
+                 ldh >= d_ff && ldy >= d_out && valid_io(h_dtype) && valid_io(out_dtype),
+             "qg_ffn_forward: bad arguments (M=%d d_in=%d d_ff=%d d_out=%d)", M, d_in, d_ff, d_out);
+  const size_t need = carve_ffn(nullptr, M, d_in, d_ff, d_out).bytes;
+  if (workspace == nullptr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if ((rc = grow(&d->arena, &d->arena_bytes, need))) return rc;
+    workspace = d->arena;
+  } else {
+    QG_REQUIRE(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "qg_ffn_forward: workspace too small or misaligned (%zu bytes needed)", need);
+  }
+  FfnWs w = carve_ffn(workspace, M, d_in, d_ff, d_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float c = 1 / (range * range);
+  const int8_t *xq1 = Xq_in;
+  int64_t ldq1 = ldxq_in;
+  const float *cx1 = Cx_in;
+  if (!preq) {
+    // ll1's row quantizer; it also arms the row-maximum buffer the first GEMM's epilogue fills
+    RowMaxIo io;
+    io.init_out = w.rowmax;
+    rc = quant_rows(X, in_dtype, M, d_in, ldx, range, mode, nullptr, w.Xq1, w.ldq1, w.Cx1, st, io);
+    if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+    xq1 = w.Xq1; ldq1 = w.ldq1; cx1 = w.Cx1;
+  } else {
+    QG_CUDA_OK(launch_kernel(fill_f32_kernel, dim3((unsigned)ceil_div(M, 256)), dim3(256), st, w.rowmax, M, -INFINITY));
+  }
+  // ll1.forward + op_relu (transformer.cu:63-67): H = relu(x @ W1 + b1), row maxima of H from the epilogue
+  bool done = false;
+  rc = gemm_dispatch(d, xq1, ldq1, W1t, ldw1t, 1, M, d_ff, d_in, H, ldh, h_dtype, cx1, Cw1, b1, c, st, nullptr, nullptr, QG_ACT_RELU,
+                     w.sk, w.sk_bytes, false, w.rowmax, &done);
+  if (rc) return rc;
+  // ll2's quantizer: scale from (H[i,0], rowmax[i]) -- no reduction pass over H -- then the codes
+  RowMaxIo io2;
+  if (done) io2.m_in = w.rowmax;
+  rc = quant_rows(H, h_dtype, M, d_ff, ldh, range, mode, nullptr, w.Xq2, w.ldq2, w.Cx2, st, io2);
+  if (rc) return cuda_status((cudaError_t)rc, "row quantizer (hidden)");
+  // ll2.forward (transformer.cu:69-71)
+  return gemm_dispatch(d, w.Xq2, w.ldq2, W2t, ldw2t, 1, M, d_out, d_ff, Y, ldy, out_dtype, w.Cx2, Cw2, b2, c, st, nullptr, nullptr,
+                       QG_ACT_NONE, w.sk, w.sk_bytes, false);
+}
+
+int qg_add_layernorm_quant_f32(const float *A, int64_t lda, const float *R, int64_t ldr, int m, int n, float *B, int64_t ldb,
+                               float range, int mode, int8_t *Xq, int64_t ldq, float *Cx, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(A && B && Xq && Cx && m > 0 && n > 0 && lda >= n && ldb >= n && ldq >= n && (R == nullptr || ldr >= n),
+             "qg_add_layernorm_quant_f32: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = add_layernorm_rows(A, lda, R, ldr, m, n, B, ldb, st, Xq, ldq, Cx, range, mode);
+  if (rc == QG_ENOTSUP) {  // very wide rows: the two passes separately
+    rc = add_layernorm_rows(A, lda, R, ldr, m, n, B, ldb, st);
+    if (rc) return cuda_status((cudaError_t)rc, "add + layernorm");
+    rc = quant_rows(B, QG_F32, m, n, ldb, range, mode, nullptr, Xq, ldq, Cx, st);
+    return rc ? cuda_status((cudaError_t)rc, "row quantizer") : QG_OK;
+  }
+  return cuda_status((cudaError_t)rc, "add + layernorm + quantize");
 }
 
 /* ---- the elementwise tail of the pipeline, op by op (src/ops/op_elemwise.cuh) ---- */

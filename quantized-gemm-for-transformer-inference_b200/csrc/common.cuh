@@ -79,6 +79,15 @@ struct SideArgs {
   int side_bf16;   // 0: fp16 operands, 1: bf16
 };
 
+// Row-maximum hand-over between a producing GEMM epilogue and the next layer's row quantizer (SURVEY.md section 8f,
+// rank 3).  m = max_{j >= 1, x_j not NaN} |x_j| (-inf when there is none), i.e. the reduction WITHOUT the signed first
+// element, which the quantizer folds itself (op_reduction.cuh:80).
+struct RowMaxIo {
+  const float *m_in = nullptr;  // take m from here instead of reducing the row
+  float *m_out = nullptr;       // store m (reduction-only use)
+  float *init_out = nullptr;    // write -inf: arms a buffer the FOLLOWING GEMM's epilogue will atomicMax into
+};
+
 // batch geometry of the fp32 product: blockIdx.z = outer * n_inner + inner selects one independent
 // product; element offsets per operand (attention: outer = sequence, inner = head)
 struct MmBatch {

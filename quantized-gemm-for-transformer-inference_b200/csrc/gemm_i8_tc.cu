@@ -849,7 +849,8 @@ bool gemm_i8_tc_supported(const void *A, int64_t lda, const void *B, int64_t ldb
 // out_kind QG_S32 writes raw accumulators; otherwise the dequantize epilogue runs.
 int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K,
                void *O, int64_t ldo, int out_kind, const float *Cx, const float *Cw, const float *bias, float c,
-               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act, int split_k) {
+               const SideArgs *side, const MultiOut *multi, int num_sms, cudaStream_t st, int act, int split_k,
+               float *rowmax) {
   if (!gemm_i8_tc_supported(A, lda, B, ldb)) {
     set_error("gemm_i8_tc: operands must be 16-byte aligned with leading dimensions multiple of 16");
     return QG_EINVAL;
@@ -860,6 +861,7 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   p.tiles_n = (int)ceil_div(N, BN);
   p.out = O; p.ldo = ldo; p.Cx = Cx; p.Cw = Cw; p.bias = bias; p.c = c;
   p.relu = (act == QG_ACT_RELU && out_kind != QG_S32) ? 1 : 0;
+  p.rowmax = (out_kind != QG_S32 && split_k <= 1) ? rowmax : nullptr;
   p.split_k = 1;
   if (split_k > 1) {  // raw partial sums: `O` and multi->dst[] are the split_k int32 slice matrices (capi.cu)
     const int num_kb = (int)ceil_div(K, BK);

@@ -29,7 +29,7 @@ template <typename T, int G, int NV>
 __global__ void __launch_bounds__(kThreads)
 quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
                   const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
-                  float *__restrict__ Cx) {
+                  float *__restrict__ Cx, RowMaxIo io) {
   constexpr int EPV = Unpack<T>::EPV;
   constexpr int RPB = kThreads / G;  // rows per block iteration
   constexpr int WPR = G / 32;        // warps per row
@@ -91,6 +91,7 @@ quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float rang
         }
       }
       m = warp_max(m);
+      if (io.m_in != nullptr) m = active ? io.m_in[row] : -INFINITY;  // the producer's epilogue already reduced columns 1..K-1
       if (WPR > 1) {  // double-buffered by iteration parity: one barrier per iteration is enough
         float *sm = s_m[it & 1], *sx0 = s_x0[it & 1];
         if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
@@ -102,6 +103,10 @@ quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float rang
         x0 = sx0[rib];
       } else {
         x0 = __shfl_sync(0xffffffffu, x0, 0);
+      }
+      if (active && g == 0) {
+        if (io.m_out != nullptr) io.m_out[row] = m;
+        if (io.init_out != nullptr) io.init_out[row] = -INFINITY;
       }
       float c;
       if (fold_first(x0, m, mode, c) && active) {
@@ -152,7 +157,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
                           const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
-                          float *__restrict__ Cx) {
+                          float *__restrict__ Cx, RowMaxIo io) {
   const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   griddep_wait();
@@ -165,6 +170,11 @@ quant_rows_generic_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, fl
     for (int j = lane; j < K; j += 32)
       if (j > 0) m = fmaxf(m, fabsf(to_f32(xr[j])));
     m = warp_max(m);
+    if (io.m_in != nullptr) m = io.m_in[row];
+    if (lane == 0) {
+      if (io.m_out != nullptr) io.m_out[row] = m;
+      if (io.init_out != nullptr) io.init_out[row] = -INFINITY;
+    }
     const float x0 = to_f32(xr[0]);
     float c;
     if (fold_first(x0, m, mode, c)) {
@@ -532,7 +542,7 @@ int twopass_scratch(int N, cudaStream_t st, unsigned long long **part, uint32_t 
 // ---- row launcher ----
 template <typename T, int G, int NV>
 void launch_rows(const T *X, int M, int K, int64_t ldx, float range, int mode, const float *sx, int8_t *Xq,
-                 int64_t ldq, float *Cx, cudaStream_t st) {
+                 int64_t ldq, float *Cx, RowMaxIo io, cudaStream_t st) {
   constexpr int RPB = kThreads / G;
   static int resident = 0;  // CTAs that fit on the device at once (per instantiation)
   if (resident == 0) {
@@ -544,21 +554,21 @@ void launch_rows(const T *X, int M, int K, int64_t ldx, float range, int mode, c
   }
   const int64_t nrb = ceil_div(M, RPB);
   const unsigned grid = (unsigned)(nrb < resident ? nrb : resident);
-  launch_kernel(quant_rows_kernel<T, G, NV>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, sx, Xq, ldq, Cx);
+  launch_kernel(quant_rows_kernel<T, G, NV>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, io);
 }
 
 template <typename T>
 int rows_dispatch(const T *X, int M, int K, int64_t ldx, float range, int mode, const float *sx, int8_t *Xq,
-                  int64_t ldq, float *Cx, cudaStream_t st) {
+                  int64_t ldq, float *Cx, RowMaxIo io, cudaStream_t st) {
   constexpr int EPV = Unpack<T>::EPV;
   const bool vec_ok = (K % EPV == 0) && aligned(X, 16) && ((ldx * sizeof(T)) % 16 == 0) &&
                       (Xq == nullptr || (aligned(Xq, EPV) && ldq % EPV == 0));
   if (!vec_ok) {
     return (int)launch_kernel(quant_rows_generic_kernel<T>, dim3((unsigned)ceil_div(M, kThreads / 32)), dim3(kThreads), st,
-                              X, M, K, ldx, range, mode, sx, Xq, ldq, Cx);
+                              X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, io);
   }
   const int nvec = K / EPV;
-#define QG_ROWS(G, NV) launch_rows<T, G, NV>(X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st)
+#define QG_ROWS(G, NV) launch_rows<T, G, NV>(X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, io, st)
   if (nvec <= 32) QG_ROWS(32, 1);
   else if (nvec <= 64) QG_ROWS(32, 2);
   else if (nvec <= 128) QG_ROWS(32, 4);
@@ -633,11 +643,11 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
 
 // ---- entry points used by capi.cu ----
 int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, const float *sx,
-               int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st) {
+               int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st, RowMaxIo io) {
   switch (dtype) {
-    case QG_F32: return rows_dispatch((const float *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st);
-    case QG_F16: return rows_dispatch((const __half *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st);
-    case QG_BF16: return rows_dispatch((const __nv_bfloat16 *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, st);
+    case QG_F32: return rows_dispatch((const float *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, io, st);
+    case QG_F16: return rows_dispatch((const __half *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, io, st);
+    case QG_BF16: return rows_dispatch((const __nv_bfloat16 *)X, M, K, ldx, range, mode, sx, Xq, ldq, Cx, io, st);
   }
   return QG_EINVAL;
 }

@@ -2,7 +2,7 @@
 // softmax(scale * A) and ADD & NORM with the reference kernels' arithmetic (src/ops/op_softmax.cuh,
 // src/ops/op_layernorm.cuh).  Both are defined by ascending-order running sums per row, which is what
 // the kernel structures below are built around.  Not on the quantized hot path.
-#include "common.cuh"
+#include "quant_common.cuh"
 
 namespace qg {
 
@@ -228,9 +228,21 @@ softmax_warp_rows_kernel(const float *A, int64_t lda, int M, int N, float scale,
 // shared-memory copy of the CTA's rows.  Rows per CTA shrink with N so that rows + squares fit.
 constexpr int kLnThreads = 256;
 
+// QUANT: the normalised row is also absmax-quantized for the linear layer that consumes it (SURVEY.md section 8f rank 3:
+// "fuse the preceding add & norm with the row quantizer"): Cx[i] = max(b[i,0], max_{j>=1} |b[i,j]|) and
+// Xq[i,j] = low8(trunc(b[i,j] * (range / Cx[i]))), the arithmetic of quant_rows_kernel, from the shared-memory copy.
+struct RowQuantOut {
+  int8_t *Xq;
+  int64_t ldq;
+  float *Cx;
+  float range;
+  int mode;
+};
+
+template <bool QUANT>
 __global__ void __launch_bounds__(kLnThreads)
 add_layernorm_cta_rows_kernel(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, int rows_per_cta,
-                              float *B, int64_t ldb) {  // B may alias A or R
+                              float *B, int64_t ldb, RowQuantOut qo) {  // B may alias A or R
   extern __shared__ double sm_rows_d[];
   const int ldsq = N + 1, ldrow = N + 1;  // odd strides: 32 threads walking 32 rows hit 32 banks
   double *sq = sm_rows_d;                                                   // [rows_per_cta][N+1] exact squares
@@ -308,9 +320,41 @@ add_layernorm_cta_rows_kernel(const float *A, int64_t lda, const float *R, int64
     __syncthreads();
     for (int e = t; e < rows * N; e += kLnThreads) {
       const int r = e / N, j = e - r * N;
-      B[(int64_t)(r0 + r) * ldb + j] = (row[r * ldrow + j] - s_mean[r]) / s_var[r];
+      const float v = (row[r * ldrow + j] - s_mean[r]) / s_var[r];
+      B[(int64_t)(r0 + r) * ldb + j] = v;
+      if (QUANT) row[r * ldrow + j] = v;
     }
     __syncthreads();
+    if (QUANT) {  // a warp per row: reduce, fold the signed first element, emit packed codes
+      const int lane = t & 31, warp = t >> 5;
+      for (int r = warp; r < rows; r += kLnThreads / 32) {
+        const float *x = row + r * ldrow;
+        float m = -INFINITY;
+        for (int j = 1 + lane; j < N; j += 32) m = fmaxf(m, fabsf(x[j]));
+        m = warp_max(m);
+        float c;
+        if (fold_first(x[0], m, qo.mode, c)) {
+          for (int j = 1; j < N; j++)
+            if (x[j] == x[j]) { c = -x[j]; break; }
+        }
+        if (lane == 0) qo.Cx[r0 + r] = c;
+        const float scale = __fdiv_rn(qo.range, c);
+        int8_t *q = qo.Xq + (int64_t)(r0 + r) * qo.ldq;
+        if (((reinterpret_cast<uintptr_t>(q) | (uintptr_t)qo.ldq) & 3) == 0) {
+          for (int j = 4 * lane; j < N; j += 128) {
+            uint32_t wv = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (j + e < N) wv |= quant_code_u8(x[j + e], scale) << (8 * e);
+            if (j + 4 <= N) *reinterpret_cast<uint32_t *>(q + j) = wv;
+            else for (int e = 0; j + e < N; e++) q[j + e] = (int8_t)((wv >> (8 * e)) & 0xffu);
+          }
+        } else {
+          for (int j = lane; j < N; j += 32) q[j] = (int8_t)quant_code_u8(x[j], scale);
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -334,16 +378,22 @@ static void warp_rows_launch(void (*kern)(KArgs...), size_t smem, int M, cudaStr
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// quant != nullptr: also emit int8 codes + Cx of the result (returns QG_ENOTSUP when this width has no fused form, so that
+// the caller can run the row quantizer separately)
 int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, float *B, int64_t ldb,
-                       cudaStream_t st) {
+                       cudaStream_t st, int8_t *Xq, int64_t ldq, float *Cx, float range, int mode) {
+  const bool quant = Xq != nullptr;
+  RowQuantOut qo = {Xq, ldq, Cx, range, mode};
+  if (quant && N > kWarpRowMaxN) return QG_ENOTSUP;
   if (N <= kWarpRowMaxN) {
     // rows + squares of a CTA's rows in at most 192 KB of shared memory, at most 32 rows (one warp of serial sums)
     int rpc = (int)((192 << 10) / ((size_t)(N + 1) * 12));
     rpc = rpc > 32 ? 32 : rpc;
     while (rpc > 1 && ceil_div(M, rpc) < 148) rpc >>= 1;  // short matrices: spread over the SMs first
     const size_t smem = (size_t)rpc * (N + 1) * 12;
-    static bool opted[kMaxDevices] = {};
-    smem_optin(add_layernorm_cta_rows_kernel, 200 << 10, opted);
+    static bool opted[kMaxDevices] = {}, opted_q[kMaxDevices] = {};
+    if (quant) smem_optin(add_layernorm_cta_rows_kernel<true>, 200 << 10, opted_q);
+    else smem_optin(add_layernorm_cta_rows_kernel<false>, 200 << 10, opted);
     const int64_t ctas = ceil_div(M, rpc);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ctas < 148 * 8 ? ctas : 148 * 8));
@@ -356,7 +406,8 @@ int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr,
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     count_launch();
-    cudaLaunchKernelEx(&cfg, add_layernorm_cta_rows_kernel, A, lda, R, ldr, M, N, rpc, B, ldb);
+    if (quant) cudaLaunchKernelEx(&cfg, add_layernorm_cta_rows_kernel<true>, A, lda, R, ldr, M, N, rpc, B, ldb, qo);
+    else cudaLaunchKernelEx(&cfg, add_layernorm_cta_rows_kernel<false>, A, lda, R, ldr, M, N, rpc, B, ldb, qo);
     return (int)cudaGetLastError();
   }
   if (M >= 148 * 128)

@@ -69,6 +69,16 @@ class PreparedLinear:
 ACT_NONE, ACT_RELU = 0, 1
 
 
+def ffn_chain(ll1: "PreparedLinear", ll2: "PreparedLinear", x, hidden: torch.Tensor, y: torch.Tensor, xq=None, cx=None) -> None:
+    """ll1.forward -> op_relu -> ll2.forward (transformer.cu:63-71) as one qg_ffn_forward call; the input either as floats
+    (x) or as int8 codes + Cx (from add_layernorm_quant)."""
+    for lin in (ll1, ll2):
+        if lin._wq is None:
+            lin._wq = _qg.prepare_weights(lin.w, lin.range, lin.mode)
+    (W1t, Cw1), (W2t, Cw2) = ll1._wq, ll2._wq
+    _qg.ffn_forward(x, W1t, Cw1, ll1.b, W2t, Cw2, ll2.b, hidden, y, ll1.range, ll1.mode, Xq=xq, Cx=cx)
+
+
 class EncoderBlock:
     """One iteration of the Encoder loop, transformer.cu:24-76."""
 
@@ -91,13 +101,18 @@ class EncoderBlock:
             self._buf = (torch.empty((T, self.d_model), device=device), torch.empty((T, self.d_ff), device=device))
         return self._buf
 
-    def forward(self, x: torch.Tensor, out: torch.Tensor, batch: int = 1) -> None:
+    def forward(self, x: torch.Tensor, out: torch.Tensor, batch: int = 1, fused: bool = True) -> None:
         mh, ffn = self._buffers(x.shape[0], x.device)
         self.attn.forward(x, x, mh, batch=batch)   # :27-50
         self.W_O.forward(mh, out)                  # :54
-        add_layernorm(out, mh, out)                # :57-58
-        self.ll1.forward(out, ffn, ACT_RELU)       # :63-67
-        self.ll2.forward(ffn, out)                 # :69-71
+        if fused:
+            # ADD & NORM emits ll1's int8 codes, ll1's epilogue the row maxima ll2's quantizer needs
+            xq, cx = _qg.add_layernorm_quant(out, mh, out)            # :57-58 (+ ll1's row quantizer)
+            ffn_chain(self.ll1, self.ll2, None, ffn, out, xq, cx)     # :63-71
+        else:
+            add_layernorm(out, mh, out)                # :57-58
+            self.ll1.forward(out, ffn, ACT_RELU)       # :63-67
+            self.ll2.forward(ffn, out)                 # :69-71
         add_layernorm(out, mh, out)                # :74-75
 
 
@@ -132,9 +147,8 @@ class DecoderBlock:
         add_layernorm(out, mh, out)                                # :123-124
         self.cross_attn.forward(out, enc_output, mh, batch=batch)  # :127-140 (queries from the decoder, keys/values from the encoder)
         self.W_O2.forward(mh, out)                                 # :144
-        add_layernorm(out, mh, out)                                # :148-149
-        self.ll1.forward(out, ffn, ACT_RELU)                       # :154-158
-        self.ll2.forward(ffn, out)                                 # :160-162
+        xq, cx = _qg.add_layernorm_quant(out, mh, out)             # :148-149 (+ ll1's row quantizer)
+        ffn_chain(self.ll1, self.ll2, None, ffn, out, xq, cx)      # :154-162
         add_layernorm(out, mh, out)                                # :165-166
 
 
