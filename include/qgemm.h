@@ -186,11 +186,14 @@ QG_API int qg_outlier_mask_f32(const float *A, int m, int k, int64_t lda, float 
 QG_API int qg_outlier_cols(const void *X, int dtype, int m, int k, int64_t ldx, float thr, int *idx,
                            int max_idx, int *count, qg_stream_t stream);
 QG_API size_t qg_outlier_workspace_bytes(int m, int n, int k);
-/* LinearLayer::forward with the feature columns idx[0..n_idx) (device, ascending, n_idx <= 16) taken
+/* LinearLayer::forward with the feature columns idx[0..n_idx) (device, ascending, n_idx <= 64) taken
  * out of the int8 path: X's outlier columns are zeroed before the row quantizer, and
  * fp16(X[:,idx]) @ fp16(W[idx,:]) (bf16 when X is bf16) is accumulated in fp32 inside the GEMM
- * epilogue: y = fl(fl(dequant + side) + bias).  W is the original [K,N] weight, Wt/Cw its prepared
- * int8 form (qg_prepare_weights: column scales over ALL rows, so they do not depend on idx). */
+ * epilogue: y = fl(fl(dequant + side) + bias), the side sum an fma chain in ascending idx order (the
+ * order is part of the result, which is why it runs on the CUDA cores).  Up to 16 columns the epilogue
+ * double-buffers its fp32 copy of W[idx, tile]; from 17 to 64 it gives up one stage of the operand ring
+ * for it.  More than 64: QG_ENOTSUP.  W is the original [K,N] weight, Wt/Cw its prepared int8 form
+ * (qg_prepare_weights: column scales over ALL rows, so they do not depend on idx). */
 QG_API int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, const void *W, int64_t ldw,
                                      int w_dtype, const int8_t *Wt, int64_t ldwt, const float *Cw,
                                      const float *bias, const int *idx, int n_idx, void *Y, int64_t ldy,
@@ -274,6 +277,35 @@ QG_API int qg_ffn_forward(const void *X, int64_t ldx, int in_dtype, const int8_t
 QG_API int qg_add_layernorm_quant_f32(const float *A, int64_t lda, const float *R, int64_t ldr, int m, int n, float *B,
                                       int64_t ldb, float range, int mode, int8_t *Xq, int64_t ldq, float *Cx,
                                       qg_stream_t stream);
+
+/* ---- Megatron pairing: column-parallel fc1 -> row-parallel fc2 ----------------------
+ * The FFN of src/transformer.cu:63-71 (ll1.forward -> op_relu -> ll2.forward) split over P GPUs so that the only exchange is a
+ * reduce-scatter of fc2's partial products instead of an all-gather of fc1's (much larger) output:
+ *   rank p holds W1[:, F_p] and W2[F_p, :] for its slice F_p of the d_ff hidden features; it computes
+ *   H_p = relu(x W1[:, F_p] + b1[F_p]) (bit-identical to the same columns of the single-GPU layer), quantizes H_p row-wise
+ *   with scales taken over ITS slice, and forms the partial product part_p = dequant(Hq_p . Wq2_p) with the scales of the slice
+ *   (Cx2_p per row, Cw2_p per column of W2[F_p, :]).  y = ((part_0 + part_1) + ... + part_{P-1}) + b2, every addition rounded
+ *   to fp32 in ascending rank order.  This differs from the single-GPU result in the last bits (per-slice scales) -- it is its
+ *   own, explicitly specified mode, matched bit for bit by the CPU restatement (oracle.megatron_ffn).
+ * The exchange is carried by the kernels themselves over peer-mapped memory: the GEMM epilogue of fc2 stores column block b
+ * of part_p straight into slot p of the GPU that owns block b (qg_ffn_forward_rowpar / qg_gemm_s8_dequant_scatter: part_dst[b]
+ * is that slot, an [m, block_cols] matrix with leading dimension ld_part; block_cols a multiple of 32 columns for fp32 and
+ * 64 for 16-bit partials), and qg_reduce_partials adds the P slots in order, adds the bias and writes the owner's block to
+ * `out` and to the same block of the peers' matrices (the all-gather that completes the all-reduce; n_peers = 0: keep it
+ * sharded).  The caller brackets the two with barriers (all slots written before the reduce; all reduces done before the
+ * next forward's stores). */
+QG_API int qg_gemm_s8_dequant_scatter(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_t ldwt, const float *Cx,
+                                      const float *Cw, int m, int n, int k, float range, void *const *part_dst, int n_dst,
+                                      int block_cols, int64_t ld_part, int part_dtype, qg_stream_t stream);
+QG_API int qg_ffn_forward_rowpar(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in, int64_t ldxq_in,
+                                 const float *Cx_in, const int8_t *W1t, int64_t ldw1t, const float *Cw1, const float *b1,
+                                 const int8_t *W2t, int64_t ldw2t, const float *Cw2, void *H, int64_t ldh, int h_dtype,
+                                 void *const *part_dst, int n_dst, int block_cols, int64_t ld_part, int part_dtype, int m,
+                                 int d_in, int d_ff_local, int d_out, float range, int mode, void *workspace,
+                                 size_t workspace_bytes, qg_stream_t stream);
+QG_API int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part,
+                              const float *bias, void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int m,
+                              int n, qg_stream_t stream);
 
 /* ---- the elementwise tail of the pipeline, op by op ------------------------------------------------
  * The fused epilogue makes these unnecessary on the fast path; they let the reference's step-by-step

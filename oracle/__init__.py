@@ -360,6 +360,38 @@ def encoder_block(X, Wqkv, W_O, W1, b1, W2, b2, heads, batch=1, range_=127.0, mo
     return add_layernorm(out, mh)                                                    # :74-75
 
 
+def megatron_ffn(X, W1, b1, W2, b2, bounds, range_=127.0, mode=MODE_REF_EXACT, h_dtype="f32", part_dtype="f32",
+                 out_dtype="f32", return_parts=False):
+    """Megatron pairing of the FFN of src/transformer.cu:63-71 (ll1 -> relu -> ll2) over len(bounds) ranks; the
+    specification is ours (parity UNPINNED: the reference has no multi-GPU code), see include/qgemm.h.
+
+    bounds[p] = (lo, hi): rank p's slice of the d_ff hidden features.  H_p = relu(quantized_mm(X, W1[:, lo:hi]) + b1[lo:hi])
+    rounded to h_dtype (the same bits as those columns of the single-GPU layer); part_p = quantized_mm(H_p, W2[lo:hi, :])
+    with the row scales of H_p and the column scales of W2[lo:hi, :] (per-slice scales), rounded to part_dtype;
+    y = ((part_0 + part_1) + ...) + b2, fp32 additions in ascending rank order, rounded to out_dtype."""
+    X = _f32(X)
+    parts = []
+    for lo, hi in bounds:
+        h = relu(quantized_mm(X, W1[:, lo:hi], range_, mode, bias=None if b1 is None else np.asarray(b1).reshape(-1)[lo:hi]))
+        h = np.asarray(_to_f32(round_to(h_dtype, h)))
+        part = quantized_mm(h, W2[lo:hi, :], range_, mode)
+        parts.append(np.asarray(_to_f32(round_to(part_dtype, part))))
+    y = parts[0].copy()
+    for p in parts[1:]:
+        y = (y + p).astype(np.float32)
+    if b2 is not None:
+        y = (y + _f32(np.asarray(b2).reshape(1, -1))).astype(np.float32)
+    y = round_to(out_dtype, y)
+    return (y, parts) if return_parts else y
+
+
+def _to_f32(a):
+    """numpy float32 view of round_to()'s result (bf16 comes back as a torch tensor)."""
+    if isinstance(a, np.ndarray):
+        return a.astype(np.float32)
+    return a.float().numpy()
+
+
 # ---------------------------------------------------------------------------------------------
 # Timed CPU baseline (oracle/qfast.c): the same pipeline, threaded and vectorised (AVX-512 VNNI
 # int8 GEMM behind a run-time check).  Used by bench.py's cpu_baseline / --impl reference legs;

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_mm_f32",
     "qg_softmax_rows_f32", "qg_attention_forward", "qg_linear_forward_act", "qg_add_layernorm_f32",
     "qg_linear_forward_q", "qg_quantize_rows_given_max", "qg_ffn_workspace_bytes", "qg_ffn_forward",
-    "qg_add_layernorm_quant_f32",
+    "qg_add_layernorm_quant_f32", "qg_gemm_s8_dequant_scatter", "qg_ffn_forward_rowpar", "qg_reduce_partials",
     "qg_add_f32", "qg_subtract_f32", "qg_multiply_f32", "qg_multiply_const_f32", "qg_relu_f32", "qg_dequantize_outer_f32",
 ]
 
@@ -373,6 +373,62 @@ def ffn_forward(X, W1t, Cw1, b1, W2t, Cw2, b2, H: torch.Tensor, Y: torch.Tensor,
            "qg_ffn_forward")
 
 
+def ffn_workspace_bytes(m: int, d_in: int, d_ff: int, d_out: int) -> int:
+    return int(lib().qg_ffn_workspace_bytes(m, d_in, d_ff, d_out))
+
+
+def _ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+    return arr
+
+
+def gemm_s8_dequant_scatter(Xq, Wt, Cx, Cw, part_ptrs, block_cols: int, ld_part: int, part_dtype: torch.dtype,
+                            n: int, range_: float = 127.0) -> None:
+    """Row-parallel linear's GEMM (qg_gemm_s8_dequant_scatter): column block b of dequant(Xq . Wt^T) is stored to
+    part_ptrs[b] (device addresses of [M, block_cols] matrices, possibly on peer GPUs)."""
+    M, K = Xq.shape
+    pq, ldq = _dev2d(Xq)
+    pw, ldw = _dev2d(Wt)
+    _check(lib().qg_gemm_s8_dequant_scatter(pq, ldq, pw, ldw, _vec(Cx, M), _vec(Cw, n), M, n, K, C.c_float(range_),
+                                            _ptr_array(part_ptrs), len(part_ptrs), block_cols, C.c_int64(ld_part),
+                                            _DT[part_dtype], _stream()), "qg_gemm_s8_dequant_scatter")
+
+
+def ffn_forward_rowpar(X, W1t, Cw1, b1, W2t, Cw2, H: torch.Tensor, part_ptrs, block_cols: int, ld_part: int,
+                       part_dtype: torch.dtype, d_out: int, range_: float = 127.0, mode: int = MODE_REF_EXACT,
+                       Xq: torch.Tensor | None = None, Cx: torch.Tensor | None = None,
+                       workspace: torch.Tensor | None = None) -> None:
+    """This rank's half of a Megatron FFN pair (qg_ffn_forward_rowpar): H = relu(x W1_p + b1_p), then the partial product
+    H W2_p scattered by column block into part_ptrs (see include/qgemm.h)."""
+    M = (Xq if Xq is not None else X).shape[0]
+    d_in, d_ff = W1t.shape[1], W1t.shape[0]
+    assert W2t.shape == (d_out, d_ff) and H.shape == (M, d_ff)
+    px, ldx, dtx = (None, C.c_int64(0), QG_F32) if X is None else (*_dev2d(X), _dt(X))
+    pxq, ldxq = (None, C.c_int64(0)) if Xq is None else _dev2d(Xq)
+    pcx = None if Cx is None else _vec(Cx.reshape(-1), M)
+    p1, ld1 = _dev2d(W1t)
+    p2, ld2 = _dev2d(W2t)
+    ph, ldh = _dev2d(H)
+    ws_p, ws_n = (None, 0) if workspace is None else (C.c_void_p(workspace.data_ptr()), workspace.numel())
+    _check(lib().qg_ffn_forward_rowpar(px, ldx, dtx, pxq, ldxq, pcx, p1, ld1, _vec(Cw1, d_ff),
+                                       None if b1 is None else _vec(b1.reshape(-1), d_ff), p2, ld2, _vec(Cw2, d_out), ph, ldh,
+                                       _dt(H), _ptr_array(part_ptrs), len(part_ptrs), block_cols, C.c_int64(ld_part),
+                                       _DT[part_dtype], M, d_in, d_ff, d_out, C.c_float(range_), mode, ws_p, C.c_size_t(ws_n),
+                                       _stream()), "qg_ffn_forward_rowpar")
+
+
+def reduce_partials(slots: torch.Tensor, bias, out: torch.Tensor, peer_ptrs=(), n: int | None = None) -> None:
+    """out[:, :n] = ((slots[0] + slots[1]) + ...) + bias in ascending slot order (qg_reduce_partials); the result is also
+    stored to the same block of the peers' matrices (device addresses in peer_ptrs, leading dimension = out's)."""
+    P, M, bc = slots.shape
+    n = bc if n is None else n
+    po, ldo = _dev2d(out)
+    _check(lib().qg_reduce_partials(C.c_void_p(slots.data_ptr()), C.c_int64(slots.stride(0)), P, _dt(slots),
+                                    C.c_int64(slots.stride(1)), None if bias is None else _vec(bias.reshape(-1), n), po,
+                                    _ptr_array(peer_ptrs) if len(peer_ptrs) else None, len(peer_ptrs), ldo, _dt(out), M, n,
+                                    _stream()), "qg_reduce_partials")
+
+
 def add_layernorm_quant(A: torch.Tensor, R, B: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT):
     """ADD & NORM (transformer.cu:57-58) that also returns the int8 codes + Cx of its result (qg_add_layernorm_quant_f32)."""
     M, N = A.shape
@@ -401,7 +457,7 @@ def quantized_mm_host(X, W, range_: float = 127.0, mode: int = MODE_REF_EXACT, b
     return out
 
 
-MAX_OUTLIER_COLS = 16
+MAX_OUTLIER_COLS = 64
 
 
 def outlier_cols(X: torch.Tensor, thr: float, max_idx: int = 1024):

@@ -21,6 +21,8 @@ int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range,
                int8_t *Wq, int64_t ldq, float *Cw, bool transpose, cudaStream_t st);
 int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
+int reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
+                    void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st);
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
                  int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c,
                  const SideArgs *side, cudaStream_t st, int act = QG_ACT_NONE);
@@ -512,7 +514,7 @@ int qg_linear_forward_act(const void *X, int64_t ldx, int in_dtype, const int8_t
 }
 
 // ---- outlier decomposition ------------------------------------------------------------------
-static const int kMaxOutlierCols = 16;  // what the fused epilogue takes (gemm_i8_tc.cu: kSideMax)
+static const int kMaxOutlierCols = 64;  // what the fused epilogue takes (gemm_i8_tc.cu: kSideMax)
 
 struct OutlierWs {
   uint32_t *mask;
@@ -594,6 +596,7 @@ int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, const vo
   OutlierWs o = carve_outlier(reinterpret_cast<char *>(workspace) + w.bytes, M, N, K);
   cudaStream_t st = (cudaStream_t)stream;
   const int no_pad = (int)round_up(n_idx, 8);
+  o.ldxo = no_pad <= 16 ? 16 : no_pad;  // rows of Xo as short as this call's outlier count allows (the block is sized for the maximum)
   const int side_bf16 = (in_dtype == QG_BF16) ? 1 : 0;
   rc = outlier_mask_from_idx(idx, n_idx, K, o.mask, o.wbase, st);
   if (rc) return cuda_status((cudaError_t)rc, "outlier mask");
@@ -910,18 +913,22 @@ size_t qg_ffn_workspace_bytes(int M, int d_in, int d_ff, int d_out) {
   return carve_ffn(nullptr, M, d_in, d_ff, d_out).bytes;
 }
 
-int qg_ffn_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in, int64_t ldxq_in, const float *Cx_in,
-                   const int8_t *W1t, int64_t ldw1t, const float *Cw1, const float *b1, const int8_t *W2t, int64_t ldw2t,
-                   const float *Cw2, const float *b2, void *H, int64_t ldh, int h_dtype, void *Y, int64_t ldy, int out_dtype,
-                   int M, int d_in, int d_ff, int d_out, float range, int mode, void *workspace, size_t workspace_bytes,
-                   qg_stream_t stream) {
+}  // extern "C"
+
+// scatter != NULL: the second GEMM is the row-parallel half of a Megatron pair -- its output (this rank's partial
+// product) leaves through the scattering epilogue, Y being destination 0
+static int ffn_chain(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in, int64_t ldxq_in, const float *Cx_in,
+                     const int8_t *W1t, int64_t ldw1t, const float *Cw1, const float *b1, const int8_t *W2t, int64_t ldw2t,
+                     const float *Cw2, const float *b2, void *H, int64_t ldh, int h_dtype, void *Y, int64_t ldy, int out_dtype,
+                     int M, int d_in, int d_ff, int d_out, float range, int mode, void *workspace, size_t workspace_bytes,
+                     qg_stream_t stream, const MultiOut *scatter) {
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
   const bool preq = Xq_in != nullptr;
   QG_REQUIRE((preq ? (Cx_in != nullptr && ldxq_in >= d_in) : (X != nullptr && ldx >= d_in && valid_io(in_dtype))) && W1t && Cw1 &&
                  W2t && Cw2 && H && Y && M > 0 && d_in > 0 && d_ff > 0 && d_out > 0 && ldw1t >= d_in && ldw2t >= d_ff &&
-                 ldh >= d_ff && ldy >= d_out && valid_io(h_dtype) && valid_io(out_dtype),
+                 ldh >= d_ff && (scatter != nullptr || ldy >= d_out) && valid_io(h_dtype) && valid_io(out_dtype),
              "qg_ffn_forward: bad arguments (M=%d d_in=%d d_ff=%d d_out=%d)", M, d_in, d_ff, d_out);
   const size_t need = carve_ffn(nullptr, M, d_in, d_ff, d_out).bytes;
   if (workspace == nullptr) {
@@ -959,8 +966,74 @@ int qg_ffn_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in
   rc = quant_rows(H, h_dtype, M, d_ff, ldh, range, mode, nullptr, w.Xq2, w.ldq2, w.Cx2, st, io2);
   if (rc) return cuda_status((cudaError_t)rc, "row quantizer (hidden)");
   // ll2.forward (transformer.cu:69-71)
-  return gemm_dispatch(d, w.Xq2, w.ldq2, W2t, ldw2t, 1, M, d_out, d_ff, Y, ldy, out_dtype, w.Cx2, Cw2, b2, c, st, nullptr, nullptr,
+  return gemm_dispatch(d, w.Xq2, w.ldq2, W2t, ldw2t, 1, M, d_out, d_ff, Y, ldy, out_dtype, w.Cx2, Cw2, b2, c, st, nullptr, scatter,
                        QG_ACT_NONE, w.sk, w.sk_bytes, false);
+}
+
+extern "C" {
+
+int qg_ffn_forward(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in, int64_t ldxq_in, const float *Cx_in,
+                   const int8_t *W1t, int64_t ldw1t, const float *Cw1, const float *b1, const int8_t *W2t, int64_t ldw2t,
+                   const float *Cw2, const float *b2, void *H, int64_t ldh, int h_dtype, void *Y, int64_t ldy, int out_dtype,
+                   int M, int d_in, int d_ff, int d_out, float range, int mode, void *workspace, size_t workspace_bytes,
+                   qg_stream_t stream) {
+  return ffn_chain(X, ldx, in_dtype, Xq_in, ldxq_in, Cx_in, W1t, ldw1t, Cw1, b1, W2t, ldw2t, Cw2, b2, H, ldh, h_dtype, Y, ldy,
+                   out_dtype, M, d_in, d_ff, d_out, range, mode, workspace, workspace_bytes, stream, nullptr);
+}
+
+/* ---- Megatron pairing: column-parallel fc1 -> row-parallel fc2 ---- */
+static int scatter_args(const char *who, void *const *part_dst, int n_dst, int block_cols, int64_t ld_part, int n, MultiOut *mo) {
+  QG_REQUIRE(part_dst && n_dst >= 1 && n_dst <= kMaxExtraOut + 1 && block_cols > 0 && ld_part >= block_cols &&
+                 (int64_t)block_cols * n_dst >= n,
+             "%s: bad scatter arguments (n_dst=%d block_cols=%d ld_part=%lld n=%d)", who, n_dst, block_cols, (long long)ld_part, n);
+  for (int i = 0; i < n_dst; i++) QG_REQUIRE(part_dst[i] != nullptr, "%s: part_dst[%d] is NULL", who, i);
+  *mo = MultiOut();
+  mo->n = n_dst - 1;
+  for (int i = 1; i < n_dst; i++) mo->dst[i - 1] = part_dst[i];
+  mo->scatter_cols = block_cols;
+  return QG_OK;
+}
+
+int qg_gemm_s8_dequant_scatter(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_t ldwt, const float *Cx, const float *Cw,
+                               int M, int N, int K, float range, void *const *part_dst, int n_dst, int block_cols,
+                               int64_t ld_part, int part_dtype, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(Xq && Wt && Cx && Cw && M > 0 && N > 0 && K > 0 && ldxq >= K && ldwt >= K && valid_io(part_dtype),
+             "qg_gemm_s8_dequant_scatter: bad arguments");
+  MultiOut mo;
+  if ((rc = scatter_args("qg_gemm_s8_dequant_scatter", part_dst, n_dst, block_cols, ld_part, N, &mo))) return rc;
+  return gemm_dispatch(d, Xq, ldxq, Wt, ldwt, 1, M, N, K, part_dst[0], ld_part, part_dtype, Cx, Cw, nullptr, 1 / (range * range),
+                       (cudaStream_t)stream, nullptr, &mo);
+}
+
+int qg_ffn_forward_rowpar(const void *X, int64_t ldx, int in_dtype, const int8_t *Xq_in, int64_t ldxq_in, const float *Cx_in,
+                          const int8_t *W1t, int64_t ldw1t, const float *Cw1, const float *b1, const int8_t *W2t, int64_t ldw2t,
+                          const float *Cw2, void *H, int64_t ldh, int h_dtype, void *const *part_dst, int n_dst, int block_cols,
+                          int64_t ld_part, int part_dtype, int M, int d_in, int d_ff_local, int d_out, float range, int mode,
+                          void *workspace, size_t workspace_bytes, qg_stream_t stream) {
+  MultiOut mo;
+  int rc = scatter_args("qg_ffn_forward_rowpar", part_dst, n_dst, block_cols, ld_part, d_out, &mo);
+  if (rc) return rc;
+  // ld_part stands in for ldy; the chain's own check (ldy >= d_out) does not apply to a scattered output
+  QG_REQUIRE(valid_io(part_dtype), "qg_ffn_forward_rowpar: bad partial dtype");
+  return ffn_chain(X, ldx, in_dtype, Xq_in, ldxq_in, Cx_in, W1t, ldw1t, Cw1, b1, W2t, ldw2t, Cw2, nullptr, H, ldh, h_dtype,
+                   part_dst[0], ld_part, part_dtype, M, d_in, d_ff_local, d_out, range, mode, workspace, workspace_bytes, stream, &mo);
+}
+
+int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
+                       void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int m, int n, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(slots && out && n_slots >= 1 && m > 0 && n > 0 && ld_part >= n && ldo >= n && valid_io(part_dtype) &&
+                 valid_io(out_dtype) && n_peers >= 0 && n_peers <= kMaxExtraOut && (n_peers == 0 || peers) &&
+                 (n_slots == 1 || slot_stride >= (int64_t)(m - 1) * ld_part + n),
+             "qg_reduce_partials: bad arguments");
+  return cuda_status((cudaError_t)reduce_partials(slots, slot_stride, n_slots, part_dtype, ld_part, bias, out, peers, n_peers, ldo,
+                                                  out_dtype, m, n, (cudaStream_t)stream),
+                     "qg_reduce_partials");
 }
 
 int qg_add_layernorm_quant_f32(const float *A, int64_t lda, const float *R, int64_t ldr, int m, int n, float *B, int64_t ldb,

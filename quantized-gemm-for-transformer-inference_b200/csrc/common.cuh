@@ -75,7 +75,7 @@ struct SideArgs {
   int64_t ldxo;
   const void *Wo;  // [no_pad, ldwo] 16-bit rows W[idx[o], :]
   int64_t ldwo;
-  int no_pad;      // 0, 8 or 16
+  int no_pad;      // a multiple of 8, at most 64
   int side_bf16;   // 0: fp16 operands, 1: bf16
 };
 
@@ -102,6 +102,9 @@ constexpr int kMaxExtraOut = 7;
 struct MultiOut {
   void *dst[kMaxExtraOut];
   int n;
+  // > 0: scatter instead of replicate -- column block b (scatter_cols columns) goes to destination b only
+  // (0 = the call's own output pointer, b >= 1 = dst[b-1]); see GemmParams::scatter_cols
+  int scatter_cols;
 };
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -75,6 +75,95 @@ elemwise_kernel(const void *__restrict__ A, int64_t lda, const float *__restrict
 
 inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Reduce half of the row-parallel linear's reduce-scatter: the partial products of the P
+// ranks sit in P slots of this GPU's memory (written there by the peers' GEMM epilogues); out = ((s_0 + s_1) + ...) + bias
+// in ascending slot order, every addition rounded to fp32 -- a fixed order, so every run and every rank count gives the
+// bits the CPU restatement gives.  The result goes to `out` and, when peers are given, to the same block of their
+// matrices (the all-gather that completes an all-reduce, as plain 16-byte stores over NVLink).
+struct ReducePeers {
+  void *dst[kMaxExtraOut];
+  int n;
+};
+template <typename PT, typename OT, bool VEC>
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const PT *__restrict__ slots, int64_t slot_stride, int n_slots, int64_t ld_part,
+                       const float *__restrict__ bias, OT *__restrict__ out, ReducePeers peers, int64_t ldo, int M, int N) {
+  constexpr int W = VEC ? 4 : 1;
+  const int j = (blockIdx.x * 256 + threadIdx.x) * W;
+  griddep_wait();
+  if (j >= N) return;
+  float bv[W];
+#pragma unroll
+  for (int e = 0; e < W; e++) bv[e] = bias != nullptr ? bias[j + e] : 0.0f;
+  for (int i = blockIdx.y; i < M; i += gridDim.y) {
+    float acc[W];
+    for (int s = 0; s < n_slots; s++) {
+      const PT *src = slots + (int64_t)s * slot_stride + (int64_t)i * ld_part + j;
+      float v[W];
+      if (VEC) {
+        if (sizeof(PT) == 4) {
+          const float4 f = *reinterpret_cast<const float4 *>(src);
+          v[0] = f.x; v[1 % W] = f.y; v[2 % W] = f.z; v[3 % W] = f.w;
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2 *>(src);
+          const PT *h = reinterpret_cast<const PT *>(&u);
+#pragma unroll
+          for (int e = 0; e < W; e++) v[e] = to_f32<PT>(h[e]);
+        }
+      } else {
+        v[0] = to_f32<PT>(src[0]);
+      }
+#pragma unroll
+      for (int e = 0; e < W; e++) acc[e] = s == 0 ? v[e] : __fadd_rn(acc[e], v[e]);
+    }
+    if (bias != nullptr) {
+#pragma unroll
+      for (int e = 0; e < W; e++) acc[e] = __fadd_rn(acc[e], bv[e]);
+    }
+    OT r[W];
+#pragma unroll
+    for (int e = 0; e < W; e++) r[e] = from_f32<OT>(acc[e]);
+    for (int d = -1; d < peers.n; d++) {
+      OT *dst = (d < 0 ? out : reinterpret_cast<OT *>(peers.dst[d])) + (int64_t)i * ldo + j;
+      if (VEC) {
+        if (sizeof(OT) == 4) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(r);
+        else *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(r);
+      } else {
+        dst[0] = r[0];
+      }
+    }
+  }
+}
+
+template <typename PT, typename OT>
+int launch_reduce(const void *slots, int64_t slot_stride, int n_slots, int64_t ld_part, const float *bias, void *out,
+                  const ReducePeers &peers, int64_t ldo, int M, int N, cudaStream_t st) {
+  bool vec = N % 4 == 0 && ld_part % 4 == 0 && slot_stride % 4 == 0 && ldo % 4 == 0 &&
+             (reinterpret_cast<uintptr_t>(slots) % (4 * sizeof(PT))) == 0 && (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(OT))) == 0;
+  for (int d = 0; d < peers.n; d++) vec = vec && (reinterpret_cast<uintptr_t>(peers.dst[d]) % (4 * sizeof(OT))) == 0;
+  const int w = vec ? 4 : 1;
+  const unsigned gx = (unsigned)ceil_div(N, 256 * w);
+  unsigned gy = (unsigned)(148 * 16 / gx);
+  gy = gy < 1 ? 1 : gy;
+  gy = gy > (unsigned)M ? (unsigned)M : gy;
+  dim3 grid(gx, gy);
+  if (vec)
+    return (int)launch_kernel(reduce_partials_kernel<PT, OT, true>, grid, dim3(256), st, (const PT *)slots, slot_stride, n_slots,
+                              ld_part, bias, (OT *)out, peers, ldo, M, N);
+  return (int)launch_kernel(reduce_partials_kernel<PT, OT, false>, grid, dim3(256), st, (const PT *)slots, slot_stride, n_slots,
+                            ld_part, bias, (OT *)out, peers, ldo, M, N);
+}
+template <typename PT>
+int reduce_out(int out_dtype, const void *slots, int64_t slot_stride, int n_slots, int64_t ld_part, const float *bias, void *out,
+               const ReducePeers &peers, int64_t ldo, int M, int N, cudaStream_t st) {
+  switch (out_dtype) {
+    case QG_F32: return launch_reduce<PT, float>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st);
+    case QG_F16: return launch_reduce<PT, __half>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st);
+    case QG_BF16: return launch_reduce<PT, __nv_bfloat16>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st);
+  }
+  return QG_EINVAL;
+}
+
 template <int OP>
 int launch_op(const void *A, int64_t lda, const float *B, int64_t ldb, int bmode, float c, float *O, int64_t ldo, int M, int N,
               cudaStream_t st) {
@@ -104,6 +193,20 @@ int elemwise(int op, const void *A, int64_t lda, const float *B, int64_t ldb, in
     case OP_DEQ: return launch_op<OP_DEQ>(A, lda, B, ldb, bmode, c, O, ldo, M, N, st);
     case OP_SCALE: return launch_op<OP_SCALE>(A, lda, nullptr, 0, 3, c, O, ldo, M, N, st);
     case OP_RELU: return launch_op<OP_RELU>(A, lda, nullptr, 0, 3, 0.0f, O, ldo, M, N, st);
+  }
+  return QG_EINVAL;
+}
+
+// slots: [n_slots][M][ld_part] of part_dtype (slot_stride elements apart); out / peers: [M, ldo] of out_dtype
+int reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
+                    void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st) {
+  ReducePeers pr = {};
+  pr.n = n_peers;
+  for (int d = 0; d < n_peers; d++) pr.dst[d] = peers[d];
+  switch (part_dtype) {
+    case QG_F32: return reduce_out<float>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st);
+    case QG_F16: return reduce_out<__half>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st);
+    case QG_BF16: return reduce_out<__nv_bfloat16>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st);
   }
   return QG_EINVAL;
 }

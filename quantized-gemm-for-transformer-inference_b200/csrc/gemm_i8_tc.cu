@@ -82,13 +82,21 @@ struct GemmParams {
   // extra destinations (peer GPUs): same block, same ldo; TMA maps in ExtraMaps, raw pointers here
   int n_extra;
   void *extra_out[kMaxExtraOut];
+  // scatter_cols > 0 (row-parallel linear): the N columns are cut into blocks of scatter_cols
+  // columns and block b is stored ONLY to destination b (0: out / map_o, b >= 1: extra_out[b-1] / xmaps.m[b-1]), each an
+  // [M, scatter_cols] matrix with leading dimension ldo -- the scatter half of a reduce-scatter done by the epilogue.
+  int scatter_cols;
 };
 
 struct ExtraMaps {
   CUtensorMap m[kMaxExtraOut];
 };
 
-constexpr int kSideMax = 16;  // outlier columns the fused epilogue can take
+// Outlier side product in the epilogue (CUDA cores, fp32 FMA chain in ascending outlier order -- the order is part of
+// the result, which is why this is not a tensor-core product).  Up to kSideDbl columns the fp32 Wo tile is double
+// buffered by accumulator stage; up to kSideMax it is single buffered in a region that also takes the ring's last stage.
+constexpr int kSideDbl = 16;
+constexpr int kSideMax = 64;
 
 template <int CG, bool B_MN, bool SIDE = false>
 struct Cfg {
@@ -97,9 +105,12 @@ struct Cfg {
   static constexpr int kBBytes = kBLoadN * BK;            // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (CG == 1 ? 4 : 6) - (SIDE ? 1 : 0);  // one stage pays for the Wo tile
-  static constexpr int kSideBytes = SIDE ? 2 * kSideMax * BN * 4 : 0;  // fp32 Wo tile, double buffered
+  static constexpr int kSideBytes = SIDE ? 2 * kSideDbl * BN * 4 : 0;  // fp32 Wo tile, double buffered (32 KB)
   static constexpr int kOutStaging = kEpiWarps * kStageOutBytes;       // 32 KB
-  // [small area | pad to 1024 | operand ring | output staging | Wo tile].  Without static shared memory the
+  // more than kSideDbl outlier columns: the ring runs one stage shorter and the Wo tile (single buffered) takes that
+  // stage plus the 32 KB behind it
+  static_assert(!SIDE || kStageBytes + 2 * kSideDbl * BN * 4 >= kSideMax * BN * 4, "big Wo tile");
+  // [small area | pad to 1024 | operand ring | Wo tile | output staging].  Without static shared memory the
   // dynamic segment starts 1024-byte aligned, so the pad is 3072 - kSmallBytes and the total is exactly the
   // 227 KB a CTA may have (the kernel checks the layout against %dynamic_smem_size and traps otherwise).
   static constexpr int kSmemBytes = 3072 + kStages * kStageBytes + kOutStaging + kSideBytes;
@@ -149,8 +160,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   float *scale_s = reinterpret_cast<float *>(smem_raw + 256);  // [kEpiWarps][cw 32 | bias 32]
   // 128B swizzle atoms repeat every 1024 B: align the ring
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + kSmallBytes + 1023) & ~uintptr_t(1023));
-  uint8_t *smem_out = smem + kStages * C::kStageBytes;
-  float *wo_s = reinterpret_cast<float *>(smem_out + C::kOutStaging);  // [2][kSideMax][BN] (SIDE only)
+  // SIDE only: [2][kSideDbl][BN] behind the ring, or [kSideMax][BN] starting at the ring's last stage
+  const bool side_big = SIDE && p.no_pad > kSideDbl;
+  float *wo_s = reinterpret_cast<float *>(smem + (kStages - (side_big ? 1 : 0)) * C::kStageBytes);
+  uint8_t *smem_out = smem + kStages * C::kStageBytes + C::kSideBytes;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -160,7 +173,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (threadIdx.x == 0) {  // the layout must fit what was launched (it does when the segment is 1024-byte aligned)
     uint32_t dyn;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (reinterpret_cast<uint8_t *>(wo_s) + C::kSideBytes > smem_raw + dyn) {
+    if (smem_out + C::kOutStaging > smem_raw + dyn) {
       printf("[qgemm] gemm_i8_tc: shared-memory layout exceeds the %u bytes launched\n", dyn);
       __trap();
     }
@@ -383,6 +396,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       float cx = 0.0f;
       if (kDequant) {
         if (SIDE) {
+          // fp32 copy of Wo[:, tile columns]; small tiles alternate between two buffers with the accumulator stage,
+          // the big one is reused, so every warp must be done with the previous tile's copy first
+          float *wo_tile = wo_s + (side_big ? 0 : (int)as * kSideDbl * BN);
+          if (side_big) named_bar_sync(1, 32 * kEpiWarps);
           for (int i = epi_tid; i < p.no_pad * bn; i += 32 * kEpiWarps) {
             const int o = i / bn, cc = i - o * bn, col = n_base + cc;
             float wv = 0.0f;
@@ -390,53 +407,46 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               if (p.side_bf16) wv = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p.Wo)[(int64_t)o * p.ldwo + col]);
               else wv = __half2float(reinterpret_cast<const __half *>(p.Wo)[(int64_t)o * p.ldwo + col]);
             }
-            wo_s[(as * kSideMax + o) * BN + cc] = wv;
+            wo_tile[o * BN + cc] = wv;
           }
           named_bar_sync(1, 32 * kEpiWarps);
         }
         if (row < p.M) cx = __ldg(p.Cx + row);
       }
-      float xo[SIDE ? kSideMax : 1];
-      if (SIDE) {
-#pragma unroll
-        for (int o8 = 0; o8 < kSideMax; o8 += 8) {
-          uint4 xv = make_uint4(0, 0, 0, 0);
-          if (o8 < p.no_pad && row < p.M)
-            xv = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(p.Xo) + (int64_t)row * p.ldxo + o8);
-          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            if (p.side_bf16) {
-              xo[o8 + 2 * i] = __uint_as_float(xw[i] << 16);
-              xo[o8 + 2 * i + 1] = __uint_as_float(xw[i] & 0xffff0000u);
-            } else {
-              const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&xw[i]));
-              xo[o8 + 2 * i] = f2.x;
-              xo[o8 + 2 * i + 1] = f2.y;
-            }
-          }
-        }
-      }
-      // side[j] = sum_o xo[o] * Wo[o][cbase + j], o ascending, fp32 fma chain from +0
+      // side[j] = sum_o xo[o] * Wo[o][cbase + j], o ascending, fp32 fma chain from +0; the row's outlier entries are
+      // fetched eight at a time (16 bytes of Xo, L1-resident after the first chunk)
       auto side_chunk = [&](int cbase, float (&sd)[32]) {
 #pragma unroll
         for (int j = 0; j < 32; j++) sd[j] = 0.0f;
         if (SIDE) {
-          const float *wo = wo_s + as * kSideMax * BN + cbase;
+          const float *wo = wo_s + (side_big ? 0 : (int)as * kSideDbl * BN) + cbase;
+#pragma unroll 1
+          for (int ob = 0; ob < p.no_pad; ob += 8) {
+            uint4 xv = make_uint4(0, 0, 0, 0);
+            if (row < p.M) xv = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(p.Xo) + (int64_t)row * p.ldxo + ob));
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            float xo[8];
 #pragma unroll
-          for (int ob = 0; ob < kSideMax; ob += 8) {
-            if (ob < p.no_pad) {
+            for (int i = 0; i < 4; i++) {
+              if (p.side_bf16) {
+                xo[2 * i] = __uint_as_float(xw[i] << 16);
+                xo[2 * i + 1] = __uint_as_float(xw[i] & 0xffff0000u);
+              } else {
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&xw[i]));
+                xo[2 * i] = f2.x;
+                xo[2 * i + 1] = f2.y;
+              }
+            }
 #pragma unroll
-              for (int o = ob; o < ob + 8; o++) {
-                const float4 *wp = reinterpret_cast<const float4 *>(wo + o * BN);
+            for (int o = 0; o < 8; o++) {
+              const float4 *wp = reinterpret_cast<const float4 *>(wo + (ob + o) * BN);
 #pragma unroll
-                for (int j4 = 0; j4 < 8; j4++) {
-                  const float4 wv = wp[j4];
-                  sd[4 * j4] = __fmaf_rn(xo[o], wv.x, sd[4 * j4]);
-                  sd[4 * j4 + 1] = __fmaf_rn(xo[o], wv.y, sd[4 * j4 + 1]);
-                  sd[4 * j4 + 2] = __fmaf_rn(xo[o], wv.z, sd[4 * j4 + 2]);
-                  sd[4 * j4 + 3] = __fmaf_rn(xo[o], wv.w, sd[4 * j4 + 3]);
-                }
+              for (int j4 = 0; j4 < 8; j4++) {
+                const float4 wv = wp[j4];
+                sd[4 * j4] = __fmaf_rn(xo[o], wv.x, sd[4 * j4]);
+                sd[4 * j4 + 1] = __fmaf_rn(xo[o], wv.y, sd[4 * j4 + 1]);
+                sd[4 * j4 + 2] = __fmaf_rn(xo[o], wv.z, sd[4 * j4 + 2]);
+                sd[4 * j4 + 3] = __fmaf_rn(xo[o], wv.w, sd[4 * j4 + 3]);
               }
             }
           }
@@ -543,6 +553,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (lane == 0) {  // always lane 0: bulk async-groups are per thread
             if (p.split_k > 1) {  // this k-slice's partial sums
               tma_store_2d(cur_slice > 0 ? &xmaps.m[cur_slice - 1] : &map_o, stage_u32, n_base + c0, m_base + q * 32);
+            } else if (p.scatter_cols > 0) {  // the column block's owner only, at its local column
+              const int owner = (n_base + c0) / p.scatter_cols;
+              tma_store_2d(owner > 0 ? &xmaps.m[owner - 1] : &map_o, stage_u32, n_base + c0 - owner * p.scatter_cols, m_base + q * 32);
             } else {
               if (p.store_hint) tma_store_2d_hint(&map_o, stage_u32, n_base + c0, m_base + q * 32, store_policy);
               else tma_store_2d(&map_o, stage_u32, n_base + c0, m_base + q * 32);
@@ -552,10 +565,16 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_store_commit();
           }
         } else if (row < p.M) {
-          const int d_first = (p.split_k > 1 && cur_slice > 0) ? cur_slice - 1 : -1;  // split-K: one destination, the slice's
-          const int d_end = p.split_k > 1 ? d_first + 1 : p.n_extra;
+          int d_first = (p.split_k > 1 && cur_slice > 0) ? cur_slice - 1 : -1;  // split-K: one destination, the slice's
+          int d_end = p.split_k > 1 ? d_first + 1 : p.n_extra;
+          int col_off = n_base + c0;
+          if (p.scatter_cols > 0) {  // one destination: the owner of this column block
+            d_first = col_off / p.scatter_cols - 1;
+            d_end = d_first + 1;
+            col_off -= (d_first + 1) * p.scatter_cols;
+          }
           for (int d = d_first; d < d_end; d++) {  // local matrix, then the peers' copies
-            OutT *dst = reinterpret_cast<OutT *>(d < 0 ? p.out : p.extra_out[d]) + (int64_t)row * p.ldo + n_base + c0;
+            OutT *dst = reinterpret_cast<OutT *>(d < 0 ? p.out : p.extra_out[d]) + (int64_t)row * p.ldo + col_off;
             const int ncols = min(OT::kCols, p.N - (n_base + c0));
             if (ncols == OT::kCols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
@@ -752,6 +771,7 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   const int base_tiles = p.tiles_m * p.tiles_n;
   int max_clusters = num_sms / CG;
   p.nstages = C::kStages;
+  if (SIDE && p.no_pad > kSideDbl) p.nstages = C::kStages - 1;  // the big Wo tile takes the ring's last stage
   static const bool dbg_noload = getenv("QG_DBG_NOLOAD") != nullptr, dbg_all_half = getenv("QG_DBG_ALL_HALF") != nullptr;
   p.dbg_noload = dbg_noload ? 1 : 0;
   static const bool dbg_noepi = getenv("QG_DBG_NOEPI") != nullptr, no_last_ring = getenv("QG_NO_LAST_RING") != nullptr;
@@ -761,12 +781,12 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   static const int store_hint = [] { const char *e = getenv("QG_STORE_HINT"); return e ? atoi(e) : 0; }();
   p.store_hint = store_hint;
   // the ring must hold 8 warps x 4 chunks x 4 KB = 128 KB (it does in every configuration: >= 144 KB)
-  p.last_ring = (!no_last_ring && C::kStages * C::kStageBytes >= kEpiWarps * 4 * kStageOutBytes) ? 1 : 0;
+  p.last_ring = (!no_last_ring && (int)p.nstages * C::kStageBytes >= kEpiWarps * 4 * kStageOutBytes) ? 1 : 0;
   static const int max_clusters_env = [] { const char *e = getenv("QG_DBG_MAX_CLUSTERS"); return e ? atoi(e) : 0; }();
   static const char *dbg_stages = getenv("QG_DBG_STAGES");
   if (const char *e = dbg_stages) {
     const int v = atoi(e);
-    if (v >= 1 && v <= C::kStages) p.nstages = (uint32_t)v;
+    if (v >= 1 && v <= (int)p.nstages) p.nstages = (uint32_t)v;
   }
   if (max_clusters_env > 0 && max_clusters_env < max_clusters) max_clusters = max_clusters_env;  // experiment: fewer SMs
   p.full_tiles = base_tiles;
@@ -920,6 +940,24 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   }
   static ExtraMaps xm_zero = {};
   ExtraMaps xm = xm_zero;
+  const int scatter_cols = (multi != nullptr && p.split_k == 1) ? multi->scatter_cols : 0;
+  if (scatter_cols > 0) {
+    const int chunk = (int)(128 / osz);  // columns one store carries: a chunk must not straddle two owners
+    if (scatter_cols % chunk != 0 || (int64_t)scatter_cols * (multi->n + 1) < N || ldo < scatter_cols) {
+      set_error("gemm_i8_tc: scatter blocks must be multiples of %d columns and cover N (scatter_cols=%d, %d destinations, N=%d)",
+                chunk, scatter_cols, multi->n + 1, N);
+      return QG_EINVAL;
+    }
+    p.scatter_cols = scatter_cols;
+    if (p.tma_store) {  // destination 0 is an [M, scatter_cols] block too
+      CUtensorMapDataType odt = out_kind == QG_S32   ? CU_TENSOR_MAP_DATA_TYPE_INT32
+                                : out_kind == QG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                : out_kind == QG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      rc = make_map_2d(&mo, odt, osz, O, M, scatter_cols, ldo, 32, (uint32_t)(128 / osz));
+      if (rc) return rc;
+    }
+  }
   if (multi != nullptr && multi->n > 0) {
     if (multi->n > kMaxExtraOut || (out_kind == QG_S32 && p.split_k == 1)) {
       set_error("gemm_i8_tc: at most %d extra destinations, floating-point output", kMaxExtraOut);
@@ -936,7 +974,7 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
                                 : out_kind == QG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                      : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
       for (int d = 0; d < multi->n; d++) {
-        rc = make_map_2d(&xm.m[d], odt, osz, multi->dst[d], M, N, ldo, 32, (uint32_t)(128 / osz));
+        rc = make_map_2d(&xm.m[d], odt, osz, multi->dst[d], M, scatter_cols > 0 ? scatter_cols : N, ldo, 32, (uint32_t)(128 / osz));
         if (rc) return rc;
       }
     }

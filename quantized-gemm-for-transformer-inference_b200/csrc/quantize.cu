@@ -7,9 +7,11 @@
 // with HBM-bound kernels that read the matrix with 16-byte loads, reduce with warp shuffles and
 // write packed int8 codes plus the fp32 absmax.  The arithmetic (and its quirks: signed first
 // element, IEEE 127/x, truncate-and-wrap cast) is reproduced exactly; see oracle/qoracle.c.
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 
 #include "quant_common.cuh"
@@ -448,6 +450,242 @@ quant_cols_t_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float ra
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Columns in ONE launch, one HBM read of W: the panel pipeline.
+//
+// W is cut into column panels small enough to stay in L2 (<= ~16 MiB).  A column group (32*EPV columns) goes
+// through two phases -- phase 1 reduces |W[k,j]| (k >= 1) per column, phase 2 folds the signed row 0, forms the
+// scale and writes the codes.  The persistent grid is split by role: "readers" (most CTAs) walk the phase-1 items
+// of all panels in panel order and never wait, so HBM streams W once at full rate; "writers" walk the phase-2
+// items in the same order, about one panel behind, and find their rows in L2.  Work is handed out per WARP with a
+// STATIC round-robin and no block-level barrier exists in the loop: an item is one column group x R rows, streamed
+// with 8 independent 16-byte loads in flight per lane.  A writer item waits until all phase-1 items of ITS column
+// group have arrived (one counter per group, each on its own cache line).
+// What this design replaced, measured (4096^2 fp32, two launches = 23.5 us): whole CTAs synchronising per item
+// (38-48 us) and per-warp items claimed from a ticket counter (50 us) -- both read W from HBM once, as intended
+// (ncu: 67 MB), and both were bound by the atomics: a contended same-address atomicAdd retires every ~4.4 ns on
+// this part, so thousands of ticket claims serialise into tens of microseconds.  Hence no tickets.
+// Every CTA of the grid is resident (grid <= occupancy x SMs), so writers spinning on a counter cannot keep a
+// reader from running.  The scratch restores itself (the last CTA to leave resets counters and maxima): a call
+// leaves no state behind -- safe under CUDA-graph replay; one scratch per (device, stream).
+// ------------------------------------------------------------------------------------------
+constexpr int64_t kPipeMinBytes = 8ll << 20;
+constexpr int kExitFan = 16;     // exit counting is two-level so that no address sees more than grid / 16 atomics
+constexpr int kLineInts = 32;    // one counter per 128-byte line
+struct ColsPipeGeom {
+  int n_groups;          // column groups of 32*EPV columns
+  int groups_per_panel;  // G
+  int n_panels;
+  int rows_per_item;     // R: rows of a phase-1 item
+  int rows_per_item2;    // rows of a phase-2 item
+  int c1, c2;            // row chunks per column group in phase 1 (rows 1..K-1) / phase 2 (rows 0..K-1)
+  int items1, items2;    // phase-1 / phase-2 items over all panels
+  int readers_of;        // role pattern: blockIdx % readers_of < readers_in  ->  reader
+  int readers_in;
+};
+// device scratch, all zero / -inf between calls: [exit counters | arrive[n_groups] (one per line) | part[n_cols]]
+struct ColsPipeScratch {
+  int exit_top, pad[kLineInts - 1];
+  int exit_leaf[kExitFan][kLineInts];
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 4)
+quant_cols_pipe_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, ColsPipeGeom g,
+                       ColsPipeScratch *__restrict__ sc, int *__restrict__ arrive, int *__restrict__ part,
+                       int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
+  constexpr int EPV = Unpack<T>::EPV;
+  constexpr int U = 8;             // loads in flight per lane
+  constexpr int NW = kThreads / 32;
+  constexpr uint32_t kNaN = sizeof(T) == 4 ? 0x7fc00000u : (std::is_same<T, __half>::value ? 0x7e007e00u : 0x7fc07fc0u);
+  __shared__ float s_m[2][NW][32 * EPV + 1];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int role_pos = (int)(blockIdx.x % g.readers_of), role_blk = (int)(blockIdx.x / g.readers_of);
+  const bool reader = role_pos < g.readers_in;
+  griddep_wait();
+  griddep_trigger_early();
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+  const int chunks = reader ? g.c1 : g.c2;
+  const int n_items = reader ? g.items1 : g.items2;
+  const int rows_item = reader ? g.rows_per_item : g.rows_per_item2;
+  const int per_panel = g.groups_per_panel * chunks;  // items of a full panel (only the last panel may be narrower)
+  // this CTA's position among the CTAs of its role, and their number (the grid is a multiple of the role pattern)
+  const int role_ctas = (int)(gridDim.x / g.readers_of) * (reader ? g.readers_in : g.readers_of - g.readers_in);
+  const int my_cta = reader ? role_blk * g.readers_in + role_pos
+                            : role_blk * (g.readers_of - g.readers_in) + (role_pos - g.readers_in);
+  auto decode = [&](int item, int &grp, int &chunk) {
+    int panel = item / per_panel;
+    if (panel >= g.n_panels) panel = g.n_panels - 1;
+    const int local = item - panel * per_panel;
+    const int gp = min(g.groups_per_panel, g.n_groups - panel * g.groups_per_panel);
+    grp = panel * g.groups_per_panel + local % gp;
+    chunk = local / gp;
+  };
+
+  if (reader) {
+    // An item is one column group x R rows; warp w takes rows k0 + w, k0 + w + 8, ...  The loop is software-pipelined:
+    // the loads of the NEXT item are issued before this item's reduction, atomics and fence, so the per-item
+    // synchronisation chain runs under memory latency instead of adding to it.
+    uint4 r[U];
+    auto issue = [&](int item) {
+      int grp, chunk;
+      decode(item, grp, chunk);
+      const int col = (grp * 32 + lane) * EPV;
+      const int k0 = 1 + chunk * rows_item, k1 = min(K, k0 + rows_item);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int k = k0 + warp + NW * u;
+        r[u] = (col < N && k < k1) ? ldg16_hint(W + col + (int64_t)k * ldw, pol_keep) : make_uint4(kNaN, kNaN, kNaN, kNaN);
+      }
+    };
+    int item = my_cta;
+    if (item < n_items) issue(item);
+    int prev_grp = -1;  // the item whose arrival is still owed: it is published one iteration late, when the fence is free
+    for (int it = 0; item < n_items; item += role_ctas, it++) {
+      int grp, chunk;
+      decode(item, grp, chunk);
+      float m[EPV];
+#pragma unroll
+      for (int e = 0; e < EPV; e++) m[e] = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < U; u++) {  // rows past the chunk hold NaNs, which fmaxf skips like the reduction skips real ones
+        float f[EPV];
+        Unpack<T>::run(r[u], f);
+#pragma unroll
+        for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
+      }
+      {  // a chunk taller than NW * U rows: the remaining rows, not pipelined
+        const int col = (grp * 32 + lane) * EPV;
+        const int k0 = 1 + chunk * rows_item, k1 = min(K, k0 + rows_item);
+        for (int k = k0 + warp + NW * U; k < k1 && col < N; k += NW) {
+          float f[EPV];
+          Unpack<T>::run(ldg16_hint(W + col + (int64_t)k * ldw, pol_keep), f);
+#pragma unroll
+          for (int e = 0; e < EPV; e++) m[e] = fmaxf(m[e], fabsf(f[e]));
+        }
+      }
+      // the previous item's atomics were issued a whole load round trip ago: this fence finds nothing to wait for
+      if (prev_grp >= 0 && threadIdx.x < 32 * EPV) __threadfence();
+      float(*sm)[32 * EPV + 1] = s_m[it & 1];
+#pragma unroll
+      for (int e = 0; e < EPV; e++) sm[warp][lane * EPV + e] = m[e];
+      __syncthreads();  // the only barrier of an iteration (s_m alternates, so the next write needs none)
+      if (threadIdx.x == 0 && prev_grp >= 0) atomicAdd(arrive + prev_grp * kLineInts, 1);
+      for (int c = threadIdx.x; c < 32 * EPV; c += kThreads) {
+        float v = sm[0][c];
+#pragma unroll
+        for (int y = 1; y < NW; y++) v = fmaxf(v, sm[y][c]);
+        const int gc = grp * 32 * EPV + c;
+        if (gc < N && v >= 0.0f) atomicMax(part + gc, __float_as_int(v));  // candidates >= +0, initial value -inf
+      }
+      if (item + role_ctas < n_items) issue(item + role_ctas);
+      prev_grp = grp;
+    }
+    if (prev_grp >= 0) {
+      if (threadIdx.x < 32 * EPV) __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(arrive + prev_grp * kLineInts, 1);
+    }
+  } else {
+    for (int item = my_cta; item < n_items; item += role_ctas) {
+      int grp, chunk;
+      decode(item, grp, chunk);
+      const int col = (grp * 32 + lane) * EPV;
+      const T *base = W + col;
+      if (g.c1 > 0) {  // all phase-1 items of this column group have arrived?
+        if (lane == 0)
+          while (ld_acquire_gpu(arrive + grp * kLineInts) < g.c1) __nanosleep(64);
+        __syncwarp();
+      }
+      if (col < N) {
+        float s[EPV];
+        float x0[EPV];
+        Unpack<T>::run(ldg16(base), x0);
+#pragma unroll
+        for (int e = 0; e < EPV; e++) {
+          float c;
+          if (fold_first(x0[e], __int_as_float(__ldcg(part + col + e)), mode, c)) {
+            for (int k = 1; k < K; k++) {
+              const float x = to_f32(base[(int64_t)k * ldw + e]);
+              if (x == x) { c = -x; break; }
+            }
+          }
+          if (chunk == 0 && warp == 0 && Cw != nullptr) Cw[col + e] = c;
+          s[e] = __fdiv_rn(range, c);
+        }
+        const int k0 = chunk * rows_item, k1 = min(K, k0 + rows_item);
+        auto emit = [&](const uint4 &r, int k) {
+          float f[EPV];
+          Unpack<T>::run(r, f);
+          uint32_t w[EPV / 4];
+#pragma unroll
+          for (int q = 0; q < EPV / 4; q++)
+            w[q] = quant_code_u8(f[4 * q], s[4 * q]) | (quant_code_u8(f[4 * q + 1], s[4 * q + 1]) << 8) |
+                   (quant_code_u8(f[4 * q + 2], s[4 * q + 2]) << 16) | (quant_code_u8(f[4 * q + 3], s[4 * q + 3]) << 24);
+          int8_t *dst = Wq + (int64_t)k * ldq + col;
+          if (EPV == 4) *reinterpret_cast<uint32_t *>(dst) = w[0];
+          else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[EPV / 4 - 1]);
+        };
+        // rows k0 + warp + 8 * (4 s + u): two register sets of four loads, one in flight while the other is converted
+        constexpr int UH = U / 2;
+        auto ld = [&](uint4 (&r)[UH], int st) {
+#pragma unroll
+          for (int u = 0; u < UH; u++) {
+            const int k = k0 + warp + NW * (UH * st + u);
+            if (k < k1) r[u] = ldg16_hint(base + (int64_t)k * ldw, pol_drop);
+          }
+        };
+        auto put = [&](const uint4 (&r)[UH], int st) {
+#pragma unroll
+          for (int u = 0; u < UH; u++) {
+            const int k = k0 + warp + NW * (UH * st + u);
+            if (k < k1) emit(r[u], k);
+          }
+        };
+        const int n_steps = (k1 - k0 + NW * UH - 1) / (NW * UH);
+        uint4 ra[UH], rb[UH];
+        ld(ra, 0);
+        for (int st = 0; st < n_steps; st += 2) {
+          ld(rb, st + 1);
+          put(ra, st);
+          ld(ra, st + 2);
+          put(rb, st + 1);
+        }
+      }
+    }
+  }
+  // the last CTA out puts the scratch back (two-level count: leaf = blockIdx % 16)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int leaf = (int)(blockIdx.x % kExitFan);
+    const int leaf_size = (int)((gridDim.x - leaf + kExitFan - 1) / kExitFan);
+    int last = 0;
+    if (atomicAdd(&sc->exit_leaf[leaf][0], 1) == leaf_size - 1) {
+      const int leaves = (int)min((unsigned)kExitFan, gridDim.x);
+      last = atomicAdd(&sc->exit_top, 1) == leaves - 1;
+    }
+    s_last = last;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int ng = g.n_groups * 32 * EPV;
+    const int neg_inf = __float_as_int(-INFINITY);
+    for (int j = threadIdx.x; j < ng; j += kThreads) part[j] = neg_inf;
+    for (int j = threadIdx.x; j < g.n_groups; j += kThreads) arrive[j * kLineInts] = 0;
+    if (threadIdx.x < kExitFan) sc->exit_leaf[threadIdx.x][0] = 0;
+    if (threadIdx.x == 0) sc->exit_top = 0;
+  }
+}
+
 // Any N / alignment: one thread per column (coalesced across threads), scalar accesses.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -539,6 +777,110 @@ int twopass_scratch(int N, cudaStream_t st, unsigned long long **part, uint32_t 
   return 0;
 }
 
+// Scratch of the panel pipeline: [ColsPipeScratch | arrive[groups] one per line | part[cols]], zero / -inf at rest,
+// one per (device, stream).
+struct PipeState {
+  ColsPipeScratch *sc = nullptr;
+  int cols = 0;
+};
+__global__ void pipe_scratch_init_kernel(int *words, int n_zero, int n_total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_total) words[i] = i < n_zero ? 0 : __float_as_int(-INFINITY);
+}
+int pipe_scratch(int n_cols, cudaStream_t st, ColsPipeScratch **sc, int **arrive, int **part) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, PipeState> states;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  std::lock_guard<std::mutex> lk(mu);
+  PipeState &s = states[std::make_pair(dev, st)];
+  if (s.cols < n_cols) {
+    if (s.sc) { cudaStreamSynchronize(st); cudaFree(s.sc); s.sc = nullptr; }
+    s.cols = (int)round_up(n_cols < 16384 ? 16384 : n_cols, 4096);
+    const size_t head = sizeof(ColsPipeScratch) / sizeof(int), arr = (size_t)(s.cols / 128) * kLineInts;  // >= one group per 128 columns
+    if ((e = cudaMalloc(&s.sc, sizeof(int) * (head + arr + (size_t)s.cols))) != cudaSuccess) { s = PipeState(); return (int)e; }
+    const int n_total = (int)(head + arr + (size_t)s.cols);
+    pipe_scratch_init_kernel<<<(unsigned)ceil_div(n_total, 256), 256, 0, st>>>(reinterpret_cast<int *>(s.sc), (int)(head + arr), n_total);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  }
+  *sc = s.sc;
+  *arrive = reinterpret_cast<int *>(s.sc) + sizeof(ColsPipeScratch) / sizeof(int);
+  *part = *arrive + (size_t)(s.cols / 128) * kLineInts;
+  return 0;
+}
+
+// Geometry of the panel pipeline.  Defaults: panels of <= 16 MiB, warp items of 32 rows, 4 CTAs per SM, 5 of 8 CTAs read.
+// QG_COLS_PIPE = "0" switches the pipeline off (two launches); "G,R,readers_in,readers_of[,ctas_per_sm[,R2]]" overrides.
+struct PipeTune { int on = 1, G = 0, R = 0, rin = 0, rof = 0, per_sm = 0, R2 = 0; };
+const PipeTune &pipe_tune() {
+  static const PipeTune t = [] {
+    PipeTune v;
+    if (const char *e = getenv("QG_COLS_PIPE")) {
+      int a = 0, b = 0, c = 0, d = 0, f = 0, h = 0;
+      const int n = sscanf(e, "%d,%d,%d,%d,%d,%d", &a, &b, &c, &d, &f, &h);
+      if (n == 1 && a == 0) v.on = 0;
+      if (n >= 4) { v.G = a; v.R = b; v.rin = c; v.rof = d; }
+      if (n >= 5) v.per_sm = f;
+      if (n >= 6) v.R2 = h;
+    }
+    return v;
+  }();
+  return t;
+}
+
+template <typename T>
+int cols_pipe_launch(const T *W, int K, int N, int64_t ldw, float range, int mode, int8_t *Wq, int64_t ldq, float *Cw,
+                     cudaStream_t st) {
+  constexpr int EPV = Unpack<T>::EPV;
+  const PipeTune &tune = pipe_tune();
+  static int per_sm_occ = 0, sms = 0;
+  if (per_sm_occ == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_occ, quant_cols_pipe_kernel<T>, kThreads, 0);
+    if (per_sm_occ <= 0) per_sm_occ = 1;
+    if (sms <= 0) sms = 148;
+  }
+  int per_sm = tune.per_sm > 0 ? tune.per_sm : 4;
+  if (per_sm > per_sm_occ) per_sm = per_sm_occ;
+  ColsPipeGeom g = {};
+  g.readers_of = tune.rof > 0 ? tune.rof : 8;
+  g.readers_in = tune.rin > 0 ? tune.rin : 5;
+  if (g.readers_in >= g.readers_of) g.readers_in = g.readers_of - 1;
+  if (g.readers_in < 1 || per_sm < 2) return -1;
+  g.n_groups = (int)ceil_div(N, 32 * EPV);
+  const int64_t group_row_bytes = 32 * 16;  // one column group of one row
+  int G = tune.G > 0 ? tune.G : (int)((16ll << 20) / ((int64_t)K * group_row_bytes));
+  if (G < 1) G = 1;
+  if (G > g.n_groups) G = g.n_groups;
+  g.groups_per_panel = G;
+  g.n_panels = (int)ceil_div(g.n_groups, G);
+  const int R = tune.R > 0 ? (int)round_up(tune.R, 8) : 64, R2 = tune.R2 > 0 ? (int)round_up(tune.R2, 8) : 256;
+  g.rows_per_item = R;
+  g.rows_per_item2 = R2;
+  g.c1 = K > 1 ? (int)ceil_div(K - 1, R) : 0;
+  g.c2 = (int)ceil_div(K, R2);
+  const int64_t i1 = (int64_t)g.n_groups * g.c1, i2 = (int64_t)g.n_groups * g.c2;
+  if (i1 + i2 > 0x3fffffff) return -1;  // caller falls back to the two-launch form
+  g.items1 = (int)i1;
+  g.items2 = (int)i2;
+  static const int dbg = [] { const char *e = getenv("QG_COLS_PIPE_DBG"); return e ? atoi(e) : 0; }();
+  if (dbg == 1) g.items2 = 0;               // timing experiment: readers alone (no codes are written)
+  if (dbg == 2) { g.items1 = 0; g.c1 = 0; }  // timing experiment: writers alone, nothing to wait for (wrong scales)
+  ColsPipeScratch *sc = nullptr;
+  int *part = nullptr, *arrive = nullptr;
+  int rc = pipe_scratch(g.n_groups * 32 * EPV, st, &sc, &arrive, &part);
+  if (rc) return rc;
+  // every CTA must be resident: a multiple of the role pattern, at most occupancy x SMs
+  unsigned grid = (unsigned)(per_sm * sms);
+  grid -= grid % (unsigned)g.readers_of;
+  if (grid < (unsigned)g.readers_of) return -1;
+  return (int)launch_kernel(quant_cols_pipe_kernel<T>, dim3(grid), dim3(kThreads), st, W, K, N, ldw, range, mode, g, sc, arrive,
+                            part, Wq, ldq, Cw);
+}
+
 // ---- row launcher ----
 template <typename T, int G, int NV>
 void launch_rows(const T *X, int M, int K, int64_t ldx, float range, int mode, const float *sx, int8_t *Xq,
@@ -615,6 +957,12 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
   if (!vec_ok) {
     return (int)launch_kernel(quant_cols_generic_kernel<T>, dim3((unsigned)ceil_div(N, kThreads)), dim3(kThreads), st, W, K,
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
+  }
+  // one launch, one HBM read of W (panel pipeline) once the matrix is large enough for the second read to matter
+  if (!transpose && sw == nullptr && Wq != nullptr && pipe_tune().on &&
+      (int64_t)K * N * (int64_t)sizeof(T) >= (int64_t)kPipeMinBytes) {
+    const int rc = cols_pipe_launch(W, K, N, ldw, range, mode, Wq, ldq, Cw, st);
+    if (rc >= 0) return rc;
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
   const int rpc = cols_rows_per_cta(K, col_tiles, transpose ? 32 : 8);

@@ -43,7 +43,8 @@ def test_outlier_column_detection(qg, oracle, shape, dt):
 @pytest.mark.parametrize("variant", ["SIMT", "TC_1SM", "TC_2SM"])
 @pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
 @pytest.mark.parametrize("shape,n_out", [((128, 256, 512), 6), ((200, 300, 520), 3), ((512, 768, 1024), 13),
-                                         ((64, 64, 4096), 16), ((256, 512, 256), 0), ((130, 264, 1000), 8)])
+                                         ((64, 64, 4096), 16), ((256, 512, 256), 0), ((130, 264, 1000), 8),
+                                         ((384, 512, 1024), 17), ((300, 520, 768), 40), ((256, 768, 2048), 64)])
 def test_linear_forward_with_outlier_decomposition(qg, oracle, shape, n_out, dt, variant):
     M, N, K = shape
     rng = np.random.default_rng(seed_of(shape, dt, n_out))
@@ -91,3 +92,14 @@ def test_decomposition_reduces_error_on_outlier_features(qg):
     e0 = (y0.float() - ref).abs().mean().item()
     e1 = (y1.float() - ref).abs().mean().item()
     assert e1 < 0.5 * e0, (e0, e1)
+
+
+def test_too_many_outlier_columns_is_an_error(qg):
+    """More columns than the fused epilogue takes (64): a clean QG_ENOTSUP, nothing written out of bounds."""
+    M, K, N = 128, 512, 256
+    X = torch.randn((M, K), device=DEV)
+    lin = qg.LinearLayer(K, N, device=DEV)
+    y = torch.empty((M, N), device=DEV)
+    idx = torch.arange(0, 65, dtype=torch.int32, device=DEV)
+    with pytest.raises((qg.QGemmError, AssertionError)):
+        lin.forward_outlier(X, y, idx)

@@ -154,6 +154,49 @@ def quantizers(size, dt="f32"):
             "cols_gbs": (K * N * (es + 1) + 4 * N) / c / 1e3, "cols_t_us": ct, "cols_t_gbs": (K * N * (es + 1) + 4 * N) / ct / 1e3}
 
 
+def cols_pipe(size, dt="f32", nbuf=3):
+    """Column quantizer alone on rotating weight buffers (cold W) + a digest of its outputs for cross-configuration parity."""
+    import hashlib
+
+    import torch
+
+    qg = pkg()
+    K = N = size
+    tdt = {"f32": torch.float32, "f16": torch.float16}[dt]
+    es = 4 if dt == "f32" else 2
+    torch.manual_seed(0)
+    Ws = [(torch.rand((K, N), device="cuda") * 2 - 1).to(tdt) for _ in range(nbuf)]
+    Wq = torch.empty((K, N), dtype=torch.int8, device="cuda")
+    Cw = torch.empty(N, device="cuda")
+    i = [0]
+
+    def cols():
+        i[0] = (i[0] + 1) % nbuf
+        qg.absmax_quant_cols(Ws[i[0]], 127.0, 0, Wq, Cw)
+
+    us = bench(cols, iters=60, warm=10)
+    qg.absmax_quant_cols(Ws[0], 127.0, 0, Wq, Cw)
+    torch.cuda.synchronize()
+    h = hashlib.sha256(Wq.cpu().numpy().tobytes() + Cw.cpu().numpy().tobytes()).hexdigest()[:16]
+    # same call captured in a CUDA graph and replayed on changing weights (the scratch must restore itself)
+    g = torch.cuda.CUDAGraph()
+    Wg = Ws[1].clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        qg.absmax_quant_cols(Wg, 127.0, 0, Wq, Cw)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            qg.absmax_quant_cols(Wg, 127.0, 0, Wq, Cw)
+    Wg.copy_(Ws[0] * 0.5)
+    g.replay()
+    torch.cuda.synchronize()
+    hg = hashlib.sha256(Wq.cpu().numpy().tobytes() + Cw.cpu().numpy().tobytes()).hexdigest()[:16]
+    qg.absmax_quant_cols(Ws[0] * 0.5, 127.0, 0, Wq, Cw)
+    torch.cuda.synchronize()
+    hg_ref = hashlib.sha256(Wq.cpu().numpy().tobytes() + Cw.cpu().numpy().tobytes()).hexdigest()[:16]
+    return {"cols_us": us, "cols_gbs": (K * N * (es + 1) + 4 * N) / us / 1e3, "digest": h, "graph_replay_ok": hg == hg_ref}
+
+
 def full_op(size, out="f32"):
     import torch
 
@@ -282,6 +325,50 @@ EXPERIMENTS = {
     "r2_inop_4096_noring": (gemm_inop, (4096,), {"QG_NO_LAST_RING": "1"}),
     "r2_inop_4096_f16": (gemm_inop, (4096, "f16"), {}),
     "r2_inop_8192": (gemm_inop, (8192,), {}),
+    "r2_cpipe_off_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "0"}),
+    "r2_cpipe_def_4096": (cols_pipe, (4096,), {}),
+    "r2_cpipe_1_64_5of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,5,8,4,128"}),
+    "r2_cpipe_1_64_1of2_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,1,2,4,128"}),
+    "r2_cpipe_1_64_3of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,3,8,4,128"}),
+    "r2_cpipe_1_64_3of4_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,3,4,4,128"}),
+    "r2_cpipe_1_64_5of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,5,8,4,256"}),
+    "r2_cpipe_1_64_1of2_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,1,2,4,256"}),
+    "r2_cpipe_1_64_3of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,3,8,4,256"}),
+    "r2_cpipe_1_64_3of4_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "1,64,3,4,4,256"}),
+    "r2_cpipe_2_64_5of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,5,8,4,128"}),
+    "r2_cpipe_2_64_1of2_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,1,2,4,128"}),
+    "r2_cpipe_2_64_3of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,3,8,4,128"}),
+    "r2_cpipe_2_64_3of4_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,3,4,4,128"}),
+    "r2_cpipe_2_64_5of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,5,8,4,256"}),
+    "r2_cpipe_2_64_1of2_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,1,2,4,256"}),
+    "r2_cpipe_2_64_3of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,3,8,4,256"}),
+    "r2_cpipe_2_64_3of4_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "2,64,3,4,4,256"}),
+    "r2_cpipe_4_64_5of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,5,8,4,128"}),
+    "r2_cpipe_4_64_1of2_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,1,2,4,128"}),
+    "r2_cpipe_4_64_3of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,3,8,4,128"}),
+    "r2_cpipe_4_64_3of4_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,3,4,4,128"}),
+    "r2_cpipe_4_64_5of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,5,8,4,256"}),
+    "r2_cpipe_4_64_1of2_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,1,2,4,256"}),
+    "r2_cpipe_4_64_3of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,3,8,4,256"}),
+    "r2_cpipe_4_64_3of4_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,3,4,4,256"}),
+    "r2_cpipe_8_64_5of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,5,8,4,128"}),
+    "r2_cpipe_8_64_1of2_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,1,2,4,128"}),
+    "r2_cpipe_8_64_3of8_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,3,8,4,128"}),
+    "r2_cpipe_8_64_3of4_p4_128_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,3,4,4,128"}),
+    "r2_cpipe_8_64_5of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,5,8,4,256"}),
+    "r2_cpipe_8_64_1of2_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,1,2,4,256"}),
+    "r2_cpipe_8_64_3of8_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,3,8,4,256"}),
+    "r2_cpipe_8_64_3of4_p4_256_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "8,64,3,4,4,256"}),
+    "r2_cdbg_readers_4_64_5of8": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,5,8,4,256", "QG_COLS_PIPE_DBG": "1"}),
+    "r2_cdbg_writers_4_64_5of8": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,5,8,4,256", "QG_COLS_PIPE_DBG": "2"}),
+    "r2_cdbg_readers_4_64_7of8": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,7,8,4,256", "QG_COLS_PIPE_DBG": "1"}),
+    "r2_cdbg_writers_4_64_1of8": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,1,8,4,256", "QG_COLS_PIPE_DBG": "2"}),
+    "r2_cpipe_off_4096_f16": (cols_pipe, (4096, "f16"), {"QG_COLS_PIPE": "0"}),
+    "r2_cpipe_def_4096_f16": (cols_pipe, (4096, "f16"), {}),
+    "r2_cpipe_off_8192": (cols_pipe, (8192,), {"QG_COLS_PIPE": "0"}),
+    "r2_cpipe_def_8192": (cols_pipe, (8192,), {}),
+    "r2_cpipe_off_2048": (cols_pipe, (2048,), {"QG_COLS_PIPE": "0"}),
+    "r2_cpipe_def_2048": (cols_pipe, (2048,), {}),
     "quant_4096": (quantizers, (4096,), {}),
     "quant_4096_twopass": (quantizers, (4096,), {"QG_COLS_TWO_PASS": "1"}),
     "quant_4096_f16": (quantizers, (4096, "f16"), {}),
