@@ -168,6 +168,13 @@ QG_API int qg_gemm_s8_dequant_ex(const int8_t *Xq, int64_t ldxq, const int8_t *B
                                  const float *Cx, const float *Cw, const float *bias, int m, int n, int k,
                                  float range, void *O, void *const *peers, int n_peers, int out_dtype,
                                  int64_t ldo, qg_stream_t stream);
+/* The same exchange done by the NVSwitch (NVLS): O_mc is the multicast (multimem) address of the block O in a symmetric
+ * allocation bound on every GPU of the group -- the epilogue issues ONE multimem.st per 16 bytes and the switch writes it into
+ * every GPU's matrix, the caller's own included, so the sender's egress is 1x the block instead of (P-1)x.  Floating-point
+ * output, n a multiple of 16 bytes' worth of elements. */
+QG_API int qg_gemm_s8_dequant_mc(const int8_t *Xq, int64_t ldxq, const int8_t *B, int64_t ldb, int b_kmajor, const float *Cx,
+                                 const float *Cw, const float *bias, int m, int n, int k, float range, void *O, void *O_mc,
+                                 int out_dtype, int64_t ldo, qg_stream_t stream);
 
 /* ---- host-buffer form of a9 (pageable or pinned host pointers; H2D + compute + D2H) --------- */
 /* what a caller holding host tensors (Tensor<T>{h,w,false}, toDevice/toHost at

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_prepare_weights", "qg_gemm_s8t_dequant",
     "qg_linear_forward",
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
-    "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_mm_f32",
+    "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_gemm_s8_dequant_mc", "qg_mm_f32",
     "qg_softmax_rows_f32", "qg_attention_forward", "qg_linear_forward_act", "qg_add_layernorm_f32",
     "qg_linear_forward_q", "qg_quantize_rows_given_max", "qg_ffn_workspace_bytes", "qg_ffn_forward",
     "qg_add_layernorm_quant_f32", "qg_gemm_s8_dequant_scatter", "qg_ffn_forward_rowpar", "qg_reduce_partials",
@@ -283,6 +283,21 @@ def gemm_s8_dequant_ex(Xq, B, b_kmajor: bool, Cx, Cw, out, peer_ptrs=(), range_:
     _check(lib().qg_gemm_s8_dequant_ex(pa, lda, pb, ldb, 1 if b_kmajor else 0, _vec(Cx.reshape(-1), M),
                                        _vec(Cw.reshape(-1), N), pbias, M, N, K, C.c_float(range_), po, arr, n, _dt(out),
                                        ldo, _stream()), "qg_gemm_s8_dequant_ex")
+
+
+def gemm_s8_dequant_mc(Xq, B, b_kmajor: bool, Cx, Cw, out, mc_ptr: int, range_: float = 127.0, bias=None) -> None:
+    """The same GEMM with the exchange done by the NVSwitch: `mc_ptr` is the multicast (multimem) address of the block `out`
+    inside a symmetric allocation; one store per 16 bytes reaches every GPU's matrix, this one's included."""
+    M, K = Xq.shape
+    N = B.shape[0] if b_kmajor else B.shape[1]
+    assert out.shape == (M, N) and mc_ptr
+    pa, lda = _dev2d(Xq)
+    pb, ldb = _dev2d(B)
+    po, ldo = _dev2d(out)
+    pbias = None if bias is None else _vec(bias.reshape(-1), N)
+    _check(lib().qg_gemm_s8_dequant_mc(pa, lda, pb, ldb, 1 if b_kmajor else 0, _vec(Cx.reshape(-1), M),
+                                       _vec(Cw.reshape(-1), N), pbias, M, N, K, C.c_float(range_), po, C.c_void_p(int(mc_ptr)),
+                                       _dt(out), ldo, _stream()), "qg_gemm_s8_dequant_mc")
 
 
 def workspace_bytes(M: int, N: int, K: int) -> int:

@@ -104,11 +104,16 @@ class FusedColumnParallelLinear:
     [M, N] result lives in symmetric memory (torch.distributed._symmetric_memory: peer-mapped over
     NVLink), and each rank's epilogue TMA-stores its column block into all of them while its main
     loop is still running.  Two cross-GPU barriers bracket a forward (peers are done reading the
-    previous result / every block has landed)."""
+    previous result / every block has landed).  On an NVSwitch fabric the stores go to the allocation's MULTICAST address
+    instead (multimem.st): the switch replicates them, the sender's egress is 1x its block instead of (P-1)x."""
 
     def __init__(self, w_full: torch.Tensor, bias: Optional[torch.Tensor], rank: int, world: int, group=None,
-                 align: int = 16, range_: float = 127.0, mode: int = 0):
+                 align: int = 16, range_: float = 127.0, mode: int = 0, multicast: Optional[bool] = None):
         from . import prepare_weights
+        import os
+
+        # multicast=None: use the NVSwitch multicast mapping when the symmetric allocation has one (QG_NO_MULTICAST=1 forbids it)
+        self.multicast = (os.environ.get("QG_NO_MULTICAST") is None) if multicast is None else bool(multicast)
 
         self.rank, self.world, self.align = rank, world, align
         self.group = group if group is not None else dist.group.WORLD
@@ -131,9 +136,13 @@ class FusedColumnParallelLinear:
         self.hdl = symm_mem.rendezvous(self.out, self.group)
         es = self.out.element_size()
         self.peer_ptrs = [int(self.hdl.buffer_ptrs[r]) + self.lo * es for r in range(self.world) if r != self.rank]
+        # NVSwitch multicast mapping of the same allocation (0 when the fabric has none): one store reaches every GPU
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        ok = mc != 0 and self.multicast and ((self.hi - self.lo) * es) % 16 == 0 and (self.lo * es) % 16 == 0 and (self.n * es) % 16 == 0
+        self.mc_ptr = mc + self.lo * es if ok else 0
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        from . import absmax_quant_rows, gemm_s8_dequant_ex
+        from . import absmax_quant_rows, gemm_s8_dequant_ex, gemm_s8_dequant_mc
 
         m = x.shape[0]
         self._ensure_out(m, x.dtype, x.device)
@@ -143,7 +152,11 @@ class FusedColumnParallelLinear:
             self._cx = torch.empty(m, dtype=torch.float32, device=x.device)
         absmax_quant_rows(x, self.range, self.mode, self._xq, self._cx)
         self.hdl.barrier(channel=0)  # every peer has finished with the previous contents of its matrix
-        gemm_s8_dequant_ex(self._xq, self.wt, True, self._cx, self.cw, self.out[:, self.lo:self.hi], self.peer_ptrs,
-                           self.range, self.b)
+        if self.mc_ptr:
+            gemm_s8_dequant_mc(self._xq, self.wt, True, self._cx, self.cw, self.out[:, self.lo:self.hi], self.mc_ptr,
+                               self.range, self.b)
+        else:
+            gemm_s8_dequant_ex(self._xq, self.wt, True, self._cx, self.cw, self.out[:, self.lo:self.hi], self.peer_ptrs,
+                               self.range, self.b)
         self.hdl.barrier(channel=1)  # all blocks of all ranks have landed
         return self.out

@@ -249,14 +249,14 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
   // of work is all a problem with M <= 128 has, so it takes the 1-SM kernel
   if (variant == QG_GEMM_AUTO) variant = !tc_ok ? QG_GEMM_SIMT : (M > 128 ? QG_GEMM_TC_2SM : QG_GEMM_TC_1SM);
   if (variant == QG_GEMM_SIMT || !tc_ok) {
-    if (multi != nullptr && multi->n > 0) {
+    if (multi != nullptr && (multi->n > 0 || multi->mc != nullptr)) {
       set_error("extra destinations need the tensor-core path (16-byte aligned operands)");
       return QG_ENOTSUP;
     }
     return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st, act);
   }
   const int cg = variant == QG_GEMM_TC_2SM ? 2 : 1;
-  int sk = (side == nullptr && (multi == nullptr || multi->n == 0)) ? choose_split_k(d->sm_count, cg, M, N, K, out_kind) : 1;
+  int sk = (side == nullptr && (multi == nullptr || (multi->n == 0 && multi->mc == nullptr))) ? choose_split_k(d->sm_count, cg, M, N, K, out_kind) : 1;
   // split-K: int32 partial sums of every k-slice, then one pass that adds them and runs the epilogue.
   // The slices live in the caller's workspace (qg_workspace_bytes reserves them); entry points without a
   // workspace argument use a grow-only per-device buffer (sk_arena; documented as shared in qgemm.h).  A
@@ -656,6 +656,23 @@ int qg_gemm_s8_dequant_ex(const int8_t *Xq, int64_t ldxq, const int8_t *B, int64
   for (int i = 0; i < n_peers; i++) mo.dst[i] = peers[i];
   return gemm_dispatch(d, Xq, ldxq, B, ldb, b_kmajor ? 1 : 0, M, N, K, O, ldo, out_dtype, Cx, Cw, bias, 1 / (range * range),
                        (cudaStream_t)stream, nullptr, n_peers > 0 ? &mo : nullptr);
+}
+
+/* The same with the exchange done by the NVSwitch: O_mc is the multicast (multimem) address of the block O -- one store
+ * reaches every GPU's matrix, the caller's own included (O itself is only used for alignment checks). */
+int qg_gemm_s8_dequant_mc(const int8_t *Xq, int64_t ldxq, const int8_t *B, int64_t ldb, int b_kmajor, const float *Cx,
+                          const float *Cw, const float *bias, int M, int N, int K, float range, void *O, void *O_mc,
+                          int out_dtype, int64_t ldo, qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(Xq && B && Cx && Cw && O && O_mc && M > 0 && N > 0 && K > 0 && ldxq >= K && ldb >= (b_kmajor ? K : N) && ldo >= N &&
+                 valid_io(out_dtype),
+             "qg_gemm_s8_dequant_mc: bad arguments");
+  MultiOut mo = {};
+  mo.mc = O_mc;
+  return gemm_dispatch(d, Xq, ldxq, B, ldb, b_kmajor ? 1 : 0, M, N, K, O, ldo, out_dtype, Cx, Cw, bias, 1 / (range * range),
+                       (cudaStream_t)stream, nullptr, &mo);
 }
 
 int qg_quantized_mm_host(const float *X_host, const float *W_host, float *O_host, int M, int N, int K, float range,

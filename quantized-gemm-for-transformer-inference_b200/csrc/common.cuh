@@ -102,6 +102,10 @@ constexpr int kMaxExtraOut = 7;
 struct MultiOut {
   void *dst[kMaxExtraOut];
   int n;
+  // != NULL: the NVSwitch multicast address of the same block (a multimem address covering EVERY GPU's matrix, the
+  // caller's included).  The epilogue then issues one multimem.st per 16 bytes instead of one store per GPU: the
+  // switch replicates, so the sender's NVLink egress is 1x the block instead of (P-1)x.  dst[] / n are ignored.
+  void *mc;
   // > 0: scatter instead of replicate -- column block b (scatter_cols columns) goes to destination b only
   // (0 = the call's own output pointer, b >= 1 = dst[b-1]); see GemmParams::scatter_cols
   int scatter_cols;
@@ -257,6 +261,17 @@ __device__ __forceinline__ uint64_t l2_policy(int kind) {  // 1: evict_first, 2:
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// 16 bytes to every GPU bound to the multicast object behind `mc_addr` (NVLS; the switch replicates the write)
+__device__ __forceinline__ void multimem_st128(void *mc_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc_addr), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 template <int N> __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");

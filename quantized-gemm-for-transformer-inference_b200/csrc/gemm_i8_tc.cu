@@ -86,6 +86,8 @@ struct GemmParams {
   // columns and block b is stored ONLY to destination b (0: out / map_o, b >= 1: extra_out[b-1] / xmaps.m[b-1]), each an
   // [M, scatter_cols] matrix with leading dimension ldo -- the scatter half of a reduce-scatter done by the epilogue.
   int scatter_cols;
+  // NVSwitch multicast address of `out` (same block, same ldo) or NULL: one multimem.st per 16 bytes reaches every GPU
+  void *mc_out;
 };
 
 struct ExtraMaps {
@@ -536,6 +538,26 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (x == 0x12345678u && p.M < 0) wsc[lane] = 1.0f;
           return;
         }
+        if (p.mc_out != nullptr) {
+          // multicast exchange: the chunk is transposed through the staging tile (lanes own rows, a store wants
+          // consecutive bytes) and leaves as 8 multimem.st per lane; the switch writes it into every GPU's matrix
+          __syncwarp();  // the previous chunk's reads of the tile are done
+#pragma unroll
+          for (int j4 = 0; j4 < 8; j4++)
+            sts128(stage_u32_own + lane * 128 + ((j4 ^ (lane & 7)) << 4), w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
+          __syncwarp();
+          const int c16 = lane & 7;
+          const int gcol = n_base + c0 + c16 * (16 / (int)sizeof(OutT));
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int r = i * 4 + (lane >> 3);
+            const uint4 v = lds128u(stage_u32_own + r * 128 + ((c16 ^ (r & 7)) << 4));
+            const int grow = m_base + q * 32 + r;
+            if (grow < p.M && gcol < p.N)  // N is a multiple of the 16-byte vector (host-checked)
+              multimem_st128(reinterpret_cast<OutT *>(p.mc_out) + (int64_t)grow * p.ldo + gcol, v.x, v.y, v.z, v.w);
+          }
+          return;
+        }
         if (p.tma_store) {
           uint32_t stage_u32 = stage_u32_own;
           if (ring_stage) {
@@ -958,7 +980,14 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
       if (rc) return rc;
     }
   }
-  if (multi != nullptr && multi->n > 0) {
+  if (multi != nullptr && multi->mc != nullptr && p.split_k == 1 && scatter_cols == 0) {
+    if (out_kind == QG_S32 || !aligned16(multi->mc) || (ldo * osz) % 16 != 0 || (N * osz) % 16 != 0) {
+      set_error("gemm_i8_tc: the multicast exchange needs a floating-point output, 16-byte aligned rows and N a multiple of %d",
+                (int)(16 / osz));
+      return QG_EINVAL;
+    }
+    p.mc_out = multi->mc;
+  } else if (multi != nullptr && multi->n > 0) {
     if (multi->n > kMaxExtraOut || (out_kind == QG_S32 && p.split_k == 1)) {
       set_error("gemm_i8_tc: at most %d extra destinations, floating-point output", kMaxExtraOut);
       return QG_EINVAL;

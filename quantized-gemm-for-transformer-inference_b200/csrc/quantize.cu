@@ -469,7 +469,11 @@ quant_cols_t_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float ra
 // reader from running.  The scratch restores itself (the last CTA to leave resets counters and maxima): a call
 // leaves no state behind -- safe under CUDA-graph replay; one scratch per (device, stream).
 // ------------------------------------------------------------------------------------------
-constexpr int64_t kPipeMinBytes = 8ll << 20;
+// Where the pipeline is used.  Measured on B200 (fp32, us per call, two launches -> one launch): 2048^2 (16 MiB) 16.5 -> 13.4-14.3;
+// 4096^2 (64 MiB) 23.5 -> 28.5-31; 8192^2 (256 MiB) 93 -> 102-108.  It does read W from HBM once (ncu: 67 MB at 4096^2 against
+// 134 MB), but at 64 MiB and beyond two free-running streaming launches at the HBM roof beat one launch whose second half
+// waits on the first; it wins where a launch boundary costs more than the second read (QG_COLS_PIPE=1 forces it on).
+constexpr int64_t kPipeMinBytes = 8ll << 20, kPipeMaxBytes = 24ll << 20;
 constexpr int kExitFan = 16;     // exit counting is two-level so that no address sees more than grid / 16 atomics
 constexpr int kLineInts = 32;    // one counter per 128-byte line
 struct ColsPipeGeom {
@@ -812,7 +816,7 @@ int pipe_scratch(int n_cols, cudaStream_t st, ColsPipeScratch **sc, int **arrive
 
 // Geometry of the panel pipeline.  Defaults: panels of <= 16 MiB, warp items of 32 rows, 4 CTAs per SM, 5 of 8 CTAs read.
 // QG_COLS_PIPE = "0" switches the pipeline off (two launches); "G,R,readers_in,readers_of[,ctas_per_sm[,R2]]" overrides.
-struct PipeTune { int on = 1, G = 0, R = 0, rin = 0, rof = 0, per_sm = 0, R2 = 0; };
+struct PipeTune { int on = 1, force = 0, G = 0, R = 0, rin = 0, rof = 0, per_sm = 0, R2 = 0; };
 const PipeTune &pipe_tune() {
   static const PipeTune t = [] {
     PipeTune v;
@@ -820,7 +824,8 @@ const PipeTune &pipe_tune() {
       int a = 0, b = 0, c = 0, d = 0, f = 0, h = 0;
       const int n = sscanf(e, "%d,%d,%d,%d,%d,%d", &a, &b, &c, &d, &f, &h);
       if (n == 1 && a == 0) v.on = 0;
-      if (n >= 4) { v.G = a; v.R = b; v.rin = c; v.rof = d; }
+      if (n == 1 && a == 1) v.force = 1;
+      if (n >= 4) { v.G = a; v.R = b; v.rin = c; v.rof = d; v.force = 1; }
       if (n >= 5) v.per_sm = f;
       if (n >= 6) v.R2 = h;
     }
@@ -852,7 +857,7 @@ int cols_pipe_launch(const T *W, int K, int N, int64_t ldw, float range, int mod
   if (g.readers_in < 1 || per_sm < 2) return -1;
   g.n_groups = (int)ceil_div(N, 32 * EPV);
   const int64_t group_row_bytes = 32 * 16;  // one column group of one row
-  int G = tune.G > 0 ? tune.G : (int)((16ll << 20) / ((int64_t)K * group_row_bytes));
+  int G = tune.G > 0 ? tune.G : (int)((8ll << 20) / ((int64_t)K * group_row_bytes));
   if (G < 1) G = 1;
   if (G > g.n_groups) G = g.n_groups;
   g.groups_per_panel = G;
@@ -960,7 +965,8 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
   }
   // one launch, one HBM read of W (panel pipeline) once the matrix is large enough for the second read to matter
   if (!transpose && sw == nullptr && Wq != nullptr && pipe_tune().on &&
-      (int64_t)K * N * (int64_t)sizeof(T) >= (int64_t)kPipeMinBytes) {
+      (int64_t)K * N * (int64_t)sizeof(T) >= kPipeMinBytes &&
+      ((int64_t)K * N * (int64_t)sizeof(T) <= kPipeMaxBytes || pipe_tune().force)) {
     const int rc = cols_pipe_launch(W, K, N, ldw, range, mode, Wq, ldq, Cw, st);
     if (rc >= 0) return rc;
   }

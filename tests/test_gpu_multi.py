@@ -62,7 +62,7 @@ def test_column_parallel_matches_single_gpu(shape, dt):
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
-def _worker_fused(rank, world, port, shape, dt, ret):
+def _worker_fused(rank, world, port, shape, dt, ret, multicast=None):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -79,7 +79,7 @@ def _worker_fused(rank, world, port, shape, dt, ret):
         X = (torch.rand((M, K), generator=g) * 2 - 1).to(tdt).cuda()
         W = (torch.rand((K, N), generator=g) * 2 - 1).to(tdt).cuda()
         b = torch.randn(N, generator=g).cuda()
-        layer = cp.FusedColumnParallelLinear(W, b, rank, world)
+        layer = cp.FusedColumnParallelLinear(W, b, rank, world, multicast=multicast)
         ok = True
         for _ in range(3):  # repeated forwards reuse the symmetric buffer
             y = layer.forward(X)
@@ -90,8 +90,25 @@ def _worker_fused(rank, world, port, shape, dt, ret):
             view = torch.int32 if dt == "f32" else torch.int16
             ok = ok and bool(torch.equal(y.view(view), full.view(view)))
         ret[rank] = ok
+        ret["mc_%d" % rank] = bool(layer.mc_ptr)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,dt", [((512, 1024, 768), "f32"), ((300, 2048, 520), "f16"), ((4096, 4096, 1024), "f16")])
+def test_multicast_exchange_matches_single_gpu(shape, dt):
+    """The gather done by the NVSwitch (multimem.st to the symmetric allocation's multicast address): same bits.  Skipped when
+    the fabric offers no multicast mapping (the unicast form is then what FusedColumnParallelLinear runs)."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_fused, args=(world, _free_port(), shape, dt, ret, True), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+    if not all(ret.get("mc_%d" % r) for r in range(world)):
+        pytest.skip("no multicast mapping on this box: the unicast path ran (and matched)")
 
 
 @pytest.mark.parametrize("shape,dt", [((512, 1024, 768), "f32"), ((300, 2048, 520), "f16"), ((4096, 4096, 1024), "f16")])
@@ -103,5 +120,5 @@ def test_fused_epilogue_gather_matches_single_gpu(shape, dt):
     import torch.multiprocessing as mp
 
     ret = mp.Manager().dict()
-    mp.spawn(_worker_fused, args=(world, _free_port(), shape, dt, ret), nprocs=world, join=True)
+    mp.spawn(_worker_fused, args=(world, _free_port(), shape, dt, ret, False), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
