@@ -105,6 +105,12 @@ QG_API int qg_absmax_quant_rows(const void *X, int dtype, int m, int k, int64_t 
 QG_API int qg_absmax_quant_cols(const void *W, int dtype, int k, int n, int64_t ldw, float range,
                                 int mode, int8_t *Wq, int64_t ldq, float *Cw, float *scratch,
                                 qg_stream_t stream);
+/* Both quantizers of one op_quantized_mm call (a1-a4 on X and on W) -- same codes and scales as the two calls above.  Large
+ * problems whose W still fits in L2 run column pass 1, then column pass 2 (L2-bound) SIDE BY SIDE with the row quantizer
+ * (HBM-bound) in one launch, which is what qg_quantized_mm does internally. */
+QG_API int qg_absmax_quant_rows_cols(const void *X, int64_t ldx, const void *W, int64_t ldw, int dtype, int m, int n, int k,
+                                     float range, int mode, int8_t *Xq, int64_t ldxq, float *Cx, int8_t *Wq, int64_t ldwq,
+                                     float *Cw, qg_stream_t stream);
 
 /* ---- a5: op_mm<int8_t,int>(A, B, C)  src/ops/op_mm.cuh:49-65 ------------------------------ */
 /* exact int32 accumulation (equals the reference's fp32-FMA accumulator while every partial
@@ -299,7 +305,7 @@ QG_API int qg_add_layernorm_quant_f32(const float *A, int64_t lda, const float *
  * is that slot, an [m, block_cols] matrix with leading dimension ld_part; block_cols a multiple of 32 columns for fp32 and
  * 64 for 16-bit partials), and qg_reduce_partials adds the P slots in order, adds the bias and writes the owner's block to
  * `out` and to the same block of the peers' matrices (the all-gather that completes the all-reduce; n_peers = 0: keep it
- * sharded).  The caller brackets the two with barriers (all slots written before the reduce; all reduces done before the
+ * sharded; out_mc != NULL: the block's NVSwitch multicast address, one multimem.st instead of n_peers + 1 stores).  The caller brackets the two with barriers (all slots written before the reduce; all reduces done before the
  * next forward's stores). */
 QG_API int qg_gemm_s8_dequant_scatter(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_t ldwt, const float *Cx,
                                       const float *Cw, int m, int n, int k, float range, void *const *part_dst, int n_dst,
@@ -311,8 +317,8 @@ QG_API int qg_ffn_forward_rowpar(const void *X, int64_t ldx, int in_dtype, const
                                  int d_in, int d_ff_local, int d_out, float range, int mode, void *workspace,
                                  size_t workspace_bytes, qg_stream_t stream);
 QG_API int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part,
-                              const float *bias, void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int m,
-                              int n, qg_stream_t stream);
+                              const float *bias, void *out, void *const *peers, int n_peers, void *out_mc, int64_t ldo,
+                              int out_dtype, int m, int n, qg_stream_t stream);
 
 /* ---- the elementwise tail of the pipeline, op by op ------------------------------------------------
  * The fused epilogue makes these unnecessary on the fast path; they let the reference's step-by-step

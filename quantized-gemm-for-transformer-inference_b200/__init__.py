@@ -27,7 +27,7 @@ GEMM_AUTO, GEMM_SIMT, GEMM_TC_1SM, GEMM_TC_2SM = 0, 1, 2, 3
 ABI_SYMBOLS = [
     "qg_version", "qg_last_error", "qg_device_info", "qg_set_gemm_variant", "qg_launch_count",
     "qg_absmax_rows", "qg_absmax_cols", "qg_inv_divide_f32", "qg_quantize_rows", "qg_quantize_cols",
-    "qg_absmax_quant_rows", "qg_absmax_quant_cols", "qg_gemm_s8s8s32", "qg_dequantize_s32",
+    "qg_absmax_quant_rows", "qg_absmax_quant_cols", "qg_absmax_quant_rows_cols", "qg_gemm_s8s8s32", "qg_dequantize_s32",
     "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_prepare_weights", "qg_gemm_s8t_dequant",
     "qg_linear_forward",
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
@@ -219,6 +219,21 @@ def absmax_quant_cols(W: torch.Tensor, range_: float = 127.0, mode: int = MODE_R
     _check(lib().qg_absmax_quant_cols(pw, _dt(W), K, N, ldw, C.c_float(range_), mode, pq, ldq, _vec(Cw, N),
                                       None, _stream()), "qg_absmax_quant_cols")
     return Wq, Cw
+
+
+def absmax_quant_rows_cols(X: torch.Tensor, W: torch.Tensor, Xq: torch.Tensor, Cx: torch.Tensor, Wq: torch.Tensor,
+                           Cw: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT) -> None:
+    """Both quantizers of one op (qg_absmax_quant_rows_cols): same results as absmax_quant_rows + absmax_quant_cols; large
+    problems overlap the column quantizer's second pass with the row quantizer in one launch."""
+    M, K = X.shape
+    N = W.shape[1]
+    assert W.shape[0] == K and X.dtype == W.dtype
+    px, ldx = _dev2d(X)
+    pw, ldw = _dev2d(W)
+    pxq, ldxq = _dev2d(Xq)
+    pwq, ldwq = _dev2d(Wq)
+    _check(lib().qg_absmax_quant_rows_cols(px, ldx, pw, ldw, _dt(X), M, N, K, C.c_float(range_), mode, pxq, ldxq, _vec(Cx, M),
+                                           pwq, ldwq, _vec(Cw, N), _stream()), "qg_absmax_quant_rows_cols")
 
 
 def gemm_s8_dequant(Xq, Wq, Cx, Cw, out, range_: float = 127.0, bias=None) -> None:
@@ -432,7 +447,7 @@ def ffn_forward_rowpar(X, W1t, Cw1, b1, W2t, Cw2, H: torch.Tensor, part_ptrs, bl
                                        _stream()), "qg_ffn_forward_rowpar")
 
 
-def reduce_partials(slots: torch.Tensor, bias, out: torch.Tensor, peer_ptrs=(), n: int | None = None) -> None:
+def reduce_partials(slots: torch.Tensor, bias, out: torch.Tensor, peer_ptrs=(), n: int | None = None, mc_ptr: int = 0) -> None:
     """out[:, :n] = ((slots[0] + slots[1]) + ...) + bias in ascending slot order (qg_reduce_partials); the result is also
     stored to the same block of the peers' matrices (device addresses in peer_ptrs, leading dimension = out's)."""
     P, M, bc = slots.shape
@@ -440,8 +455,9 @@ def reduce_partials(slots: torch.Tensor, bias, out: torch.Tensor, peer_ptrs=(), 
     po, ldo = _dev2d(out)
     _check(lib().qg_reduce_partials(C.c_void_p(slots.data_ptr()), C.c_int64(slots.stride(0)), P, _dt(slots),
                                     C.c_int64(slots.stride(1)), None if bias is None else _vec(bias.reshape(-1), n), po,
-                                    _ptr_array(peer_ptrs) if len(peer_ptrs) else None, len(peer_ptrs), ldo, _dt(out), M, n,
-                                    _stream()), "qg_reduce_partials")
+                                    _ptr_array(peer_ptrs) if len(peer_ptrs) else None, len(peer_ptrs),
+                                    C.c_void_p(int(mc_ptr)) if mc_ptr else None, ldo, _dt(out), M, n, _stream()),
+           "qg_reduce_partials")
 
 
 def add_layernorm_quant(A: torch.Tensor, R, B: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT):

@@ -19,10 +19,13 @@ int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range,
                int8_t *Xq, int64_t ldq, float *Cx, cudaStream_t st, RowMaxIo io = RowMaxIo());
 int quant_cols(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, const float *sw,
                int8_t *Wq, int64_t ldq, float *Cw, bool transpose, cudaStream_t st);
+int quant_rows_cols_fused(const void *X, const void *W, int dtype, int M, int N, int K, int64_t ldx, int64_t ldw, float range, int mode,
+                          int8_t *Xq, int64_t ldxq, float *Cx, int8_t *Wq, int64_t ldwq, float *Cw, cudaStream_t st);
 int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
 int reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
-                    void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st);
+                    void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st,
+                    void *out_mc = nullptr);
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
                  int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c,
                  const SideArgs *side, cudaStream_t st, int act = QG_ACT_NONE);
@@ -454,14 +457,40 @@ int qg_quantized_mm(const void *X, int64_t ldx, const void *W, int64_t ldw, int 
   rc = get_workspace(d, workspace, workspace_bytes, M, N, K, &w);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
-  if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
   // per-call weight quantization; QG_PERCALL_KMAJOR=0 keeps the reference's [K,N] code layout (MN-major operand)
   const bool kmajor = percall_kmajor();
-  rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, kmajor ? w.ldxq : w.ldwq, w.Cw, kmajor, st);
-  if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
+  // large problems: column pass 1, then column pass 2 (L2-bound) side by side with the row quantizer (HBM-bound) in one launch
+  rc = kmajor ? -1 : quant_rows_cols_fused(X, W, in_dtype, M, N, K, ldx, ldw, range, mode, w.Xq, w.ldxq, w.Cx, w.Wq, w.ldwq, w.Cw, st);
+  if (rc > 0) return cuda_status((cudaError_t)rc, "fused quantizers");
+  if (rc < 0) {
+    rc = quant_rows(X, in_dtype, M, K, ldx, range, mode, nullptr, w.Xq, w.ldxq, w.Cx, st);
+    if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+    rc = quant_cols(W, in_dtype, K, N, ldw, range, mode, nullptr, w.Wq, kmajor ? w.ldxq : w.ldwq, w.Cw, kmajor, st);
+    if (rc) return cuda_status((cudaError_t)rc, "column quantizer");
+  }
   return gemm_dispatch(d, w.Xq, w.ldxq, w.Wq, kmajor ? w.ldxq : w.ldwq, kmajor ? 1 : 0, M, N, K, O, ldo, out_dtype, w.Cx,
                        w.Cw, bias, 1 / (range * range), st, nullptr, nullptr, QG_ACT_NONE, w.splitk, w.splitk_bytes, false);
+}
+
+/* Both quantizers of the op in one call (a1-a4 for X and for W): the same codes and scales as qg_absmax_quant_rows +
+ * qg_absmax_quant_cols; large problems run column pass 1, then column pass 2 side by side with the row quantizer. */
+int qg_absmax_quant_rows_cols(const void *X, int64_t ldx, const void *W, int64_t ldw, int dtype, int M, int N, int K, float range,
+                              int mode, int8_t *Xq, int64_t ldxq, float *Cx, int8_t *Wq, int64_t ldwq, float *Cw,
+                              qg_stream_t stream) {
+  DeviceState *d;
+  int rc = device_state(&d);
+  if (rc) return rc;
+  QG_REQUIRE(X && W && Xq && Cx && Wq && Cw && M > 0 && N > 0 && K > 0 && ldx >= K && ldw >= N && ldxq >= K && ldwq >= N &&
+                 valid_io(dtype),
+             "qg_absmax_quant_rows_cols: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = quant_rows_cols_fused(X, W, dtype, M, N, K, ldx, ldw, range, mode, Xq, ldxq, Cx, Wq, ldwq, Cw, st);
+  if (rc > 0) return cuda_status((cudaError_t)rc, "fused quantizers");
+  if (rc == 0) return QG_OK;
+  rc = quant_rows(X, dtype, M, K, ldx, range, mode, nullptr, Xq, ldxq, Cx, st);
+  if (rc) return cuda_status((cudaError_t)rc, "row quantizer");
+  rc = quant_cols(W, dtype, K, N, ldw, range, mode, nullptr, Wq, ldwq, Cw, false, st);
+  return rc ? cuda_status((cudaError_t)rc, "column quantizer") : QG_OK;
 }
 
 int qg_prepare_weights(const void *W, int dtype, int K, int N, int64_t ldw, float range, int mode, int8_t *Wt,
@@ -1040,7 +1069,8 @@ int qg_ffn_forward_rowpar(const void *X, int64_t ldx, int in_dtype, const int8_t
 }
 
 int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
-                       void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int m, int n, qg_stream_t stream) {
+                       void *out, void *const *peers, int n_peers, void *out_mc, int64_t ldo, int out_dtype, int m, int n,
+                       qg_stream_t stream) {
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
@@ -1049,7 +1079,7 @@ int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int 
                  (n_slots == 1 || slot_stride >= (int64_t)(m - 1) * ld_part + n),
              "qg_reduce_partials: bad arguments");
   return cuda_status((cudaError_t)reduce_partials(slots, slot_stride, n_slots, part_dtype, ld_part, bias, out, peers, n_peers, ldo,
-                                                  out_dtype, m, n, (cudaStream_t)stream),
+                                                  out_dtype, m, n, (cudaStream_t)stream, out_mc),
                      "qg_reduce_partials");
 }
 

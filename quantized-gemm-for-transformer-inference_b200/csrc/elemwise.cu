@@ -83,6 +83,7 @@ inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 struct ReducePeers {
   void *dst[kMaxExtraOut];
   int n;
+  void *mc;  // != NULL (vector path only): the block's NVSwitch multicast address -- one multimem.st reaches every GPU, `out` included
 };
 template <typename PT, typename OT, bool VEC>
 __global__ void __launch_bounds__(256)
@@ -123,6 +124,13 @@ reduce_partials_kernel(const PT *__restrict__ slots, int64_t slot_stride, int n_
     OT r[W];
 #pragma unroll
     for (int e = 0; e < W; e++) r[e] = from_f32<OT>(acc[e]);
+    if (VEC && peers.mc != nullptr) {
+      OT *dst = reinterpret_cast<OT *>(peers.mc) + (int64_t)i * ldo + j;
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(r);
+      if (sizeof(OT) == 4) multimem_st128(dst, w[0], w[1 % W], w[2 % W], w[3 % W]);
+      else asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(__uint_as_float(w[0])), "f"(__uint_as_float(w[1 % W])) : "memory");
+      continue;
+    }
     for (int d = -1; d < peers.n; d++) {
       OT *dst = (d < 0 ? out : reinterpret_cast<OT *>(peers.dst[d])) + (int64_t)i * ldo + j;
       if (VEC) {
@@ -141,6 +149,8 @@ int launch_reduce(const void *slots, int64_t slot_stride, int n_slots, int64_t l
   bool vec = N % 4 == 0 && ld_part % 4 == 0 && slot_stride % 4 == 0 && ldo % 4 == 0 &&
              (reinterpret_cast<uintptr_t>(slots) % (4 * sizeof(PT))) == 0 && (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(OT))) == 0;
   for (int d = 0; d < peers.n; d++) vec = vec && (reinterpret_cast<uintptr_t>(peers.dst[d]) % (4 * sizeof(OT))) == 0;
+  ReducePeers pr = peers;
+  if (!vec || (reinterpret_cast<uintptr_t>(pr.mc) % (4 * sizeof(OT))) != 0) pr.mc = nullptr;  // multicast needs the vector path
   const int w = vec ? 4 : 1;
   const unsigned gx = (unsigned)ceil_div(N, 256 * w);
   unsigned gy = (unsigned)(148 * 16 / gx);
@@ -149,9 +159,9 @@ int launch_reduce(const void *slots, int64_t slot_stride, int n_slots, int64_t l
   dim3 grid(gx, gy);
   if (vec)
     return (int)launch_kernel(reduce_partials_kernel<PT, OT, true>, grid, dim3(256), st, (const PT *)slots, slot_stride, n_slots,
-                              ld_part, bias, (OT *)out, peers, ldo, M, N);
+                              ld_part, bias, (OT *)out, pr, ldo, M, N);
   return (int)launch_kernel(reduce_partials_kernel<PT, OT, false>, grid, dim3(256), st, (const PT *)slots, slot_stride, n_slots,
-                            ld_part, bias, (OT *)out, peers, ldo, M, N);
+                            ld_part, bias, (OT *)out, pr, ldo, M, N);
 }
 template <typename PT>
 int reduce_out(int out_dtype, const void *slots, int64_t slot_stride, int n_slots, int64_t ld_part, const float *bias, void *out,
@@ -199,8 +209,10 @@ int elemwise(int op, const void *A, int64_t lda, const float *B, int64_t ldb, in
 
 // slots: [n_slots][M][ld_part] of part_dtype (slot_stride elements apart); out / peers: [M, ldo] of out_dtype
 int reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
-                    void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st) {
+                    void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st,
+                    void *out_mc) {
   ReducePeers pr = {};
+  pr.mc = out_mc;
   pr.n = n_peers;
   for (int d = 0; d < n_peers; d++) pr.dst[d] = peers[d];
   switch (part_dtype) {

@@ -7,6 +7,7 @@
 // with HBM-bound kernels that read the matrix with 16-byte loads, reduce with warp shuffles and
 // write packed int8 codes plus the fp32 absmax.  The arithmetic (and its quirks: signed first
 // element, IEEE 127/x, truncate-and-wrap cast) is reproduced exactly; see oracle/qoracle.c.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -27,11 +28,13 @@ namespace {
 //   sx_in != NULL : scales given (plain op_multiply<T,int8_t>), no reduction
 //   Xq   == NULL  : reduction only (plain op_absmax)
 // ------------------------------------------------------------------------------------------
-template <typename T, int G, int NV>
-__global__ void __launch_bounds__(kThreads)
-quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
-                  const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
-                  float *__restrict__ Cx, RowMaxIo io) {
+// first_rb / rb_stride: the row blocks this CTA walks (blockIdx.x / gridDim.x when the kernel is on its own; a sub-range
+// of the grid when it shares a launch with the column quantizer's second pass).  STREAM: X is loaded with an L2
+// evict-first hint (it is read once, and must not push out the weight matrix the other half of the launch re-reads).
+template <typename T, int G, int NV, bool STREAM = false>
+__device__ __forceinline__ void quant_rows_body(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
+                                                const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
+                                                float *__restrict__ Cx, RowMaxIo io, int first_rb, int rb_stride) {
   constexpr int EPV = Unpack<T>::EPV;
   constexpr int RPB = kThreads / G;  // rows per block iteration
   constexpr int WPR = G / 32;        // warps per row
@@ -45,23 +48,23 @@ quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float rang
   const int nvec = K / EPV;
   const int nrb = (M + RPB - 1) / RPB;
 
+  const uint64_t pol_stream = STREAM ? l2_policy_evict_first() : 0;
   auto load = [&](uint4 (&dst)[NVC], int rb) {
     const int row = rb * RPB + rib;
     const T *xr = X + (int64_t)(row < M ? row : 0) * ldx;
 #pragma unroll
     for (int v = 0; v < NVC; v++) {
       const int idx = v * G + g;
-      dst[v] = (row < M && idx < nvec) ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
+      if (row < M && idx < nvec) dst[v] = STREAM ? ldg16_hint(xr + (int64_t)idx * EPV, pol_stream) : ldg16(xr + (int64_t)idx * EPV);
+      else dst[v] = make_uint4(0, 0, 0, 0);
     }
   };
 
   uint4 raw[NVC], nxt[NVC];
-  int rb = blockIdx.x;
-  griddep_wait();
-  griddep_trigger_early();
+  int rb = first_rb;
   if (NV > 0 && rb < nrb) load(raw, rb);
-  for (int it = 0; rb < nrb; rb += gridDim.x, it++) {
-    if (kPrefetch && rb + (int)gridDim.x < nrb) load(nxt, rb + gridDim.x);
+  for (int it = 0; rb < nrb; rb += rb_stride, it++) {
+    if (kPrefetch && rb + rb_stride < nrb) load(nxt, rb + rb_stride);
     else griddep_launch_dependents();  // last row block of this CTA: let the next kernel ramp up
     const int row = rb * RPB + rib;
     const bool active = row < M;
@@ -148,10 +151,20 @@ quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float rang
     if (kPrefetch) {
 #pragma unroll
       for (int v = 0; v < NVC; v++) raw[v] = nxt[v];
-    } else if (NV > 0 && rb + (int)gridDim.x < nrb) {
-      load(raw, rb + gridDim.x);
+    } else if (NV > 0 && rb + rb_stride < nrb) {
+      load(raw, rb + rb_stride);
     }
   }
+}
+
+template <typename T, int G, int NV>
+__global__ void __launch_bounds__(kThreads)
+quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
+                  const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
+                  float *__restrict__ Cx, RowMaxIo io) {
+  griddep_wait();
+  griddep_trigger_early();
+  quant_rows_body<T, G, NV>(X, M, K, ldx, range, mode, sx_in, Xq, ldq, Cx, io, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // Any K, any alignment: one warp per row, scalar accesses.  Same arithmetic.
@@ -210,17 +223,14 @@ __device__ __forceinline__ float part_value(unsigned long long v, uint32_t epoch
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
-absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, int rows_per_cta,
-                           unsigned long long *__restrict__ part, uint32_t epoch) {
+__device__ __forceinline__ void absmax_cols_partial_body(const T *__restrict__ W, int K, int N, int64_t ldw, int rows_per_cta,
+                                                         unsigned long long *__restrict__ part, uint32_t epoch, int col_tile,
+                                                         int row_chunk, float (*s_m)[32 * Unpack<T>::EPV + 1]) {
   constexpr int EPV = Unpack<T>::EPV;
-  __shared__ float s_m[8][32 * EPV + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = (blockIdx.x * 32 + tx) * EPV;
-  const int k0 = 1 + blockIdx.y * rows_per_cta;
+  const int col = (col_tile * 32 + tx) * EPV;
+  const int k0 = 1 + row_chunk * rows_per_cta;
   const int k1 = min(K, k0 + rows_per_cta);
-  griddep_wait();
-  griddep_trigger_early();
 #ifndef QG_COLS_NO_L2_HINTS
   const uint64_t pol = l2_policy_evict_last();
 #define QG_LD1(p) ldg16_hint(p, pol)
@@ -259,9 +269,19 @@ absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, i
     float r = s_m[0][c];
 #pragma unroll
     for (int y = 1; y < 8; y++) r = fmaxf(r, s_m[y][c]);
-    const int gc = blockIdx.x * 32 * EPV + c;
+    const int gc = col_tile * 32 * EPV + c;
     if (gc < N && r >= 0.0f) atomicMax(part + gc, ((unsigned long long)epoch << 32) | __float_as_uint(r));
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+absmax_cols_partial_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, int rows_per_cta,
+                           unsigned long long *__restrict__ part, uint32_t epoch) {
+  __shared__ float s_m[8][32 * Unpack<T>::EPV + 1];
+  griddep_wait();
+  griddep_trigger_early();
+  absmax_cols_partial_body<T>(W, K, N, ldw, rows_per_cta, part, epoch, (int)blockIdx.x, (int)blockIdx.y, s_m);
 }
 
 // finalize only (plain op_absmax on a [K,N] matrix): Cw[j] from row 0 and part[j]
@@ -284,19 +304,13 @@ __global__ void absmax_cols_finalize_kernel(const T *__restrict__ W, int K, int 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
-quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
-                  int rows_per_cta, const unsigned long long *__restrict__ part, uint32_t epoch,
-                  const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
+__device__ __forceinline__ void quant_cols_body(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
+                                                int rows_per_cta, const unsigned long long *__restrict__ part, uint32_t epoch,
+                                                const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq,
+                                                float *__restrict__ Cw, int col_tile, int row_chunk) {
   constexpr int EPV = Unpack<T>::EPV;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = (blockIdx.x * 32 + tx) * EPV;
-  griddep_wait();
-  griddep_trigger_early();
-  // the GEMM that follows may set itself up (barriers, TMEM, descriptors) while this pass streams:
-  // a consistent 0.4-1.2 us per call (93.4 vs 93.8 us at 4096^3, same box).  The same trigger in
-  // pass 1 or in every kernel is a loss (common.cuh: griddep_trigger_early).
-  griddep_launch_dependents();
+  const int col = (col_tile * 32 + tx) * EPV;
   if (col >= N) return;
   const T *base = W + col;
   float s[EPV];
@@ -312,14 +326,14 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
           if (x == x) { c = -x; break; }
         }
       }
-      if (blockIdx.y == 0 && ty == 0 && Cw != nullptr) Cw[col + e] = c;
+      if (row_chunk == 0 && ty == 0 && Cw != nullptr) Cw[col + e] = c;
       s[e] = __fdiv_rn(range, c);
     }
   } else {
 #pragma unroll
     for (int e = 0; e < EPV; e++) s[e] = sw_in[col + e];
   }
-  const int k0 = blockIdx.y * rows_per_cta;
+  const int k0 = row_chunk * rows_per_cta;
   const int k1 = min(K, k0 + rows_per_cta);
   auto emit = [&](const uint4 &r, int k) {
     float f[EPV];
@@ -354,6 +368,43 @@ quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float rang
     for (int u = 0; u < 4; u++) emit(r[u], k - 8 * u);
   }
   for (; k >= k0; k -= 8) emit(QG_LD2(base + (int64_t)k * ldw), k);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+quant_cols_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
+                  int rows_per_cta, const unsigned long long *__restrict__ part, uint32_t epoch,
+                  const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq, float *__restrict__ Cw) {
+  griddep_wait();
+  griddep_trigger_early();
+  // the GEMM that follows may set itself up (barriers, TMEM, descriptors) while this pass streams:
+  // a consistent 0.4-1.2 us per call (93.4 vs 93.8 us at 4096^3, same box).  The same trigger in
+  // pass 1 or in every kernel is a loss (common.cuh: griddep_trigger_early).
+  griddep_launch_dependents();
+  quant_cols_body<T>(W, K, N, ldw, range, mode, rows_per_cta, part, epoch, sw_in, Wq, ldq, Cw, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// Wavefront form of the two passes: the columns are cut into slabs, and launch i runs pass 1 over slab i TOGETHER with
+// pass 2 over slab i-1 (blockIdx.z picks the role).  Every CTA streams freely -- the only dependency is on the previous
+// launch -- and pass 2 finds its slab where the previous launch's pass 1 left it, in L2.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cols_wave_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int rows_per_cta1,
+                 int rows_per_cta2, unsigned long long *__restrict__ part, uint32_t epoch, int8_t *__restrict__ Wq, int64_t ldq,
+                 float *__restrict__ Cw, int tile1_first, int tile1_count, int tile2_first, int tile2_count, int chunks1,
+                 int chunks2, int last) {
+  __shared__ float s_m[8][32 * Unpack<T>::EPV + 1];
+  griddep_wait();
+  griddep_trigger_early();
+  if (last) griddep_launch_dependents();  // the GEMM's set-up may overlap the final slab's codes
+  if (blockIdx.z == 0) {
+    if ((int)blockIdx.x < tile1_count && (int)blockIdx.y < chunks1)
+      absmax_cols_partial_body<T>(W, K, N, ldw, rows_per_cta1, part, epoch, tile1_first + (int)blockIdx.x, (int)blockIdx.y, s_m);
+  } else {
+    if ((int)blockIdx.x < tile2_count && (int)blockIdx.y < chunks2)
+      quant_cols_body<T>(W, K, N, ldw, range, mode, rows_per_cta2, part, epoch, nullptr, Wq, ldq, Cw,
+                         tile2_first + (int)blockIdx.x, (int)blockIdx.y);
+  }
 }
 
 // Pass 2 with transposed output: codes go out as Wt[n][k] (K contiguous), the K-major operand layout
@@ -447,6 +498,32 @@ quant_cols_t_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float ra
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; i++) v[i] = vn[i];
+  }
+}
+
+#ifndef QG_FUSED_MIN_CTAS
+#define QG_FUSED_MIN_CTAS 5
+#endif
+// The op's two quantizers share one launch where they complement each other (qg_quantized_mm): the column quantizer's
+// second pass re-reads W out of L2 and is bound by L2 throughput, the row quantizer streams X from HBM and is bound by
+// HBM -- run side by side (CTAs [0, cols_ctas) take pass-2 tiles, the rest walk the rows of X) they overlap instead of
+// queueing: pass 1 -> [pass 2 || rows] -> GEMM.  No dependency between the two halves; X is loaded evict-first so that
+// it does not push W out of L2 before pass 2 has read it.
+template <typename T, int G, int NV>
+__global__ void __launch_bounds__(kThreads, (NV <= 4 ? QG_FUSED_MIN_CTAS : 2))
+quant_cols2_rows_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode, int rows_per_cta,
+                        const unsigned long long *__restrict__ part, uint32_t epoch, int8_t *__restrict__ Wq, int64_t ldq,
+                        float *__restrict__ Cw, int col_tiles, int cols_ctas, const T *__restrict__ X, int M, int64_t ldx,
+                        int8_t *__restrict__ Xq, int64_t ldxq, float *__restrict__ Cx) {
+  griddep_wait();
+  griddep_trigger_early();
+  if ((int)blockIdx.x < cols_ctas) {
+    griddep_launch_dependents();
+    quant_cols_body<T>(W, K, N, ldw, range, mode, rows_per_cta, part, epoch, nullptr, Wq, ldq, Cw, (int)blockIdx.x % col_tiles,
+                       (int)blockIdx.x / col_tiles);
+  } else {
+    quant_rows_body<T, G, NV, true>(X, M, K, ldx, range, mode, nullptr, Xq, ldxq, Cx, RowMaxIo(), (int)blockIdx.x - cols_ctas,
+                                    (int)gridDim.x - cols_ctas);
   }
 }
 
@@ -971,6 +1048,27 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
     if (rc >= 0) return rc;
   }
   const int col_tiles = (int)ceil_div(N, 32 * EPV);
+  static const int wave_slabs = [] { const char *e = getenv("QG_COLS_WAVE"); return e ? atoi(e) : 0; }();
+  if (wave_slabs >= 2 && !transpose && sw == nullptr && Wq != nullptr && K > 1 && col_tiles >= wave_slabs) {
+    unsigned long long *part = nullptr;
+    uint32_t epoch = 0;
+    int rc = twopass_scratch(N, st, &part, &epoch);
+    if (rc) return rc;
+    const int per = (int)ceil_div(col_tiles, wave_slabs);
+    // each role gets half of the resident CTAs of a launch
+    const int rpc1 = cols_rows_per_cta(K, 2 * per, 8), rpc2 = rpc1;
+    const int chunks1 = (int)ceil_div(K - 1, rpc1), chunks2 = (int)ceil_div(K, rpc2);
+    for (int i = 0; i <= wave_slabs; i++) {
+      const int t1_first = i * per, t1_count = i < wave_slabs ? std::min(per, col_tiles - t1_first) : 0;
+      const int t2_first = (i - 1) * per, t2_count = i >= 1 ? std::min(per, col_tiles - t2_first) : 0;
+      dim3 grid((unsigned)std::max(std::max(t1_count, t2_count), 1), (unsigned)std::max(chunks1, chunks2), 2);
+      cudaError_t e = launch_kernel(cols_wave_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, range, mode, rpc1, rpc2, part,
+                                    epoch, Wq, ldq, Cw, t1_first, t1_count > 0 ? t1_count : 0, t2_first, t2_count > 0 ? t2_count : 0,
+                                    chunks1, chunks2, i == wave_slabs ? 1 : 0);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+  }
   const int rpc = cols_rows_per_cta(K, col_tiles, transpose ? 32 : 8);
   unsigned long long *part = nullptr;
   uint32_t epoch = 0;
@@ -993,7 +1091,88 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
                             Wq, ldq, Cw);
 }
 
+// pass 1 over W, then [pass 2 over W || row quantizer over X] in one launch.  Returns -1 when the shapes are outside what
+// the fused launch covers (the caller then runs the two quantizers one after the other).
+template <typename T, int G, int NV>
+int fused_launch(const T *W, int K, int N, int64_t ldw, float range, int mode, int8_t *Wq, int64_t ldq, float *Cw, const T *X,
+                 int M, int64_t ldx, int8_t *Xq, int64_t ldxq, float *Cx, cudaStream_t st) {
+  constexpr int EPV = Unpack<T>::EPV;
+  static int per_sm = 0, sms = 0;
+  if (per_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quant_cols2_rows_kernel<T, G, NV>, kThreads, 0);
+    if (per_sm <= 0) per_sm = 1;
+    if (sms <= 0) sms = 148;
+  }
+  static const int cols_share_pct = [] { const char *e = getenv("QG_FUSED_COLS_PCT"); return e && atoi(e) > 0 && atoi(e) < 100 ? atoi(e) : 45; }();
+  const int resident = per_sm * sms;
+  const int col_tiles = (int)ceil_div(N, 32 * EPV);
+  // pass 2 on its share of the resident CTAs, one wave; the rest walk the rows of X
+  int cols_target = resident * cols_share_pct / 100;
+  if (cols_target < col_tiles) cols_target = col_tiles;
+  const int chunks = cols_target / col_tiles > 0 ? cols_target / col_tiles : 1;
+  int rpc2 = (int)round_up(ceil_div(K, chunks), 8);
+  if (rpc2 < 32) rpc2 = 32;
+  const int cols_ctas = col_tiles * (int)ceil_div(K, rpc2);
+  constexpr int RPB = kThreads / G;
+  int rows_ctas = resident - cols_ctas;
+  const int nrb = (int)ceil_div(M, RPB);
+  if (rows_ctas > nrb) rows_ctas = nrb;
+  if (rows_ctas < sms) return -1;
+  unsigned long long *part = nullptr;
+  uint32_t epoch = 0;
+  int rc = twopass_scratch(N, st, &part, &epoch);
+  if (rc) return rc;
+  {  // pass 1: all resident CTAs, as when it runs alone
+    const int rpc1 = cols_rows_per_cta(K, col_tiles, 8);
+    dim3 grid(col_tiles, (unsigned)ceil_div(K - 1, rpc1));
+    cudaError_t e = launch_kernel(absmax_cols_partial_kernel<T>, grid, dim3(kThreads), st, W, K, N, ldw, rpc1, part, epoch);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)launch_kernel(quant_cols2_rows_kernel<T, G, NV>, dim3((unsigned)(cols_ctas + rows_ctas)), dim3(kThreads), st, W, K, N,
+                            ldw, range, mode, rpc2, part, epoch, Wq, ldq, Cw, col_tiles, cols_ctas, X, M, ldx, Xq, ldxq, Cx);
+}
+
+template <typename T>
+int fused_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, int8_t *Wq, int64_t ldq, float *Cw, const T *X,
+                   int M, int64_t ldx, int8_t *Xq, int64_t ldxq, float *Cx, cudaStream_t st) {
+  constexpr int EPV = Unpack<T>::EPV;
+  static const bool off = getenv("QG_NO_FUSED_QUANT") != nullptr;
+  const bool w_ok = (N % EPV == 0) && aligned(W, 16) && ((ldw * sizeof(T)) % 16 == 0) && aligned(Wq, EPV) && ldq % EPV == 0 && K > 1;
+  const bool x_ok = (K % EPV == 0) && aligned(X, 16) && ((ldx * sizeof(T)) % 16 == 0) && aligned(Xq, EPV) && ldxq % EPV == 0;
+  // large enough for both halves to fill their share of the machine (small problems are launch-bound either way), and W
+  // small enough to still be in L2 when pass 2 comes for it: beyond that pass 2 is HBM-bound like the row quantizer and
+  // sharing a launch only halves what each gets (8192^2 fp32, 256 MiB: 541.6 us per op fused against 526.8 us apart)
+  const int64_t w_bytes = (int64_t)K * N * (int64_t)sizeof(T);
+  if (off || !w_ok || !x_ok || (int64_t)K * N < (4ll << 20) || (int64_t)M * K < (4ll << 20) || w_bytes > (80ll << 20)) return -1;
+  const int nvec = K / EPV;
+#define QG_FUSED(G, NV) return fused_launch<T, G, NV>(W, K, N, ldw, range, mode, Wq, ldq, Cw, X, M, ldx, Xq, ldxq, Cx, st)
+  if (nvec > 256 && nvec <= 512) QG_FUSED(128, 4);
+  if (nvec > 512 && nvec <= 1024) QG_FUSED(256, 4);
+  if (nvec > 1024 && nvec <= 2048) QG_FUSED(256, 8);
+#undef QG_FUSED
+  return -1;
+}
+
 }  // namespace
+
+// The op's two quantizers together (qg_quantized_mm, weights in the reference's [K,N] code layout): -1 = not covered,
+// run quant_rows and quant_cols separately.
+int quant_rows_cols_fused(const void *X, const void *W, int dtype, int M, int N, int K, int64_t ldx, int64_t ldw, float range, int mode,
+                          int8_t *Xq, int64_t ldxq, float *Cx, int8_t *Wq, int64_t ldwq, float *Cw, cudaStream_t st) {
+  switch (dtype) {
+    case QG_F32:
+      return fused_dispatch((const float *)W, K, N, ldw, range, mode, Wq, ldwq, Cw, (const float *)X, M, ldx, Xq, ldxq, Cx, st);
+    case QG_F16:
+      return fused_dispatch((const __half *)W, K, N, ldw, range, mode, Wq, ldwq, Cw, (const __half *)X, M, ldx, Xq, ldxq, Cx, st);
+    case QG_BF16:
+      return fused_dispatch((const __nv_bfloat16 *)W, K, N, ldw, range, mode, Wq, ldwq, Cw, (const __nv_bfloat16 *)X, M, ldx, Xq,
+                            ldxq, Cx, st);
+  }
+  return -1;
+}
 
 // ---- entry points used by capi.cu ----
 int quant_rows(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, const float *sx,

@@ -99,9 +99,14 @@ class MegatronFFN:
                 self.out_hdl = symm_mem.rendezvous(self.out, grp)
                 eo = self.out.element_size()
                 self.peer_out = [int(self.out_hdl.buffer_ptrs[r]) + self.olo * eo for r in range(self.world) if r != self.rank]
+                import os
+
+                mc = int(getattr(self.out_hdl, "multicast_ptr", 0) or 0)  # NVSwitch multicast mapping of the result, if any
+                self.out_mc = mc + self.olo * eo if mc and os.environ.get("QG_NO_MULTICAST") is None else 0
             else:
                 self.out = torch.empty((m, self.ohi - self.olo), dtype=self.out_dtype, device=device)
                 self.peer_out = []
+                self.out_mc = 0
             self._fresh = True
         else:
             self.slots = torch.empty((max(self.world, 1), m, self.bc), dtype=self.part_dtype, device=device)
@@ -184,7 +189,7 @@ class MegatronFFN:
         n = self.ohi - self.olo
         if n > 0:
             own = self.out[:, self.olo:self.ohi] if self.gather else self.out
-            reduce_partials(self.slots, None if self.b2 is None else self.b2[self.olo:self.ohi], own, self.peer_out, n)
+            reduce_partials(self.slots, None if self.b2 is None else self.b2[self.olo:self.ohi], own, self.peer_out, n, self.out_mc)
         if self.gather:
             # (c) every block of every rank's result is in place; it also orders the next forward's stores after this reduce
             self.out_hdl.barrier(channel=0)

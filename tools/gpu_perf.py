@@ -363,6 +363,15 @@ EXPERIMENTS = {
     "r2_cdbg_writers_4_64_5of8": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,5,8,4,256", "QG_COLS_PIPE_DBG": "2"}),
     "r2_cdbg_readers_4_64_7of8": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,7,8,4,256", "QG_COLS_PIPE_DBG": "1"}),
     "r2_cdbg_writers_4_64_1of8": (cols_pipe, (4096,), {"QG_COLS_PIPE": "4,64,1,8,4,256", "QG_COLS_PIPE_DBG": "2"}),
+    "r2_cwave2_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "0", "QG_COLS_WAVE": "2"}),
+    "r2_cwave3_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "0", "QG_COLS_WAVE": "3"}),
+    "r2_cwave4_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "0", "QG_COLS_WAVE": "4"}),
+    "r2_cwave8_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "0", "QG_COLS_WAVE": "8"}),
+    "r2_cwave0_4096": (cols_pipe, (4096,), {"QG_COLS_PIPE": "0"}),
+    "r2_cwave2_8192": (cols_pipe, (8192,), {"QG_COLS_PIPE": "0", "QG_COLS_WAVE": "2"}),
+    "r2_cwave8_8192": (cols_pipe, (8192,), {"QG_COLS_PIPE": "0", "QG_COLS_WAVE": "8"}),
+    "r2_cwave16_8192": (cols_pipe, (8192,), {"QG_COLS_PIPE": "0", "QG_COLS_WAVE": "16"}),
+    "r2_cwave0_8192": (cols_pipe, (8192,), {"QG_COLS_PIPE": "0"}),
     "r2_cpipe_off_4096_f16": (cols_pipe, (4096, "f16"), {"QG_COLS_PIPE": "0"}),
     "r2_cpipe_def_4096_f16": (cols_pipe, (4096, "f16"), {}),
     "r2_cpipe_off_8192": (cols_pipe, (8192,), {"QG_COLS_PIPE": "0"}),
