@@ -346,7 +346,9 @@ def run_ours(args):
                     hdls.append(h)
                     peer_ptrs.append([int(h.buffer_ptrs[r]) + rank * N * 4 for r in range(world) if r != rank])
                     mc = int(getattr(h, "multicast_ptr", 0) or 0)
-                    mc_ptrs.append(mc + rank * N * 4 if mc and os.environ.get("QG_NO_MULTICAST") is None and N % 4 == 0 else 0)
+                    # opt-in (QG_MULTICAST=1): measured SLOWER than the unicast TMA stores for this gather -- every GPU must still
+                    # receive (P-1) blocks, and ingress is what bounds it (N=8: 814.6 vs 775.5 us per step, profiles/r2_scaling_run19.json)
+                    mc_ptrs.append(mc + rank * N * 4 if mc and os.environ.get("QG_MULTICAST") == "1" and N % 4 == 0 else 0)
                 exchange = "fused: GEMM epilogue TMA-stores into every peer's result over NVLink (symmetric memory)"
                 if all(mc_ptrs):  # NVSwitch multicast mapping: one multimem.st per 16 bytes, replicated by the switch
                     exchange = ("fused: GEMM epilogue stores every tile once to the symmetric buffer's NVSwitch multicast "

@@ -102,7 +102,7 @@ class MegatronFFN:
                 import os
 
                 mc = int(getattr(self.out_hdl, "multicast_ptr", 0) or 0)  # NVSwitch multicast mapping of the result, if any
-                self.out_mc = mc + self.olo * eo if mc and os.environ.get("QG_NO_MULTICAST") is None else 0
+                self.out_mc = mc + self.olo * eo if mc and os.environ.get("QG_MULTICAST") == "1" else 0  # opt-in: see colpar.py
             else:
                 self.out = torch.empty((m, self.ohi - self.olo), dtype=self.out_dtype, device=device)
                 self.peer_out = []

@@ -109,6 +109,29 @@ def test_col_quantizer_bit_exact(qg, oracle, shape, dt):
         assert np.array_equal(Wq.cpu().numpy(), eq), f"codes mismatch mode {mode}"
 
 
+@pytest.mark.parametrize("shape,dt", [((2048, 2048, 2048), "f32"), ((1024, 4096, 4096), "f32"), ((1024, 512, 8192), "f32"),
+                                      ((2048, 2048, 4096), "f16"), ((1024, 2048, 8192), "bf16"), ((600, 1000, 4096), "f32"),
+                                      ((64, 64, 128), "f32")])
+def test_both_quantizers_in_one_call_bit_exact(qg, oracle, shape, dt):
+    """qg_absmax_quant_rows_cols: on large problems column pass 2 runs side by side with the row quantizer in one launch
+    (the first five shapes take that path, the last two the separate launches) -- same codes and scales either way."""
+    M, N, K = shape
+    rng = np.random.default_rng(seed_of(shape, dt, "both"))
+    X = to_dev(make_edge_matrix(rng, M, K), dt)
+    W = to_dev(np.ascontiguousarray(make_edge_matrix(rng, N, K).T), dt)
+    Xh, Wh = as_f32_np(X), as_f32_np(W)
+    for mode in (qg.MODE_REF_EXACT, qg.MODE_TRUE_ABSMAX):
+        Xq = torch.full((M, K), 77, dtype=torch.int8, device=DEV)
+        Wq = torch.full((K, N), 77, dtype=torch.int8, device=DEV)
+        Cx, Cw = torch.full((M,), -1.0, device=DEV), torch.full((N,), -1.0, device=DEV)
+        qg.absmax_quant_rows_cols(X, W, Xq, Cx, Wq, Cw, 127.0, mode)
+        ex, ecx = oracle.absmax_quant_rows(Xh, 127.0, mode)
+        ew, ecw = oracle.absmax_quant_cols(Wh, 127.0, mode)
+        assert same_f32(Cx.cpu().numpy(), ecx) and same_f32(Cw.cpu().numpy(), ecw), f"scales mismatch mode {mode}"
+        assert np.array_equal(Xq.cpu().numpy(), ex), f"row codes mismatch mode {mode}"
+        assert np.array_equal(Wq.cpu().numpy(), ew), f"column codes mismatch mode {mode}"
+
+
 @pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
 @pytest.mark.parametrize("shape", COL_SHAPES + [(4096, 4096), (300, 2050)])
 def test_prepare_weights_is_transposed_column_quantizer(qg, oracle, shape, dt):

@@ -202,6 +202,66 @@ def timing_quantize_case(M=2048, N=512, K=512):
     return res
 
 
+def ffn_chain_case(name, M, d_in, d_ff, d_out, dt=torch.float16):
+    """ll1 -> relu -> ll2 (src/transformer.cu:63-71): two LinearLayer::forward calls + op_relu apart, against the one-call chain
+    whose first epilogue applies the ReLU and hands the row maxima to the second layer's quantizer."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    X = [torch.randn((M, d_in), device=DEV, generator=g).to(dt) for _ in range(2)]
+    l1 = qg.LinearLayer(d_in, d_ff, device=DEV, dtype=dt)
+    l2 = qg.LinearLayer(d_ff, d_out, device=DEV, dtype=dt)
+    for l in (l1, l2):
+        l.w.normal_(0, 0.02, generator=g)
+        l.b.normal_(0, 0.1, generator=g)
+    W1t, Cw1 = l1.quantize_weights()
+    W2t, Cw2 = l2.quantize_weights()
+    H = torch.empty((M, d_ff), dtype=dt, device=DEV)
+    Y = torch.empty((M, d_out), dtype=dt, device=DEV)
+    Y2 = torch.empty_like(Y)
+
+    def apart(i):
+        l1.forward(X[i & 1], H)
+        H.relu_()
+        l2.forward(H, Y2)
+
+    def chain(i):
+        qg.ffn_forward(X[i & 1], W1t, Cw1, l1.b, W2t, Cw2, l2.b, H, Y)
+
+    apart(0); chain(0)
+    torch.cuda.synchronize()
+    res = {"name": name, "M": M, "d_in": d_in, "d_ff": d_ff, "d_out": d_out, "dtype": str(dt).split(".")[-1],
+           "same_bits": bool(torch.equal(Y.view(torch.int16 if dt != torch.float32 else torch.int32),
+                                         Y2.view(torch.int16 if dt != torch.float32 else torch.int32)))}
+    res["apart_us"] = timed(apart)
+    res["chain_us"] = timed(chain)
+    ops = 2.0 * M * d_ff * (d_in + d_out)
+    res["chain_tops"] = ops / res["chain_us"] / 1e6
+    w1, w2 = l1.w.to(torch.float16), l2.w.to(torch.float16)
+    x16 = [x.to(torch.float16) for x in X]
+    res["fp16_two_gemms_relu_us"] = timed(lambda i: torch.matmul(torch.relu_(torch.matmul(x16[i & 1], w1)), w2))
+    del l1, l2, X, H, Y, Y2, w1, w2, x16
+    torch.cuda.empty_cache()
+    return res
+
+
+def outlier_sweep_case(M=16384, K=4096, N=4096, dt=torch.float16):
+    """config 4's out-projection with 0 .. 64 outlier feature dims: cost of the decomposition against the plain int8 linear."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    res = {"name": "opt6.7b_out_outlier_sweep", "M": M, "K": K, "N": N, "dtype": str(dt).split(".")[-1], "us": {}}
+    lin = qg.LinearLayer(K, N, device=DEV, dtype=dt)
+    lin.w.normal_(0, 0.02, generator=g)
+    lin.b.zero_()
+    lin.quantize_weights()
+    y = torch.empty((M, N), dtype=dt, device=DEV)
+    X = torch.randn((M, K), device=DEV, generator=g).to(dt)
+    res["us"]["plain"] = timed(lambda i: lin.forward(X, y))
+    for n in (6, 8, 16, 24, 32, 48, 64):
+        cols = torch.randperm(K, device=DEV, generator=g)[:n].sort().values.to(torch.int32)
+        res["us"][str(n)] = timed(lambda i: lin.forward_outlier(X, y, cols))
+    del lin, X, y
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     out = []
     out.append(timing_quantize_case())  # config 0: both shapes found in the reference's timing driver
@@ -215,6 +275,10 @@ def main():
         out.append(linear_case(name, T, K, N, torch.float16, outliers=6))
     for name, K, N in (("opt66b_fc1_shard_of_8", 9216, 36864 // 8), ("opt66b_fc2_shard_of_8", 36864, 9216 // 8)):  # config 5
         out.append(linear_case(name, 4096, K, N, torch.float16))
+    out.append(outlier_sweep_case())
+    out.append(ffn_chain_case("ffn_config3_4096x512x2048", 4096, 512, 2048, 512, torch.float32))
+    out.append(ffn_chain_case("ffn_opt6.7b_T4096", 4096, 4096, 16384, 4096, torch.float16))
+    out.append(ffn_chain_case("ffn_4096_cubed", 4096, 4096, 4096, 4096, torch.float16))
     out.append(attention_case())  # config 3 building block
     out.append(transformer_case())  # config 3
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
