@@ -45,8 +45,12 @@ class MegatronFFN:
     def __init__(self, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor], rank: int,
                  world: int, group=None, exchange: str = "fused", h_dtype: torch.dtype = torch.float32,
                  part_dtype: torch.dtype = torch.float32, out_dtype: torch.dtype = torch.float32, gather: bool = True,
-                 compute: Optional[Callable] = None, range_: float = 127.0, mode: int = 0, align: int = 16):
+                 compute: Optional[Callable] = None, range_: float = 127.0, mode: int = 0, align: int = 16, chunks: int = 0):
         assert exchange in ("fused", "collective")
+        # fused exchange: the tokens are cut into `chunks` row blocks; block c's reduce + gather (side stream) runs under block
+        # c+1's GEMMs.  0 = choose (4 blocks of >= 512 rows when the batch allows it).  Rows are independent, so the result does
+        # not depend on the chunking.
+        self.chunks = chunks
         self.rank, self.world, self.group = rank, world, group
         self.exchange, self.gather = exchange, gather
         self.h_dtype, self.part_dtype, self.out_dtype = h_dtype, part_dtype, out_dtype
@@ -171,6 +175,21 @@ class MegatronFFN:
             out[:, lo:hi] = allb[b][:, : hi - lo]
         return out
 
+    def _row_blocks(self, m: int):
+        c = self.chunks
+        if c <= 0:
+            # measured on the OPT-66B FFN, T = 4096 (profiles/r2_megatron_opt66b_p{2,8}_row_blocks_run2{0,1}.json): at P = 2 the
+            # exchange is a small share and cutting the GEMMs costs more than it hides (1004 -> 1079 us with 4 blocks); at P = 8
+            # fp32 partials gain from 4 blocks (772 -> 659 us), 16-bit partials from 2 (539 -> 505 us), 8 blocks always lose
+            if self.world <= 2 or m < 2048:
+                c = 1
+            else:
+                c = 4 if self.part_dtype == torch.float32 else 2
+        c = max(1, min(c, m // 256 if m >= 256 else 1))
+        step = -(-m // c)
+        step = -(-step // 256) * 256  # whole 2-SM tiles per block
+        return [(r0, min(r0 + step, m)) for r0 in range(0, m, step)]
+
     def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
         from . import ffn_forward_rowpar, reduce_partials
 
@@ -178,19 +197,37 @@ class MegatronFFN:
             self._prepare(x.device)
         m = x.shape[0]
         self._ensure(m, x.device)
+        blocks = self._row_blocks(m)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=x.device)
+        side = self._side
         # (a) every peer has finished reducing the previous contents of its slots (and reading its previous result)
         if self._fresh or not self.gather:
             self.slots_hdl.barrier(channel=0)
             self._fresh = False
-        ffn_forward_rowpar(x, self.w1t, self.cw1, self.b1, self.w2t, self.cw2, self.h, self.part_ptrs, self.bc, self.bc,
-                           self.part_dtype, self.d_out, self.range, self.mode, workspace=self.ws)
-        # (b) all partial products have landed in their owners' slots
-        self.slots_hdl.barrier(channel=1)
         n = self.ohi - self.olo
-        if n > 0:
-            own = self.out[:, self.olo:self.ohi] if self.gather else self.out
-            reduce_partials(self.slots, None if self.b2 is None else self.b2[self.olo:self.ohi], own, self.peer_out, n, self.out_mc)
-        if self.gather:
-            # (c) every block of every rank's result is in place; it also orders the next forward's stores after this reduce
-            self.out_hdl.barrier(channel=0)
+        es, eo = self.slots.element_size(), self.out.element_size()
+        bias = None if self.b2 is None else self.b2[self.olo:self.ohi]
+        side.wait_stream(main)
+        for r0, r1 in blocks:
+            ptrs = [p + r0 * self.bc * es for p in self.part_ptrs]
+            ffn_forward_rowpar(x[r0:r1], self.w1t, self.cw1, self.b1, self.w2t, self.cw2, self.h[r0:r1], ptrs, self.bc, self.bc,
+                               self.part_dtype, self.d_out, self.range, self.mode, workspace=self.ws)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(side):  # this block's exchange tail runs under the next block's GEMMs
+                side.wait_event(done)
+                # (b) every rank's partial products of this row block have landed in their owners' slots
+                self.slots_hdl.barrier(channel=1)
+                if n > 0:
+                    own = self.out[r0:r1, self.olo:self.ohi] if self.gather else self.out[r0:r1]
+                    ldo = self.out.stride(0)
+                    peers = [p + r0 * ldo * eo for p in self.peer_out]
+                    reduce_partials(self.slots[:, r0:r1, :], bias, own, peers, n, self.out_mc + r0 * ldo * eo if self.out_mc else 0)
+        with torch.cuda.stream(side):
+            if self.gather:
+                # (c) every block of every rank's result is in place; it also orders the next forward's stores after this reduce
+                self.out_hdl.barrier(channel=0)
+        main.wait_stream(side)
         return self.out

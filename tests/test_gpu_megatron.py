@@ -102,7 +102,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, dts, gather, ret):
+def _worker(rank, world, port, shape, dts, gather, ret, chunks=0):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -119,7 +119,7 @@ def _worker(rank, world, port, shape, dts, gather, ret):
         X, W1, b1, W2, b2 = _data(*shape, seed=11)
         t = lambda a: torch.from_numpy(a).cuda()
         kw = dict(h_dtype=TDT[h_dt], part_dtype=TDT[p_dt], out_dtype=TDT[o_dt], gather=gather)
-        fused = mg.MegatronFFN(t(W1), t(b1), t(W2), t(b2), rank, world, exchange="fused", **kw)
+        fused = mg.MegatronFFN(t(W1), t(b1), t(W2), t(b2), rank, world, exchange="fused", chunks=chunks, **kw)
         coll = mg.MegatronFFN(t(W1), t(b1), t(W2), t(b2), rank, world, exchange="collective", **kw)
         bounds = [cp.shard_bounds(d_ff, world, r, 16) for r in range(world)]
         want = oracle.megatron_ffn(X, W1, b1, W2, b2, bounds, h_dtype=h_dt, part_dtype=p_dt, out_dtype=o_dt)
@@ -140,12 +140,14 @@ def _worker(rank, world, port, shape, dts, gather, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shape,dts,gather", [
-    ((512, 256, 1024, 512), ("f32", "f32", "f32"), True),
-    ((300, 128, 768, 200), ("f16", "f32", "f16"), True),
-    ((1024, 512, 2048, 1152), ("f16", "bf16", "f16"), False),
+@pytest.mark.parametrize("shape,dts,gather,chunks", [
+    ((512, 256, 1024, 512), ("f32", "f32", "f32"), True, 1),
+    ((300, 128, 768, 200), ("f16", "f32", "f16"), True, 0),
+    ((1024, 512, 2048, 1152), ("f16", "bf16", "f16"), False, 2),
+    ((2304, 256, 1024, 512), ("f16", "f32", "f16"), True, 0),   # 4 row blocks, the last one ragged (2304 = 3 x 768 ... rounded to tiles)
+    ((1100, 128, 512, 320), ("f32", "f32", "f32"), True, 3),
 ])
-def test_megatron_ffn_fused_exchange_matches_oracle(shape, dts, gather):
+def test_megatron_ffn_fused_exchange_matches_oracle(shape, dts, gather, chunks):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -155,5 +157,5 @@ def test_megatron_ffn_fused_exchange_matches_oracle(shape, dts, gather):
 
     oracle.build()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), shape, dts, gather, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, dts, gather, ret, chunks), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)

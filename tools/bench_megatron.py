@@ -23,6 +23,7 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 dev = torch.device("cuda", lr)
 small = "--small" in sys.argv
+only_fused = "--only-fused" in sys.argv  # skip the collective / column-parallel / local legs (already measured): fused exchange and its row-block variants only
 T, D, F = (1024, 1024, 4096) if small else (4096, 9216, 36864)
 part_dts = [torch.float32, torch.bfloat16]
 
@@ -60,18 +61,26 @@ for pdt in part_dts:
     torch.cuda.synchronize()
     res[f"fused_eq_collective_bits_{tag}"] = bool(torch.equal(y_f.view(torch.int16), y_c.view(torch.int16)))
     res[f"fused_us_{tag}"] = timed(lambda: fused.forward(x))
-    res[f"collective_us_{tag}"] = timed(lambda: coll.forward(x))
-    res[f"local_us_{tag}"] = timed(lambda: coll._partial_blocks(x))
+    res[f"fused_row_blocks_{tag}"] = len(fused._row_blocks(T))
+    if not only_fused:
+        res[f"collective_us_{tag}"] = timed(lambda: coll.forward(x))
+        res[f"local_us_{tag}"] = timed(lambda: coll._partial_blocks(x))
     if world > 1:
-        rs = mg.MegatronFFN(W1, b1, W2, b2, rank, world, exchange="fused", gather=False, **kw)
-        res[f"fused_rs_us_{tag}"] = timed(lambda: rs.forward(x))
-        del rs
+        for c in (1, 2, 4):
+            rs = mg.MegatronFFN(W1, b1, W2, b2, rank, world, exchange="fused", gather=False, chunks=c, **kw)
+            res[f"fused_rs_us_{tag}_chunks{c}"] = timed(lambda: rs.forward(x))
+            del rs
+        for c in (1, 2, 4, 8):  # row-block pipelining of the exchange tail (the default above chooses 4 blocks at T = 4096)
+            fc = mg.MegatronFFN(W1, b1, W2, b2, rank, world, exchange="fused", gather=True, chunks=c, **kw)
+            res[f"fused_us_{tag}_chunks{c}"] = timed(lambda: fc.forward(x))
+            del fc
+            torch.cuda.empty_cache()
     res[f"fused_tops_total_{tag}"] = ops / res[f"fused_us_{tag}"] / 1e6
     res[f"exchange_bytes_out_per_rank_{tag}"] = T * fused.bc * (world - 1) * torch.empty(0, dtype=pdt).element_size()
     del fused, coll, y_f, y_c
     torch.cuda.empty_cache()
     dist.barrier()
-if world > 1:
+if world > 1 and not only_fused:
     l1 = colpar.FusedColumnParallelLinear(W1, b1, rank, world)
     l2 = colpar.FusedColumnParallelLinear(W2, b2, rank, world)
 
@@ -86,5 +95,5 @@ res["clocks_note"] = "max over ranks of CUDA-event time per forward"
 if rank == 0:
     print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in res.items()}), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open(f"gpurun_out/megatron_{world}{'_small' if small else ''}.json", "w"), indent=1)
+    json.dump(res, open(f"gpurun_out/megatron_{world}{'_small' if small else ''}{'_fused' if only_fused else ''}.json", "w"), indent=1)
 dist.destroy_process_group()
