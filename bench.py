@@ -403,15 +403,17 @@ def run_ours(args):
         if world > 1 and not fused:
             dist.all_gather_into_tensor(gathered, Os[s])
 
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-
+    # the clock sampler starts BEFORE the warm-up steps: its start-up (a 250 ms pause) would otherwise sit between the
+    # warm-up and the timed region and let the GPU fall idle right before the first timed step (one box measured 94.5 us per
+    # step that way against 92.9 us sustained); samples are filtered by power, so the idle ones do not count
     sampler = ClockSampler(local_rank)
     sample_clocks = rank == 0 and os.environ.get("QG_BENCH_NO_CLOCKS") is None
     if sample_clocks:
         sampler.start()
         time.sleep(0.25)
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
     # every rank enters the timed region together: rank 0's sampler start-up above must not show up
     # as 250 ms of waiting inside the other ranks' first exchange
     if world > 1:

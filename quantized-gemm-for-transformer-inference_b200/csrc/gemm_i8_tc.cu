@@ -402,14 +402,32 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           // the big one is reused, so every warp must be done with the previous tile's copy first
           float *wo_tile = wo_s + (side_big ? 0 : (int)as * kSideDbl * BN);
           if (side_big) named_bar_sync(1, 32 * kEpiWarps);
-          for (int i = epi_tid; i < p.no_pad * bn; i += 32 * kEpiWarps) {
-            const int o = i / bn, cc = i - o * bn, col = n_base + cc;
-            float wv = 0.0f;
-            if (col < p.N) {
-              if (p.side_bf16) wv = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p.Wo)[(int64_t)o * p.ldwo + col]);
-              else wv = __half2float(reinterpret_cast<const __half *>(p.Wo)[(int64_t)o * p.ldwo + col]);
+          // eight columns (16 bytes of Wo) per load, all of a thread's loads independent: one element per load made the
+          // fill a chain of L2 round trips per tile (64 columns: 64 dependent 2-byte loads per thread)
+          const int groups = bn >> 3;
+          for (int i = epi_tid; i < p.no_pad * groups; i += 32 * kEpiWarps) {
+            const int o = i / groups, cc = (i - o * groups) << 3, col = n_base + cc;
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (col < p.N) raw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(p.Wo) + (int64_t)o * p.ldwo + col));
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              if (p.side_bf16) {
+                f[2 * q] = __uint_as_float(rw[q] << 16);
+                f[2 * q + 1] = __uint_as_float(rw[q] & 0xffff0000u);
+              } else {
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&rw[q]));
+                f[2 * q] = f2.x;
+                f[2 * q + 1] = f2.y;
+              }
             }
-            wo_tile[o * BN + cc] = wv;
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+              if (col + e >= p.N) f[e] = 0.0f;  // the row's padding up to ldwo is readable but not part of W
+            float4 *dst = reinterpret_cast<float4 *>(wo_tile + o * BN + cc);
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
           }
           named_bar_sync(1, 32 * kEpiWarps);
         }
@@ -421,7 +439,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; j++) sd[j] = 0.0f;
         if (SIDE) {
-          const float *wo = wo_s + (side_big ? 0 : (int)as * kSideDbl * BN) + cbase;
+          // explicit shared-window loads: through the generic pointer these were LD.E.128, not LDS.128
+          const uint32_t wo_u = smem_u32(wo_s) + (uint32_t)(((side_big ? 0 : (int)as * kSideDbl * BN) + cbase) * 4);
 #pragma unroll 1
           for (int ob = 0; ob < p.no_pad; ob += 8) {
             uint4 xv = make_uint4(0, 0, 0, 0);
@@ -439,16 +458,21 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 xo[2 * i + 1] = f2.y;
               }
             }
+            // four output columns at a time: the eight shared-memory loads of a group are issued together (only two
+            // epilogue warps share a scheduler, so a load per four FMAs left the chain waiting on every LDS: ~1200
+            // cycles per outlier column and tile), then the 32 FMAs -- per column still o ascending
+            const uint32_t wrow0 = wo_u + (uint32_t)(ob * BN * 4);
 #pragma unroll
-            for (int o = 0; o < 8; o++) {
-              const float4 *wp = reinterpret_cast<const float4 *>(wo + (ob + o) * BN);
+            for (int j4 = 0; j4 < 8; j4++) {
+              float4 wv[8];
 #pragma unroll
-              for (int j4 = 0; j4 < 8; j4++) {
-                const float4 wv = wp[j4];
-                sd[4 * j4] = __fmaf_rn(xo[o], wv.x, sd[4 * j4]);
-                sd[4 * j4 + 1] = __fmaf_rn(xo[o], wv.y, sd[4 * j4 + 1]);
-                sd[4 * j4 + 2] = __fmaf_rn(xo[o], wv.z, sd[4 * j4 + 2]);
-                sd[4 * j4 + 3] = __fmaf_rn(xo[o], wv.w, sd[4 * j4 + 3]);
+              for (int o = 0; o < 8; o++) wv[o] = lds128(wrow0 + (uint32_t)(o * BN * 4 + j4 * 16));
+#pragma unroll
+              for (int o = 0; o < 8; o++) {
+                sd[4 * j4] = __fmaf_rn(xo[o], wv[o].x, sd[4 * j4]);
+                sd[4 * j4 + 1] = __fmaf_rn(xo[o], wv[o].y, sd[4 * j4 + 1]);
+                sd[4 * j4 + 2] = __fmaf_rn(xo[o], wv[o].z, sd[4 * j4 + 2]);
+                sd[4 * j4 + 3] = __fmaf_rn(xo[o], wv[o].w, sd[4 * j4 + 3]);
               }
             }
           }
@@ -924,9 +948,9 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   if (dbg_no_tma_store) p.tma_store = 0;
   p.stats = g_stats;
   if (side != nullptr && side->no_pad > 0) {
-    if (side->no_pad > kSideMax || side->no_pad % 8 != 0 || (side->ldxo % 8) != 0 ||
-        (reinterpret_cast<uintptr_t>(side->Xo) & 15) != 0) {
-      set_error("gemm_i8_tc: side product takes at most %d outlier columns (padded to 8), 16-byte aligned Xo", kSideMax);
+    if (side->no_pad > kSideMax || side->no_pad % 8 != 0 || (side->ldxo % 8) != 0 || (side->ldwo % 8) != 0 ||
+        (reinterpret_cast<uintptr_t>(side->Xo) & 15) != 0 || (reinterpret_cast<uintptr_t>(side->Wo) & 15) != 0) {
+      set_error("gemm_i8_tc: side product takes at most %d outlier columns (padded to 8), 16-byte aligned Xo / Wo rows", kSideMax);
       return QG_ENOTSUP;
     }
     p.Xo = side->Xo; p.ldxo = side->ldxo; p.Wo = side->Wo; p.ldwo = side->ldwo;

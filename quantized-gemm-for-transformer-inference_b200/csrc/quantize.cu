@@ -303,7 +303,7 @@ __global__ void absmax_cols_finalize_kernel(const T *__restrict__ W, int K, int 
   Cw[j] = c;
 }
 
-template <typename T>
+template <typename T, int UL = 4>  // UL: independent 16-byte loads in flight per thread
 __device__ __forceinline__ void quant_cols_body(const T *__restrict__ W, int K, int N, int64_t ldw, float range, int mode,
                                                 int rows_per_cta, const unsigned long long *__restrict__ part, uint32_t epoch,
                                                 const float *__restrict__ sw_in, int8_t *__restrict__ Wq, int64_t ldq,
@@ -353,19 +353,16 @@ __device__ __forceinline__ void quant_cols_body(const T *__restrict__ W, int K, 
 #else
 #define QG_LD2(p) ldg16(p)
 #endif
-  // Bottom-up, with L1::no_allocate / L2 evict-first loads (pass 1: evict-last).  The hope was that
-  // the second pass would find in L2 what the first one had just streamed; it does not: with the
-  // caches left as the pipeline leaves them ncu still counts 67 MB of DRAM reads (0.6-17 % sector
-  // hits) in either walking order and with either eviction hint (W is 64 MiB at 4096^2; smaller
-  // panels showed the same per-byte cost).  The hinted loads are kept because they are ~7 % faster
-  // (24.1 -> 22.3 us for both passes), the order because it is free.
+  // Bottom-up (the rows pass 1 read last first), with L1::no_allocate / L2 evict-first loads (pass 1: evict-last).  In the
+  // pipeline this pass IS served from L2 (tools/l2_reuse_probe.py: 14.3 us right after pass 1 against 20.5 us cold at 64 MiB);
+  // round 1's "no hits" was ncu's kernel replay, which saves and restores memory between passes and evicts everything.
   int k = k1 - 1 - ty;
-  for (; k - 24 >= k0; k -= 32) {
-    uint4 r[4];
+  for (; k - 8 * (UL - 1) >= k0; k -= 8 * UL) {
+    uint4 r[UL];
 #pragma unroll
-    for (int u = 0; u < 4; u++) r[u] = QG_LD2(base + (int64_t)(k - 8 * u) * ldw);
+    for (int u = 0; u < UL; u++) r[u] = QG_LD2(base + (int64_t)(k - 8 * u) * ldw);
 #pragma unroll
-    for (int u = 0; u < 4; u++) emit(r[u], k - 8 * u);
+    for (int u = 0; u < UL; u++) emit(r[u], k - 8 * u);
   }
   for (; k >= k0; k -= 8) emit(QG_LD2(base + (int64_t)k * ldw), k);
 }
@@ -504,6 +501,9 @@ quant_cols_t_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, float ra
 #ifndef QG_FUSED_MIN_CTAS
 #define QG_FUSED_MIN_CTAS 5
 #endif
+#ifndef QG_FUSED_COLS_LOADS
+#define QG_FUSED_COLS_LOADS 4
+#endif
 // The op's two quantizers share one launch where they complement each other (qg_quantized_mm): the column quantizer's
 // second pass re-reads W out of L2 and is bound by L2 throughput, the row quantizer streams X from HBM and is bound by
 // HBM -- run side by side (CTAs [0, cols_ctas) take pass-2 tiles, the rest walk the rows of X) they overlap instead of
@@ -519,8 +519,8 @@ quant_cols2_rows_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, floa
   griddep_trigger_early();
   if ((int)blockIdx.x < cols_ctas) {
     griddep_launch_dependents();
-    quant_cols_body<T>(W, K, N, ldw, range, mode, rows_per_cta, part, epoch, nullptr, Wq, ldq, Cw, (int)blockIdx.x % col_tiles,
-                       (int)blockIdx.x / col_tiles);
+    quant_cols_body<T, QG_FUSED_COLS_LOADS>(W, K, N, ldw, range, mode, rows_per_cta, part, epoch, nullptr, Wq, ldq, Cw,
+                                            (int)blockIdx.x % col_tiles, (int)blockIdx.x / col_tiles);
   } else {
     quant_rows_body<T, G, NV, true>(X, M, K, ldx, range, mode, nullptr, Xq, ldxq, Cx, RowMaxIo(), (int)blockIdx.x - cols_ctas,
                                     (int)gridDim.x - cols_ctas);
@@ -550,6 +550,7 @@ quant_cols2_rows_kernel(const T *__restrict__ W, int K, int N, int64_t ldw, floa
 // 4096^2 (64 MiB) 23.5 -> 28.5-31; 8192^2 (256 MiB) 93 -> 102-108.  It does read W from HBM once (ncu: 67 MB at 4096^2 against
 // 134 MB), but at 64 MiB and beyond two free-running streaming launches at the HBM roof beat one launch whose second half
 // waits on the first; it wins where a launch boundary costs more than the second read (QG_COLS_PIPE=1 forces it on).
+// 16-bit inputs lose at every size tried (4096^2 fp16: 19.8 -> 25-31 us), so the window is fp32 only.
 constexpr int64_t kPipeMinBytes = 8ll << 20, kPipeMaxBytes = 24ll << 20;
 constexpr int kExitFan = 16;     // exit counting is two-level so that no address sees more than grid / 16 atomics
 constexpr int kLineInts = 32;    // one counter per 128-byte line
@@ -1041,7 +1042,7 @@ int cols_dispatch(const T *W, int K, int N, int64_t ldw, float range, int mode, 
                               N, ldw, range, mode, sw, Wq, ldq, Cw, transpose);
   }
   // one launch, one HBM read of W (panel pipeline) once the matrix is large enough for the second read to matter
-  if (!transpose && sw == nullptr && Wq != nullptr && pipe_tune().on &&
+  if (!transpose && sw == nullptr && Wq != nullptr && pipe_tune().on && (sizeof(T) == 4 || pipe_tune().force) &&
       (int64_t)K * N * (int64_t)sizeof(T) >= kPipeMinBytes &&
       ((int64_t)K * N * (int64_t)sizeof(T) <= kPipeMaxBytes || pipe_tune().force)) {
     const int rc = cols_pipe_launch(W, K, N, ldw, range, mode, Wq, ldq, Cw, st);
