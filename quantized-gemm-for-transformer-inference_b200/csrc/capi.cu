@@ -559,7 +559,7 @@ static OutlierWs carve_outlier(void *base, int M, int N, int K) {
   const size_t words = (size_t)ceil_div(K, 32);
   w.ldxo = kMaxOutlierCols;
   w.ldwo = round_up(N, 8);
-  const size_t om = take(4 * words), ob = take(4 * words), ox = take(2 * (size_t)M * w.ldxo),
+  const size_t om = take(4 * words), ob = take(4 * (words + 1)), ox = take(2 * (size_t)M * w.ldxo),
                ow = take(2 * (size_t)kMaxOutlierCols * w.ldwo);
   char *b = reinterpret_cast<char *>(base);
   w.mask = reinterpret_cast<uint32_t *>(b + om);
@@ -629,8 +629,7 @@ int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, const vo
   const int side_bf16 = (in_dtype == QG_BF16) ? 1 : 0;
   rc = outlier_mask_from_idx(idx, n_idx, K, o.mask, o.wbase, st);
   if (rc) return cuda_status((cudaError_t)rc, "outlier mask");
-  if (no_pad > 0) {
-    QG_CUDA_OK(cudaMemsetAsync(o.Xo, 0, 2 * (size_t)M * o.ldxo, st));
+  if (no_pad > 0) {  // (the side operand's padding columns are zeroed by the row quantizer itself: no memset node in the PDL chain)
     rc = gather_wo(W, w_dtype, ldw, idx, n_idx, no_pad, N, o.Wo, o.ldwo, side_bf16, st);
     if (rc) return cuda_status((cudaError_t)rc, "outlier weight gather");
   }

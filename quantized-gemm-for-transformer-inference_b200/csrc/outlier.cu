@@ -150,138 +150,23 @@ outlier_mask_from_idx_kernel(const int *__restrict__ idx, int n_idx, int K, uint
     if (k >= 0 && k < K) atomicOr(mask + (k >> 5), 1u << (k & 31));
   }
   __syncthreads();
-  mask_prefix(mask, words, wbase);
+  const int total = mask_prefix(mask, words, wbase);
+  if (threadIdx.x == 0) wbase[words] = total;  // number of distinct outlier columns (one int past the per-word prefixes)
 }
 
-// ---- masking row quantizer --------------------------------------------------------------------
-struct RowOutlier {
-  const uint32_t *mask;  // K bits
-  const int *wbase;      // prefix popcount per mask word
-  void *Xo;              // [M, ldxo] 16-bit side operand, columns = rank of k inside O (pre-zeroed)
-  int64_t ldxo;
-  int side_bf16;         // 0: fp16, 1: bf16
-};
-
-// Removes the outlier elements of one 16-byte vector (vector index vi of `row`) from the int8 path
-// (sets them to +0) and, when `write`, stores them into the side operand.
-template <typename T>
-__device__ __forceinline__ void strip_outliers(uint4 &r, int vi, int row, const RowOutlier &ro, bool write) {
-  constexpr int EPV = Unpack<T>::EPV;
-  const int c0 = vi * EPV, b0 = c0 & 31;
-  const uint32_t word = __ldg(ro.mask + (c0 >> 5));
-  uint32_t bits = (word >> b0) & ((1u << EPV) - 1u);
-  if (bits == 0) return;
-  float f[EPV];
-  Unpack<T>::run(r, f);
-  int pos = __ldg(ro.wbase + (c0 >> 5)) + __popc(word & ((1u << b0) - 1u));
-  uint32_t *w = reinterpret_cast<uint32_t *>(&r);
-#pragma unroll
-  for (int e = 0; e < EPV; e++) {
-    if ((bits >> e) & 1u) {
-      if (write) {
-        if (ro.side_bf16) reinterpret_cast<__nv_bfloat16 *>(ro.Xo)[(int64_t)row * ro.ldxo + pos] = __float2bfloat16_rn(f[e]);
-        else reinterpret_cast<__half *>(ro.Xo)[(int64_t)row * ro.ldxo + pos] = __float2half_rn(f[e]);
-      }
-      pos++;
-      if (sizeof(T) == 4) w[e] = 0u;
-      else w[e >> 1] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
-    }
-  }
-}
-
-// One CTA per row (persistent loop); NV 16-byte vectors per thread cached in registers (NV == 0:
-// row too long, second pass re-reads it).  Same arithmetic as quant_rows_kernel on the zeroed row.
-template <typename T, int NV>
-__global__ void __launch_bounds__(kThreads)
+// The masking quantizer IS the row quantizer of quantize.cu (quant_rows_body: G threads per row, NV vectors per thread kept in
+// registers between the reduction and the codes, the next row block loaded ahead) with one hook: every vector passes
+// through strip_outliers before it is reduced, so the outlier entries read as +0 for the scale and the codes and are
+// written to the side operand.  (Round 1 had its own one-CTA-per-row kernel without the look-ahead: 51 us against 37 us
+// for the plain quantizer at 16384 x 4096 fp16.)
+template <typename T, int G, int NV>
+__global__ void __launch_bounds__(kThreads, (NV <= 4 ? 4 : 2))  // the strip code would otherwise take 96 registers: 2 CTAs per SM
 quant_rows_outlier_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
                           int8_t *__restrict__ Xq, int64_t ldq, float *__restrict__ Cx, RowOutlier ro) {
-  constexpr int EPV = Unpack<T>::EPV;
-  constexpr int NVC = NV > 0 ? NV : 1;
-  __shared__ float s_m[2][kThreads / 32];
-  __shared__ float s_x0[2];
-  const int g = threadIdx.x;
-  const int nvec = K / EPV;
   griddep_wait();
   griddep_trigger_early();
-  int it = 0;
-  for (int row = blockIdx.x; row < M; row += gridDim.x, it++) {
-    const T *xr = X + (int64_t)row * ldx;
-    uint4 raw[NVC];
-    float m = -INFINITY, x0 = 0.0f;
-    auto fold_vec = [&](const uint4 &r, int idx) {
-      float f[EPV];
-      Unpack<T>::run(r, f);
-      if (idx == 0) x0 = f[0];
-#pragma unroll
-      for (int e = 0; e < EPV; e++)
-        if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
-    };
-    if (NV > 0) {
-#pragma unroll
-      for (int v = 0; v < NVC; v++) {
-        const int idx = v * kThreads + g;
-        raw[v] = idx < nvec ? ldg16(xr + (int64_t)idx * EPV) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int v = 0; v < NVC; v++) {
-        const int idx = v * kThreads + g;
-        if (idx < nvec) {
-          strip_outliers<T>(raw[v], idx, row, ro, true);
-          fold_vec(raw[v], idx);
-        }
-      }
-    } else {
-      for (int idx = g; idx < nvec; idx += kThreads) {
-        uint4 r = ldg16(xr + (int64_t)idx * EPV);
-        strip_outliers<T>(r, idx, row, ro, true);
-        fold_vec(r, idx);
-      }
-    }
-    m = warp_max(m);
-    float *sm = s_m[it & 1];
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-    if (g == 0) s_x0[it & 1] = x0;
-    __syncthreads();
-    m = sm[0];
-#pragma unroll
-    for (int w = 1; w < kThreads / 32; w++) m = fmaxf(m, sm[w]);
-    x0 = s_x0[it & 1];
-    float c;
-    if (fold_first(x0, m, mode, c)) {
-      for (int j = 1; j < K; j++) {  // +-0 tie-break on the zeroed row: outlier columns read as +0
-        const bool outl = (__ldg(ro.mask + (j >> 5)) >> (j & 31)) & 1u;
-        const float xj = outl ? 0.0f : to_f32(xr[j]);
-        if (xj == xj) { c = -xj; break; }
-      }
-    }
-    if (g == 0 && Cx != nullptr) Cx[row] = c;
-    const float scale = __fdiv_rn(range, c);
-    int8_t *qr = Xq + (int64_t)row * ldq;
-    auto emit = [&](const uint4 &r, int idx) {
-      float f[EPV];
-      Unpack<T>::run(r, f);
-      uint32_t w[EPV / 4];
-#pragma unroll
-      for (int q = 0; q < EPV / 4; q++)
-        w[q] = quant_code_u8(f[4 * q], scale) | (quant_code_u8(f[4 * q + 1], scale) << 8) |
-               (quant_code_u8(f[4 * q + 2], scale) << 16) | (quant_code_u8(f[4 * q + 3], scale) << 24);
-      if (EPV == 4) *reinterpret_cast<uint32_t *>(qr + (int64_t)idx * 4) = w[0];
-      else *reinterpret_cast<uint2 *>(qr + (int64_t)idx * 8) = make_uint2(w[0], w[EPV / 4 - 1]);
-    };
-    if (NV > 0) {
-#pragma unroll
-      for (int v = 0; v < NVC; v++) {
-        const int idx = v * kThreads + g;
-        if (idx < nvec) emit(raw[v], idx);
-      }
-    } else {
-      for (int idx = g; idx < nvec; idx += kThreads) {
-        uint4 r = ldg16(xr + (int64_t)idx * EPV);
-        strip_outliers<T>(r, idx, row, ro, false);
-        emit(r, idx);
-      }
-    }
-  }
+  quant_rows_body<T, G, NV, false, true>(X, M, K, ldx, range, mode, nullptr, Xq, ldq, Cx, RowMaxIo(), (int)blockIdx.x,
+                                         (int)gridDim.x, ro);
 }
 
 // generic shapes: one warp per row, scalar accesses
@@ -295,6 +180,7 @@ quant_rows_outlier_generic_kernel(const T *__restrict__ X, int M, int K, int64_t
   griddep_trigger_early();
   if (row >= M) return;
   const T *xr = X + (int64_t)row * ldx;
+  if (lane == 0) zero_side_tail(row, ro);
   auto is_out = [&](int j) { return ((__ldg(ro.mask + (j >> 5)) >> (j & 31)) & 1u) != 0; };
   auto pos_of = [&](int j) { return __ldg(ro.wbase + (j >> 5)) + __popc(__ldg(ro.mask + (j >> 5)) & ((1u << (j & 31)) - 1u)); };
   float m = -INFINITY;
@@ -365,15 +251,33 @@ int rows_outlier_t(const T *X, int M, int K, int64_t ldx, float range, int mode,
     return (int)launch_kernel(quant_rows_outlier_generic_kernel<T>, dim3((unsigned)ceil_div(M, kThreads / 32)), dim3(kThreads),
                               st, X, M, K, ldx, range, mode, Xq, ldq, Cx, ro);
   const int nvec = K / EPV;
-  const unsigned grid = (unsigned)(M < 148 * 6 ? M : 148 * 6);
-  if (nvec <= 2 * kThreads)
-    return (int)launch_kernel(quant_rows_outlier_kernel<T, 2>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, Xq,
-                              ldq, Cx, ro);
-  if (nvec <= 8 * kThreads)
-    return (int)launch_kernel(quant_rows_outlier_kernel<T, 8>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, Xq,
-                              ldq, Cx, ro);
-  return (int)launch_kernel(quant_rows_outlier_kernel<T, 0>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, Xq, ldq,
-                            Cx, ro);
+#define QG_ROWS_OUTL(G, NV)                                                                                                   \
+  do {                                                                                                                        \
+    constexpr int RPB = kThreads / (G);                                                                                       \
+    static int resident = 0;                                                                                                  \
+    if (resident == 0) {                                                                                                      \
+      int per_sm = 0, dev = 0, sms = 0;                                                                                       \
+      cudaGetDevice(&dev);                                                                                                    \
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                                      \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quant_rows_outlier_kernel<T, G, NV>, kThreads, 0);               \
+      resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);                                                           \
+    }                                                                                                                         \
+    const int64_t nrb = ceil_div(M, RPB);                                                                                     \
+    const unsigned grid = (unsigned)(nrb < resident ? nrb : resident);                                                        \
+    return (int)launch_kernel(quant_rows_outlier_kernel<T, G, NV>, dim3(grid), dim3(kThreads), st, X, M, K, ldx, range, mode, \
+                              Xq, ldq, Cx, ro);                                                                               \
+  } while (0)
+  // the same (G, NV) table as the plain quantizer (quantize.cu: rows_dispatch)
+  if (nvec <= 32) QG_ROWS_OUTL(32, 1);
+  else if (nvec <= 64) QG_ROWS_OUTL(32, 2);
+  else if (nvec <= 128) QG_ROWS_OUTL(32, 4);
+  else if (nvec <= 256) QG_ROWS_OUTL(64, 4);
+  else if (nvec <= 512) QG_ROWS_OUTL(128, 4);
+  else if (nvec <= 1024) QG_ROWS_OUTL(256, 4);
+  else if (nvec <= 2048) QG_ROWS_OUTL(256, 8);
+  else if (nvec <= 4096) QG_ROWS_OUTL(256, 16);
+  else QG_ROWS_OUTL(256, 0);
+#undef QG_ROWS_OUTL
 }
 
 }  // namespace
@@ -399,7 +303,7 @@ int outlier_mask_from_idx(const int *idx, int n_idx, int K, uint32_t *mask, int 
 int quant_rows_outlier(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq, int64_t ldq,
                        float *Cx, const uint32_t *mask, const int *wbase, void *Xo, int64_t ldxo, int side_bf16,
                        cudaStream_t st) {
-  RowOutlier ro = {mask, wbase, Xo, ldxo, side_bf16};
+  RowOutlier ro = {mask, wbase, Xo, ldxo, side_bf16, wbase + (K + 31) / 32};
   switch (dtype) {
     case QG_F32: return rows_outlier_t((const float *)X, M, K, ldx, range, mode, Xq, ldq, Cx, ro, st);
     case QG_F16: return rows_outlier_t((const __half *)X, M, K, ldx, range, mode, Xq, ldq, Cx, ro, st);

@@ -28,135 +28,6 @@ namespace {
 //   sx_in != NULL : scales given (plain op_multiply<T,int8_t>), no reduction
 //   Xq   == NULL  : reduction only (plain op_absmax)
 // ------------------------------------------------------------------------------------------
-// first_rb / rb_stride: the row blocks this CTA walks (blockIdx.x / gridDim.x when the kernel is on its own; a sub-range
-// of the grid when it shares a launch with the column quantizer's second pass).  STREAM: X is loaded with an L2
-// evict-first hint (it is read once, and must not push out the weight matrix the other half of the launch re-reads).
-template <typename T, int G, int NV, bool STREAM = false>
-__device__ __forceinline__ void quant_rows_body(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
-                                                const float *__restrict__ sx_in, int8_t *__restrict__ Xq, int64_t ldq,
-                                                float *__restrict__ Cx, RowMaxIo io, int first_rb, int rb_stride) {
-  constexpr int EPV = Unpack<T>::EPV;
-  constexpr int RPB = kThreads / G;  // rows per block iteration
-  constexpr int WPR = G / 32;        // warps per row
-  constexpr int NVC = NV > 0 ? NV : 1;
-  constexpr bool kPrefetch = NV > 0 && NV <= 8;  // next row block's vectors are loaded ahead
-  __shared__ float s_m[2][kThreads / 32];
-  __shared__ float s_x0[2][RPB];
-
-  const int rib = threadIdx.x / G;
-  const int g = threadIdx.x % G;
-  const int nvec = K / EPV;
-  const int nrb = (M + RPB - 1) / RPB;
-
-  const uint64_t pol_stream = STREAM ? l2_policy_evict_first() : 0;
-  auto load = [&](uint4 (&dst)[NVC], int rb) {
-    const int row = rb * RPB + rib;
-    const T *xr = X + (int64_t)(row < M ? row : 0) * ldx;
-#pragma unroll
-    for (int v = 0; v < NVC; v++) {
-      const int idx = v * G + g;
-      if (row < M && idx < nvec) dst[v] = STREAM ? ldg16_hint(xr + (int64_t)idx * EPV, pol_stream) : ldg16(xr + (int64_t)idx * EPV);
-      else dst[v] = make_uint4(0, 0, 0, 0);
-    }
-  };
-
-  uint4 raw[NVC], nxt[NVC];
-  int rb = first_rb;
-  if (NV > 0 && rb < nrb) load(raw, rb);
-  for (int it = 0; rb < nrb; rb += rb_stride, it++) {
-    if (kPrefetch && rb + rb_stride < nrb) load(nxt, rb + rb_stride);
-    else griddep_launch_dependents();  // last row block of this CTA: let the next kernel ramp up
-    const int row = rb * RPB + rib;
-    const bool active = row < M;
-    const T *xr = X + (int64_t)(active ? row : 0) * ldx;
-    float scale;
-    if (sx_in == nullptr) {
-      float m = -INFINITY, x0 = 0.0f;
-      if (NV > 0) {
-#pragma unroll
-        for (int v = 0; v < NVC; v++) {
-          const int idx = v * G + g;
-          if (idx < nvec) {
-            float f[EPV];
-            Unpack<T>::run(raw[v], f);
-            if (idx == 0) x0 = f[0];
-#pragma unroll
-            for (int e = 0; e < EPV; e++)
-              if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
-          }
-        }
-      } else {
-        for (int idx = g; idx < nvec && active; idx += G) {
-          float f[EPV];
-          Unpack<T>::run(ldg16(xr + (int64_t)idx * EPV), f);
-          if (idx == 0) x0 = f[0];
-#pragma unroll
-          for (int e = 0; e < EPV; e++)
-            if (e > 0 || idx > 0) m = fmaxf(m, fabsf(f[e]));
-        }
-      }
-      m = warp_max(m);
-      if (io.m_in != nullptr) m = active ? io.m_in[row] : -INFINITY;  // the producer's epilogue already reduced columns 1..K-1
-      if (WPR > 1) {  // double-buffered by iteration parity: one barrier per iteration is enough
-        float *sm = s_m[it & 1], *sx0 = s_x0[it & 1];
-        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-        if (g == 0) sx0[rib] = x0;
-        __syncthreads();
-        m = sm[rib * WPR];
-#pragma unroll
-        for (int w = 1; w < WPR; w++) m = fmaxf(m, sm[rib * WPR + w]);
-        x0 = sx0[rib];
-      } else {
-        x0 = __shfl_sync(0xffffffffu, x0, 0);
-      }
-      if (active && g == 0) {
-        if (io.m_out != nullptr) io.m_out[row] = m;
-        if (io.init_out != nullptr) io.init_out[row] = -INFINITY;
-      }
-      float c;
-      if (fold_first(x0, m, mode, c) && active) {
-        for (int j = 1; j < K; j++) {  // rare: sign of the first later zero decides (+-0 tie-break)
-          const float xj = to_f32(xr[j]);
-          if (xj == xj) { c = -xj; break; }
-        }
-      }
-      if (active && g == 0 && Cx != nullptr) Cx[row] = c;
-      scale = __fdiv_rn(range, c);  // InvDivideConstFunc: b / x, IEEE division
-    } else {
-      scale = active ? sx_in[row] : 0.0f;
-    }
-    if (Xq != nullptr && active) {
-      int8_t *qr = Xq + (int64_t)row * ldq;
-      auto emit = [&](const uint4 &r, int idx) {
-        float f[EPV];
-        Unpack<T>::run(r, f);
-        uint32_t w[EPV / 4];
-#pragma unroll
-        for (int q = 0; q < EPV / 4; q++)
-          w[q] = quant_code_u8(f[4 * q], scale) | (quant_code_u8(f[4 * q + 1], scale) << 8) |
-                 (quant_code_u8(f[4 * q + 2], scale) << 16) | (quant_code_u8(f[4 * q + 3], scale) << 24);
-        if (EPV == 4) *reinterpret_cast<uint32_t *>(qr + (int64_t)idx * 4) = w[0];
-        else *reinterpret_cast<uint2 *>(qr + (int64_t)idx * 8) = make_uint2(w[0], w[EPV / 4 - 1]);
-      };
-      if (NV > 0) {
-#pragma unroll
-        for (int v = 0; v < NVC; v++) {
-          const int idx = v * G + g;
-          if (idx < nvec) emit(raw[v], idx);
-        }
-      } else {
-        for (int idx = g; idx < nvec; idx += G) emit(ldg16(xr + (int64_t)idx * EPV), idx);
-      }
-    }
-    if (kPrefetch) {
-#pragma unroll
-      for (int v = 0; v < NVC; v++) raw[v] = nxt[v];
-    } else if (NV > 0 && rb + rb_stride < nrb) {
-      load(raw, rb + rb_stride);
-    }
-  }
-}
-
 template <typename T, int G, int NV>
 __global__ void __launch_bounds__(kThreads)
 quant_rows_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float range, int mode,
