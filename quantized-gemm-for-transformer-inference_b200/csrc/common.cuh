@@ -241,6 +241,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void *desc, 
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// 2-SM load multicast to the CTAs of `cta_mask`: the box lands at the same shared-memory offset in each of them and
+// completes on the barrier at offset `bar` of each destination's pair (peer bit cleared by the caller)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const void *desc, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(desc), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void *desc, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(desc), "r"(src), "r"(c0), "r"(c1) : "memory");

@@ -141,11 +141,16 @@ __device__ __forceinline__ float stored_value(float v, __nv_bfloat16) { return _
 __device__ __forceinline__ float stored_value(float v, float) { return v; }
 __device__ __forceinline__ float stored_value(float v, int32_t) { return v; }
 
-template <int CG, bool B_MN, int OUT, bool SIDE>
+// NP: CTA pairs per cluster.  NP == 2 (CG == 2 only): a cluster of four CTAs takes a 512 x 256 tile -- two pairs on the same
+// 256 columns, 256 rows each.  The B tile is the same for both pairs, so every CTA loads only a QUARTER of it (64 of its 128
+// columns / k-rows) and TMA-multicasts it to the CTA of the same rank in the other pair: 24 KB instead of 32 KB per CTA and
+// stage come out of L2, which is what bounds the main loop once the output stores share it (section 7 of DESIGN.md).
+template <int CG, bool B_MN, int OUT, bool SIDE, int NP = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_o,
                   const __grid_constant__ ExtraMaps xmaps, const GemmParams p) {
+  static_assert(NP == 1 || (NP == 2 && CG == 2 && !SIDE), "two pairs per cluster: 2-SM tiles, no side product");
   using C = Cfg<CG, B_MN, SIDE>;
   using OT = OutTraits<OUT>;
   using OutT = typename OT::T;
@@ -169,7 +174,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cluster_rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0..CG*NP-1
+  const uint32_t cta_rank = cluster_rank & (CG - 1);                  // rank inside the CTA pair
+  const uint32_t pair = cluster_rank >> 1;                            // which pair of the cluster (NP == 2)
+  const uint32_t pair_leader = pair * 2;                              // cluster rank of this pair's leader CTA
   const bool leader = cta_rank == 0;
 
   if (threadIdx.x == 0) {  // the layout must fit what was launched (it does when the segment is 1024-byte aligned)
@@ -189,7 +197,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == kMmaWarp && lane == 0) {
     for (int i = 0; i < kStages; i++) {
       mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), NP);  // NP == 2: a slot also receives the other pair's multicast, both pairs must be done with it
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
@@ -231,8 +239,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     m_blk = ft % p.tiles_m;
     n0 = (ft / p.tiles_m) * BN + part * bn;
   };
-  const int num_clusters = gridDim.x / CG;
-  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / (CG * NP);
+  const int cluster_id = blockIdx.x / (CG * NP);
   const int num_kb_total = (p.K + BK - 1) / BK;
   // k-blocks [kb_first(slice), kb_first + kb_count) belong to a slice (the whole K without split-K)
   auto kb_first = [&](int slice) { return p.split_k > 1 ? slice * p.kb_per_slice : 0; };
@@ -254,7 +262,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int m_blk, n0, bn;
       tile_coords(t, m_blk, n0, bn);
-      const int m_base = (m_blk * CG + (int)cta_rank) * BM;
+      const int m_base = ((m_blk * NP + (int)pair) * CG + (int)cta_rank) * BM;
       const int n_base = n0 + (int)cta_rank * (bn / CG);
       const bool half = bn != BN;  // only generated for K-major B (see host side)
       const uint32_t stage_tx = C::kABytes + (uint32_t)(bn / CG) * BK;
@@ -283,7 +291,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             } else {     // one [256 (or 128) n-rows x 128 k-bytes] box
               tma_load_2d(sb, half ? &map_bh : &map_b, fb, k0, n_base);
             }
-          } else {
+          } else if (NP == 1) {
             // both CTAs' loads complete on the leader's barrier; the leader arms it for both
             uint32_t fb;
             asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(fb) : "r"(smem_u32(&full_bar[s])));
@@ -291,6 +299,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_load_2d_2sm(sa, &map_a, fb, k0, m_base);
             if (B_MN) tma_load_2d_2sm(sb, &map_b, fb, n_base, k0);
             else tma_load_2d_2sm(sb, half ? &map_bh : &map_b, fb, k0, n_base);
+          } else {
+            // two pairs: everything that lands in a pair's two CTAs (own A, own B quarter, the other pair's B quarter)
+            // completes on that pair's leader barrier -- for the multicast the barrier operand's offset (peer bit clear) is
+            // resolved inside every destination CTA's pair (the convention of CUTLASS's SM100_TMA_2SM_LOAD_MULTICAST)
+            uint32_t fb;  // shared::cluster address of this pair's leader barrier (an even rank: peer bit clear)
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(fb) : "r"(smem_u32(&full_bar[s])), "r"(pair_leader));
+            if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), 2 * stage_tx);
+            tma_load_2d_2sm(sa, &map_a, fb, k0, m_base);
+            const uint16_t mc_mask = (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank)));  // same rank in both pairs
+            const uint32_t sq = sb + pair * (uint32_t)(64 * 128);  // this pair's quarter of the B stage
+            if (B_MN) tma_load_2d_2sm_mc(sq, &map_bh, fb, n_base, k0 + (int)pair * 64, mc_mask);   // k-rows [64 pair, +64)
+            else tma_load_2d_2sm_mc(sq, &map_bh, fb, k0, n_base + (int)pair * 64, mc_mask);          // n-rows [64 pair, +64)
           }
         }
         __syncwarp();
@@ -348,10 +368,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             // frees the smem slot once the MMAs above have read it
             if (CG == 1) umma_commit(smem_u32(&empty_bar[s]));
-            else umma_commit_2sm(smem_u32(&empty_bar[s]), 0x3);
+            else umma_commit_2sm(smem_u32(&empty_bar[s]), NP == 2 ? 0xF : 0x3);  // NP == 2: the other pair writes this slot too
             if (kb == num_kb - 1) {  // accumulator complete: hand it to the epilogue
               if (CG == 1) umma_commit(smem_u32(&tfull_bar[as]));
-              else umma_commit_2sm(smem_u32(&tfull_bar[as]), 0x3);
+              else umma_commit_2sm(smem_u32(&tfull_bar[as]), (uint16_t)(0x3u << pair_leader));
             }
           }
           __syncwarp();
@@ -383,7 +403,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       int m_blk, n_base, bn;
       tile_coords(t, m_blk, n_base, bn);
-      const int m_base = (m_blk * CG + (int)cta_rank) * BM;
+      const int m_base = ((m_blk * NP + (int)pair) * CG + (int)cta_rank) * BM;
       const int row = m_base + q * 32 + lane;
       const int c_begin = hcol * (bn >> 1), c_end = c_begin + (bn >> 1);
       const bool has_bias = p.bias != nullptr;
@@ -492,7 +512,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         __syncwarp();
         if (lane == 0) {
           if (CG == 1) mbar_arrive(smem_u32(&tempty_bar[as]));
-          else mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[as]), 0);
+          else mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[as]), pair_leader);
         }
         continue;
       }
@@ -698,7 +718,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       __syncwarp();
       if (lane == 0) {
         if (CG == 1) mbar_arrive(smem_u32(&tempty_bar[as]));
-        else mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[as]), 0);
+        else mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[as]), pair_leader);
       }
       if (kDequant && p.rowmax != nullptr && row < p.M && rmax >= 0.0f)
         atomicMax(reinterpret_cast<int *>(p.rowmax) + row, __float_as_int(rmax));
@@ -807,15 +827,40 @@ int make_map_2d_uncached(CUtensorMap *map, CUtensorMapDataType dt, size_t esize,
   return QG_OK;
 }
 
-template <int CG, bool B_MN, int OUT, bool SIDE = false>
+template <int CG, bool B_MN, int OUT, bool SIDE = false, int NP = 1>
 int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo,
            const ExtraMaps &xm, GemmParams p, int num_sms, cudaStream_t st) {
   using C = Cfg<CG, B_MN, SIDE>;
-  auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT, SIDE>;
+  auto kern = gemm_i8_tc_kernel<CG, B_MN, OUT, SIDE, NP>;
   static bool configured[kMaxDevices] = {};  // per instantiation and device
   QG_CUDA_OK(smem_optin(kern, C::kSmemBytes, configured));
   const int base_tiles = p.tiles_m * p.tiles_n;
-  int max_clusters = num_sms / CG;
+  int max_clusters = num_sms / (CG * NP);
+  if (NP > 1) {  // four-CTA clusters must fit inside a GPC: ask how many can be resident at once
+    static int active[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < kMaxDevices && active[dev] == 0) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3((unsigned)(num_sms / (CG * NP) * CG * NP));
+      q.blockDim = dim3(kNumThreads);
+      q.dynamicSmemBytes = C::kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CG * NP;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = max_clusters;
+      }
+      active[dev] = n;
+    }
+    if (dev >= 0 && dev < kMaxDevices && active[dev] > 0 && active[dev] < max_clusters) max_clusters = active[dev];
+  }
   p.nstages = C::kStages;
   if (SIDE && p.no_pad > kSideDbl) p.nstages = C::kStages - 1;  // the big Wo tile takes the ring's last stage
   static const bool dbg_noload = getenv("QG_DBG_NOLOAD") != nullptr, dbg_all_half = getenv("QG_DBG_ALL_HALF") != nullptr;
@@ -842,12 +887,12 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   static const bool no_tail_split = getenv("QG_NO_TAIL_SPLIT") != nullptr;
   if (p.split_k > 1) {
     p.total_tiles = base_tiles * p.split_k;  // tile_coords divides the index by split_k first
-  } else if (!B_MN && base_tiles > max_clusters && rem > 0 && 2 * rem <= max_clusters && !no_tail_split) {
+  } else if (NP == 1 && !B_MN && base_tiles > max_clusters && rem > 0 && 2 * rem <= max_clusters && !no_tail_split) {
     p.full_tiles = base_tiles - rem;
     p.tail_split = 2;
     p.total_tiles = p.full_tiles + 2 * rem;
   }
-  if (!B_MN && dbg_all_half && p.split_k == 1) {  // experiment: every tile 128 columns wide
+  if (NP == 1 && !B_MN && dbg_all_half && p.split_k == 1) {  // experiment: every tile 128 columns wide
     p.full_tiles = 0;
     p.tail_split = 2;
     p.total_tiles = 2 * base_tiles;
@@ -855,13 +900,13 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   const int num_tiles = p.total_tiles;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * CG));
+  cfg.gridDim = dim3((unsigned)(clusters * CG * NP));
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CG * NP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -875,7 +920,17 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
 
 template <int CG, bool B_MN>
 int launch_out(int out_kind, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh, const CUtensorMap &mo,
-               const ExtraMaps &xm, const GemmParams &p, int num_sms, cudaStream_t st) {
+               const ExtraMaps &xm, const GemmParams &p, int num_sms, cudaStream_t st, int np = 1) {
+  if constexpr (CG == 2) {
+    if (np == 2 && p.Xo == nullptr) {  // two pairs per cluster, B multicast
+      switch (out_kind) {
+        case QG_S32: return launch<2, B_MN, QG_S32, false, 2>(ma, mb, mbh, mo, xm, p, num_sms, st);
+        case QG_F32: return launch<2, B_MN, QG_F32, false, 2>(ma, mb, mbh, mo, xm, p, num_sms, st);
+        case QG_F16: return launch<2, B_MN, QG_F16, false, 2>(ma, mb, mbh, mo, xm, p, num_sms, st);
+        case QG_BF16: return launch<2, B_MN, QG_BF16, false, 2>(ma, mb, mbh, mo, xm, p, num_sms, st);
+      }
+    }
+  }
   if (p.Xo != nullptr) {  // outlier side product: prepared (K-major) weights, floating-point output
     if constexpr (!B_MN) {
       switch (out_kind) {
@@ -923,7 +978,10 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   }
   GemmParams p = {};
   p.M = M; p.N = N; p.K = K;
-  p.tiles_m = (int)ceil_div(M, BM * cg);
+  // two CTA pairs per cluster (512 x 256 cluster tiles, B multicast between the pairs): QG_GEMM_NP=2
+  static const int np_env = [] { const char *e = getenv("QG_GEMM_NP"); return e ? atoi(e) : 0; }();
+  const int np = (cg == 2 && np_env == 2 && side == nullptr && split_k <= 1 && M > 256) ? 2 : 1;
+  p.tiles_m = (int)ceil_div(M, BM * cg * np);
   p.tiles_n = (int)ceil_div(N, BN);
   p.out = O; p.ldo = ldo; p.Cx = Cx; p.Cw = Cw; p.bias = bias; p.c = c;
   p.relu = (act == QG_ACT_RELU && out_kind != QG_S32) ? 1 : 0;
@@ -972,6 +1030,7 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   } else {
     rc = make_map_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, K, N, ldb, BK, 128);
     mbh = mb;
+    if (rc == 0 && np == 2) rc = make_map_2d(&mbh, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, K, N, ldb, 64, 128);  // a quarter stage: 64 k-rows
   }
   if (rc) return rc;
   if (p.tma_store) {
@@ -1034,8 +1093,8 @@ int gemm_i8_tc(int cg, const int8_t *A, int64_t lda, const int8_t *B, int64_t ld
   }
   if (cg == 1) return b_kmajor ? launch_out<1, false>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st)
                                : launch_out<1, true>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st);
-  if (cg == 2) return b_kmajor ? launch_out<2, false>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st)
-                               : launch_out<2, true>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st);
+  if (cg == 2) return b_kmajor ? launch_out<2, false>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st, np)
+                               : launch_out<2, true>(out_kind, ma, mb, mbh, mo, xm, p, num_sms, st, np);
   return QG_EINVAL;
 }
 

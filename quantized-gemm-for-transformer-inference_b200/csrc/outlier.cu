@@ -38,18 +38,17 @@ outlier_detect_kernel(const T *__restrict__ X, int M, int K, int64_t ldx, float 
       Unpack<T>::run(v, f);
 #pragma unroll
       for (int e = 0; e < EPV; e++) {
-        const float a = f[e];  // AbsCompareLTEConstFunc: inlier iff (a>=0 & a<=thr) | (a<=0 & -a<=thr)
-        const bool inl = ((a >= 0) & (a <= thr)) | ((a <= 0) & (-a <= thr));
-        bits |= (inl ? 0u : 1u) << e;
+        // AbsCompareLTEConstFunc: inlier iff (a>=0 & a<=thr) | (a<=0 & -a<=thr), i.e. |a| <= thr with NaN an outlier
+        bits |= (fabsf(f[e]) <= thr ? 0u : 1u) << e;
       }
     };
     int r = r0 + ty;
-    for (; r + 24 < r1; r += 32) {
-      uint4 v[4];
+    for (; r + 56 < r1; r += 64) {  // eight independent 16-byte loads in flight per thread
+      uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; u++) v[u] = ldg16(base + (int64_t)(r + 8 * u) * ldx);
+      for (int u = 0; u < 8; u++) v[u] = ldg16(base + (int64_t)(r + 8 * u) * ldx);
 #pragma unroll
-      for (int u = 0; u < 4; u++) scan(v[u]);
+      for (int u = 0; u < 8; u++) scan(v[u]);
     }
     for (; r < r1; r += 8) scan(ldg16(base + (int64_t)r * ldx));
   }
@@ -232,7 +231,7 @@ int detect_t(const T *X, int M, int K, int64_t ldx, float thr, uint32_t *mask, c
   if (e != cudaSuccess) return (int)e;
   if (K % EPV == 0 && aligned_to(X, 16) && (ldx * sizeof(T)) % 16 == 0) {
     const int col_tiles = (int)ceil_div(K, 32 * EPV);
-    int64_t want = ceil_div((int64_t)148 * 16, col_tiles);
+    int64_t want = ceil_div((int64_t)148 * 6, col_tiles);  // one wave of resident CTAs, as the column quantizer's pass 1
     const int rpc = (int)round_up(ceil_div(M, want > 0 ? want : 1) < 32 ? 32 : ceil_div(M, want > 0 ? want : 1), 32);
     return (int)launch_kernel(outlier_detect_kernel<T>, dim3(col_tiles, (unsigned)ceil_div(M, rpc)), dim3(kThreads), st, X, M, K,
                               ldx, thr, rpc, mask);

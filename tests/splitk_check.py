@@ -1,5 +1,5 @@
-"""Run by tests/test_gpu_parity.py::test_forced_split_k in a subprocess with QG_SPLIT_K=n (the library reads the
-switch once): int32 accumulators, dequantized outputs (fp32 / fp16 / bf16, bias, ReLU) and the whole op must stay
+"""Run by tests/test_gpu_parity.py::test_forced_split_k / test_two_pair_clusters in a subprocess with QG_SPLIT_K=n or
+QG_GEMM_NP=2 (the library reads the switches once): int32 accumulators, dequantized outputs (fp32 / fp16 / bf16, bias, ReLU) and the whole op must stay
 bit-exact against the oracle when every tensor-core product is cut into n k-slices."""
 import importlib
 import os
@@ -20,7 +20,7 @@ from test_gpu_parity import same_f32  # noqa: E402  (NaN-aware bit comparison)
 DEV = "cuda"
 rng = np.random.default_rng(int(os.environ.get("QG_SPLIT_K", "1")))
 bad = 0
-for (M, N, K) in [(128, 256, 1024), (200, 300, 1000), (130, 520, 2048), (384, 512, 640), (1024, 768, 4096)]:
+for (M, N, K) in [(128, 256, 1024), (200, 300, 1000), (130, 520, 2048), (384, 512, 640), (1024, 768, 4096), (700, 520, 1024)]:
     A = rng.integers(-127, 128, (M, K), dtype=np.int8)
     B = rng.integers(-127, 128, (K, N), dtype=np.int8)
     dA, dB = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)

@@ -304,6 +304,18 @@ def test_forced_split_k(split):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_two_pair_clusters():
+    """The GEMM with two CTA pairs per cluster (512 x 256 cluster tiles, B quarter-loads TMA-multicast between the pairs;
+    QG_GEMM_NP=2, read once per process -> subprocess): same bits as the default kernel and the oracle."""
+    import subprocess
+    import sys as _sys
+
+    env = dict(os.environ, QG_GEMM_NP="2")
+    r = subprocess.run([_sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "splitk_check.py")],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("variant", ["TC_1SM", "TC_2SM"])
 def test_gemm_large_sampled_rows(qg, oracle, variant):
     """4096^3 (BASELINE target shape): full result against torch._int_mm is not the bar -- the

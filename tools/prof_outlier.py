@@ -20,3 +20,6 @@ for rep in range(2):
         lin.forward_outlier(X, y, cols)
 torch.cuda.synchronize()
 print("ok")
+for rep in range(3):
+    qg.outlier_cols(X, 6.0)
+torch.cuda.synchronize()
