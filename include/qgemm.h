@@ -199,7 +199,8 @@ QG_API int qg_outlier_mask_f32(const float *A, int m, int k, int64_t lda, float 
 QG_API int qg_outlier_cols(const void *X, int dtype, int m, int k, int64_t ldx, float thr, int *idx,
                            int max_idx, int *count, qg_stream_t stream);
 QG_API size_t qg_outlier_workspace_bytes(int m, int n, int k);
-/* LinearLayer::forward with the feature columns idx[0..n_idx) (device, ascending, n_idx <= 64) taken
+/* LinearLayer::forward with the feature columns idx[0..n_idx) (device; any order -- the set is what counts: duplicates and
+ * out-of-range entries are dropped, both operands of the side product are filed by the column's rank; n_idx <= 64) taken
  * out of the int8 path: X's outlier columns are zeroed before the row quantizer, and
  * fp16(X[:,idx]) @ fp16(W[idx,:]) (bf16 when X is bf16) is accumulated in fp32 inside the GEMM
  * epilogue: y = fl(fl(dequant + side) + bias), the side sum an fma chain in ascending idx order (the

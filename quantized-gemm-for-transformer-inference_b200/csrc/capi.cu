@@ -35,8 +35,8 @@ int outlier_mask_from_idx(const int *idx, int n_idx, int K, uint32_t *mask, int 
 int quant_rows_outlier(const void *X, int dtype, int M, int K, int64_t ldx, float range, int mode, int8_t *Xq, int64_t ldq,
                        float *Cx, const uint32_t *mask, const int *wbase, void *Xo, int64_t ldxo, int side_bf16,
                        cudaStream_t st);
-int gather_wo(const void *W, int dtype, int64_t ldw, const int *idx, int n_idx, int no_pad, int N, void *Wo, int64_t ldwo,
-              int side_bf16, cudaStream_t st);
+int gather_wo(const void *W, int dtype, int64_t ldw, const uint32_t *mask, const int *wbase, int K, int no_pad, int N, void *Wo,
+              int64_t ldwo, int side_bf16, cudaStream_t st);
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
            float *C, int64_t ldc, cudaStream_t st, const MmBatch *batch = nullptr);
 int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st);
@@ -630,7 +630,7 @@ int qg_linear_forward_outlier(const void *X, int64_t ldx, int in_dtype, const vo
   rc = outlier_mask_from_idx(idx, n_idx, K, o.mask, o.wbase, st);
   if (rc) return cuda_status((cudaError_t)rc, "outlier mask");
   if (no_pad > 0) {  // (the side operand's padding columns are zeroed by the row quantizer itself: no memset node in the PDL chain)
-    rc = gather_wo(W, w_dtype, ldw, idx, n_idx, no_pad, N, o.Wo, o.ldwo, side_bf16, st);
+    rc = gather_wo(W, w_dtype, ldw, o.mask, o.wbase, K, no_pad, N, o.Wo, o.ldwo, side_bf16, st);
     if (rc) return cuda_status((cudaError_t)rc, "outlier weight gather");
   }
   rc = quant_rows_outlier(X, in_dtype, M, K, ldx, range, mode, w.Xq, w.ldxq, w.Cx, o.mask, o.wbase, o.Xo, o.ldxo, side_bf16,

@@ -208,16 +208,36 @@ quant_rows_outlier_generic_kernel(const T *__restrict__ X, int M, int K, int64_t
     Xq[(int64_t)row * ldq + j] = (int8_t)quant_code_u8(is_out(j) ? 0.0f : to_f32(xr[j]), scale);
 }
 
-// Wo[o][j] = 16-bit(W[idx[o], j]), zero rows for o >= n_idx
+// Wo[o][j] = 16-bit(W[k_o, j]) where k_o is the o-th set bit of the mask (the same rank the row quantizer files X[:, k_o]
+// under), zero rows for o >= count.  Taking the row from the MASK rather than from idx[o] keeps the two operands of the
+// side product paired whatever order (or duplicates, or out-of-range entries) the caller's index list has.
 template <typename T>
-__global__ void gather_wo_kernel(const T *__restrict__ W, int64_t ldw, const int *__restrict__ idx, int n_idx, int N,
-                                 void *__restrict__ Wo, int64_t ldwo, int side_bf16) {
+__global__ void gather_wo_kernel(const T *__restrict__ W, int64_t ldw, const uint32_t *__restrict__ mask,
+                                 const int *__restrict__ wbase, int words, int N, void *__restrict__ Wo, int64_t ldwo,
+                                 int side_bf16) {
+  __shared__ int s_k;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int o = blockIdx.y;
   griddep_wait();
   griddep_trigger_early();
+  if (threadIdx.x == 0) {
+    int k = -1;
+    if (o < wbase[words]) {  // wbase[words] = number of set bits
+      int lo = 0, hi = words - 1;  // last word whose prefix count is <= o
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (wbase[mid] <= o) lo = mid; else hi = mid - 1;
+      }
+      uint32_t m = mask[lo];
+      for (int r = o - wbase[lo]; r > 0; r--) m &= m - 1;
+      k = lo * 32 + __ffs(m) - 1;
+    }
+    s_k = k;
+  }
+  __syncthreads();
   if (j >= N) return;
-  const float v = o < n_idx ? to_f32(W[(int64_t)idx[o] * ldw + j]) : 0.0f;
+  const int k = s_k;
+  const float v = k >= 0 ? to_f32(W[(int64_t)k * ldw + j]) : 0.0f;
   if (side_bf16) reinterpret_cast<__nv_bfloat16 *>(Wo)[(int64_t)o * ldwo + j] = __float2bfloat16_rn(v);
   else reinterpret_cast<__half *>(Wo)[(int64_t)o * ldwo + j] = __float2half_rn(v);
 }
@@ -311,14 +331,15 @@ int quant_rows_outlier(const void *X, int dtype, int M, int K, int64_t ldx, floa
   return QG_EINVAL;
 }
 
-int gather_wo(const void *W, int dtype, int64_t ldw, const int *idx, int n_idx, int no_pad, int N, void *Wo, int64_t ldwo,
-              int side_bf16, cudaStream_t st) {
+int gather_wo(const void *W, int dtype, int64_t ldw, const uint32_t *mask, const int *wbase, int K, int no_pad, int N, void *Wo,
+              int64_t ldwo, int side_bf16, cudaStream_t st) {
   if (no_pad <= 0) return 0;
   dim3 grid((unsigned)ceil_div(N, 256), (unsigned)no_pad);
+  const int words = (K + 31) / 32;
   switch (dtype) {
-    case QG_F32: return (int)launch_kernel(gather_wo_kernel<float>, grid, dim3(256), st, (const float *)W, ldw, idx, n_idx, N, Wo, ldwo, side_bf16);
-    case QG_F16: return (int)launch_kernel(gather_wo_kernel<__half>, grid, dim3(256), st, (const __half *)W, ldw, idx, n_idx, N, Wo, ldwo, side_bf16);
-    case QG_BF16: return (int)launch_kernel(gather_wo_kernel<__nv_bfloat16>, grid, dim3(256), st, (const __nv_bfloat16 *)W, ldw, idx, n_idx, N, Wo, ldwo, side_bf16);
+    case QG_F32: return (int)launch_kernel(gather_wo_kernel<float>, grid, dim3(256), st, (const float *)W, ldw, mask, wbase, words, N, Wo, ldwo, side_bf16);
+    case QG_F16: return (int)launch_kernel(gather_wo_kernel<__half>, grid, dim3(256), st, (const __half *)W, ldw, mask, wbase, words, N, Wo, ldwo, side_bf16);
+    case QG_BF16: return (int)launch_kernel(gather_wo_kernel<__nv_bfloat16>, grid, dim3(256), st, (const __nv_bfloat16 *)W, ldw, mask, wbase, words, N, Wo, ldwo, side_bf16);
   }
   return QG_EINVAL;
 }

@@ -102,9 +102,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, dts, gather, ret, chunks=0):
+def _worker(rank, world, port, shape, dts, gather, ret, chunks=0, multicast=False):
     import torch.distributed as dist
 
+    if multicast:  # the result's gather through the NVSwitch multicast address (multimem.st in the reduce kernel)
+        os.environ["QG_MULTICAST"] = "1"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -136,8 +138,28 @@ def _worker(rank, world, port, shape, dts, gather, ret, chunks=0):
         torch.cuda.synchronize()
         ok = ok and bool(torch.equal(_bits(yc.contiguous()), _bits(want)))
         ret[rank] = ok
+        ret["mc_%d" % rank] = bool(getattr(fused, "out_mc", 0))
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,dts", [((512, 256, 1024, 512), ("f32", "f32", "f32")), ((768, 128, 768, 1152), ("f16", "bf16", "f16"))])
+def test_megatron_ffn_multicast_gather_matches_oracle(shape, dts):
+    """The all-gather half of the exchange as one multimem.st per 16 bytes (QG_MULTICAST=1): same bits.  Skipped when the
+    fabric has no multicast mapping."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import oracle
+
+    oracle.build()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), shape, dts, True, ret, 0, True), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+    if not all(ret.get("mc_%d" % r) for r in range(world)):
+        pytest.skip("no multicast mapping on this box: the unicast gather ran (and matched)")
 
 
 @pytest.mark.parametrize("shape,dts,gather,chunks", [

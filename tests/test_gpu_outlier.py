@@ -103,3 +103,21 @@ def test_too_many_outlier_columns_is_an_error(qg):
     idx = torch.arange(0, 65, dtype=torch.int32, device=DEV)
     with pytest.raises((qg.QGemmError, AssertionError)):
         lin.forward_outlier(X, y, idx)
+
+
+def test_index_list_order_does_not_matter(qg, oracle):
+    """The side product pairs X[:, k] with W[k, :] by the column's rank in the outlier MASK, so an unsorted index list, a
+    duplicate or an out-of-range entry gives the result of the sorted, de-duplicated, in-range set."""
+    M, N, K = 256, 384, 1024
+    rng = np.random.default_rng(17)
+    cols = np.array([900, 3, 512, 77, 640], dtype=np.int32)
+    X, Xh = outlier_input(rng, M, K, cols, "f16")
+    lin = qg.LinearLayer(K, N, device=DEV, dtype=torch.float16)
+    lin.w.copy_(to_dev((rng.standard_normal((K, N)) * 0.05).astype(np.float32), "f16"))
+    lin.b.copy_(to_dev(rng.standard_normal((1, N)).astype(np.float32)))
+    y = torch.empty((M, N), dtype=torch.float16, device=DEV)
+    messy = np.array([900, 3, 512, 77, 640, 3, 5000, -1], dtype=np.int32)  # unsorted, a duplicate, two out of range
+    lin.forward_outlier(X, y, torch.from_numpy(messy).to(DEV))
+    torch.cuda.synchronize()
+    expect, _ = oracle.quantized_mm_outlier(Xh, as_f32_np(lin.w), 6.0, bias=lin.b.cpu().numpy(), side_dtype="f16", idx=np.sort(cols))
+    assert torch.equal(y.cpu(), torch.from_numpy(expect).to(torch.float16))
