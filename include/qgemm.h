@@ -74,6 +74,10 @@ QG_API const char *qg_last_error(void);
 QG_API int qg_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* process-wide kernel choice for the GEMM entry points (tests / bench ablations) */
 QG_API int qg_set_gemm_variant(int variant);
+/* SMs the tensor-core GEMM may occupy (0 = all, the default).  The GEMM is persistent and takes every SM it is given; a caller that
+ * overlaps its own small kernels with it (the Megatron pair's reduce + gather of one row block under the next block's
+ * products) leaves a few SMs free for them.  Process-wide. */
+QG_API int qg_set_gemm_sm_limit(int sms);
 /* number of kernels this library has launched since load / last reset (bench "gpu_launches") */
 QG_API int64_t qg_launch_count(int reset);
 
@@ -306,7 +310,8 @@ QG_API int qg_add_layernorm_quant_f32(const float *A, int64_t lda, const float *
  * is that slot, an [m, block_cols] matrix with leading dimension ld_part; block_cols a multiple of 32 columns for fp32 and
  * 64 for 16-bit partials), and qg_reduce_partials adds the P slots in order, adds the bias and writes the owner's block to
  * `out` and to the same block of the peers' matrices (the all-gather that completes the all-reduce; n_peers = 0: keep it
- * sharded; out_mc != NULL: the block's NVSwitch multicast address, one multimem.st instead of n_peers + 1 stores).  The caller brackets the two with barriers (all slots written before the reduce; all reduces done before the
+ * sharded; out_mc != NULL: the block's NVSwitch multicast address, one multimem.st instead of n_peers + 1 stores; max_ctas > 0 bounds the
+ * grid for a caller that runs the reduction on a side stream under a GEMM, see qg_set_gemm_sm_limit).  The caller brackets the two with barriers (all slots written before the reduce; all reduces done before the
  * next forward's stores). */
 QG_API int qg_gemm_s8_dequant_scatter(const int8_t *Xq, int64_t ldxq, const int8_t *Wt, int64_t ldwt, const float *Cx,
                                       const float *Cw, int m, int n, int k, float range, void *const *part_dst, int n_dst,
@@ -317,9 +322,12 @@ QG_API int qg_ffn_forward_rowpar(const void *X, int64_t ldx, int in_dtype, const
                                  void *const *part_dst, int n_dst, int block_cols, int64_t ld_part, int part_dtype, int m,
                                  int d_in, int d_ff_local, int d_out, float range, int mode, void *workspace,
                                  size_t workspace_bytes, qg_stream_t stream);
+/* [rows, width_bytes] block copy between device buffers (peer-mapped ones included) on the copy engines, no SM involved */
+QG_API int qg_copy_2d_async(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes, int64_t width_bytes,
+                            int rows, qg_stream_t stream);
 QG_API int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part,
                               const float *bias, void *out, void *const *peers, int n_peers, void *out_mc, int64_t ldo,
-                              int out_dtype, int m, int n, qg_stream_t stream);
+                              int out_dtype, int m, int n, int max_ctas, qg_stream_t stream);
 
 /* ---- the elementwise tail of the pipeline, op by op ------------------------------------------------
  * The fused epilogue makes these unnecessary on the fast path; they let the reference's step-by-step

@@ -25,7 +25,7 @@ GEMM_AUTO, GEMM_SIMT, GEMM_TC_1SM, GEMM_TC_2SM = 0, 1, 2, 3
 
 # every symbol include/qgemm.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "qg_version", "qg_last_error", "qg_device_info", "qg_set_gemm_variant", "qg_launch_count",
+    "qg_version", "qg_last_error", "qg_device_info", "qg_set_gemm_variant", "qg_set_gemm_sm_limit", "qg_launch_count",
     "qg_absmax_rows", "qg_absmax_cols", "qg_inv_divide_f32", "qg_quantize_rows", "qg_quantize_cols",
     "qg_absmax_quant_rows", "qg_absmax_quant_cols", "qg_absmax_quant_rows_cols", "qg_gemm_s8s8s32", "qg_dequantize_s32",
     "qg_gemm_s8_dequant", "qg_workspace_bytes", "qg_quantized_mm", "qg_prepare_weights", "qg_gemm_s8t_dequant",
@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_gemm_s8_dequant_mc", "qg_mm_f32",
     "qg_softmax_rows_f32", "qg_attention_forward", "qg_linear_forward_act", "qg_add_layernorm_f32",
     "qg_linear_forward_q", "qg_quantize_rows_given_max", "qg_ffn_workspace_bytes", "qg_ffn_forward",
-    "qg_add_layernorm_quant_f32", "qg_gemm_s8_dequant_scatter", "qg_ffn_forward_rowpar", "qg_reduce_partials",
+    "qg_add_layernorm_quant_f32", "qg_gemm_s8_dequant_scatter", "qg_ffn_forward_rowpar", "qg_reduce_partials", "qg_copy_2d_async",
     "qg_add_f32", "qg_subtract_f32", "qg_multiply_f32", "qg_multiply_const_f32", "qg_relu_f32", "qg_dequantize_outer_f32",
 ]
 
@@ -104,6 +104,11 @@ def device_info():
 
 def set_gemm_variant(v: int) -> None:
     _check(lib().qg_set_gemm_variant(C.c_int(v)), "qg_set_gemm_variant")
+
+
+def set_gemm_sm_limit(sms: int) -> None:
+    """SMs the persistent tensor-core GEMM may occupy (0 = all); see qg_set_gemm_sm_limit."""
+    _check(lib().qg_set_gemm_sm_limit(int(sms)), "qg_set_gemm_sm_limit")
 
 
 def launch_count(reset: bool = False) -> int:
@@ -447,7 +452,8 @@ def ffn_forward_rowpar(X, W1t, Cw1, b1, W2t, Cw2, H: torch.Tensor, part_ptrs, bl
                                        _stream()), "qg_ffn_forward_rowpar")
 
 
-def reduce_partials(slots: torch.Tensor, bias, out: torch.Tensor, peer_ptrs=(), n: int | None = None, mc_ptr: int = 0) -> None:
+def reduce_partials(slots: torch.Tensor, bias, out: torch.Tensor, peer_ptrs=(), n: int | None = None, mc_ptr: int = 0,
+                    max_ctas: int = 0) -> None:
     """out[:, :n] = ((slots[0] + slots[1]) + ...) + bias in ascending slot order (qg_reduce_partials); the result is also
     stored to the same block of the peers' matrices (device addresses in peer_ptrs, leading dimension = out's)."""
     P, M, bc = slots.shape
@@ -456,8 +462,14 @@ def reduce_partials(slots: torch.Tensor, bias, out: torch.Tensor, peer_ptrs=(), 
     _check(lib().qg_reduce_partials(C.c_void_p(slots.data_ptr()), C.c_int64(slots.stride(0)), P, _dt(slots),
                                     C.c_int64(slots.stride(1)), None if bias is None else _vec(bias.reshape(-1), n), po,
                                     _ptr_array(peer_ptrs) if len(peer_ptrs) else None, len(peer_ptrs),
-                                    C.c_void_p(int(mc_ptr)) if mc_ptr else None, ldo, _dt(out), M, n, _stream()),
+                                    C.c_void_p(int(mc_ptr)) if mc_ptr else None, ldo, _dt(out), M, n, int(max_ctas), _stream()),
            "qg_reduce_partials")
+
+
+def copy_2d_async(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, width_bytes: int, rows: int) -> None:
+    """Block copy on the copy engines (cudaMemcpy2DAsync), device addresses given as ints (peer-mapped ones included)."""
+    _check(lib().qg_copy_2d_async(C.c_void_p(int(dst_ptr)), C.c_int64(dst_pitch), C.c_void_p(int(src_ptr)), C.c_int64(src_pitch),
+                                  C.c_int64(width_bytes), int(rows), _stream()), "qg_copy_2d_async")
 
 
 def add_layernorm_quant(A: torch.Tensor, R, B: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT):

@@ -25,7 +25,7 @@ int inv_divide(const float *a, int64_t n, float b, float *out, cudaStream_t st);
 int outlier_mask(const float *A, int M, int K, int64_t lda, float thr, float *mask, int64_t ldm, cudaStream_t st);
 int reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
                     void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st,
-                    void *out_mc = nullptr);
+                    void *out_mc = nullptr, int max_ctas = 0);
 int gemm_s8_simt(const int8_t *A, int64_t lda, const int8_t *B, int64_t ldb, int b_kmajor, int M, int N, int K, void *O,
                  int64_t ldo, int out_dtype, const float *Cx, const float *Cw, const float *bias, float c,
                  const SideArgs *side, cudaStream_t st, int act = QG_ACT_NONE);
@@ -106,6 +106,7 @@ struct DeviceState {
 static DeviceState g_dev[16];
 static std::mutex g_mu;
 static std::atomic<int> g_variant{QG_GEMM_AUTO};
+std::atomic<int> g_sm_limit{0};  // qg_set_gemm_sm_limit
 
 static int device_state(DeviceState **out) {
   int dev = 0;
@@ -259,7 +260,9 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
     return gemm_s8_simt(A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, st, act);
   }
   const int cg = variant == QG_GEMM_TC_2SM ? 2 : 1;
-  int sk = (side == nullptr && (multi == nullptr || (multi->n == 0 && multi->mc == nullptr))) ? choose_split_k(d->sm_count, cg, M, N, K, out_kind) : 1;
+  const int lim = g_sm_limit.load();
+  const int sm_count = (lim > 0 && lim < d->sm_count) ? std::max(lim, 2) : d->sm_count;
+  int sk = (side == nullptr && (multi == nullptr || (multi->n == 0 && multi->mc == nullptr))) ? choose_split_k(sm_count, cg, M, N, K, out_kind) : 1;
   // split-K: int32 partial sums of every k-slice, then one pass that adds them and runs the epilogue.
   // The slices live in the caller's workspace (qg_workspace_bytes reserves them); entry points without a
   // workspace argument use a grow-only per-device buffer (sk_arena; documented as shared in qgemm.h).  A
@@ -286,13 +289,13 @@ static int gemm_dispatch(DeviceState *d, const int8_t *A, int64_t lda, const int
     slices.n = sk - 1;
     for (int i = 1; i < sk; i++) slices.dst[i - 1] = parts + (size_t)i * slice;
     int rc = gemm_i8_tc(cg, A, lda, B, ldb, b_kmajor, M, N, K, parts, ldp, QG_S32, nullptr, nullptr, nullptr, 0.0f, nullptr,
-                        &slices, d->sm_count, st, QG_ACT_NONE, sk);
+                        &slices, sm_count, st, QG_ACT_NONE, sk);
     if (rc) return rc;
     return cuda_status((cudaError_t)splitk_reduce(parts, (int64_t)slice, sk, ldp, Cx, Cw, bias, M, N, c, act, O, out_kind, ldo, st),
                        "split-K reduce");
   }
   if (rowmax_done) *rowmax_done = rowmax != nullptr && out_kind != QG_S32;
-  return gemm_i8_tc(cg, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, multi, d->sm_count, st, act, 1,
+  return gemm_i8_tc(cg, A, lda, B, ldb, b_kmajor, M, N, K, O, ldo, out_kind, Cx, Cw, bias, c, side, multi, sm_count, st, act, 1,
                     rowmax);
 }
 
@@ -312,6 +315,15 @@ int qg_device_info(int *sm_count, int *cc_major, int *cc_minor) {
   if (sm_count) *sm_count = d->sm_count;
   if (cc_major) *cc_major = d->cc_major;
   if (cc_minor) *cc_minor = d->cc_minor;
+  return QG_OK;
+}
+
+/* SMs the tensor-core GEMM may occupy (0 = all).  A persistent GEMM takes every SM it is given; a caller that overlaps its own
+ * communication kernels with the GEMM (megatron.MegatronFFN: the ordered reduce + gather of one row block under the next
+ * block's products) leaves a few SMs free for them, as communication libraries reserve channels. */
+int qg_set_gemm_sm_limit(int sms) {
+  if (sms < 0) { set_error("bad SM limit %d", sms); return QG_EINVAL; }
+  g_sm_limit.store(sms);
   return QG_OK;
 }
 
@@ -1067,9 +1079,20 @@ int qg_ffn_forward_rowpar(const void *X, int64_t ldx, int in_dtype, const int8_t
                    part_dst[0], ld_part, part_dtype, M, d_in, d_ff_local, d_out, range, mode, workspace, workspace_bytes, stream, &mo);
 }
 
+/* [rows, width_bytes] block copy between device buffers (possibly on different GPUs of a peer-mapped allocation) by the COPY
+ * ENGINES: the gather half of the Megatron exchange when it has to run under GEMMs that hold every SM. */
+int qg_copy_2d_async(void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes, int64_t width_bytes, int rows,
+                     qg_stream_t stream) {
+  QG_REQUIRE(dst && src && width_bytes > 0 && rows > 0 && dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes,
+             "qg_copy_2d_async: bad arguments");
+  QG_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)rows,
+                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return QG_OK;
+}
+
 int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
                        void *out, void *const *peers, int n_peers, void *out_mc, int64_t ldo, int out_dtype, int m, int n,
-                       qg_stream_t stream) {
+                       int max_ctas, qg_stream_t stream) {
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
@@ -1078,7 +1101,7 @@ int qg_reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int 
                  (n_slots == 1 || slot_stride >= (int64_t)(m - 1) * ld_part + n),
              "qg_reduce_partials: bad arguments");
   return cuda_status((cudaError_t)reduce_partials(slots, slot_stride, n_slots, part_dtype, ld_part, bias, out, peers, n_peers, ldo,
-                                                  out_dtype, m, n, (cudaStream_t)stream, out_mc),
+                                                  out_dtype, m, n, (cudaStream_t)stream, out_mc, max_ctas),
                      "qg_reduce_partials");
 }
 

@@ -145,7 +145,7 @@ reduce_partials_kernel(const PT *__restrict__ slots, int64_t slot_stride, int n_
 
 template <typename PT, typename OT>
 int launch_reduce(const void *slots, int64_t slot_stride, int n_slots, int64_t ld_part, const float *bias, void *out,
-                  const ReducePeers &peers, int64_t ldo, int M, int N, cudaStream_t st) {
+                  const ReducePeers &peers, int64_t ldo, int M, int N, cudaStream_t st, int max_ctas) {
   bool vec = N % 4 == 0 && ld_part % 4 == 0 && slot_stride % 4 == 0 && ldo % 4 == 0 &&
              (reinterpret_cast<uintptr_t>(slots) % (4 * sizeof(PT))) == 0 && (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(OT))) == 0;
   for (int d = 0; d < peers.n; d++) vec = vec && (reinterpret_cast<uintptr_t>(peers.dst[d]) % (4 * sizeof(OT))) == 0;
@@ -153,7 +153,7 @@ int launch_reduce(const void *slots, int64_t slot_stride, int n_slots, int64_t l
   if (!vec || (reinterpret_cast<uintptr_t>(pr.mc) % (4 * sizeof(OT))) != 0) pr.mc = nullptr;  // multicast needs the vector path
   const int w = vec ? 4 : 1;
   const unsigned gx = (unsigned)ceil_div(N, 256 * w);
-  unsigned gy = (unsigned)(148 * 16 / gx);
+  unsigned gy = (unsigned)((max_ctas > 0 ? max_ctas : 148 * 16) / gx);  // max_ctas: a caller running this under a GEMM keeps it small
   gy = gy < 1 ? 1 : gy;
   gy = gy > (unsigned)M ? (unsigned)M : gy;
   dim3 grid(gx, gy);
@@ -165,11 +165,11 @@ int launch_reduce(const void *slots, int64_t slot_stride, int n_slots, int64_t l
 }
 template <typename PT>
 int reduce_out(int out_dtype, const void *slots, int64_t slot_stride, int n_slots, int64_t ld_part, const float *bias, void *out,
-               const ReducePeers &peers, int64_t ldo, int M, int N, cudaStream_t st) {
+               const ReducePeers &peers, int64_t ldo, int M, int N, cudaStream_t st, int max_ctas) {
   switch (out_dtype) {
-    case QG_F32: return launch_reduce<PT, float>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st);
-    case QG_F16: return launch_reduce<PT, __half>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st);
-    case QG_BF16: return launch_reduce<PT, __nv_bfloat16>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st);
+    case QG_F32: return launch_reduce<PT, float>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st, max_ctas);
+    case QG_F16: return launch_reduce<PT, __half>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st, max_ctas);
+    case QG_BF16: return launch_reduce<PT, __nv_bfloat16>(slots, slot_stride, n_slots, ld_part, bias, out, peers, ldo, M, N, st, max_ctas);
   }
   return QG_EINVAL;
 }
@@ -210,15 +210,15 @@ int elemwise(int op, const void *A, int64_t lda, const float *B, int64_t ldb, in
 // slots: [n_slots][M][ld_part] of part_dtype (slot_stride elements apart); out / peers: [M, ldo] of out_dtype
 int reduce_partials(const void *slots, int64_t slot_stride, int n_slots, int part_dtype, int64_t ld_part, const float *bias,
                     void *out, void *const *peers, int n_peers, int64_t ldo, int out_dtype, int M, int N, cudaStream_t st,
-                    void *out_mc) {
+                    void *out_mc, int max_ctas) {
   ReducePeers pr = {};
   pr.mc = out_mc;
   pr.n = n_peers;
   for (int d = 0; d < n_peers; d++) pr.dst[d] = peers[d];
   switch (part_dtype) {
-    case QG_F32: return reduce_out<float>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st);
-    case QG_F16: return reduce_out<__half>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st);
-    case QG_BF16: return reduce_out<__nv_bfloat16>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st);
+    case QG_F32: return reduce_out<float>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st, max_ctas);
+    case QG_F16: return reduce_out<__half>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st, max_ctas);
+    case QG_BF16: return reduce_out<__nv_bfloat16>(out_dtype, slots, slot_stride, n_slots, ld_part, bias, out, pr, ldo, M, N, st, max_ctas);
   }
   return QG_EINVAL;
 }

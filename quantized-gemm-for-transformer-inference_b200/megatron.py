@@ -45,12 +45,25 @@ class MegatronFFN:
     def __init__(self, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor], rank: int,
                  world: int, group=None, exchange: str = "fused", h_dtype: torch.dtype = torch.float32,
                  part_dtype: torch.dtype = torch.float32, out_dtype: torch.dtype = torch.float32, gather: bool = True,
-                 compute: Optional[Callable] = None, range_: float = 127.0, mode: int = 0, align: int = 16, chunks: int = 0):
+                 compute: Optional[Callable] = None, range_: float = 127.0, mode: int = 0, align: int = 16, chunks: int = 0,
+                 comm_sms: int = 0, gather_engine: str = "kernel"):
         assert exchange in ("fused", "collective")
         # fused exchange: the tokens are cut into `chunks` row blocks; block c's reduce + gather (side stream) runs under block
         # c+1's GEMMs.  0 = choose (4 blocks of >= 512 rows when the batch allows it).  Rows are independent, so the result does
         # not depend on the chunking.
         self.chunks = chunks
+        # SMs kept free of the (persistent) GEMMs while the tokens are processed in several row blocks, so that the side
+        # stream's barrier / reduce / gather kernels of block c actually run under block c+1's products instead of queueing
+        # behind them -- the same reason communication libraries reserve SMs for their channels
+        # (measured: the reservation costs more than it hides -- 140 instead of 148 SMs turns 72-tile products from one wave into
+        # two; P = 2: 991 -> 1220 us with 8 SMs held back.  Kept as a knob, default 0.)
+        self.comm_sms = comm_sms
+        # the gather of the reduced blocks: "kernel" = peer stores from the reduce kernel (default); "copy" = cudaMemcpy2DAsync on
+        # the copy engines, which can run under the next row block's GEMMs although those hold every SM -- measured slower all
+        # the same (P = 8, bf16 partials: 672 vs 505 us with 2 row blocks, 723 vs 537 us with 1: seven strided 2-D copies of
+        # 2304-byte rows per rank are a poor load for the engines); "auto" = copy when row blocks pipeline
+        assert gather_engine in ("auto", "kernel", "copy")
+        self.gather_engine = gather_engine
         self.rank, self.world, self.group = rank, world, group
         self.exchange, self.gather = exchange, gather
         self.h_dtype, self.part_dtype, self.out_dtype = h_dtype, part_dtype, out_dtype
@@ -191,7 +204,7 @@ class MegatronFFN:
         return [(r0, min(r0 + step, m)) for r0 in range(0, m, step)]
 
     def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
-        from . import ffn_forward_rowpar, reduce_partials
+        from . import copy_2d_async, ffn_forward_rowpar, reduce_partials
 
         if not self._prepared:
             self._prepare(x.device)
@@ -199,9 +212,14 @@ class MegatronFFN:
         self._ensure(m, x.device)
         blocks = self._row_blocks(m)
         main = torch.cuda.current_stream()
+        from . import device_info, set_gemm_sm_limit
+
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=x.device)
+            self._side = torch.cuda.Stream(device=x.device, priority=-1)
         side = self._side
+        reserve = self.comm_sms if len(blocks) > 1 else 0
+        if reserve:
+            set_gemm_sm_limit(device_info()[0] - reserve)
         # (a) every peer has finished reducing the previous contents of its slots (and reading its previous result)
         if self._fresh or not self.gather:
             self.slots_hdl.barrier(channel=0)
@@ -224,10 +242,19 @@ class MegatronFFN:
                     own = self.out[r0:r1, self.olo:self.ohi] if self.gather else self.out[r0:r1]
                     ldo = self.out.stride(0)
                     peers = [p + r0 * ldo * eo for p in self.peer_out]
-                    reduce_partials(self.slots[:, r0:r1, :], bias, own, peers, n, self.out_mc + r0 * ldo * eo if self.out_mc else 0)
+                    by_copy = self.gather and bool(peers) and (self.gather_engine == "copy" or
+                                                               (self.gather_engine == "auto" and len(blocks) > 1))
+                    reduce_partials(self.slots[:, r0:r1, :], bias, own, [] if by_copy else peers, n,
+                                    0 if by_copy else (self.out_mc + r0 * ldo * eo if self.out_mc else 0),
+                                    max_ctas=8 * reserve if reserve else 0)
+                    if by_copy:  # the owner's block to the same place in every peer's result, by the copy engines
+                        for pdst in peers:
+                            copy_2d_async(pdst, ldo * eo, own.data_ptr(), ldo * eo, n * eo, r1 - r0)
         with torch.cuda.stream(side):
             if self.gather:
                 # (c) every block of every rank's result is in place; it also orders the next forward's stores after this reduce
                 self.out_hdl.barrier(channel=0)
         main.wait_stream(side)
+        if reserve:
+            set_gemm_sm_limit(0)
         return self.out

@@ -102,7 +102,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, dts, gather, ret, chunks=0, multicast=False):
+def _worker(rank, world, port, shape, dts, gather, ret, chunks=0, multicast=False, engine="auto"):
     import torch.distributed as dist
 
     if multicast:  # the result's gather through the NVSwitch multicast address (multimem.st in the reduce kernel)
@@ -121,7 +121,7 @@ def _worker(rank, world, port, shape, dts, gather, ret, chunks=0, multicast=Fals
         X, W1, b1, W2, b2 = _data(*shape, seed=11)
         t = lambda a: torch.from_numpy(a).cuda()
         kw = dict(h_dtype=TDT[h_dt], part_dtype=TDT[p_dt], out_dtype=TDT[o_dt], gather=gather)
-        fused = mg.MegatronFFN(t(W1), t(b1), t(W2), t(b2), rank, world, exchange="fused", chunks=chunks, **kw)
+        fused = mg.MegatronFFN(t(W1), t(b1), t(W2), t(b2), rank, world, exchange="fused", chunks=chunks, gather_engine=engine, **kw)
         coll = mg.MegatronFFN(t(W1), t(b1), t(W2), t(b2), rank, world, exchange="collective", **kw)
         bounds = [cp.shard_bounds(d_ff, world, r, 16) for r in range(world)]
         want = oracle.megatron_ffn(X, W1, b1, W2, b2, bounds, h_dtype=h_dt, part_dtype=p_dt, out_dtype=o_dt)
@@ -160,6 +160,23 @@ def test_megatron_ffn_multicast_gather_matches_oracle(shape, dts):
     assert all(ret.get(r) for r in range(world)), dict(ret)
     if not all(ret.get("mc_%d" % r) for r in range(world)):
         pytest.skip("no multicast mapping on this box: the unicast gather ran (and matched)")
+
+
+@pytest.mark.parametrize("chunks", [1, 2])
+def test_megatron_ffn_copy_engine_gather_matches_oracle(chunks):
+    """The gather of the reduced blocks by cudaMemcpy2DAsync (copy engines) instead of peer stores from the reduce kernel."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import oracle
+
+    oracle.build()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), (1024, 256, 1024, 704), ("f16", "bf16", "f16"), True, ret, chunks, False, "copy"),
+             nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
 @pytest.mark.parametrize("shape,dts,gather,chunks", [

@@ -66,13 +66,15 @@ for pdt in part_dts:
         res[f"collective_us_{tag}"] = timed(lambda: coll.forward(x))
         res[f"local_us_{tag}"] = timed(lambda: coll._partial_blocks(x))
     if world > 1:
-        for c in (1, 2, 4):
+        for c in (1, 2):
             rs = mg.MegatronFFN(W1, b1, W2, b2, rank, world, exchange="fused", gather=False, chunks=c, **kw)
             res[f"fused_rs_us_{tag}_chunks{c}"] = timed(lambda: rs.forward(x))
             del rs
-        for c in (1, 2, 4, 8):  # row-block pipelining of the exchange tail (the default above chooses 4 blocks at T = 4096)
-            fc = mg.MegatronFFN(W1, b1, W2, b2, rank, world, exchange="fused", gather=True, chunks=c, **kw)
-            res[f"fused_us_{tag}_chunks{c}"] = timed(lambda: fc.forward(x))
+        # row-block pipelining of the exchange tail, with 0 / 8 / 16 SMs kept free of the GEMMs for the side stream's kernels
+        # row-block pipelining of the exchange tail; the gather by peer stores from the reduce kernel or by the copy engines
+        for c, eng in ((1, "kernel"), (1, "copy"), (2, "kernel"), (2, "copy"), (4, "kernel"), (4, "copy")):
+            fc = mg.MegatronFFN(W1, b1, W2, b2, rank, world, exchange="fused", gather=True, chunks=c, gather_engine=eng, **kw)
+            res[f"fused_us_{tag}_chunks{c}_{eng}"] = timed(lambda: fc.forward(x))
             del fc
             torch.cuda.empty_cache()
     res[f"fused_tops_total_{tag}"] = ops / res[f"fused_us_{tag}"] / 1e6
