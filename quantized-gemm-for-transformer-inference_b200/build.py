@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libqgemm.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["capi.cu", "quantize.cu", "outlier.cu", "gemm_simt.cu", "rowops.cu", "elemwise.cu", "gemm_i8_tc.cu"]
+SOURCES = ["capi.cu", "quantize.cu", "outlier.cu", "gemm_simt.cu", "rowops.cu", "elemwise.cu", "attention.cu", "gemm_i8_tc.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

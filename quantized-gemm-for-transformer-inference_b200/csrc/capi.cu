@@ -40,6 +40,8 @@ int gather_wo(const void *W, int dtype, int64_t ldw, const uint32_t *mask, const
 int mm_f32(const float *A, int64_t sa_h, int64_t sa_w, const float *B, int64_t sb_h, int64_t sb_w, int M, int N, int K,
            float *C, int64_t ldc, cudaStream_t st, const MmBatch *batch = nullptr);
 int softmax_rows(const float *A, int64_t lda, int M, int N, float scale, float *B, int64_t ldb, cudaStream_t st);
+int attention_core(const float *Q, int64_t ldq, const float *K, const float *V, int64_t ldkv, float *O, int64_t ldo, int batch,
+                   int heads, int sq, int skv, int d_k, int d_v, float scale, cudaStream_t st);
 int add_layernorm_rows(const float *A, int64_t lda, const float *R, int64_t ldr, int M, int N, float *B, int64_t ldb,
                        cudaStream_t st, int8_t *Xq = nullptr, int64_t ldq = 0, float *Cx = nullptr, float range = 127.0f,
                        int mode = QG_MODE_REF_EXACT);
@@ -868,6 +870,10 @@ int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_
     Q = proj; Kp = pkv; Vp = pkv + heads * d_k;
     ldq_ = nq; ldkv = nkv;
   }
+  const float scale = (float)(1.0 / std::sqrt((double)d_k));
+  // 2-4 in ONE kernel when a (sequence, head) fits a CTA's shared memory (attention.cu): same arithmetic, same bits
+  rc = attention_core(Q, ldq_, Kp, Vp, ldkv, out, ldo, batch, heads, sq, skv, d_k, d_v, scale, st);
+  if (rc != QG_ENOTSUP) return cuda_status((cudaError_t)rc, "attention core");
   // 2. scores = Q K^T per (sequence, head): fp32, k-ascending FMA chain like op_mm (attention.cuh:58-60)
   MmBatch bt;
   bt.n_outer = batch; bt.n_inner = heads;
@@ -877,7 +883,6 @@ int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_
   rc = mm_f32(Q, ldq_, 1, Kp, 1, ldkv, sq, skv, d_k, scores, skv, st, &bt);  // B = K^T: element (k, n) at K[n, k]
   if (rc) return cuda_status((cudaError_t)rc, "scores");
   // 3. softmax(scores / sqrt(d_k)) in place (attention.cuh:62-68)
-  const float scale = (float)(1.0 / std::sqrt((double)d_k));
   rc = softmax_rows(scores, skv, batch * heads * sq, skv, scale, scores, skv, st);
   if (rc) return cuda_status((cudaError_t)rc, "softmax");
   // 4. out[:, h*d_v : (h+1)*d_v] = P V per (sequence, head) (attention.cuh:69; the head concat of transformer.cu:43-50)

@@ -256,9 +256,42 @@ add_layernorm_cta_rows_kernel(const float *A, int64_t lda, const float *R, int64
   for (int r0 = blockIdx.x * rows_per_cta; r0 < M; r0 += gridDim.x * rows_per_cta) {
     const int rows = min(rows_per_cta, M - r0);
     if (t < 32) s_slow[t] = 0;
+    // Element-parallel phases (this load, the squares, the final division) walk the CTA's rows four columns at a time when the
+    // operands allow 16-byte accesses: one index division per four elements, four times the bytes in flight.  (ncu, 4096 x 512:
+    // the scalar form of this load alone was 31 % of the kernel's samples -- 4-byte loads, 16 KB in flight per SM.)
+    const bool vec4 = (N & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 && (R == nullptr || (ldr & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(R)) & 15) == 0;
+    const int n4 = N >> 2;
+    if (vec4) {
+      for (int e0 = t; e0 < rows * n4; e0 += kLnThreads * 4) {
+        float4 va[4], vr[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + u * kLnThreads;
+          const int r = e / n4, j = (e - r * n4) << 2;
+          va[u] = vr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < rows * n4) {
+            va[u] = *reinterpret_cast<const float4 *>(A + (int64_t)(r0 + r) * lda + j);
+            if (R != nullptr) vr[u] = *reinterpret_cast<const float4 *>(R + (int64_t)(r0 + r) * ldr + j);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + u * kLnThreads;
+          const int r = e / n4, j = (e - r * n4) << 2;
+          if (e < rows * n4) {
+            float *dst = row + r * ldrow + j;
+            dst[0] = R != nullptr ? __fadd_rn(va[u].x, vr[u].x) : va[u].x;
+            dst[1] = R != nullptr ? __fadd_rn(va[u].y, vr[u].y) : va[u].y;
+            dst[2] = R != nullptr ? __fadd_rn(va[u].z, vr[u].z) : va[u].z;
+            dst[3] = R != nullptr ? __fadd_rn(va[u].w, vr[u].w) : va[u].w;
+          }
+        }
+      }
+    }
     // eight independent loads per thread in flight (a plain loop here is a chain of DRAM round trips:
     // that, not the serial sums, was most of the first version's 73 us)
-    for (int e0 = t; e0 < rows * N; e0 += kLnThreads * 4) {
+    for (int e0 = t; !vec4 && e0 < rows * N; e0 += kLnThreads * 4) {
       float va[4], vr[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -286,7 +319,20 @@ add_layernorm_cta_rows_kernel(const float *A, int64_t lda, const float *R, int64
       s_mean[t] = mean / w;
     }
     __syncthreads();
-    for (int e = t; e < rows * N; e += kLnThreads) {
+    for (int e = t; e < rows * n4 && vec4; e += kLnThreads) {
+      const int r = e / n4, j = (e - r * n4) << 2;
+      const float mean = s_mean[r];
+      bool slow = false;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double dd = (double)(row[r * ldrow + j + c] - mean);
+        const double q = dd * dd;  // exact: 24-bit x 24-bit
+        sq[r * ldsq + j + c] = q;
+        slow |= (q != 0.0 && q < 7.888609052210118e-31) || !(q < 1e30);
+      }
+      if (slow) s_slow[r] = 1;
+    }
+    for (int e = t; e < rows * N && !vec4; e += kLnThreads) {
       const int r = e / N, j = e - r * N;
       const double dd = (double)(row[r * ldrow + j] - s_mean[r]);
       const double q = dd * dd;  // exact: 24-bit x 24-bit
@@ -318,7 +364,17 @@ add_layernorm_cta_rows_kernel(const float *A, int64_t lda, const float *R, int64
       s_var[t] = var / w;
     }
     __syncthreads();
-    for (int e = t; e < rows * N; e += kLnThreads) {
+    for (int e = t; e < rows * n4 && vec4; e += kLnThreads) {
+      const int r = e / n4, j = (e - r * n4) << 2;
+      const float mean = s_mean[r], var = s_var[r];
+      float *src = row + r * ldrow + j;
+      float4 v;
+      v.x = (src[0] - mean) / var; v.y = (src[1] - mean) / var;
+      v.z = (src[2] - mean) / var; v.w = (src[3] - mean) / var;
+      *reinterpret_cast<float4 *>(B + (int64_t)(r0 + r) * ldb + j) = v;
+      if (QUANT) { src[0] = v.x; src[1] = v.y; src[2] = v.z; src[3] = v.w; }
+    }
+    for (int e = t; e < rows * N && !vec4; e += kLnThreads) {
       const int r = e / N, j = e - r * N;
       const float v = (row[r * ldrow + j] - s_mean[r]) / s_var[r];
       B[(int64_t)(r0 + r) * ldb + j] = v;

@@ -124,7 +124,10 @@ def test_attention_matches_reference_fixture_bit_for_bit(qg, oracle, path):
 
 
 @pytest.mark.parametrize("sq,skv,d_model,d_k,d_v", [(2, 2, 3, 2, 4), (33, 33, 40, 8, 12), (64, 100, 128, 32, 16),
-                                                    (128, 128, 512, 64, 64)])
+                                                    (128, 128, 512, 64, 64),
+                                                    (250, 100, 64, 32, 32),    # four query row blocks of the one-kernel core (the reference's softmax grid stops at row 256)
+                                                    (64, 200, 64, 32, 32),     # more keys than a CTA takes: the three-kernel path
+                                                    (130, 128, 96, 64, 60)])   # ragged last row block, d_v below the tile width
 def test_attention_matches_live_reference(qg, ref, sq, skv, d_model, d_k, d_v):
     from make_ref_fixtures import run_ref_attention
 
