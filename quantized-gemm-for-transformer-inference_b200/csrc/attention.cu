@@ -93,8 +93,10 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
 #pragma unroll 4
     for (int k = 0; k < d_k; k++) {
       const float4 a0 = *reinterpret_cast<const float4 *>(sQt + k * kLdQ + ty * 4);
-      const float4 b0 = *reinterpret_cast<const float4 *>(sKV + k * kLdK + tx * 8);
-      const float4 b1 = *reinterpret_cast<const float4 *>(sKV + k * kLdK + tx * 8 + 4);
+      // a thread's eight keys are tx*4 .. tx*4+3 and 64 + tx*4 .. : sixteen lanes then read 256 contiguous bytes per load
+      // (keys tx*8 .. tx*8+7 made every 16-byte load a two-way bank conflict)
+      const float4 b0 = *reinterpret_cast<const float4 *>(sKV + k * kLdK + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4 *>(sKV + k * kLdK + 64 + tx * 4);
       const float a[4] = {a0.x, a0.y, a0.z, a0.w};
       const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -108,7 +110,7 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const float s = pad ? __fadd_rn(acc[i][j], 0.0f) : acc[i][j];
-        sS[(ty * 4 + i) * kLdS + tx * 8 + j] = __fmul_rn(s, scale);
+        sS[(ty * 4 + i) * kLdS + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4))] = __fmul_rn(s, scale);
       }
   }
   __syncthreads();  // every thread is done with K^T
@@ -131,10 +133,10 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
     sS[t * kLdS + kAttKeys] = mx;  // the padding column of the score tile
   }
   __syncthreads();
-  for (int e = t; e < rows * skv; e += kAttThreads) {
-    const int r = e / skv, j = e - r * skv;
-    sS[r * kLdS + j] = expf(__fsub_rn(sS[r * kLdS + j], sS[r * kLdS + kAttKeys]));
-  }
+  // (thread = one key column, two rows per sweep: no index division -- with a run-time row length it cost as much as the expf)
+  const int jc = t & (kAttKeys - 1);
+  for (int r = t >> 7; r < rows; r += kAttThreads / kAttKeys)
+    if (jc < skv) sS[r * kLdS + jc] = expf(__fsub_rn(sS[r * kLdS + jc], sS[r * kLdS + kAttKeys]));
   __syncthreads();
   if (t < rows) {
     const float *srow = sS + t * kLdS;
@@ -144,10 +146,8 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
     sS[t * kLdS + kAttKeys] = sum;
   }
   __syncthreads();
-  for (int e = t; e < rows * skv; e += kAttThreads) {
-    const int r = e / skv, j = e - r * skv;
-    sS[r * kLdS + j] = __fdiv_rn(sS[r * kLdS + j], sS[r * kLdS + kAttKeys]);
-  }
+  for (int r = t >> 7; r < rows; r += kAttThreads / kAttKeys)
+    if (jc < skv) sS[r * kLdS + jc] = __fdiv_rn(sS[r * kLdS + jc], sS[r * kLdS + kAttKeys]);
   __syncthreads();
 
   // ---- out = P V: 4 rows x 4 columns per thread, j ascending ----
