@@ -496,6 +496,35 @@ def run_ours(args):
     both_ms = None if kmajor else stage_ms(lambda j: qg.absmax_quant_rows_cols(Xs[j % nset], Ws[j % nset], Xq, Cx, Wq, Cw, 127.0,
                                                                               qg.MODE_REF_EXACT))
 
+    # ---- e2e at N > 1: every rank runs the host-buffer call on its own column block at the same time (pinned host X and this
+    # rank's W in, this rank's O block out; no gather -- the caller's buffers are host memory); max over ranks ----
+    e2e_multi = None
+    if world > 1 and os.environ.get("QG_BENCH_NO_E2E") is None:
+        Xh = torch.empty((M, K), dtype=torch.float32).pin_memory()
+        Wh = torch.empty((K, N), dtype=torch.float32).pin_memory()
+        Oh = torch.empty((M, N), dtype=torch.float32).pin_memory()
+        Xh.copy_(Xs[0]); Wh.copy_(Ws[0])
+        for _ in range(2):
+            qg.quantized_mm_host(Xh, Wh, out=Oh)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            qg.quantized_mm_host(Xh, Wh, out=Oh)  # blocks until Oh is written
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        same = torch.equal(Oh.to(dev).view(torch.int32), _device_result(qg, Xs[0], Ws[0], ws).view(torch.int32))
+        te = torch.tensor([e2e_ms, 0.0 if same else 1.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te[0].item())
+        e2e_multi = {"value": world * ops / e2e_ms / 1e9, "unit": "TOPS", "ms_per_step": e2e_ms,
+                     "h2d_bytes_per_step": world * (M * K + K * N) * 4, "d2h_bytes_per_step": world * M * N * 4,
+                     "api": "qg_quantized_mm_host on every rank at once (pinned host X and this rank's W -> this rank's host O block); "
+                            "bytes are whole-job totals, time is the max over ranks",
+                     "parity_vs_device_path": bool(te[1].item() == 0.0)}
+        del Xh, Wh, Oh
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -565,8 +594,8 @@ def run_ours(args):
                                     f"D2H {d2h_gbs:.1f} GB/s; floor = max(h2d_bytes/H2D, d2h_bytes/D2H) = {floor_ms:.3f} ms; "
                                     "frac = floor / measured"}}
     else:
-        e2e = {"value": None, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "host-buffer call measured at N=1 only"}
+        e2e = e2e_multi or {"value": None, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                            "note": "host-buffer call switched off (QG_BENCH_NO_E2E)"}
 
     # ---- context: LinearLayer::forward with the weights prepared once (K-major int8), fp32 and fp16 I/O ----
     cached = {}
