@@ -264,6 +264,14 @@ QG_API int qg_softmax_rows_f32(const float *A, int64_t lda, int m, int n, float 
 QG_API int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq,
                                 int skv, int d_model, const float *Wqkv, int64_t ldw, int heads, int d_k, int d_v,
                                 float range, int mode, float *out, int64_t ldo, qg_stream_t stream);
+/* The same layer with the projection weights quantized ONCE (a layer object that keeps its weights, which the reference's
+ * AttentionLayer does -- attention.cuh:20-26 -- although it re-draws them in transformer.cu's loops): Wt [heads*(2*d_k+d_v),
+ * ldwt] and Cw come from qg_prepare_weights(Wqkv).  Column scales depend only on their own column, so the result is
+ * bit-identical to qg_attention_forward on the same fp32 weights; the per-call column quantizer pass disappears. */
+QG_API int qg_attention_forward_prepared(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq,
+                                         int skv, int d_model, const int8_t *Wt, int64_t ldwt, const float *Cw, int heads,
+                                         int d_k, int d_v, float range, int mode, float *out, int64_t ldo,
+                                         qg_stream_t stream);
 
 /* ---- quantization carried across layers (the FFN of src/transformer.cu:63-71) -----
  * The reference's stack runs ll1.forward -> op_relu -> ll2.forward; on the quantized path every linear starts with

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "qg_linear_forward",
     "qg_quantized_mm_host", "qg_outlier_mask_f32", "qg_outlier_cols", "qg_outlier_workspace_bytes",
     "qg_linear_forward_outlier", "qg_linear_forward_multi", "qg_gemm_s8_dequant_ex", "qg_gemm_s8_dequant_mc", "qg_mm_f32",
-    "qg_softmax_rows_f32", "qg_attention_forward", "qg_linear_forward_act", "qg_add_layernorm_f32",
+    "qg_softmax_rows_f32", "qg_attention_forward", "qg_attention_forward_prepared", "qg_linear_forward_act", "qg_add_layernorm_f32",
     "qg_linear_forward_q", "qg_quantize_rows_given_max", "qg_ffn_workspace_bytes", "qg_ffn_forward",
     "qg_add_layernorm_quant_f32", "qg_gemm_s8_dequant_scatter", "qg_ffn_forward_rowpar", "qg_reduce_partials", "qg_copy_2d_async",
     "qg_add_f32", "qg_subtract_f32", "qg_multiply_f32", "qg_multiply_const_f32", "qg_relu_f32", "qg_dequantize_outer_f32",
@@ -605,6 +605,26 @@ def attention_forward(Xq: torch.Tensor, Xkv: torch.Tensor, Wqkv: torch.Tensor, o
                                       C.c_float(range_), mode, po, ldo, _stream()), "qg_attention_forward")
 
 
+def attention_forward_prepared(Xq: torch.Tensor, Xkv: torch.Tensor, Wt: torch.Tensor, Cw: torch.Tensor, out: torch.Tensor,
+                               heads: int, d_k: int, d_v: int, batch: int = 1, range_: float = 127.0,
+                               mode: int = MODE_REF_EXACT) -> None:
+    """qg_attention_forward_prepared: the same layer on (Wt, Cw) = prepare_weights(Wqkv) -- same bits, no per-call
+    column quantizer."""
+    assert all(t.dtype == torch.float32 and t.is_cuda for t in (Xq, Xkv, Cw, out)) and Wt.dtype == torch.int8
+    assert Xq.shape[0] % batch == 0 and Xkv.shape[0] % batch == 0
+    sq, skv, d_model = Xq.shape[0] // batch, Xkv.shape[0] // batch, Xq.shape[1]
+    ntot = heads * (2 * d_k + d_v)
+    assert Xkv.shape[1] == d_model and Wt.shape[0] == ntot and Wt.shape[1] >= d_model and Cw.numel() == ntot
+    assert out.shape == (batch * sq, heads * d_v)
+    pq, ldq = _dev2d(Xq)
+    pkv, ldkv = _dev2d(Xkv)
+    pw, ldw = _dev2d(Wt)
+    po, ldo = _dev2d(out)
+    _check(lib().qg_attention_forward_prepared(pq, ldq, pkv, ldkv, batch, sq, skv, d_model, pw, ldw, _vec(Cw.reshape(-1), ntot),
+                                               heads, d_k, d_v, C.c_float(range_), mode, po, ldo, _stream()),
+           "qg_attention_forward_prepared")
+
+
 class AttentionLayer:
     """AttentionLayer<float> (src/modules/attention.cuh:10-70): single head, no bias, no mask.
     W_q, W_k [d_model, d_k] and W_v [d_model, d_v] are views of one [d_model, 2*d_k+d_v] parameter, so
@@ -654,6 +674,19 @@ class MultiHeadAttention:
     def init_uniform(self, generator=None):
         mx = 1.0 / (self.d_k ** 0.5)
         self.W_qkv.uniform_(-mx, mx, generator=generator)
+        self._wq = None
 
-    def forward(self, Xq: torch.Tensor, Xkv: torch.Tensor, out: torch.Tensor, batch: int = 1) -> None:
-        attention_forward(Xq, Xkv, self.W_qkv, out, self.n_heads, self.d_k, self.d_v, batch, self.range, self.mode)
+    def quantize_weights(self) -> None:
+        """Column-quantize W_qkv once (call again after changing W_qkv); forward(prepared=True) then skips the per-call pass."""
+        self._wq = prepare_weights(self.W_qkv, self.range, self.mode)
+
+    def forward(self, Xq: torch.Tensor, Xkv: torch.Tensor, out: torch.Tensor, batch: int = 1, prepared: bool = False) -> None:
+        """prepared=False: the weights are quantized on every call, as op_quantized_mm does (W_qkv may change between calls).
+        prepared=True: the codes of quantize_weights() (made on first use) -- bit-identical output."""
+        if not prepared:
+            attention_forward(Xq, Xkv, self.W_qkv, out, self.n_heads, self.d_k, self.d_v, batch, self.range, self.mode)
+            return
+        if getattr(self, "_wq", None) is None:
+            self.quantize_weights()
+        Wt, Cw = self._wq
+        attention_forward_prepared(Xq, Xkv, Wt, Cw, out, self.n_heads, self.d_k, self.d_v, batch, self.range, self.mode)

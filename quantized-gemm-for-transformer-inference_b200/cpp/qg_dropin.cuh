@@ -466,15 +466,31 @@ class MultiHeadAttention {
   void init_uniform(uint64_t seed) {  // attention.cuh:40-45, every head
     const float mx = 1.0f / std::sqrt((float)d_k);
     uniform_init(W_qkv, -mx, mx, seed);
+    prepared_ = false;
   }
-  // queries from xq, keys / values from xkv (the same tensor for self-attention); out [rows, heads * d_v]
+  void invalidate() { prepared_ = false; }  // after writing W_qkv directly
+  // queries from xq, keys / values from xkv (the same tensor for self-attention); out [rows, heads * d_v].
+  // The projection weights are column-quantized on first use (same bits as quantizing them on every call).
   void forward(const TensorT<float> &xq, const TensorT<float> &xkv, TensorT<float> &out, int batch = 1) {
     assert(xq.w == d_model && xkv.w == d_model && out.h == xq.h && out.w == heads * d_v);
     assert(xq.h % batch == 0 && xkv.h % batch == 0);
-    check(qg_attention_forward(base_ptr(xq), ld_of(xq), base_ptr(xkv), ld_of(xkv), batch, xq.h / batch, xkv.h / batch, d_model,
-                               base_ptr(W_qkv), W_qkv.stride_h, heads, d_k, d_v, 127.0f, QG_MODE_REF_EXACT, base_ptr(out),
-                               ld_of(out), nullptr), "qg_attention_forward");
+    const int ntot = heads * (2 * d_k + d_v);
+    if (!prepared_) {
+      wt_ = TensorT<int8_t>(ntot, (d_model + 15) / 16 * 16, true);
+      cw_ = TensorT<float>(1, ntot, true);
+      check(qg_prepare_weights(base_ptr(W_qkv), QG_F32, d_model, ntot, W_qkv.stride_h, 127.0f, QG_MODE_REF_EXACT, wt_.rawp,
+                               wt_.stride_h, cw_.rawp, nullptr), "qg_prepare_weights");
+      prepared_ = true;
+    }
+    check(qg_attention_forward_prepared(base_ptr(xq), ld_of(xq), base_ptr(xkv), ld_of(xkv), batch, xq.h / batch, xkv.h / batch,
+                                        d_model, wt_.rawp, wt_.stride_h, cw_.rawp, heads, d_k, d_v, 127.0f, QG_MODE_REF_EXACT,
+                                        base_ptr(out), ld_of(out), nullptr), "qg_attention_forward_prepared");
   }
+
+ private:
+  TensorT<int8_t> wt_;
+  TensorT<float> cw_;
+  bool prepared_ = false;
 };
 
 template <class TensorF>

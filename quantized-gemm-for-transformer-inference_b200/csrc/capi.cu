@@ -825,15 +825,19 @@ int qg_softmax_rows_f32(const float *A, int64_t lda, int m, int n, float scale, 
   return cuda_status((cudaError_t)softmax_rows(A, lda, m, n, scale, B, ldb, (cudaStream_t)stream), "softmax");
 }
 
-int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq, int skv,
-                         int d_model, const float *Wqkv, int64_t ldw, int heads, int d_k, int d_v, float range, int mode,
-                         float *out, int64_t ldo, qg_stream_t stream) {
+// shared by qg_attention_forward (fp32 weights, quantized on every call like op_quantized_mm) and
+// qg_attention_forward_prepared (codes + column scales from qg_prepare_weights): exactly one of Wqkv / Wt is non-NULL
+static int attention_forward_impl(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq, int skv,
+                                  int d_model, const float *Wqkv, int64_t ldw, const int8_t *Wt, int64_t ldwt, const float *Cw,
+                                  int heads, int d_k, int d_v, float range, int mode, float *out, int64_t ldo,
+                                  qg_stream_t stream) {
   DeviceState *d;
   int rc = device_state(&d);
   if (rc) return rc;
   const int nq = heads * d_k, nkv = heads * (d_k + d_v), ntot = nq + nkv;
-  QG_REQUIRE(Xq && Xkv && Wqkv && out && batch > 0 && sq > 0 && skv > 0 && d_model > 0 && heads > 0 && d_k > 0 && d_v > 0 &&
-                 ldxq >= d_model && ldxkv >= d_model && ldw >= ntot && ldo >= heads * d_v,
+  QG_REQUIRE(Xq && Xkv && out && batch > 0 && sq > 0 && skv > 0 && d_model > 0 && heads > 0 && d_k > 0 && d_v > 0 &&
+                 ldxq >= d_model && ldxkv >= d_model && ldo >= heads * d_v &&
+                 ((Wqkv && ldw >= ntot) || (Wt && Cw && ldwt >= d_model && ldwt % 16 == 0)),
              "qg_attention_forward: bad arguments");
   const bool self = (Xq == Xkv) && sq == skv && ldxq == ldxkv;
   const int64_t tq = (int64_t)batch * sq, tkv = (int64_t)batch * skv;
@@ -850,23 +854,24 @@ int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_
   float *scores = proj + round_up((int64_t)proj_elems, 64);
   // 1. projections through the quantized linear path (attention.cuh:54-56 re-pointed).  Row scales
   //    depend only on X and column scales only on their own column, so one product against the
-  //    concatenated [W_q | W_k | W_v] of all heads is bit-identical to the separate ones.
+  //    concatenated [W_q | W_k | W_v] of all heads is bit-identical to the separate ones -- and a column block of the
+  //    prepared codes (rows [c0, c1) of Wt, Cw + c0) to the prepared codes of that block alone.
+  auto project = [&](const float *X, int64_t ldx, int64_t rows, int c0, int n, float *P) -> int {
+    if (Wt) return qg_linear_forward(X, ldx, QG_F32, Wt + (int64_t)c0 * ldwt, ldwt, Cw + c0, nullptr, P, n, QG_F32, (int)rows, n,
+                                     d_model, range, mode, nullptr, 0, stream);
+    return qg_quantized_mm(X, ldx, Wqkv + c0, ldw, QG_F32, P, n, QG_F32, (int)rows, n, d_model, range, mode, nullptr, nullptr, 0,
+                           stream);
+  };
   const float *Q, *Kp, *Vp;
   int64_t ldq_, ldkv;
   if (self) {
-    rc = qg_quantized_mm(Xq, ldxq, Wqkv, ldw, QG_F32, proj, ntot, QG_F32, (int)tq, ntot, d_model, range, mode, nullptr,
-                         nullptr, 0, stream);
-    if (rc) return rc;
+    if ((rc = project(Xq, ldxq, tq, 0, ntot, proj))) return rc;
     Q = proj; Kp = proj + nq; Vp = proj + nq + heads * d_k;
     ldq_ = ldkv = ntot;
   } else {  // the 3-argument form transformer.cu:37,132 expects: queries from Xq, keys / values from Xkv
     float *pkv = proj + (size_t)tq * nq;
-    rc = qg_quantized_mm(Xq, ldxq, Wqkv, ldw, QG_F32, proj, nq, QG_F32, (int)tq, nq, d_model, range, mode, nullptr, nullptr,
-                         0, stream);
-    if (rc) return rc;
-    rc = qg_quantized_mm(Xkv, ldxkv, Wqkv + nq, ldw, QG_F32, pkv, nkv, QG_F32, (int)tkv, nkv, d_model, range, mode, nullptr,
-                         nullptr, 0, stream);
-    if (rc) return rc;
+    if ((rc = project(Xq, ldxq, tq, 0, nq, proj))) return rc;
+    if ((rc = project(Xkv, ldxkv, tkv, nq, nkv, pkv))) return rc;
     Q = proj; Kp = pkv; Vp = pkv + heads * d_k;
     ldq_ = nq; ldkv = nkv;
   }
@@ -891,6 +896,20 @@ int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_
   bt.c_outer = (int64_t)sq * ldo;         bt.c_inner = d_v;
   rc = mm_f32(scores, skv, 1, Vp, ldkv, 1, sq, d_v, skv, out, ldo, st, &bt);
   return cuda_status((cudaError_t)rc, "P*V");
+}
+
+int qg_attention_forward(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq, int skv,
+                         int d_model, const float *Wqkv, int64_t ldw, int heads, int d_k, int d_v, float range, int mode,
+                         float *out, int64_t ldo, qg_stream_t stream) {
+  return attention_forward_impl(Xq, ldxq, Xkv, ldxkv, batch, sq, skv, d_model, Wqkv, ldw, nullptr, 0, nullptr, heads, d_k, d_v,
+                                range, mode, out, ldo, stream);
+}
+
+int qg_attention_forward_prepared(const float *Xq, int64_t ldxq, const float *Xkv, int64_t ldxkv, int batch, int sq, int skv,
+                                  int d_model, const int8_t *Wt, int64_t ldwt, const float *Cw, int heads, int d_k, int d_v,
+                                  float range, int mode, float *out, int64_t ldo, qg_stream_t stream) {
+  return attention_forward_impl(Xq, ldxq, Xkv, ldxkv, batch, sq, skv, d_model, nullptr, 0, Wt, ldwt, Cw, heads, d_k, d_v, range,
+                                mode, out, ldo, stream);
 }
 
 /* ---- quantization carried across layers ---- */

@@ -103,7 +103,7 @@ class EncoderBlock:
 
     def forward(self, x: torch.Tensor, out: torch.Tensor, batch: int = 1, fused: bool = True) -> None:
         mh, ffn = self._buffers(x.shape[0], x.device)
-        self.attn.forward(x, x, mh, batch=batch)   # :27-50
+        self.attn.forward(x, x, mh, batch=batch, prepared=True)   # :27-50 (codes of W_q | W_k | W_v made once)
         self.W_O.forward(mh, out)                  # :54
         if fused:
             # ADD & NORM emits ll1's int8 codes, ll1's epilogue the row maxima ll2's quantizer needs
@@ -142,10 +142,10 @@ class DecoderBlock:
         if self._buf is None or self._buf[0].shape[0] != T:
             self._buf = (torch.empty((T, self.d_model), device=x.device), torch.empty((T, self.d_ff), device=x.device))
         mh, ffn = self._buf
-        self.self_attn.forward(x, x, mh, batch=batch)              # :99-116
+        self.self_attn.forward(x, x, mh, batch=batch, prepared=True)              # :99-116
         self.W_O1.forward(mh, out)                                 # :119
         add_layernorm(out, mh, out)                                # :123-124
-        self.cross_attn.forward(out, enc_output, mh, batch=batch)  # :127-140 (queries from the decoder, keys/values from the encoder)
+        self.cross_attn.forward(out, enc_output, mh, batch=batch, prepared=True)  # :127-140 (queries from the decoder, keys/values from the encoder)
         self.W_O2.forward(mh, out)                                 # :144
         xq, cx = _qg.add_layernorm_quant(out, mh, out)             # :148-149 (+ ll1's row quantizer)
         ffn_chain(self.ll1, self.ll2, None, ffn, out, xq, cx)      # :154-162

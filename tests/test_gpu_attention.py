@@ -184,3 +184,27 @@ def test_cross_attention_multi_head_vs_oracle(qg, oracle):
     qg.attention_forward(to_dev(Xq), to_dev(Xkv), to_dev(W), out, heads, 8, 8, batch)
     exp = oracle.multi_head_attention(Xq, Xkv, W, heads, 8, 8, batch)
     np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=ATTN_RTOL, atol=ATTN_ATOL)
+
+
+@pytest.mark.parametrize("batch,sq,skv,d_model,heads", [(1, 6, 6, 8, 4), (3, 20, 20, 40, 4), (2, 10, 14, 24, 3), (2, 128, 128, 512, 8),
+                                                         (2, 128, 96, 512, 8), (1, 70, 200, 72, 2)])
+def test_prepared_projection_weights_give_the_same_bits(qg, batch, sq, skv, d_model, heads):
+    """qg_attention_forward_prepared: W_q | W_k | W_v column-quantized once (qg_prepare_weights) instead of on every call.
+    A column's scale and codes depend only on that column, so self- and cross-attention (whose K / V projection uses a row
+    block of the prepared codes) must equal the per-call form bit for bit -- d_model not a multiple of 16 included."""
+    rng = np.random.default_rng(batch * 1000 + sq * 10 + skv)
+    Xq = to_dev(rng.random((batch * sq, d_model), dtype=np.float32) * 2 - 1)
+    Xkv = Xq if sq == skv else to_dev(rng.random((batch * skv, d_model), dtype=np.float32) * 2 - 1)
+    mha = qg.MultiHeadAttention(d_model, heads)
+    mha.init_uniform(torch.Generator(device="cuda").manual_seed(5))
+    a = torch.empty((batch * sq, d_model), device="cuda")
+    b = torch.full_like(a, float("nan"))
+    mha.forward(Xq, Xkv, a, batch=batch)
+    mha.forward(Xq, Xkv, b, batch=batch, prepared=True)
+    assert same_f32(a.cpu().numpy(), b.cpu().numpy())
+    # new weights: the cache is dropped by init_uniform, and quantize_weights() refreshes it after a direct write
+    mha.W_qkv.mul_(0.5)
+    mha.quantize_weights()
+    mha.forward(Xq, Xkv, a, batch=batch)
+    mha.forward(Xq, Xkv, b, batch=batch, prepared=True)
+    assert same_f32(a.cpu().numpy(), b.cpu().numpy())
