@@ -30,9 +30,18 @@ constexpr int kAttDim = 64;    // d_k, d_v
 constexpr int kAttThreads = 256;
 constexpr int kLdQ = kAttRows + 4;   // Q^T tile [k][row]: rows padded so that 16-byte reads stay aligned
 constexpr int kLdK = kAttKeys + 4;   // K^T tile [k][key]; the same region holds V [key][kAttDim] after the scores
-constexpr int kLdS = kAttKeys + 1;   // score tile rows: odd stride, 32 rows walked by 32 threads hit 32 banks (+ one column: max / sum)
+constexpr int kLdSt = kAttRows + 4;  // score tile, TRANSPOSED [key][row]: a thread's four rows of one key are one 16-byte access
 constexpr int kKVFloats = kAttDim * kLdK > kAttKeys * kAttDim ? kAttDim * kLdK : kAttKeys * kAttDim;
-constexpr size_t kAttSmem = sizeof(float) * ((size_t)kAttDim * kLdQ + (size_t)kKVFloats + (size_t)kAttRows * kLdS);  // 84 KB: two CTAs per SM
+constexpr size_t kAttSmem =
+    sizeof(float) * ((size_t)kAttDim * kLdQ + (size_t)kKVFloats + (size_t)kAttKeys * kLdSt + kAttRows);  // 85 KB: two CTAs per SM
+
+// Where key `key` sits in a row of the staged K^T.  Thread tx of the score phase owns keys tx, tx + 16, ..., tx + 112 (so that the
+// four rows x eight keys it produces go into the transposed score tile as eight conflict-free 16-byte stores); this placement
+// puts them at positions tx*4 .. tx*4+3 and 64 + tx*4 .. : two 16-byte loads, sixteen lanes reading 256 contiguous bytes each.
+__device__ __forceinline__ int key_pos(int key) {
+  const int c = key >> 4, tx = key & 15;
+  return ((c >> 2) << 6) + (tx << 2) + (c & 3);
+}
 
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__restrict__ K, int64_t ldk,
@@ -41,7 +50,8 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
   extern __shared__ float att_smem[];
   float *sQt = att_smem;                      // [d_k][kLdQ]   Q^T of this row block
   float *sKV = sQt + kAttDim * kLdQ;          // [d_k][kLdK]   K^T, then [skv][kAttDim] V
-  float *sS = sKV + kKVFloats;                // [rows][kLdS]  scores -> probabilities
+  float *sSt = sKV + kKVFloats;               // [keys][kLdSt] scores -> probabilities, transposed
+  float *sStat = sSt + kAttKeys * kLdSt;      // [rows]        row maximum, then row sum
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int m0 = blockIdx.y * kAttRows;
   const int rows = min(kAttRows, sq - m0);
@@ -67,7 +77,7 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
   // ---- stage Q^T, K^T.  A warp fetches 8 rows x 64 bytes per request (whole 32-byte sectors; with one row per lane half of
   //      every sector was wasted and each request touched 32 lines) and the transposed stores conflict two ways at most ----
   const int kq4 = d_k >> 2;
-  auto stage_t = [&](const float *__restrict__ src, int64_t ld, int n_rows_tile, int n_rows, float *dst, int ldd) {
+  auto stage_t = [&](const float *__restrict__ src, int64_t ld, int n_rows_tile, int n_rows, float *dst, int ldd, bool keys) {
     const int lane = t & 31, rl = lane & 7, kl = lane >> 3;  // 8 rows x 4 vectors per warp request
     const int row_groups = n_rows_tile >> 3;
     for (int w = t >> 5; w < row_groups * (kAttDim / 16); w += kAttThreads / 32) {
@@ -75,15 +85,16 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
       if (k4 >= kq4) continue;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < n_rows) v = *reinterpret_cast<const float4 *>(src + (int64_t)r * ld + 4 * k4);
-      dst[(4 * k4 + 0) * ldd + r] = v.x; dst[(4 * k4 + 1) * ldd + r] = v.y;
-      dst[(4 * k4 + 2) * ldd + r] = v.z; dst[(4 * k4 + 3) * ldd + r] = v.w;
+      const int c = keys ? key_pos(r) : r;
+      dst[(4 * k4 + 0) * ldd + c] = v.x; dst[(4 * k4 + 1) * ldd + c] = v.y;
+      dst[(4 * k4 + 2) * ldd + c] = v.z; dst[(4 * k4 + 3) * ldd + c] = v.w;
     }
   };
-  stage_t(Q, ldq, kAttRows, rows, sQt, kLdQ);
-  stage_t(K, ldk, kAttKeys, skv, sKV, kLdK);
+  stage_t(Q, ldq, kAttRows, rows, sQt, kLdQ, false);
+  stage_t(K, ldk, kAttKeys, skv, sKV, kLdK, true);
   __syncthreads();
 
-  // ---- scores: 4 rows x 8 keys per thread, k ascending ----
+  // ---- scores: 4 rows x 8 keys per thread (keys tx + 16 j), k ascending ----
   {
     float acc[4][8];
 #pragma unroll
@@ -93,8 +104,7 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
 #pragma unroll 4
     for (int k = 0; k < d_k; k++) {
       const float4 a0 = *reinterpret_cast<const float4 *>(sQt + k * kLdQ + ty * 4);
-      // a thread's eight keys are tx*4 .. tx*4+3 and 64 + tx*4 .. : sixteen lanes then read 256 contiguous bytes per load
-      // (keys tx*8 .. tx*8+7 made every 16-byte load a two-way bank conflict)
+      // positions tx*4 .. and 64 + tx*4 .. of the staged row hold this thread's keys (key_pos): sixteen lanes read 256 contiguous bytes
       const float4 b0 = *reinterpret_cast<const float4 *>(sKV + k * kLdK + tx * 4);
       const float4 b1 = *reinterpret_cast<const float4 *>(sKV + k * kLdK + 64 + tx * 4);
       const float a[4] = {a0.x, a0.y, a0.z, a0.w};
@@ -106,12 +116,13 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
     }
     const bool pad = (d_k % 32) != 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 8; j++) {
+      float sc[4];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float s = pad ? __fadd_rn(acc[i][j], 0.0f) : acc[i][j];
-        sS[(ty * 4 + i) * kLdS + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4))] = __fmul_rn(s, scale);
-      }
+      for (int i = 0; i < 4; i++) sc[i] = __fmul_rn(pad ? __fadd_rn(acc[i][j], 0.0f) : acc[i][j], scale);
+      // key tx + 16 j, rows ty*4 .. ty*4+3: one 16-byte store; a warp's 32 stores cover all banks four times (no conflict)
+      *reinterpret_cast<float4 *>(sSt + (tx + 16 * j) * kLdSt + ty * 4) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    }
   }
   __syncthreads();  // every thread is done with K^T
 #pragma unroll
@@ -120,34 +131,36 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
     *reinterpret_cast<float4 *>(sKV + (e >> 4) * kAttDim + 4 * (e & 15)) = vreg[u];
   }
 
-  // ---- softmax.  Only the row maximum and the running sum walk a row in order (one thread per row); the exponentials and
-  //      the divisions are independent per element and are done by all threads ----
+  // ---- softmax.  Only the row maximum and the running sum walk a row in order (one thread per row; consecutive threads read
+  //      consecutive words of a key's line); the exponentials and the divisions are independent per element, all threads ----
   if (t < rows) {
-    const float *srow = sS + t * kLdS;
-    float mx = srow[0];
+    float mx = sSt[t];
 #pragma unroll 8
     for (int j = 1; j < skv; j++) {
-      const float v = srow[j];
+      const float v = sSt[j * kLdSt + t];
       if (v > mx) mx = v;  // strict '>' from column 0: NaNs never replace, a NaN at column 0 stays
     }
-    sS[t * kLdS + kAttKeys] = mx;  // the padding column of the score tile
+    sStat[t] = mx;
   }
   __syncthreads();
-  // (thread = one key column, two rows per sweep: no index division -- with a run-time row length it cost as much as the expf)
-  const int jc = t & (kAttKeys - 1);
-  for (int r = t >> 7; r < rows; r += kAttThreads / kAttKeys)
-    if (jc < skv) sS[r * kLdS + jc] = expf(__fsub_rn(sS[r * kLdS + jc], sS[r * kLdS + kAttKeys]));
+  // (thread = one query row, every fourth key: no index division, conflict-free)
+  const int er = t & (kAttRows - 1), ej0 = t >> 6;
+  if (er < rows) {
+    const float mx = sStat[er];
+    for (int j = ej0; j < skv; j += kAttThreads / kAttRows) sSt[j * kLdSt + er] = expf(__fsub_rn(sSt[j * kLdSt + er], mx));
+  }
   __syncthreads();
   if (t < rows) {
-    const float *srow = sS + t * kLdS;
     float sum = 0.0f;
 #pragma unroll 8
-    for (int j = 0; j < skv; j++) sum = __fadd_rn(sum, srow[j]);  // ascending order: part of the result
-    sS[t * kLdS + kAttKeys] = sum;
+    for (int j = 0; j < skv; j++) sum = __fadd_rn(sum, sSt[j * kLdSt + t]);  // ascending order: part of the result
+    sStat[t] = sum;
   }
   __syncthreads();
-  for (int r = t >> 7; r < rows; r += kAttThreads / kAttKeys)
-    if (jc < skv) sS[r * kLdS + jc] = __fdiv_rn(sS[r * kLdS + jc], sS[r * kLdS + kAttKeys]);
+  if (er < rows) {
+    const float sum = sStat[er];
+    for (int j = ej0; j < skv; j += kAttThreads / kAttRows) sSt[j * kLdSt + er] = __fdiv_rn(sSt[j * kLdSt + er], sum);
+  }
   __syncthreads();
 
   // ---- out = P V: 4 rows x 4 columns per thread, j ascending ----
@@ -160,9 +173,13 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
 #pragma unroll 4
     for (int j = 0; j < skv; j++) {
       const float4 v = *reinterpret_cast<const float4 *>(sKV + j * kAttDim + tx * 4);
+      // this thread's four rows of key j in one 16-byte load (four 4-byte loads before the tile was transposed: the phase was
+      // bound by shared-memory wavefronts, six per sixteen FMAs; now three)
+      const float4 p4 = *reinterpret_cast<const float4 *>(sSt + j * kLdSt + ty * 4);
+      const float pr[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const float p = sS[(ty * 4 + i) * kLdS + j];
+        const float p = pr[i];
         acc[i][0] = __fmaf_rn(p, v.x, acc[i][0]);
         acc[i][1] = __fmaf_rn(p, v.y, acc[i][1]);
         acc[i][2] = __fmaf_rn(p, v.z, acc[i][2]);
