@@ -33,7 +33,7 @@ constexpr int kLdK = kAttKeys + 4;   // K^T tile [k][key]; the same region holds
 constexpr int kLdSt = kAttRows + 4;  // score tile, TRANSPOSED [key][row]: a thread's four rows of one key are one 16-byte access
 constexpr int kKVFloats = kAttDim * kLdK > kAttKeys * kAttDim ? kAttDim * kLdK : kAttKeys * kAttDim;
 constexpr size_t kAttSmem =
-    sizeof(float) * ((size_t)kAttDim * kLdQ + (size_t)kKVFloats + (size_t)kAttKeys * kLdSt + kAttRows);  // 85 KB: two CTAs per SM
+    sizeof(float) * ((size_t)kAttDim * kLdQ + (size_t)kKVFloats + (size_t)kAttKeys * kLdSt + 5 * kAttRows);  // 85 KB: two CTAs per SM
 
 // Where key `key` sits in a row of the staged K^T.  Thread tx of the score phase owns keys tx, tx + 16, ..., tx + 112 (so that the
 // four rows x eight keys it produces go into the transposed score tile as eight conflict-free 16-byte stores); this placement
@@ -51,7 +51,7 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
   float *sQt = att_smem;                      // [d_k][kLdQ]   Q^T of this row block
   float *sKV = sQt + kAttDim * kLdQ;          // [d_k][kLdK]   K^T, then [skv][kAttDim] V
   float *sSt = sKV + kKVFloats;               // [keys][kLdSt] scores -> probabilities, transposed
-  float *sStat = sSt + kAttKeys * kLdSt;      // [rows]        row maximum, then row sum
+  float *sStat = sSt + kAttKeys * kLdSt;      // [rows] row maximum, then row sum; [4][rows] partial maxima behind it
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int m0 = blockIdx.y * kAttRows;
   const int rows = min(kAttRows, sq - m0);
@@ -75,23 +75,48 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
     vreg[u] = (r < skv && c4 < dv4) ? *reinterpret_cast<const float4 *>(V + (int64_t)r * ldv + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // ---- stage Q^T, K^T.  A warp fetches 8 rows x 64 bytes per request (whole 32-byte sectors; with one row per lane half of
-  //      every sector was wasted and each request touched 32 lines) and the transposed stores conflict two ways at most ----
+  //      every sector was wasted and each request touched 32 lines).  All of a thread's loads (4 of Q, 8 of K, besides the 8 of
+  //      V above) are issued before the first transposed store: a load-store-load-store loop was a chain of eight global-memory
+  //      round trips per warp (ncu: 14 % of the kernel's samples sat on the two store instructions, waiting for their load) ----
   const int kq4 = d_k >> 2;
-  auto stage_t = [&](const float *__restrict__ src, int64_t ld, int n_rows_tile, int n_rows, float *dst, int ldd, bool keys) {
-    const int lane = t & 31, rl = lane & 7, kl = lane >> 3;  // 8 rows x 4 vectors per warp request
-    const int row_groups = n_rows_tile >> 3;
-    for (int w = t >> 5; w < row_groups * (kAttDim / 16); w += kAttThreads / 32) {
-      const int r = (w % row_groups) * 8 + rl, k4 = (w / row_groups) * 4 + kl;
-      if (k4 >= kq4) continue;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < n_rows) v = *reinterpret_cast<const float4 *>(src + (int64_t)r * ld + 4 * k4);
-      const int c = keys ? key_pos(r) : r;
-      dst[(4 * k4 + 0) * ldd + c] = v.x; dst[(4 * k4 + 1) * ldd + c] = v.y;
-      dst[(4 * k4 + 2) * ldd + c] = v.z; dst[(4 * k4 + 3) * ldd + c] = v.w;
+  {
+    const int lane = t & 31, rl = lane & 7, kl = lane >> 3, wid = t >> 5;  // 8 rows x 4 vectors per warp request
+    constexpr int kWarps = kAttThreads / 32;
+    constexpr int kQReq = (kAttRows / 8) * (kAttDim / 16) / kWarps;   // 4 requests per warp
+    constexpr int kKReq = (kAttKeys / 8) * (kAttDim / 16) / kWarps;   // 8
+    float4 qreg[kQReq], kreg[kKReq];
+#pragma unroll
+    for (int u = 0; u < kQReq; u++) {
+      const int w = wid + u * kWarps;
+      const int r = (w % (kAttRows / 8)) * 8 + rl, k4 = (w / (kAttRows / 8)) * 4 + kl;
+      qreg[u] = (r < rows && k4 < kq4) ? *reinterpret_cast<const float4 *>(Q + (int64_t)r * ldq + 4 * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  };
-  stage_t(Q, ldq, kAttRows, rows, sQt, kLdQ, false);
-  stage_t(K, ldk, kAttKeys, skv, sKV, kLdK, true);
+#pragma unroll
+    for (int u = 0; u < kKReq; u++) {
+      const int w = wid + u * kWarps;
+      const int r = (w % (kAttKeys / 8)) * 8 + rl, k4 = (w / (kAttKeys / 8)) * 4 + kl;
+      kreg[u] = (r < skv && k4 < kq4) ? *reinterpret_cast<const float4 *>(K + (int64_t)r * ldk + 4 * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kQReq; u++) {
+      const int w = wid + u * kWarps;
+      const int r = (w % (kAttRows / 8)) * 8 + rl, k4 = (w / (kAttRows / 8)) * 4 + kl;
+      if (k4 < kq4) {
+        sQt[(4 * k4 + 0) * kLdQ + r] = qreg[u].x; sQt[(4 * k4 + 1) * kLdQ + r] = qreg[u].y;
+        sQt[(4 * k4 + 2) * kLdQ + r] = qreg[u].z; sQt[(4 * k4 + 3) * kLdQ + r] = qreg[u].w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kKReq; u++) {
+      const int w = wid + u * kWarps;
+      const int r = (w % (kAttKeys / 8)) * 8 + rl, k4 = (w / (kAttKeys / 8)) * 4 + kl;
+      if (k4 < kq4) {
+        const int c = key_pos(r);
+        sKV[(4 * k4 + 0) * kLdK + c] = kreg[u].x; sKV[(4 * k4 + 1) * kLdK + c] = kreg[u].y;
+        sKV[(4 * k4 + 2) * kLdK + c] = kreg[u].z; sKV[(4 * k4 + 3) * kLdK + c] = kreg[u].w;
+      }
+    }
+  }
   __syncthreads();
 
   // ---- scores: 4 rows x 8 keys per thread (keys tx + 16 j), k ascending ----
@@ -133,18 +158,33 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
 
   // ---- softmax.  Only the row maximum and the running sum walk a row in order (one thread per row; consecutive threads read
   //      consecutive words of a key's line); the exponentials and the divisions are independent per element, all threads ----
-  if (t < rows) {
-    float mx = sSt[t];
+  // row maximum: mx = S[i,0], then strict '>' updates over j (a NaN never replaces, a NaN at column 0 stays, of equal values
+  // the first stays).  Four threads per row take 32 keys each -- the three that do not own column 0 start from -inf, which no
+  // value loses to and which never wins the strict comparison below -- and the partial results are merged in key order: the
+  // same value as the one-thread walk, a quarter of its dependent chain.
+  const int er = t & (kAttRows - 1), ej0 = t >> 6;
+  {
+    const int j0 = ej0 * (kAttKeys / 4), j1 = min(skv, j0 + kAttKeys / 4);
+    float mx = ej0 == 0 ? sSt[er] : -INFINITY;
 #pragma unroll 8
-    for (int j = 1; j < skv; j++) {
-      const float v = sSt[j * kLdSt + t];
-      if (v > mx) mx = v;  // strict '>' from column 0: NaNs never replace, a NaN at column 0 stays
+    for (int j = j0 + (ej0 == 0 ? 1 : 0); j < j1; j++) {
+      const float v = sSt[j * kLdSt + er];
+      if (v > mx) mx = v;
+    }
+    sStat[kAttRows + ej0 * kAttRows + er] = mx;
+  }
+  __syncthreads();
+  if (t < rows) {
+    float mx = sStat[kAttRows + t];
+#pragma unroll
+    for (int q = 1; q < 4; q++) {
+      const float v = sStat[kAttRows + q * kAttRows + t];
+      if (v > mx) mx = v;
     }
     sStat[t] = mx;
   }
   __syncthreads();
   // (thread = one query row, every fourth key: no index division, conflict-free)
-  const int er = t & (kAttRows - 1), ej0 = t >> 6;
   if (er < rows) {
     const float mx = sStat[er];
     for (int j = ej0; j < skv; j += kAttThreads / kAttRows) sSt[j * kLdSt + er] = expf(__fsub_rn(sSt[j * kLdSt + er], mx));
@@ -170,7 +210,7 @@ attention_core_kernel(const float *__restrict__ Q, int64_t ldq, const float *__r
     for (int i = 0; i < 4; i++)
 #pragma unroll
       for (int c = 0; c < 4; c++) acc[i][c] = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < skv; j++) {
       const float4 v = *reinterpret_cast<const float4 *>(sKV + j * kAttDim + tx * 4);
       // this thread's four rows of key j in one 16-byte load (four 4-byte loads before the tile was transposed: the phase was
