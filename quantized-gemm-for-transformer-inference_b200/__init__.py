@@ -475,7 +475,9 @@ def copy_2d_async(dst_ptr: int, dst_pitch: int, src_ptr: int, src_pitch: int, wi
 def add_layernorm_quant(A: torch.Tensor, R, B: torch.Tensor, range_: float = 127.0, mode: int = MODE_REF_EXACT):
     """ADD & NORM (transformer.cu:57-58) that also returns the int8 codes + Cx of its result (qg_add_layernorm_quant_f32)."""
     M, N = A.shape
-    Xq = torch.zeros((M, (N + 15) // 16 * 16), dtype=torch.int8, device=A.device)[:, :N]
+    ldq = (N + 15) // 16 * 16
+    # the padding columns up to the 16-byte leading dimension must read as zero codes; without padding nothing needs clearing
+    Xq = (torch.empty if ldq == N else torch.zeros)((M, ldq), dtype=torch.int8, device=A.device)[:, :N]
     Cx = torch.empty(M, dtype=torch.float32, device=A.device)
     pa, lda = _dev2d(A)
     pb, ldb = _dev2d(B)
