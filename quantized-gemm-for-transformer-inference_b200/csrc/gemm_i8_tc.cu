@@ -892,7 +892,13 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
     p.tail_split = 2;
     p.total_tiles = p.full_tiles + 2 * rem;
   }
-  if (NP == 1 && !B_MN && dbg_all_half && p.split_k == 1) {  // experiment: every tile 128 columns wide
+  // A product that fills at most half the machine with 256-column tiles (config 3's 4096 x 512 x 512 and 4096 x 512 x 2048
+  // linears: 32 tiles on 74 CTA pairs) is all epilogue -- one exposed 128 KB tile per CTA behind a main loop of a few k-blocks.
+  // 128-column tiles put it on twice the CTAs with half the epilogue each (role counters, run 43: 6.7 -> 4.75 us and 9.5 -> 7.0 us);
+  // a narrower MMA costs the same as a wide one, but here the MMAs are a fraction of the launch.
+  static const bool no_small_half = getenv("QG_NO_SMALL_HALF") != nullptr;
+  const bool small_half = !no_small_half && !no_tail_split && base_tiles > 0 && 2 * base_tiles <= max_clusters && p.N % BN == 0;
+  if (NP == 1 && !B_MN && (dbg_all_half || small_half) && p.split_k == 1) {  // every tile 128 columns wide
     p.full_tiles = 0;
     p.tail_split = 2;
     p.total_tiles = 2 * base_tiles;
