@@ -897,7 +897,8 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mbh,
   // 128-column tiles put it on twice the CTAs with half the epilogue each (role counters, run 43: 6.7 -> 4.75 us and 9.5 -> 7.0 us);
   // a narrower MMA costs the same as a wide one, but here the MMAs are a fraction of the launch.
   static const bool no_small_half = getenv("QG_NO_SMALL_HALF") != nullptr;
-  const bool small_half = !no_small_half && !no_tail_split && base_tiles > 0 && 2 * base_tiles <= max_clusters && p.N % BN == 0;
+  const bool small_half = !no_small_half && !no_tail_split && base_tiles > 0 && 2 * base_tiles <= max_clusters && p.N % BN == 0 &&
+                          p.n_extra == 0 && p.mc_out == nullptr;  // (the exchange epilogues were validated on the 2-GPU box without it)
   if (NP == 1 && !B_MN && (dbg_all_half || small_half) && p.split_k == 1) {  // every tile 128 columns wide
     p.full_tiles = 0;
     p.tail_split = 2;
