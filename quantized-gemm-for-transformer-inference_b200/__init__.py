@@ -666,6 +666,7 @@ class MultiHeadAttention:
         self.d_model, self.n_heads, self.range, self.mode = d_model, n_heads, range_, mode
         self.d_k = self.d_v = d_model // n_heads  # transformer.cu:21-22
         self.W_qkv = torch.empty((d_model, n_heads * (2 * self.d_k + self.d_v)), dtype=torch.float32, device=device)
+        self._wq = None  # (Wt, Cw) of quantize_weights(); dropped by init_uniform
 
     def head_weights(self, h: int):
         """(W_q, W_k, W_v) views of head h, each [d_model, d_k]."""
@@ -688,7 +689,7 @@ class MultiHeadAttention:
         if not prepared:
             attention_forward(Xq, Xkv, self.W_qkv, out, self.n_heads, self.d_k, self.d_v, batch, self.range, self.mode)
             return
-        if getattr(self, "_wq", None) is None:
+        if self._wq is None:
             self.quantize_weights()
         Wt, Cw = self._wq
         attention_forward_prepared(Xq, Xkv, Wt, Cw, out, self.n_heads, self.d_k, self.d_v, batch, self.range, self.mode)
